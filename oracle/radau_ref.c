@@ -1,0 +1,787 @@
+/* ORACLE (test infrastructure, NOT product code) -- scalar C restatement of RadauDAE.
+ *
+ * One system at a time, plain C99, no vector tricks.  It restates the algorithm of the
+ * reference `scipyDAE/radauDAE.py` (RadauDAE._step_impl :515-791, solve_collocation_system
+ * :793-949, predict_factor :52-98, dense output :951-982, constructor :263-422) and of the
+ * solve_ivp driver loop that slices t_eval (radauDAE.py:1079-1157 / scipy ivp.py:659-732),
+ * for the dense branch with an analytic (or constant) Jacobian.
+ *
+ * Arithmetic contract ("the spec").  The reference's numbers come out
+ * of numpy + OpenBLAS, whose rounding cannot be reproduced elsewhere (the
+ * reference is not even bit-reproducible against itself across OpenBLAS kernel families).
+ * This restatement therefore fixes ONE explicit evaluation order -- right-looking LU with
+ * partial pivoting and reciprocal pivots, fma() where written, x**0.25 as sqrt(sqrt(x)),
+ * divisions by the Newton/error scales done as multiplications by a reciprocal, norms as
+ * sqrt(sum)*rsqrt(size) -- so that an independent implementation of the same spec (the CUDA
+ * kernels) can be compared with it BIT FOR BIT, while this file itself is pinned to the
+ * reference statistically (tests/test_oracle_c.py: every t_eval value within the parity
+ * tolerance of the reference-generated fixtures and identical accepted/rejected counts on
+ * the well-conditioned configurations).  Compile with -ffp-contract=off: fma() calls are the
+ * only fused operations.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load the shared object built from this file.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---- Radau IIA constants, radauDAE.py:11-48 (hex values: SURVEY 3.4) ---- */
+static const double RC[3] = {0x1.3d8b64657caeap-3, 0x1.4a36c0803a6dfp-1, 1.0};
+static const double RE[3] = {-0x1.418fd8baffe05p+3, 0x1.61d41b2d54580p+0, -0x1.5555555555555p-2};
+static const double MU_REAL = 0x1.d1a48d83e731dp+1;
+static const double MU_CR = 0x1.572db93e0c672p+1, MU_CI = -0x1.86747f2c3fcb6p+1;
+static const double RT[3][3] = {
+    {0x1.82d23845d677bp-4, -0x1.214a74c403bf7p-3, 0x1.ebff91a6d688ep-6},
+    {0x1.0037de70aa1edp-2, 0x1.a20e91e20b551p-3, -0x1.8821fa2a36dedp-2},
+    {1.0, 1.0, 0.0}};
+static const double RTI[3][3] = {
+    {0x1.0b70201a79c46p+2, 0x1.4f8c15da84e86p-2, 0x1.0bf7ff59d56efp-1},
+    {-0x1.0b70201a79c46p+2, -0x1.4f8c15da84e86p-2, 0x1.e810014c55221p-2},
+    {0x1.017885a24a7f2p-1, -0x1.4934e6fcaa598p+1, 0x1.312c0cf7bdfd1p-1}};
+static const double RP[3][3] = {
+    {0x1.418fd8baffe05p+3, -0x1.9a12ce7b30915p+4, 0x1.f295c43b61425p+3},
+    {-0x1.61d41b2d54580p+0, 0x1.497af24bb677ep+3, -0x1.1d406ee60becfp+3},
+    {0x1.5555555555555p-2, -0x1.5555555555555p+1, 0x1.aaaaaaaaaaaabp+1}};
+
+/* ---- options: field-for-field the constructor keywords of radauDAE.py:263-278 ---- */
+typedef struct {
+    double first_step;  /* <=0: reference default with a mass matrix, min(1e-6,|tb-t0|) (:313) */
+    double max_step;
+    double newton_tol;  /* <=0: max(10 eps/rtol, min(0.03, sqrt(rtol))) (:322) */
+    double factor_on_non_convergence, safety_factor, min_factor, max_factor;
+    double jac_recompute_factor;
+    int32_t max_newton_ite;
+    int32_t max_bad_ite; /* <0: 1 if any var_index>1 else 0 (:406-410) */
+    int32_t scale_residuals, scale_newton_norm, scale_error, zero_algebraic_error;
+    int32_t always_2nd_estimate, predictive_controller, predictive_newton_stop;
+    int32_t extrapolated_guess, all_newton_iterations, constant_dt;
+    int64_t nmax_step;  /* <=0: unlimited (solve_ivp_custom :1081) */
+} orc_options;
+
+enum { ST_FINISHED = 0, ST_TOO_SMALL = -1, ST_LU_FAILED = -2, ST_NMAX = 2 };
+enum { C_NFEV, C_NJEV, C_NLU, C_NSTEP, C_NACC, C_NREJ, C_NFAIL, C_NSOLVE, C_NSOLVE_ERR, C_COUNT };
+
+/* ---- problems: same parameter vectors as dae_scipy_b200/problems.py ---- */
+enum { PB_PENDULUM3 = 0, PB_PENDULUM2 = 1, PB_PENDULUM1 = 2, PB_ROBERTSON = 3, PB_TRANSISTOR = 4,
+       PB_NPENDULUM = 5 };
+
+typedef struct {
+    int problem, n;
+    const double *p; /* this system's parameters */
+    /* n-pendulum derived constants */
+    int nn;
+    double *m, *inv_m, *r0s;
+} prob_ctx;
+
+/* pendulum.py:130-148 (index 3), :151-166 (index 2), :169-184 (index 1); p = (m, g, r0) */
+static void pend_rhs(const prob_ctx *c, double t, const double *X, double *f) {
+    (void)t;
+    double m = c->p[0], g = c->p[1], r0 = c->p[2];
+    double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
+    f[0] = vx;
+    f[1] = vy;
+    f[2] = -x * l / m;
+    f[3] = -g - (y * l) / m;
+    if (c->problem == PB_PENDULUM3) f[4] = x * x + y * y - r0 * r0;
+    else if (c->problem == PB_PENDULUM2) f[4] = x * vx + y * vy;
+    else f[4] = l * (x * x + y * y) / m + g * y - (vx * vx + vy * vy);
+}
+static void pend_jac(const prob_ctx *c, double t, const double *X, double *J) {
+    (void)t;
+    double m = c->p[0], g = c->p[1];
+    double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
+    memset(J, 0, 25 * sizeof(double));
+    J[0 * 5 + 2] = 1.0;
+    J[1 * 5 + 3] = 1.0;
+    J[2 * 5 + 0] = -l / m; J[2 * 5 + 4] = -x / m;
+    J[3 * 5 + 1] = -l / m; J[3 * 5 + 4] = -y / m;
+    if (c->problem == PB_PENDULUM3) { J[4 * 5 + 0] = 2 * x; J[4 * 5 + 1] = 2 * y; }
+    else if (c->problem == PB_PENDULUM2) { J[20] = vx; J[21] = vy; J[22] = x; J[23] = y; }
+    else {
+        J[20] = 2 * x * l / m; J[21] = 2 * y * l / m + g; J[22] = -2 * vx; J[23] = -2 * vy;
+        J[24] = (x * x + y * y) / m;
+    }
+}
+/* robertson.py:80-87; p = (k1,k2,k3) */
+static void rob_rhs(const prob_ctx *c, double t, const double *y, double *f) {
+    (void)t;
+    double k1 = c->p[0], k2 = c->p[1], k3 = c->p[2];
+    f[0] = -k1 * y[0] + k2 * y[1] * y[2];
+    f[1] = k1 * y[0] - k2 * y[1] * y[2] - k3 * (y[1] * y[1]);
+    f[2] = y[0] + y[1] + y[2] - 1;
+}
+static void rob_jac(const prob_ctx *c, double t, const double *y, double *J) {
+    (void)t;
+    double k1 = c->p[0], k2 = c->p[1], k3 = c->p[2];
+    J[0] = -k1; J[1] = k2 * y[2]; J[2] = k2 * y[1];
+    J[3] = k1;  J[4] = -k2 * y[2] - 2 * k3 * y[1]; J[5] = -k2 * y[1];
+    J[6] = 1; J[7] = 1; J[8] = 1;
+}
+/* transistor_amplifier.py:33-56; p = (C1,C2,C3,R0,R1,R2,R3,R4,R5,Ub,Ua,w) */
+static void tra_rhs(const prob_ctx *c, double t, const double *y, double *f) {
+    const double *p = c->p;
+    double R0 = p[3], R1 = p[4], R2 = p[5], R3 = p[6], R4 = p[7], R5 = p[8], Ub = p[9];
+    double Ue = p[10] * sin(p[11] * t);
+    double fT = 1e-6 * (exp((y[1] - y[2]) / 0.026) - 1);
+    f[0] = (Ue - y[0]) / R0;
+    f[1] = Ub / R2 - y[1] * (1 / R1 + 1 / R2) - 0.01 * fT;
+    f[2] = fT - y[2] / R3;
+    f[3] = Ub / R4 - y[3] / R4 - 0.99 * fT;
+    f[4] = -y[4] / R5;
+}
+static void tra_jac(const prob_ctx *c, double t, const double *y, double *J) {
+    (void)t;
+    const double *p = c->p;
+    double R0 = p[3], R1 = p[4], R2 = p[5], R3 = p[6], R4 = p[7], R5 = p[8];
+    double df = 1e-6 * exp((y[1] - y[2]) / 0.026) / 0.026;
+    memset(J, 0, 25 * sizeof(double));
+    J[0] = -1 / R0;
+    J[6] = -(1 / R1 + 1 / R2) - 0.01 * df; J[7] = 0.01 * df;
+    J[11] = df; J[12] = -df - 1 / R3;
+    J[16] = -0.99 * df; J[17] = 0.99 * df; J[18] = -1 / R4;
+    J[24] = -1 / R5;
+}
+static void tra_mass(const double *p, double *M) {
+    double C1 = p[0], C2 = p[1], C3 = p[2];
+    memset(M, 0, 25 * sizeof(double));
+    M[0] = C1; M[1] = -C1; M[5] = -C1; M[6] = C1; M[12] = C2;
+    M[18] = C3; M[19] = -C3; M[23] = -C3; M[24] = C3;
+}
+/* recursive_pendulum.py:93-118; unknowns interleaved (x,y,vx,vy,lambda) per node */
+#define GRAV 9.81
+static void npe_rhs(const prob_ctx *c, double t, const double *X, double *f) {
+    (void)t;
+    int nn = c->nn;
+    double a_prev = 0, b_prev = 0; /* lambda_i dx_i / rs_i of node i, consumed by node i-1 */
+    /* walk from the last node to the first so that the (i+1) term is at hand */
+    for (int i = nn - 1; i >= 0; --i) {
+        const double *q = X + 5 * i;
+        double dx = (i == 0) ? q[0] : q[0] - q[-5];
+        double dy = (i == 0) ? q[1] : q[1] - q[-4];
+        double rs = dx * dx + dy * dy;
+        double a = q[4] * dx / rs, b = q[4] * dy / rs;
+        double *o = f + 5 * i;
+        o[0] = q[2];
+        o[1] = q[3];
+        if (i == nn - 1) {
+            o[2] = c->inv_m[i] * a;
+            o[3] = c->inv_m[i] * (b - c->m[i] * GRAV);
+        } else {
+            o[2] = c->inv_m[i] * (a - a_prev);
+            o[3] = c->inv_m[i] * (b - b_prev - c->m[i] * GRAV);
+        }
+        o[4] = rs - c->r0s[i];
+        a_prev = a; b_prev = b;
+    }
+}
+/* analytic Jacobian of npe_rhs, dense [N][N]; same formulas as oracle/problems_numpy.py */
+static void npe_jac(const prob_ctx *c, double t, const double *X, double *J) {
+    (void)t;
+    int nn = c->nn, N = 5 * nn;
+    memset(J, 0, (size_t)N * N * sizeof(double));
+    for (int i = 0; i < nn; ++i) {
+        const double *q = X + 5 * i;
+        double dx = (i == 0) ? q[0] : q[0] - q[-5];
+        double dy = (i == 0) ? q[1] : q[1] - q[-4];
+        double rs = dx * dx + dy * dy, l = q[4];
+        double rs2 = rs * rs;
+        double adx = l * (rs - 2 * dx * dx) / rs2, ady = l * (-2 * dx * dy) / rs2;
+        double bdy = l * (rs - 2 * dy * dy) / rs2, bdx = ady;
+        double al = dx / rs, bl = dy / rs;
+        int r = 5 * i;
+        double im = c->inv_m[i];
+#define JJ(a, b) J[(size_t)(a) * N + (b)]
+        JJ(r, r + 2) = 1.0;
+        JJ(r + 1, r + 3) = 1.0;
+        JJ(r + 2, r) += im * adx; JJ(r + 2, r + 1) += im * ady; JJ(r + 2, r + 4) += im * al;
+        JJ(r + 3, r) += im * bdx; JJ(r + 3, r + 1) += im * bdy; JJ(r + 3, r + 4) += im * bl;
+        if (i > 0) {
+            JJ(r + 2, r - 5) -= im * adx; JJ(r + 2, r - 4) -= im * ady;
+            JJ(r + 3, r - 5) -= im * bdx; JJ(r + 3, r - 4) -= im * bdy;
+            /* node i-1 sees -a_i, -b_i */
+            double imp = c->inv_m[i - 1];
+            int rp = r - 5;
+            JJ(rp + 2, r) -= imp * adx; JJ(rp + 2, r + 1) -= imp * ady; JJ(rp + 2, r + 4) -= imp * al;
+            JJ(rp + 2, rp) += imp * adx; JJ(rp + 2, rp + 1) += imp * ady;
+            JJ(rp + 3, r) -= imp * bdx; JJ(rp + 3, r + 1) -= imp * bdy; JJ(rp + 3, r + 4) -= imp * bl;
+            JJ(rp + 3, rp) += imp * bdx; JJ(rp + 3, rp + 1) += imp * bdy;
+        }
+        JJ(r + 4, r) = 2 * dx; JJ(r + 4, r + 1) = 2 * dy;
+        if (i > 0) { JJ(r + 4, r - 5) = -2 * dx; JJ(r + 4, r - 4) = -2 * dy; }
+#undef JJ
+    }
+}
+
+/* recursive_pendulum.py:63-73: node masses 1/(n-1) (last one 1), rods 2/n */
+static void npe_constants(prob_ctx *c) {
+    int nn = c->nn;
+    c->m = malloc(sizeof(double) * nn); c->inv_m = malloc(sizeof(double) * nn); c->r0s = malloc(sizeof(double) * nn);
+    for (int i = 0; i < nn; ++i) {
+        double m = (i == nn - 1) ? 1.0 : 1.0 / (nn - 1);
+        double r0 = 2.0 / nn;
+        c->m[i] = m; c->inv_m[i] = 1 / m; c->r0s[i] = r0 * r0;
+    }
+}
+
+static void prob_rhs(const prob_ctx *c, double t, const double *y, double *f) {
+    switch (c->problem) {
+    case PB_ROBERTSON: rob_rhs(c, t, y, f); break;
+    case PB_TRANSISTOR: tra_rhs(c, t, y, f); break;
+    case PB_NPENDULUM: npe_rhs(c, t, y, f); break;
+    default: pend_rhs(c, t, y, f);
+    }
+}
+static void prob_jac(const prob_ctx *c, double t, const double *y, double *J) {
+    switch (c->problem) {
+    case PB_ROBERTSON: rob_jac(c, t, y, J); break;
+    case PB_TRANSISTOR: tra_jac(c, t, y, J); break;
+    case PB_NPENDULUM: npe_jac(c, t, y, J); break;
+    default: pend_jac(c, t, y, J);
+    }
+}
+
+int orc_problem_dims(int problem, int *n, int *n_params) {
+    switch (problem) {
+    case PB_PENDULUM3: case PB_PENDULUM2: case PB_PENDULUM1: *n = 5; *n_params = 3; return 0;
+    case PB_ROBERTSON: *n = 3; *n_params = 3; return 0;
+    case PB_TRANSISTOR: *n = 5; *n_params = 12; return 0;
+    case PB_NPENDULUM: *n = -1; *n_params = 0; return 0; /* n = 5*nodes given by the caller */
+    }
+    return -1;
+}
+
+/* test hooks: evaluate rhs / jacobian of one system (used to check the problem restatements) */
+int orc_eval_rhs_jac(int problem, int n, const double *p, double t, const double *y, double *f,
+                     double *J) {
+    prob_ctx c = {problem, n, p, 0, NULL, NULL, NULL};
+    if (problem == PB_NPENDULUM) { c.nn = n / 5; npe_constants(&c); }
+    if (f) prob_rhs(&c, t, y, f);
+    if (J) prob_jac(&c, t, y, J);
+    free(c.m); free(c.inv_m); free(c.r0s);
+    return 0;
+}
+
+/* ---- linear algebra of the spec ---- */
+typedef struct {
+    int n, kl, ku;       /* band limits used only to skip structural zeros (results identical) */
+    double *lr;          /* real LU [n][n], reciprocal pivots on the diagonal */
+    double *lcr, *lci;   /* complex LU, split re/im, reciprocal pivots on the diagonal */
+    int *pr, *pc;        /* pivot rows */
+} lu_pair;
+
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* right-looking LU, partial pivoting on |a| (first maximum), reciprocal pivot stored */
+static void lu_real(lu_pair *L) {
+    int n = L->n;
+    double *A = L->lr;
+    for (int k = 0; k < n; ++k) {
+        int rmax = imin(n - 1, k + L->kl);
+        int cmax = imin(n - 1, k + L->ku + L->kl);
+        int p = k;
+        double best = fabs(A[k * n + k]);
+        for (int r = k + 1; r <= rmax; ++r) {
+            double v = fabs(A[r * n + k]);
+            if (v > best) { best = v; p = r; }
+        }
+        L->pr[k] = p;
+        if (p != k) /* active part only: multipliers stay where they were computed (dgbtrf style) */
+            for (int c = k; c <= cmax; ++c) { double tmp = A[k * n + c]; A[k * n + c] = A[p * n + c]; A[p * n + c] = tmp; }
+        double rcp = 1.0 / A[k * n + k];
+        A[k * n + k] = rcp;
+        for (int r = k + 1; r <= rmax; ++r) {
+            double l = A[r * n + k] * rcp;
+            A[r * n + k] = l;
+            for (int c = k + 1; c <= cmax; ++c) A[r * n + c] = fma(-l, A[k * n + c], A[r * n + c]);
+        }
+    }
+}
+static void solve_real(const lu_pair *L, double *b) {
+    int n = L->n;
+    const double *A = L->lr;
+    for (int k = 0; k < n; ++k) {
+        int p = L->pr[k];
+        if (p != k) { double tmp = b[k]; b[k] = b[p]; b[p] = tmp; }
+        int rmax = imin(n - 1, k + L->kl);
+        double bk = b[k];
+        for (int r = k + 1; r <= rmax; ++r) b[r] = fma(-A[r * n + k], bk, b[r]);
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        int cmax = imin(n - 1, k + L->ku + L->kl);
+        double s = b[k];
+        for (int c = k + 1; c <= cmax; ++c) s = fma(-A[k * n + c], b[c], s);
+        b[k] = s * A[k * n + k];
+    }
+}
+/* complex: pivot on |re|+|im| (BLAS izamax), reciprocal pivot = conj(p)/|p|^2 */
+static void lu_cplx(lu_pair *L) {
+    int n = L->n;
+    double *R = L->lcr, *I = L->lci;
+    for (int k = 0; k < n; ++k) {
+        int rmax = imin(n - 1, k + L->kl);
+        int cmax = imin(n - 1, k + L->ku + L->kl);
+        int p = k;
+        double best = fabs(R[k * n + k]) + fabs(I[k * n + k]);
+        for (int r = k + 1; r <= rmax; ++r) {
+            double v = fabs(R[r * n + k]) + fabs(I[r * n + k]);
+            if (v > best) { best = v; p = r; }
+        }
+        L->pc[k] = p;
+        if (p != k)
+            for (int c = k; c <= cmax; ++c) {
+                double tmp = R[k * n + c]; R[k * n + c] = R[p * n + c]; R[p * n + c] = tmp;
+                tmp = I[k * n + c]; I[k * n + c] = I[p * n + c]; I[p * n + c] = tmp;
+            }
+        double pr = R[k * n + k], pi = I[k * n + k];
+        double invd = 1.0 / fma(pr, pr, pi * pi);
+        double qr = pr * invd, qi = -(pi * invd);
+        R[k * n + k] = qr; I[k * n + k] = qi;
+        for (int r = k + 1; r <= rmax; ++r) {
+            double ar = R[r * n + k], ai = I[r * n + k];
+            double lr = fma(ar, qr, -(ai * qi));
+            double li = fma(ar, qi, ai * qr);
+            R[r * n + k] = lr; I[r * n + k] = li;
+            for (int c = k + 1; c <= cmax; ++c) {
+                double ur = R[k * n + c], ui = I[k * n + c];
+                double xr = R[r * n + c], xi = I[r * n + c];
+                xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
+                xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
+                R[r * n + c] = xr; I[r * n + c] = xi;
+            }
+        }
+    }
+}
+static void solve_cplx(const lu_pair *L, double *br, double *bi) {
+    int n = L->n;
+    const double *R = L->lcr, *I = L->lci;
+    for (int k = 0; k < n; ++k) {
+        int p = L->pc[k];
+        if (p != k) {
+            double tmp = br[k]; br[k] = br[p]; br[p] = tmp;
+            tmp = bi[k]; bi[k] = bi[p]; bi[p] = tmp;
+        }
+        int rmax = imin(n - 1, k + L->kl);
+        double xr = br[k], xi = bi[k];
+        for (int r = k + 1; r <= rmax; ++r) {
+            double lr = R[r * n + k], li = I[r * n + k];
+            double yr = br[r], yi = bi[r];
+            yr = fma(-lr, xr, yr); yr = fma(li, xi, yr);
+            yi = fma(-lr, xi, yi); yi = fma(-li, xr, yi);
+            br[r] = yr; bi[r] = yi;
+        }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        int cmax = imin(n - 1, k + L->ku + L->kl);
+        double sr = br[k], si = bi[k];
+        for (int c = k + 1; c <= cmax; ++c) {
+            double ur = R[k * n + c], ui = I[k * n + c];
+            sr = fma(-ur, br[c], sr); sr = fma(ui, bi[c], sr);
+            si = fma(-ur, bi[c], si); si = fma(-ui, br[c], si);
+        }
+        double qr = R[k * n + k], qi = I[k * n + k];
+        br[k] = fma(sr, qr, -(si * qi));
+        bi[k] = fma(sr, qi, si * qr);
+    }
+}
+
+/* M.v with M dense row-major; the fma chain runs over the columns in increasing order and
+ * skips structural zeros of M (adding an exact zero changes nothing) */
+static void mass_mv(int n, const double *M, const int *mlo, const int *mhi, const double *v, double *o) {
+    for (int r = 0; r < n; ++r) {
+        double s = 0.0;
+        int first = 1;
+        for (int c = mlo[r]; c <= mhi[r]; ++c) {
+            double m = M[r * n + c];
+            if (m == 0.0) continue;
+            if (first) { s = m * v[c]; first = 0; }
+            else s = fma(m, v[c], s);
+        }
+        o[r] = s;
+    }
+}
+
+static double hpow(double h, int e) { return e == 0 ? 1.0 : (e == 1 ? h : h * h); }
+
+/* predict_factor, radauDAE.py:52-98 */
+static double gustafsson(double h_abs, double h_abs_old, double err, double err_old, int hist, int predictive) {
+    double mult;
+    if (!predictive || !hist || err == 0.0) mult = 1.0;
+    else mult = h_abs / h_abs_old * sqrt(sqrt(err_old / err));
+    double base = 1.0 / sqrt(sqrt(err)); /* err == 0 -> +inf, clamped by the caller */
+    return (mult < 1.0 ? mult : 1.0) * base;
+}
+
+typedef struct {
+    int n;
+    double *y, *f, *yold, *Q /*[n][3]*/, *W /*[3][n]*/, *Z /*[3][n]*/, *F, *J, *M;
+    double *fr, *fcr, *fci, *mw0, *mw1, *mw2, *inv_ns, *inv_es, *ze, *err, *tmp, *hs;
+    int *mlo, *mhi;
+    lu_pair lu;
+} work;
+
+static void *xcalloc(size_t n, size_t s) { void *p = calloc(n ? n : 1, s); if (!p) abort(); return p; }
+
+static void work_alloc(work *w, int n) {
+    w->n = n;
+    size_t N = (size_t)n;
+    w->y = xcalloc(N, 8); w->f = xcalloc(N, 8); w->yold = xcalloc(N, 8);
+    w->Q = xcalloc(3 * N, 8); w->W = xcalloc(3 * N, 8); w->Z = xcalloc(3 * N, 8); w->F = xcalloc(N, 8);
+    w->J = xcalloc(N * N, 8); w->M = xcalloc(N * N, 8);
+    w->fr = xcalloc(N, 8); w->fcr = xcalloc(N, 8); w->fci = xcalloc(N, 8);
+    w->mw0 = xcalloc(N, 8); w->mw1 = xcalloc(N, 8); w->mw2 = xcalloc(N, 8);
+    w->inv_ns = xcalloc(N, 8); w->inv_es = xcalloc(N, 8); w->ze = xcalloc(N, 8);
+    w->err = xcalloc(N, 8); w->tmp = xcalloc(N, 8); w->hs = xcalloc(N, 8);
+    w->mlo = xcalloc(N, sizeof(int)); w->mhi = xcalloc(N, sizeof(int));
+    w->lu.n = n;
+    w->lu.lr = xcalloc(N * N, 8); w->lu.lcr = xcalloc(N * N, 8); w->lu.lci = xcalloc(N * N, 8);
+    w->lu.pr = xcalloc(N, sizeof(int)); w->lu.pc = xcalloc(N, sizeof(int));
+}
+static void work_free(work *w) {
+    free(w->y); free(w->f); free(w->yold); free(w->Q); free(w->W); free(w->Z); free(w->F);
+    free(w->J); free(w->M); free(w->fr); free(w->fcr); free(w->fci); free(w->mw0); free(w->mw1);
+    free(w->mw2); free(w->inv_ns); free(w->inv_es); free(w->ze); free(w->err); free(w->tmp);
+    free(w->hs); free(w->mlo); free(w->mhi);
+    free(w->lu.lr); free(w->lu.lcr); free(w->lu.lci); free(w->lu.pr); free(w->lu.pc);
+}
+
+/* Z_i = (T W)_i, fma chain over the stages in order 0,1,2; T[2] = (1,1,0) */
+static void stage_Z(int n, const double *W, int i, double *z) {
+    if (i == 2) { for (int c = 0; c < n; ++c) z[c] = W[c] + W[n + c]; return; }
+    for (int c = 0; c < n; ++c) {
+        double v = RT[i][0] * W[c];
+        v = fma(RT[i][1], W[n + c], v);
+        z[c] = fma(RT[i][2], W[2 * n + c], v);
+    }
+}
+
+/* Integrate one system.  Layout of the batch arrays is SoA: element (row, sys) at row*B+sys. */
+static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, const double *mass_in,
+                          const double *jac_const, const int *var_index, const double *atol,
+                          double rtol, double t0, double tb, const double *t_eval, int T, int64_t B,
+                          int64_t sys, const double *y0, double *y_eval, int *n_eval_out,
+                          double *t_final, double *y_final, int *status_out, int *counters) {
+    const int n = w->n;
+    int cnt[C_COUNT] = {0};
+    const int MAXIT = o->max_newton_ite;
+    const double dir = (tb != t0) ? (tb > t0 ? 1.0 : -1.0) : 1.0;
+    const double tol = (o->newton_tol > 0) ? o->newton_tol
+                       : fmax(10 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
+    int nmax_bad = o->max_bad_ite;
+    int n_alg = 0;
+    for (int c = 0; c < n; ++c) if (var_index[c] != 0) ++n_alg;
+    if (nmax_bad < 0) {
+        nmax_bad = 0;
+        for (int c = 0; c < n; ++c) if (var_index[c] > 1) nmax_bad = 1;
+    }
+    const double rsq3n = 1.0 / sqrt(3.0 * n), rsqn = 1.0 / sqrt((double)n);
+    const double rsqdiff = 1.0 / sqrt((double)(n - n_alg));
+    const int has_jac_fn = (jac_const == NULL);
+
+    /* mass matrix: given (shared) or the problem's own */
+    if (mass_in) memcpy(w->M, mass_in, sizeof(double) * n * n);
+    else if (pc->problem == PB_TRANSISTOR) tra_mass(pc->p, w->M);
+    else { /* pendulum.py:139-140, robertson.py:78, recursive_pendulum.py:120-127: identity with a
+              zero on the rows of the algebraic unknowns (last of 5 / last of 3) */
+        memset(w->M, 0, sizeof(double) * n * n);
+        int blk = (pc->problem == PB_ROBERTSON) ? 3 : 5;
+        for (int c = 0; c < n; ++c) w->M[c * n + c] = (c % blk == blk - 1) ? 0.0 : 1.0;
+    }
+    for (int r = 0; r < n; ++r) {
+        int lo = n, hi = -1;
+        for (int c = 0; c < n; ++c) if (w->M[r * n + c] != 0.0) { if (c < lo) lo = c; if (c > hi) hi = c; }
+        w->mlo[r] = lo; w->mhi[r] = hi;
+    }
+    /* band limits of (mu/h M - J): only used to skip exact zeros in the LU loops */
+    if (pc->problem == PB_NPENDULUM && mass_in == NULL && jac_const == NULL) { w->lu.kl = 9; w->lu.ku = 7; }
+    else { w->lu.kl = n; w->lu.ku = n; }
+
+    double t = t0;
+    for (int c = 0; c < n; ++c) w->y[c] = y0[(int64_t)c * B + sys];
+    prob_rhs(pc, t, w->y, w->f); cnt[C_NFEV] = 1;                    /* :304 */
+    double h_abs_state = (o->first_step > 0) ? o->first_step : dir * fmin(1e-6, fabs(tb - t0)); /* :307-315 */
+    double h_abs_old_state = 0, err_old_state = 0;
+    int hist_state = 0;
+    if (has_jac_fn) { prob_jac(pc, t, w->y, w->J); cnt[C_NJEV] = 1; } /* :483-484 */
+    else memcpy(w->J, jac_const, sizeof(double) * n * n);
+    int current_jac = 1, lu_valid = 0, have_sol = 0;
+    double h_sol = 0, t_sol_old = 0, inv_h_lu = 1.0;
+    int status = 1; /* running */
+    int ei = 0;     /* next t_eval index */
+    int64_t nsteps = 0;
+
+    if (t == tb) { /* OdeSolver.step corner case, scipy base.py:193-198 */
+        for (; ei < T; ++ei)
+            for (int c = 0; c < n; ++c) y_eval[((int64_t)ei * n + c) * B + sys] = w->y[c];
+        status = ST_FINISHED;
+    }
+
+    while (status == 1) {
+        ++nsteps;
+        if (o->nmax_step > 0 && nsteps > o->nmax_step) { status = ST_NMAX; break; }
+        /* ---------------- prologue, :516-562 */
+        cnt[C_NSTEP]++;
+        double min_step = fmax(1e-20, 10 * fabs(nextafter(t, dir * INFINITY) - t));
+        double h_abs, h_abs_old = h_abs_old_state, err_old = err_old_state;
+        int hist = hist_state;
+        if (h_abs_state > o->max_step) { h_abs = o->max_step; hist = 0; }
+        else if (h_abs_state < min_step) { h_abs = min_step; hist = 0; }
+        else h_abs = h_abs_state;
+        if (fabs(tb - (t + dir * h_abs)) < 1e-2 * h_abs) { h_abs = fabs(tb - t); lu_valid = 0; }
+        int rejected = 0, accepted = 0;
+        int n_iter = 0;
+        double rate = 0, h = 0, t_new = t, error_norm = 0, safety = 0;
+        int have_rate = 0;
+
+        while (!accepted) {
+            if (h_abs < min_step) { status = ST_TOO_SMALL; break; }
+            h = h_abs * dir;
+            t_new = t + h;
+            if (dir * (t_new - tb) > 0) t_new = tb;
+            h = t_new - t;
+            h_abs = fabs(h);
+            /* Newton scale, :585-588, kept as a reciprocal */
+            for (int c = 0; c < n; ++c) {
+                int ve = var_index[c] > 1 ? var_index[c] - 1 : 0;
+                double hp = o->scale_newton_norm ? hpow(h, ve) : 1.0;
+                w->inv_ns[c] = hp / (atol[c] + fabs(w->y[c]) * rtol);
+            }
+            int converged = 0;
+            for (;;) { /* convergence loop :591-647 */
+                /* starting guess :580-583 -> W = TI Z0 (recomputed on a retry: Z0 is never mutated) */
+                if (!have_sol || !o->extrapolated_guess) memset(w->W, 0, sizeof(double) * 3 * n);
+                else {
+                    for (int i = 0; i < 3; ++i) {
+                        double tt = t + h * RC[i];
+                        double x = (tt - t_sol_old) / h_sol;
+                        double p2 = x * x, p3 = p2 * x;
+                        for (int c = 0; c < n; ++c) {
+                            double v = w->Q[c * 3 + 0] * x;
+                            v = fma(w->Q[c * 3 + 1], p2, v);
+                            v = fma(w->Q[c * 3 + 2], p3, v);
+                            v = v + w->yold[c];
+                            w->Z[i * n + c] = v - w->y[c];
+                        }
+                    }
+                    for (int k = 0; k < 3; ++k)
+                        for (int c = 0; c < n; ++c) {
+                            double v = RTI[k][0] * w->Z[c];
+                            v = fma(RTI[k][1], w->Z[n + c], v);
+                            w->W[k * n + c] = fma(RTI[k][2], w->Z[2 * n + c], v);
+                        }
+                }
+                if (!lu_valid) { /* :594-613 */
+                    if (o->scale_residuals) inv_h_lu = 1.0 / h;
+                    for (int c = 0; c < n; ++c)
+                        w->hs[c] = (o->scale_residuals && var_index[c] >= 1) ? inv_h_lu : 1.0;
+                    double mr = MU_REAL / h, mcr = MU_CR / h, mci = MU_CI / h;
+                    for (int r = 0; r < n; ++r)
+                        for (int c = 0; c < n; ++c) {
+                            double m = w->M[r * n + c], j = w->J[r * n + c], s = w->hs[r];
+                            w->lu.lr[r * n + c] = s * fma(mr, m, -j);
+                            w->lu.lcr[r * n + c] = s * fma(mcr, m, -j);
+                            w->lu.lci[r * n + c] = s * (mci * m);
+                        }
+                    lu_real(&w->lu);
+                    lu_cplx(&w->lu);
+                    cnt[C_NLU]++;
+                    lu_valid = 1;
+                }
+                /* ------------- simplified Newton, :793-949 */
+                double mr = MU_REAL / h, mcr = MU_CR / h, mci = MU_CI / h;
+                double dwn_old = 0;
+                int have_old = 0, nbad = 0, k;
+                have_rate = 0; rate = 0;
+                converged = 0;
+                for (k = 0; k < MAXIT; ++k) {
+                    int finite = 1;
+                    for (int i = 0; i < 3; ++i) {
+                        stage_Z(n, w->W, i, w->tmp);
+                        for (int c = 0; c < n; ++c) w->tmp[c] = w->y[c] + w->tmp[c];
+                        prob_rhs(pc, t + h * RC[i], w->tmp, w->F);
+                        for (int c = 0; c < n; ++c) {
+                            double Fv = w->F[c];
+                            if (!isfinite(Fv)) finite = 0;
+                            if (i == 0) {
+                                w->fr[c] = RTI[0][0] * Fv; w->fcr[c] = RTI[1][0] * Fv; w->fci[c] = RTI[2][0] * Fv;
+                            } else {
+                                w->fr[c] = fma(RTI[0][i], Fv, w->fr[c]);
+                                w->fcr[c] = fma(RTI[1][i], Fv, w->fcr[c]);
+                                w->fci[c] = fma(RTI[2][i], Fv, w->fci[c]);
+                            }
+                        }
+                    }
+                    cnt[C_NFEV] += 3;
+                    if (!finite) break;
+                    mass_mv(n, w->M, w->mlo, w->mhi, w->W, w->mw0);
+                    mass_mv(n, w->M, w->mlo, w->mhi, w->W + n, w->mw1);
+                    mass_mv(n, w->M, w->mlo, w->mhi, w->W + 2 * n, w->mw2);
+                    for (int c = 0; c < n; ++c) {
+                        double a = fma(-mr, w->mw0[c], w->fr[c]);
+                        double br = fma(-mcr, w->mw1[c], w->fcr[c]); br = fma(mci, w->mw2[c], br);
+                        double bi = fma(-mcr, w->mw2[c], w->fci[c]); bi = fma(-mci, w->mw1[c], bi);
+                        w->fr[c] = a * w->hs[c]; w->fcr[c] = br * w->hs[c]; w->fci[c] = bi * w->hs[c];
+                    }
+                    solve_real(&w->lu, w->fr);
+                    solve_cplx(&w->lu, w->fcr, w->fci);
+                    cnt[C_NSOLVE]++;
+                    double s = 0;
+                    for (int c = 0; c < n; ++c) { double v = w->fr[c] * w->inv_ns[c]; s = fma(v, v, s); }
+                    for (int c = 0; c < n; ++c) { double v = w->fcr[c] * w->inv_ns[c]; s = fma(v, v, s); }
+                    for (int c = 0; c < n; ++c) { double v = w->fci[c] * w->inv_ns[c]; s = fma(v, v, s); }
+                    double dwn = sqrt(s) * rsq3n;
+                    for (int c = 0; c < n; ++c) {
+                        w->W[c] += w->fr[c]; w->W[n + c] += w->fcr[c]; w->W[2 * n + c] += w->fci[c];
+                    }
+                    double dw_true = 0, dw_true_max = 0;
+                    if (have_old) {
+                        rate = dwn / dwn_old; have_rate = 1;
+                        double inv1 = 1.0 / (1.0 - rate);
+                        dw_true = rate * inv1 * dwn;
+                        double rp = rate;
+                        for (int e = 1; e < MAXIT - k; ++e) rp *= rate;
+                        dw_true_max = rp * inv1 * dwn;
+                    }
+                    if (dwn < tol) { converged = 1; break; }
+                    if (have_rate) {
+                        if (rate >= 1) {
+                            if (rate < 100 && nbad < nmax_bad) { nbad++; continue; }
+                            if (!o->all_newton_iterations) break;
+                        }
+                        if (dw_true < tol) { converged = 1; break; }
+                        if (dw_true_max > tol && o->predictive_newton_stop) {
+                            if (nbad < nmax_bad) { nbad++; continue; }
+                            if (!o->all_newton_iterations) break;
+                        }
+                    }
+                    dwn_old = dwn; have_old = 1;
+                }
+                n_iter = (k < MAXIT) ? k + 1 : MAXIT;
+                safety = o->safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter); /* :631 */
+                if (converged) break;
+                if (current_jac) break;                                            /* :638-641 */
+                prob_jac(pc, t, w->y, w->J); cnt[C_NJEV]++;                        /* :643 */
+                current_jac = 1; lu_valid = 0;
+            }
+            if (!converged) {                                                      /* :650-658 */
+                cnt[C_NFAIL]++;
+                h_abs *= o->factor_on_non_convergence;
+                lu_valid = 0;
+                continue;
+            }
+            for (int i = 0; i < 3; ++i) stage_Z(n, w->W, i, w->Z + i * n);
+            if (o->constant_dt) { accepted = 1; error_norm = 0; break; }
+            /* ------------- error estimate, :669-711 */
+            for (int c = 0; c < n; ++c) {
+                double v = w->Z[c] * RE[0];
+                v = fma(w->Z[n + c], RE[1], v);
+                v = fma(w->Z[2 * n + c], RE[2], v);
+                w->ze[c] = v / h;
+                double ynew = w->y[c] + w->Z[2 * n + c];
+                int ve = var_index[c] > 1 ? var_index[c] - 1 : 0;
+                double hp = o->scale_error ? hpow(h, ve) : 1.0;
+                w->inv_es[c] = hp / (atol[c] + fmax(fabs(w->y[c]), fabs(ynew)) * rtol);
+            }
+            mass_mv(n, w->M, w->mlo, w->mhi, w->ze, w->mw0);
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 0) for (int c = 0; c < n; ++c) w->err[c] = w->f[c] + w->mw0[c];
+                else {
+                    for (int c = 0; c < n; ++c) w->tmp[c] = w->y[c] + w->err[c];
+                    prob_rhs(pc, t, w->tmp, w->F); cnt[C_NFEV]++;
+                    for (int c = 0; c < n; ++c) w->err[c] = w->F[c] + w->mw0[c];
+                }
+                solve_real(&w->lu, w->err);    /* rhs deliberately NOT scaled by hscale */
+                cnt[C_NSOLVE_ERR]++;
+                double s = 0;
+                for (int c = 0; c < n; ++c) {
+                    if (o->zero_algebraic_error && var_index[c] != 0) { w->err[c] = 0.0; continue; }
+                    double v = w->err[c] * w->inv_es[c]; s = fma(v, v, s);
+                }
+                error_norm = sqrt(s) * (o->zero_algebraic_error ? rsqdiff : rsqn);
+                if (!(error_norm > 1 && (o->always_2nd_estimate || rejected))) break;
+            }
+            if (error_norm > 1) {                                                   /* :713-733 */
+                double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, o->predictive_controller);
+                h_abs *= fmax(o->min_factor, safety * factor);
+                lu_valid = 0; rejected = 1; cnt[C_NREJ]++;
+            } else { cnt[C_NACC]++; accepted = 1; }
+        }
+        if (status != 1) break;
+        /* ---------------- epilogue, :742-784 */
+        int recompute = has_jac_fn && n_iter > 2 && have_rate && rate > o->jac_recompute_factor;
+        double factor;
+        if (o->constant_dt) factor = o->max_step / h_abs;
+        else factor = fmin(o->max_factor, safety * gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, o->predictive_controller));
+        if (!recompute && factor < 1.2) factor = 1; else lu_valid = 0;
+        for (int c = 0; c < n; ++c) { w->yold[c] = w->y[c]; w->y[c] = w->y[c] + w->Z[2 * n + c]; }
+        prob_rhs(pc, t_new, w->y, w->f); cnt[C_NFEV]++;
+        if (recompute) { prob_jac(pc, t_new, w->y, w->J); cnt[C_NJEV]++; current_jac = 1; }
+        else if (has_jac_fn) current_jac = 0;
+        h_abs_old_state = h_abs_state; err_old_state = error_norm; hist_state = 1;
+        h_abs_state = h_abs * factor;
+        for (int c = 0; c < n; ++c)
+            for (int j = 0; j < 3; ++j) {
+                double v = w->Z[c] * RP[0][j];
+                v = fma(w->Z[n + c], RP[1][j], v);
+                w->Q[c * 3 + j] = fma(w->Z[2 * n + c], RP[2][j], v);
+            }
+        t_sol_old = t; h_sol = t_new - t; have_sol = 1;
+        t = t_new;
+        /* ---------------- driver: finished? t_eval points inside (t_old, t] */
+        if (dir * (t - tb) >= 0) status = ST_FINISHED;
+        while (ei < T && (dir > 0 ? t_eval[ei] <= t : t_eval[ei] >= t)) {
+            double x = (t_eval[ei] - t_sol_old) / h_sol;
+            double p2 = x * x, p3 = p2 * x;
+            for (int c = 0; c < n; ++c) {
+                double v = w->Q[c * 3 + 0] * x;
+                v = fma(w->Q[c * 3 + 1], p2, v);
+                v = fma(w->Q[c * 3 + 2], p3, v);
+                y_eval[((int64_t)ei * n + c) * B + sys] = v + w->yold[c];
+            }
+            ++ei;
+        }
+    }
+    for (int e = ei; e < T; ++e)
+        for (int c = 0; c < n; ++c) y_eval[((int64_t)e * n + c) * B + sys] = NAN;
+    n_eval_out[sys] = ei;
+    t_final[sys] = t;
+    for (int c = 0; c < n; ++c) y_final[(int64_t)c * B + sys] = w->y[c];
+    status_out[sys] = status;
+    for (int k = 0; k < C_COUNT; ++k) counters[(int64_t)k * B + sys] = cnt[k];
+}
+
+/* Batch entry.  All pointers are host pointers; SoA layouts as in include/brdae.h.
+ * mass / jac_const: [n][n] row-major shared by the batch, or NULL (problem's own). */
+int orc_solve(int problem, int n, int n_params, int64_t B, const double *y0, const double *params,
+              const double *mass, const double *jac_const, const int32_t *var_index,
+              const double *atol, double rtol, double t0, double t_bound, const double *t_eval,
+              int T, const orc_options *opts, double *y_eval, int32_t *n_eval, double *t_final,
+              double *y_final, int32_t *status, int32_t *counters, int nthreads) {
+    if (n <= 0 || B < 0) return -1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel
+    {
+        work w;
+        work_alloc(&w, n);
+        double *p = xcalloc((size_t)(n_params > 0 ? n_params : 1), 8);
+        prob_ctx pc = {problem, n, p, 0, NULL, NULL, NULL};
+        if (problem == PB_NPENDULUM) { pc.nn = n / 5; npe_constants(&pc); }
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t s = 0; s < B; ++s) {
+            for (int k = 0; k < n_params; ++k) p[k] = params[(int64_t)k * B + s];
+            integrate_one(&pc, &w, opts, mass, jac_const, var_index, atol, rtol, t0, t_bound, t_eval, T, B,
+                          s, y0, y_eval, n_eval, t_final, y_final, status, counters);
+        }
+        free(p); free(pc.m); free(pc.inv_m); free(pc.r0s);
+        work_free(&w);
+    }
+    return 0;
+}
