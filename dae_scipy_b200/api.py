@@ -1,0 +1,345 @@
+"""solve_ivp_batched — the batched drop-in for `solve_ivp(fun, t_span, y0, method=RadauDAE, ...)`.
+
+Mirror of the reference's user-facing call (reference README.md:19-21; option surface
+scipyDAE/radauDAE.py:263-278; driver radauDAE.py:990-1195 / scipy ivp.py:560-760) for an
+ensemble of B independent systems.  What changes with respect to the reference call:
+
+  * `fun`/`jac` closures become a problem name (a CUDA device functor, see problems.py);
+    per-system parameters are a [B, p] array;
+  * `y0` is [B, n]; results carry a leading system axis: `y` is [B, n, T];
+  * `status`, `success`, `nfev`, `njev`, `nlu` and the RadauDAE counters are per-system arrays.
+
+Everything numerical happens in libbrdae.so (hand-written CUDA for sm_100a) through the C ABI
+of include/brdae.h; torch tensors are only the device buffers.  Without the built library or
+without a CUDA device the call raises — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import warnings
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from .problems import Problem, get_problem
+
+
+class RadauDAE:
+    """Marker for `method=`: the batched Radau IIA(5) DAE solver (reference class
+    scipyDAE/radauDAE.py:126).  It only names the method; the stepping lives in the kernels."""
+    name = "RadauDAE"
+
+
+def warn_extraneous(extraneous):
+    """scipy common.py:27-43 — same warning text."""
+    if extraneous:
+        warnings.warn("The following arguments have no effect for a chosen solver: "
+                      f"{', '.join(f'`{x}`' for x in extraneous)}.", stacklevel=3)
+
+
+@dataclass
+class HostBatch:
+    """Validated, host-side description of one call (small uniform arrays + options)."""
+    problem: Problem
+    n: int
+    B: int
+    t0: float
+    t_bound: float
+    t_eval: np.ndarray          # float64 [T], in user order (monotone in the direction of integration)
+    rtol: float
+    atol: np.ndarray            # float64 [n]
+    var_index: np.ndarray       # int32 [n]
+    mass: np.ndarray | None     # float64 [n, n] shared matrix, None = the problem's own (device functor)
+    jac_const: np.ndarray | None
+    options: _abi.BrdaeOptions
+
+    def struct(self, ptr) -> _abi.BrdaeBatch:
+        """Fill a brdae_batch; `ptr` maps field name -> address of the batch-sized buffers."""
+        b = _abi.BrdaeBatch()
+        b.problem = self.problem.problem_id
+        b.n = self.n
+        b.n_params = self.problem.n_params
+        b.n_t_eval = self.t_eval.size
+        b.n_systems = self.B
+        b.rtol = self.rtol
+        b.t0 = self.t0
+        b.t_bound = self.t_bound
+        b.mass = self.mass.ctypes.data if self.mass is not None else None
+        b.jac_const = self.jac_const.ctypes.data if self.jac_const is not None else None
+        b.var_index = self.var_index.ctypes.data
+        b.atol = self.atol.ctypes.data
+        for k in ("y0", "params", "t_eval", "y_eval", "n_eval", "t_final", "y_final", "status", "counters"):
+            setattr(b, k, ptr.get(k))
+        return b
+
+
+def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mass_matrix="problem",
+            var_index=None, jac="analytic", params=None, **options) -> HostBatch:
+    """Argument validation of solve_ivp + RadauDAE.__init__, for a batch.
+
+    Raises the same ValueErrors as the reference path: t_eval checks (scipy ivp.py:603-621 /
+    radauDAE.py:1018-1028), tolerance checks (scipy common.py:45-60), mass-matrix and Jacobian
+    shape checks (radauDAE.py:447-462, 499-510), first_step/max_step (common.py:10-24).
+    """
+    prob = get_problem(problem)
+    if len(y0_shape) != 2:
+        raise ValueError("`y0` must be 2-dimensional [B, n] for the batched solver.")
+    B, n = int(y0_shape[0]), int(y0_shape[1])
+    if prob.n and n != prob.n:
+        raise ValueError(f"problem {prob.name!r} has {prob.n} unknowns, `y0` has {n}.")
+    if not prob.n and (n <= 0 or n % 5):
+        raise ValueError("`y0` of the n-pendulum must have 5*nodes columns.")
+    t0, tf = float(t_span[0]), float(t_span[1])
+
+    if t_eval is None:
+        te = np.empty(0)
+    else:
+        te = np.asarray(t_eval, dtype=np.float64)
+        if te.ndim != 1:
+            raise ValueError("`t_eval` must be 1-dimensional.")
+        if np.any(te < min(t0, tf)) or np.any(te > max(t0, tf)):
+            raise ValueError("Values in `t_eval` are not within `t_span`.")
+        d = np.diff(te)
+        if tf > t0 and np.any(d <= 0) or tf < t0 and np.any(d >= 0):
+            raise ValueError("Values in `t_eval` are not properly sorted.")
+        te = np.ascontiguousarray(te)
+
+    rtol = float(rtol)
+    if rtol < 100 * np.finfo(float).eps:
+        warnings.warn("At least one element of `rtol` is too small. "
+                      f"Setting `rtol = np.maximum(rtol, {100 * np.finfo(float).eps})`.", stacklevel=3)
+        rtol = 100 * np.finfo(float).eps
+    at = np.asarray(atol, dtype=np.float64)
+    if at.ndim > 0 and at.shape != (n,):
+        raise ValueError("`atol` has wrong shape.")
+    if np.any(at < 0):
+        raise ValueError("`atol` must be positive.")
+    at = np.ascontiguousarray(np.broadcast_to(at, (n,)))
+
+    if var_index is None:
+        vi = np.zeros(n, dtype=np.int32)                   # radauDAE.py:389-390: all differential
+    else:
+        v = np.asarray(var_index)
+        if v.ndim != 1 or v.size != n:
+            raise ValueError("`var_index` must be a 1-D array with one entry per unknown.")
+        if np.any(v != np.round(v)) or np.any(v < 0) or np.any(v > 3):
+            raise ValueError("`var_index` entries must be integers between 0 and 3.")
+        vi = np.ascontiguousarray(v, dtype=np.int32)
+
+    mass = None
+    if isinstance(mass_matrix, str):
+        if mass_matrix != "problem":
+            raise ValueError("`mass_matrix` must be None, an [n, n] array or the string 'problem'.")
+    elif mass_matrix is None:
+        mass = np.eye(n)                                   # radauDAE.py:448-449
+    elif callable(mass_matrix):
+        raise ValueError("`mass_matrix` should be a constant matrix, but is callable")
+    else:
+        mass = np.ascontiguousarray(np.asarray(mass_matrix, dtype=np.float64))
+        if mass.shape != (n, n):
+            raise ValueError("`mass_matrix` is expected to have shape {}, but actually has {}."
+                             .format((n, n), mass.shape))
+        # the problem's own constant matrix -> the kernel with the compile-time mass structure
+        if not prob.per_system_mass and np.array_equal(mass, prob.mass(n=n)):
+            mass = None
+
+    jac_const = None
+    if isinstance(jac, str):
+        if jac != "analytic":
+            raise ValueError("`jac` must be 'analytic' or a constant [n, n] matrix.")
+    elif jac is None:
+        raise NotImplementedError(
+            "finite-difference Jacobians (jac=None in the reference, radauDAE.py:468-481) are not "
+            "available in the batched solver yet; use jac='analytic' or a constant matrix.")
+    elif callable(jac):
+        raise ValueError("Python Jacobian callables cannot run on the device; use jac='analytic'.")
+    else:
+        jac_const = np.ascontiguousarray(np.asarray(jac, dtype=np.float64))
+        if jac_const.shape != (n, n):
+            raise ValueError(f"`jac` is expected to have shape {(n, n)}, but actually has {jac_const.shape}.")
+
+    first_step = options.get("first_step")
+    if first_step is not None:
+        if first_step <= 0:
+            raise ValueError("`first_step` must be positive.")
+        if first_step > abs(tf - t0):
+            raise ValueError("`first_step` exceeds bounds.")
+    ignored = {k: options.pop(k) for k in list(options) if k in _abi.IGNORED_OPTS}
+    del ignored
+    extraneous = {k: options.pop(k) for k in list(options) if k not in _abi.SOLVER_OPTION_NAMES}
+    warn_extraneous(extraneous)
+    opts = _abi.make_options(**options)
+    if n > 8 and prob.name != "npendulum":
+        raise ValueError("thread-per-system kernels support at most 8 unknowns.")
+    return HostBatch(problem=prob, n=n, B=B, t0=t0, t_bound=tf, t_eval=te, rtol=rtol, atol=at,
+                     var_index=vi, mass=mass, jac_const=jac_const, options=opts)
+
+
+class BatchedOdeResult:
+    """OdeResult with a leading system axis (scipy ivp.py `OdeResult`; radauDAE.py:1183-1194).
+
+    Tensors stay on the device they were computed on; `.numpy()` copies everything to the host.
+      t [T]; y [B, n, T] (NaN after a failure point); n_eval [B]; status [B]; success [B];
+      t_final [B]; y_final [B, n]; nfev, njev, nlu, nstep, naccpt, nrejct, nfailed, nlusolve,
+      nlusolve_errorest [B].
+    """
+
+    def __init__(self, t, y_eval_tnb, n_eval, status, t_final, y_final_nb, counters_cb):
+        self.t = t
+        self._y_eval = y_eval_tnb           # [T, n, B] as written by the kernel (coalesced SoA)
+        self.n_eval = n_eval
+        self.status = status
+        self.t_final = t_final
+        self._y_final = y_final_nb          # [n, B]
+        self.counters = counters_cb         # [9, B]
+
+    @property
+    def y(self):
+        return self._y_eval.permute(2, 1, 0)    # [B, n, T] view, no copy
+
+    @property
+    def y_final(self):
+        return self._y_final.t()
+
+    @property
+    def success(self):
+        return self.status >= 0
+
+    def __getattr__(self, name):
+        if name in _abi.COUNTER_NAMES:
+            return self.counters[_abi.COUNTER_NAMES.index(name)]
+        raise AttributeError(name)
+
+    def message(self, i):
+        return _abi.MESSAGES.get(int(self.status[i]), "unknown status")
+
+    def numpy(self):
+        out = {"t": np.asarray(self.t), "y": self.y.cpu().numpy(), "n_eval": self.n_eval.cpu().numpy(),
+               "status": self.status.cpu().numpy(), "t_final": self.t_final.cpu().numpy(),
+               "y_final": self.y_final.cpu().numpy(), "counters": self.counters.t().cpu().numpy()}
+        for i, name in enumerate(_abi.COUNTER_NAMES):
+            out[name] = out["counters"][:, i]
+        out["success"] = out["status"] >= 0
+        return out
+
+
+def _as_device_f64(x, device, torch):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64)
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device)
+
+
+def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_eval=None,
+                      dense_output=False, events=None, device=None, stream=None, **options):
+    """Integrate B independent systems  M y' = f(t, y)  from t_span[0] to t_span[1] on one GPU.
+
+    Parameters follow `scipy.integrate.solve_ivp(..., method=RadauDAE, **options)` of the
+    reference (all RadauDAE keywords keep their names and defaults: rtol, atol, first_step,
+    max_step, mass_matrix, var_index, newton_tol, max_newton_ite, max_bad_ite, min_factor,
+    max_factor, safety_factor, factor_on_non_convergence, scale_residuals, scale_newton_norm,
+    scale_error, zero_algebraic_error, jacobianRecomputeFactor, bAlwaysApply2ndEstimate,
+    bUsePredictiveController, bUsePredictiveNewtonStoppingCriterion, bUseExtrapolatedGuess,
+    bPerformAllNewtonIterations, constant_dt, nmax_step), with these batch-specific ones:
+
+    problem : str | Problem — device functor providing f and its analytic Jacobian.
+    y0      : [B, n] array or tensor.       params : [B, p] array/tensor, None = defaults.
+    mass_matrix : 'problem' (default: the problem's own matrix, per-system for the transistor),
+                  an [n, n] array shared by the ensemble, or None (identity, as in the reference).
+    var_index   : [n] integers 0..3 or None (all differential), as in the reference.
+    jac         : 'analytic' (default) or a constant [n, n] matrix.
+    """
+    import torch
+
+    if not (method is RadauDAE or method == "RadauDAE"):
+        raise ValueError("`method` must be RadauDAE.")
+    if events:
+        raise NotImplementedError("events are not supported by the batched solver")
+    if dense_output:
+        raise NotImplementedError("dense_output=True (a ragged OdeSolution per system) is not available; "
+                                  "pass the times you need through `t_eval`.")
+    if not torch.cuda.is_available():
+        raise RuntimeError("solve_ivp_batched needs a CUDA device; there is no CPU fallback.")
+    lib = _abi.load()
+    dev = torch.device(device) if device is not None else (
+        y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+
+    hb = prepare(problem, t_span, tuple(y0.shape), t_eval=t_eval, params=params, **options)
+    prob, n, B, T = hb.problem, hb.n, hb.B, hb.t_eval.size
+    y0_d = _as_device_f64(y0, dev, torch)
+    if not torch.isfinite(y0_d).all():
+        raise ValueError("All components of the initial state `y0` must be finite.")
+    y0_soa = y0_d.t().contiguous()                                         # [n, B]
+    if prob.n_params:
+        p = prob.default_params(B) if params is None else params
+        if tuple(p.shape) != (B, prob.n_params):
+            raise ValueError(f"`params` must have shape {(B, prob.n_params)}.")
+        par_soa = _as_device_f64(p, dev, torch).t().contiguous()           # [p, B]
+    else:
+        par_soa = None
+
+    with torch.cuda.device(dev):
+        te_d = torch.as_tensor(hb.t_eval).to(dev) if T else None
+        y_eval = torch.empty((max(T, 1), n, B), dtype=torch.float64, device=dev)
+        n_eval = torch.empty(B, dtype=torch.int32, device=dev)
+        t_final = torch.empty(B, dtype=torch.float64, device=dev)
+        y_final = torch.empty((n, B), dtype=torch.float64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        counters = torch.empty((_abi.NCOUNTERS, B), dtype=torch.int32, device=dev)
+        ptr = {"y0": y0_soa.data_ptr(), "params": par_soa.data_ptr() if par_soa is not None else None,
+               "t_eval": te_d.data_ptr() if T else None, "y_eval": y_eval.data_ptr() if T else None,
+               "n_eval": n_eval.data_ptr(), "t_final": t_final.data_ptr(), "y_final": y_final.data_ptr(),
+               "status": status.data_ptr(), "counters": counters.data_ptr()}
+        batch = hb.struct(ptr)
+        ws_bytes = int(lib.brdae_workspace_bytes(C.byref(batch), C.byref(hb.options)))
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+        cu_stream = stream if stream is not None else torch.cuda.current_stream(dev)
+        _abi.check(lib.brdae_solve(C.byref(batch), C.byref(hb.options), ws.data_ptr(), ws_bytes,
+                                   C.c_void_p(cu_stream.cuda_stream)), "brdae_solve")
+        ws.record_stream(cu_stream)
+    res = BatchedOdeResult(hb.t_eval, y_eval[:T], n_eval, status, t_final, y_final, counters)
+    res._keepalive = (y0_soa, par_soa, te_d, ws)
+    return res
+
+
+def solve_ivp_batched_host(problem, t_span, y0, params=None, *, t_eval=None, **options):
+    """Same call with numpy arrays in and out, through `brdae_solve_host` (the library does the
+    device allocation and the copies).  This is the entry a numpy/scipy user of the reference
+    binds to; it is what bench.py times as the end-to-end path."""
+    lib = _abi.load()
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    hb = prepare(problem, t_span, y0.shape, t_eval=t_eval, params=params, **options)
+    prob, n, B, T = hb.problem, hb.n, hb.B, hb.t_eval.size
+    y0_soa = np.ascontiguousarray(y0.T)
+    if prob.n_params:
+        p = prob.default_params(B) if params is None else np.asarray(params, dtype=np.float64)
+        if p.shape != (B, prob.n_params):
+            raise ValueError(f"`params` must have shape {(B, prob.n_params)}.")
+        par_soa = np.ascontiguousarray(p.T)
+    else:
+        par_soa = None
+    out = {"y_eval": np.empty((max(T, 1), n, B)), "n_eval": np.empty(B, dtype=np.int32),
+           "t_final": np.empty(B), "y_final": np.empty((n, B)), "status": np.empty(B, dtype=np.int32),
+           "counters": np.empty((_abi.NCOUNTERS, B), dtype=np.int32)}
+    ptr = {k: v.ctypes.data for k, v in out.items()}
+    ptr.update({"y0": y0_soa.ctypes.data, "params": par_soa.ctypes.data if par_soa is not None else None,
+                "t_eval": hb.t_eval.ctypes.data if T else None})
+    if not T:
+        ptr["y_eval"] = None
+    batch = hb.struct(ptr)
+    _abi.check(lib.brdae_solve_host(C.byref(batch), C.byref(hb.options)), "brdae_solve_host")
+    res = {"t": hb.t_eval, "y": out["y_eval"][:T].transpose(2, 1, 0), "n_eval": out["n_eval"],
+           "status": out["status"], "success": out["status"] >= 0, "t_final": out["t_final"],
+           "y_final": out["y_final"].T, "counters": out["counters"].T}
+    for i, name in enumerate(_abi.COUNTER_NAMES):
+        res[name] = out["counters"][i]
+    return res
+
+
+def fp64_peak_tflops(ms_target: float = 50.0) -> float:
+    """Measured FP64 FMA throughput of the current device in TFLOP/s (roofline denominator)."""
+    lib = _abi.load()
+    f = C.c_double(0.0)
+    _abi.check(lib.brdae_fp64_peak_probe(C.c_double(ms_target), C.byref(f), None), "brdae_fp64_peak_probe")
+    return f.value / 1e12

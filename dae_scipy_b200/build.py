@@ -1,0 +1,78 @@
+"""Build libbrdae.so (hand-written CUDA for sm_100a) in-tree with nvcc.
+
+`python -m dae_scipy_b200.build` or `dae_scipy_b200.build.build()`.  Every translation unit is
+compiled with `-gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false` (no implicit
+FMA contraction: the fma() calls in the kernels are the arithmetic contract)
+and the objects are linked into `dae_scipy_b200/libbrdae.so`, which travels to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libbrdae.so")
+
+SOURCES = ["brdae_abi.cu", "dispatch.cu", "k1_pendulum.cu", "k1_robertson.cu", "k1_transistor.cu",
+           "k2_npendulum.cu", "fp64_peak.cu"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
+              "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _newest_header_mtime():
+    m = 0.0
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".cuh", ".h")):
+                m = max(m, os.path.getmtime(os.path.join(root, f)))
+    return m
+
+
+def _compile(src, force, hdr_mtime, log):
+    obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+    path = os.path.join(CSRC, src)
+    if (not force and os.path.exists(obj)
+            and os.path.getmtime(obj) >= max(os.path.getmtime(path), hdr_mtime)):
+        return obj, ""
+    cmd = [_nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return obj, r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdr = _newest_header_mtime()
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        results = list(ex.map(lambda s: _compile(s, force, hdr, verbose), SOURCES))
+    objs = [o for o, _ in results]
+    ptxas_log = "\n".join(log for _, log in results if log)
+    if ptxas_log:
+        with open(os.path.join(OBJDIR, "ptxas.log"), "w") as f:
+            f.write(ptxas_log)
+        if verbose:
+            print(ptxas_log)
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+               "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,30 @@
+// dispatch.cu -- (problem, mass kind) -> kernel launcher.
+#include "kernels.cuh"
+
+namespace brdae {
+
+static int route(int problem, bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s,
+                 LaunchGeom *g, bool geom_only) {
+    switch (problem) {
+    case BRDAE_PENDULUM3: return k1_pendulum(3, dense_mass, a, sms, s, g, geom_only);
+    case BRDAE_PENDULUM2: return k1_pendulum(2, dense_mass, a, sms, s, g, geom_only);
+    case BRDAE_PENDULUM1: return k1_pendulum(1, dense_mass, a, sms, s, g, geom_only);
+    case BRDAE_ROBERTSON: return k1_robertson(dense_mass, a, sms, s, g, geom_only);
+    case BRDAE_TRANSISTOR: return k1_transistor(dense_mass, a, sms, s, g, geom_only);
+    case BRDAE_NPENDULUM: return k2_npendulum(dense_mass, a, b, sms, s, g, geom_only);
+    }
+    return BRDAE_ERR_UNKNOWN_PROBLEM;
+}
+
+int launch_geometry(int problem, bool dense_mass, int n, int64_t B, int sms, LaunchGeom *g) {
+    SolveArgs a{};
+    a.B = B; a.n = n;
+    return route(problem, dense_mass, a, nullptr, sms, nullptr, g, true);
+}
+
+int launch_solver(int problem, bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t stream) {
+    LaunchGeom g;
+    return route(problem, dense_mass, a, b, sms, stream, &g, false);
+}
+
+}  // namespace brdae

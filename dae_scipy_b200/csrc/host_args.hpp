@@ -1,0 +1,96 @@
+// host_args.hpp -- host-side marshalling shared by the C-ABI translation unit (and by the
+// CPU simulation harness under tests/host_sim that single-steps the kernel source for debugging):
+// batch validation and the uniform quantities the reference's constructor derives
+// (radauDAE.py:263-422: newton_tol :322, NMAX_BAD :400-410, h_abs :307-315).
+#pragma once
+#include <cmath>
+#include <cstring>
+
+#include "radau_common.cuh"
+
+namespace brdae {
+
+constexpr size_t kCounterBytes = 256;
+
+struct ProblemInfo { const char *name; int32_t id, n, n_params; };
+static const ProblemInfo kProblems[] = {
+    {"pendulum3", BRDAE_PENDULUM3, 5, 3}, {"pendulum2", BRDAE_PENDULUM2, 5, 3},
+    {"pendulum1", BRDAE_PENDULUM1, 5, 3}, {"robertson", BRDAE_ROBERTSON, 3, 3},
+    {"transistor", BRDAE_TRANSISTOR, 5, 12}, {"npendulum", BRDAE_NPENDULUM, 0, 0},
+};
+
+inline const ProblemInfo *find_problem(int32_t id) {
+    for (const auto &p : kProblems) if (p.id == id) return &p;
+    return nullptr;
+}
+
+inline int validate(const brdae_batch *b, const brdae_options *o) {
+    if (!b || !o) return BRDAE_ERR_BAD_ARGUMENT;
+    const ProblemInfo *pi = find_problem(b->problem);
+    if (!pi) return BRDAE_ERR_UNKNOWN_PROBLEM;
+    if (b->n_systems < 0 || b->n_t_eval < 0) return BRDAE_ERR_BAD_ARGUMENT;
+    if (pi->n > 0 && b->n != pi->n) return BRDAE_ERR_BAD_ARGUMENT;
+    if (pi->n == 0 && (b->n <= 0 || b->n % 5 != 0)) return BRDAE_ERR_BAD_ARGUMENT;
+    if (b->n_params != pi->n_params) return BRDAE_ERR_BAD_ARGUMENT;
+    if (b->n_systems > 0) {
+        if (!b->y0 || !b->n_eval || !b->t_final || !b->y_final || !b->status || !b->counters) return BRDAE_ERR_BAD_ARGUMENT;
+        if (pi->n_params > 0 && !b->params) return BRDAE_ERR_BAD_ARGUMENT;
+        if (b->n_t_eval > 0 && (!b->t_eval || !b->y_eval)) return BRDAE_ERR_BAD_ARGUMENT;
+    }
+    if (!b->atol) return BRDAE_ERR_BAD_ARGUMENT;
+    if (!(b->rtol > 0) || !(o->max_step > 0) || o->max_newton_ite < 1) return BRDAE_ERR_BAD_ARGUMENT;
+    for (int c = 0; c < b->n; ++c) {
+        if (!(b->atol[c] >= 0)) return BRDAE_ERR_BAD_ARGUMENT;
+        if (b->var_index && (b->var_index[c] < 0 || b->var_index[c] > 3)) return BRDAE_ERR_BAD_ARGUMENT;
+    }
+    if (o->first_step > 0 && o->first_step > std::fabs(b->t_bound - b->t0)) return BRDAE_ERR_BAD_ARGUMENT;
+    return BRDAE_OK;
+}
+
+// uniform quantities the reference's constructor derives
+inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options *o, void *workspace) {
+    std::memset(&a, 0, sizeof(a));
+    a.B = b->n_systems; a.T = b->n_t_eval; a.n = b->n;
+    a.y0 = b->y0; a.params = b->params; a.t_eval = b->t_eval;
+    a.y_eval = b->y_eval; a.n_eval = b->n_eval; a.t_final = b->t_final; a.y_final = b->y_final;
+    a.status = b->status; a.counters = b->counters;
+    a.work_counter = static_cast<unsigned long long *>(workspace);
+    a.scratch = reinterpret_cast<double *>(static_cast<char *>(workspace) + kCounterBytes);
+    a.t0 = b->t0; a.tb = b->t_bound;
+    a.dir = (b->t_bound != b->t0) ? (b->t_bound > b->t0 ? 1.0 : -1.0) : 1.0;     // scipy base.py:166
+    a.rtol = b->rtol;
+    a.h0 = (o->first_step > 0) ? o->first_step : a.dir * std::fmin(1e-6, std::fabs(b->t_bound - b->t0));  // :313
+    a.max_step = o->max_step;
+    a.newton_tol = (o->newton_tol > 0) ? o->newton_tol
+                   : std::fmax(10 * 2.220446049250313e-16 / b->rtol, std::fmin(0.03, std::sqrt(b->rtol)));  // :322
+    a.nonconv_factor = o->factor_on_non_convergence; a.safety_factor = o->safety_factor;
+    a.min_factor = o->min_factor; a.max_factor = o->max_factor; a.jac_recompute = o->jac_recompute_factor;
+    a.nmax_step = o->nmax_step; a.maxit = o->max_newton_ite;
+    int nmax_bad = o->max_bad_ite, n_alg = 0;
+    if (nmax_bad < 0) {                                                            // :400-410
+        nmax_bad = 0;
+        for (int c = 0; c < b->n; ++c) if (b->var_index && b->var_index[c] > 1) nmax_bad = 1;
+    }
+    for (int c = 0; c < b->n; ++c) if (b->var_index && b->var_index[c] != 0) ++n_alg;
+    a.nmax_bad = nmax_bad;
+    a.rsq3n = 1.0 / std::sqrt(3.0 * b->n);
+    a.rsqn = 1.0 / std::sqrt((double)b->n);
+    a.rsq_nondiff = 1.0 / std::sqrt((double)(b->n - n_alg));
+    a.scale_residuals = o->scale_residuals; a.scale_newton_norm = o->scale_newton_norm;
+    a.scale_error = o->scale_error; a.zero_algebraic_error = o->zero_algebraic_error;
+    a.always_2nd = o->always_2nd_estimate; a.predictive_controller = o->predictive_controller;
+    a.predictive_newton = o->predictive_newton_stop; a.extrapolate = o->extrapolated_guess;
+    a.all_newton = o->all_newton_iterations; a.constant_dt = o->constant_dt;
+    a.has_jac_const = b->jac_const != nullptr;
+    if (b->n <= BRDAE_NMAX_SMALL) {
+        for (int c = 0; c < b->n; ++c) {
+            a.atol[c] = b->atol[c];
+            a.var_index[c] = b->var_index ? b->var_index[c] : 0;
+        }
+        if (b->mass) std::memcpy(a.mass, b->mass, sizeof(double) * b->n * b->n);
+        if (b->jac_const) std::memcpy(a.jac_const, b->jac_const, sizeof(double) * b->n * b->n);
+    }
+}
+
+
+}  // namespace brdae

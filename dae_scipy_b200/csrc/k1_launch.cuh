@@ -1,0 +1,23 @@
+// k1_launch.cuh -- launch helper shared by the k1_*.cu translation units.
+#pragma once
+#include "kernels.cuh"
+#include "radau_k1.cuh"
+
+namespace brdae {
+
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS>
+int k1_launch(const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
+    constexpr int smem = K1Layout<Prob>::SLOTS * BLOCK * (int)sizeof(double);
+    int64_t want = (a.B + BLOCK - 1) / BLOCK;
+    int64_t cap = (int64_t)(sms > 0 ? sms : 148) * MIN_BLOCKS;  // persistent grid: resident CTAs only
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    if (g) { g->grid = grid; g->block = BLOCK; g->smem = smem; }
+    if (geom_only) return BRDAE_OK;
+    auto kern = k1_kernel<Prob, Mass, BLOCK, MIN_BLOCKS>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BRDAE_ERR_CUDA;
+    kern<<<grid, BLOCK, smem, s>>>(a);
+    return cudaPeekAtLastError() == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;
+}
+
+}  // namespace brdae

@@ -1,0 +1,20 @@
+// k1_pendulum.cu -- K1 instantiations for the single pendulum, index 3 / 2 / 1.
+#include "k1_launch.cuh"
+
+namespace brdae {
+
+template <int INDEX>
+static int go(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
+    using Prob = Pendulum<INDEX>;
+    if (dense_mass) return k1_launch<Prob, MassDense<5>, 128, 2>(a, sms, s, g, geom_only);
+    return k1_launch<Prob, typename Prob::Mass, 128, 2>(a, sms, s, g, geom_only);
+}
+
+int k1_pendulum(int index, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
+    if (index == 3) return go<3>(dense_mass, a, sms, s, g, geom_only);
+    if (index == 2) return go<2>(dense_mass, a, sms, s, g, geom_only);
+    if (index == 1) return go<1>(dense_mass, a, sms, s, g, geom_only);
+    return BRDAE_ERR_UNKNOWN_PROBLEM;
+}
+
+}  // namespace brdae

@@ -1,0 +1,27 @@
+// kernels.cuh -- host-side interface between the C-ABI translation unit and the kernel
+// translation units (one per problem family so that they compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "radau_common.cuh"
+
+namespace brdae {
+
+struct LaunchGeom { int grid, block, smem; };
+
+// geometry that launch_solver would use (no launch)
+int launch_geometry(int problem, bool dense_mass, int n, int64_t B, int sms, LaunchGeom *g);
+// launch the kernel matching (problem, mass kind) on `stream`
+int launch_solver(int problem, bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t stream);
+
+// per-problem launchers (k1_*.cu); geom_only: fill *g and return without launching
+int k1_pendulum(int index, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+int k1_robertson(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+int k1_transistor(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+// CTA-per-system banded kernel for the n-pendulum chain (k2_npendulum.cu)
+int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+size_t k2_scratch_bytes(int n, int sms);
+
+int fp64_peak_probe(double ms_target, double *flops, cudaStream_t s, int sms);
+
+}  // namespace brdae

@@ -1,0 +1,165 @@
+// problems.cuh -- device functors for the reference's test problems (right-hand side, analytic
+// Jacobian, mass-matrix policy).  Expression order follows the reference closures:
+//   pendulum index 3/2/1 ... scipyDAE/tests/pendulum.py:129-184
+//   Robertson DAE .......... scipyDAE/tests/robertson.py:78-87
+//   transistor amplifier ... scipyDAE/tests/transistor_amplifier.py:33-56 (Jacobian: analytic
+//                            form of the complex-step derivative at :61-65)
+// A functor exposes
+//   N, NP                          state size, number of per-system parameters
+//   struct P; load(P&, params, B, idx)
+//   rhs(P, t, y[N], f[N]);  jac(P, t, y[N], J[N][N])
+//   using Mass = ...               default mass-matrix policy (see below)
+// Mass policies describe a constant matrix M through a compile-time sparsity pattern nz(r,c)
+// and a value getter, so that the generic kernel code skips structural zeros at compile time.
+#pragma once
+#include "radau_common.cuh"
+
+namespace brdae {
+
+// ---------------------------------------------------------------- mass-matrix policies
+// diag(b_0..b_{N-1}) with b_r = bit r of ONES (1.0) else 0.0
+template <int N_, unsigned ONES>
+struct MassDiag01 {
+    static constexpr int N = N_;
+    static BRDAE_CX bool nz(int r, int c) { return r == c && ((ONES >> r) & 1u); }
+    template <class P>
+    static BRDAE_HD double get(const P &, const SolveArgs &, int, int) { return 1.0; }
+};
+// user-supplied dense matrix shared by the ensemble (SolveArgs::mass, row-major)
+template <int N_>
+struct MassDense {
+    static constexpr int N = N_;
+    static BRDAE_CX bool nz(int, int) { return true; }
+    template <class P>
+    static BRDAE_HD double get(const P &, const SolveArgs &a, int r, int c) { return a.mass[r * N + c]; }
+};
+
+// M.v : fma chain over the structurally non-zero columns in increasing order (first term a
+// plain product) -- the same chain as mass_mv() of the scalar restatement
+template <class Mass, class P, int N>
+BRDAE_HD void mass_mv(const P &p, const SolveArgs &a, const double (&v)[N], double (&o)[N]) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        double s = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            if (Mass::nz(r, c)) {
+                double m = Mass::get(p, a, r, c);
+                s = first ? m * v[c] : fma(m, v[c], s);
+                first = false;
+            }
+        }
+        o[r] = s;
+    }
+}
+template <class Mass, int N>
+BRDAE_CX bool mass_row_empty(int r) {
+    for (int c = 0; c < N; ++c)
+        if (Mass::nz(r, c)) return false;
+    return true;
+}
+
+// ---------------------------------------------------------------- pendulum (index 3, 2, 1)
+template <int INDEX>
+struct Pendulum {
+    static constexpr int N = 5, NP = 3;
+    struct P { double m, g, r0; };
+    using Mass = MassDiag01<5, 0x0Fu>;  // pendulum.py:139-140
+    static BRDAE_HD void load(P &p, const double *params, int64_t B, int64_t i) {
+        p.m = params[i]; p.g = params[B + i]; p.r0 = params[2 * B + i];
+    }
+    static BRDAE_HD void rhs(const P &p, double, const double (&X)[5], double (&f)[5]) {
+        const double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
+        f[0] = vx;
+        f[1] = vy;
+        f[2] = -x * l / p.m;
+        f[3] = -p.g - (y * l) / p.m;
+        if (INDEX == 3) f[4] = x * x + y * y - p.r0 * p.r0;
+        else if (INDEX == 2) f[4] = x * vx + y * vy;
+        else f[4] = l * (x * x + y * y) / p.m + p.g * y - (vx * vx + vy * vy);
+    }
+    static BRDAE_HD void jac(const P &p, double, const double (&X)[5], double (&J)[5][5]) {
+        const double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) J[r][c] = 0.0;
+        J[0][2] = 1.0;
+        J[1][3] = 1.0;
+        J[2][0] = -l / p.m; J[2][4] = -x / p.m;
+        J[3][1] = -l / p.m; J[3][4] = -y / p.m;
+        if (INDEX == 3) { J[4][0] = 2 * x; J[4][1] = 2 * y; }
+        else if (INDEX == 2) { J[4][0] = vx; J[4][1] = vy; J[4][2] = x; J[4][3] = y; }
+        else {
+            J[4][0] = 2 * x * l / p.m; J[4][1] = 2 * y * l / p.m + p.g; J[4][2] = -2 * vx;
+            J[4][3] = -2 * vy; J[4][4] = (x * x + y * y) / p.m;
+        }
+    }
+};
+
+// ---------------------------------------------------------------- Robertson DAE
+struct Robertson {
+    static constexpr int N = 3, NP = 3;
+    struct P { double k1, k2, k3; };
+    using Mass = MassDiag01<3, 0x3u>;  // robertson.py:78
+    static BRDAE_HD void load(P &p, const double *params, int64_t B, int64_t i) {
+        p.k1 = params[i]; p.k2 = params[B + i]; p.k3 = params[2 * B + i];
+    }
+    static BRDAE_HD void rhs(const P &p, double, const double (&y)[3], double (&f)[3]) {
+        f[0] = -p.k1 * y[0] + p.k2 * y[1] * y[2];
+        f[1] = p.k1 * y[0] - p.k2 * y[1] * y[2] - p.k3 * (y[1] * y[1]);
+        f[2] = y[0] + y[1] + y[2] - 1;
+    }
+    static BRDAE_HD void jac(const P &p, double, const double (&y)[3], double (&J)[3][3]) {
+        J[0][0] = -p.k1; J[0][1] = p.k2 * y[2]; J[0][2] = p.k2 * y[1];
+        J[1][0] = p.k1; J[1][1] = -p.k2 * y[2] - 2 * p.k3 * y[1]; J[1][2] = -p.k2 * y[1];
+        J[2][0] = 1; J[2][1] = 1; J[2][2] = 1;
+    }
+};
+
+// ---------------------------------------------------------------- transistor amplifier
+struct Transistor {
+    static constexpr int N = 5, NP = 12;
+    struct P { double C1, C2, C3, R0, R1, R2, R3, R4, R5, Ub, Ua, w; };
+    // M = [[C1,-C1,0,0,0],[-C1,C1,0,0,0],[0,0,C2,0,0],[0,0,0,C3,-C3],[0,0,0,-C3,C3]]
+    struct Mass {
+        static constexpr int N = 5;
+        static BRDAE_CX bool nz(int r, int c) {
+            return (r < 2 && c < 2) || (r == 2 && c == 2) || (r >= 3 && c >= 3);
+        }
+        static BRDAE_HD double get(const P &p, const SolveArgs &, int r, int c) {
+            if (r < 2) return r == c ? p.C1 : -p.C1;
+            if (r == 2) return p.C2;
+            return r == c ? p.C3 : -p.C3;
+        }
+    };
+    static BRDAE_HD void load(P &p, const double *q, int64_t B, int64_t i) {
+        p.C1 = q[i]; p.C2 = q[B + i]; p.C3 = q[2 * B + i]; p.R0 = q[3 * B + i]; p.R1 = q[4 * B + i];
+        p.R2 = q[5 * B + i]; p.R3 = q[6 * B + i]; p.R4 = q[7 * B + i]; p.R5 = q[8 * B + i];
+        p.Ub = q[9 * B + i]; p.Ua = q[10 * B + i]; p.w = q[11 * B + i];
+    }
+    static BRDAE_HD void rhs(const P &p, double t, const double (&y)[5], double (&f)[5]) {
+        const double Ue = p.Ua * sin(p.w * t);
+        const double fT = 1e-6 * (exp((y[1] - y[2]) / 0.026) - 1);
+        f[0] = (Ue - y[0]) / p.R0;
+        f[1] = p.Ub / p.R2 - y[1] * (1 / p.R1 + 1 / p.R2) - 0.01 * fT;
+        f[2] = fT - y[2] / p.R3;
+        f[3] = p.Ub / p.R4 - y[3] / p.R4 - 0.99 * fT;
+        f[4] = -y[4] / p.R5;
+    }
+    static BRDAE_HD void jac(const P &p, double, const double (&y)[5], double (&J)[5][5]) {
+        const double df = 1e-6 * exp((y[1] - y[2]) / 0.026) / 0.026;
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) J[r][c] = 0.0;
+        J[0][0] = -1 / p.R0;
+        J[1][1] = -(1 / p.R1 + 1 / p.R2) - 0.01 * df; J[1][2] = 0.01 * df;
+        J[2][1] = df; J[2][2] = -df - 1 / p.R3;
+        J[3][1] = -0.99 * df; J[3][2] = 0.99 * df; J[3][3] = -1 / p.R4;
+        J[4][4] = -1 / p.R5;
+    }
+};
+
+}  // namespace brdae

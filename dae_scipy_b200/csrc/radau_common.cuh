@@ -1,0 +1,93 @@
+// radau_common.cuh -- shared declarations of the batched RadauDAE kernels (sm_100a).
+//
+// Radau IIA tableau transforms: radauDAE.py:11-48 (values as exact hex literals).
+// Arithmetic contract: DESIGN.md section 4 -- the translation unit is compiled with
+// -fmad=false, so the fma() calls written in the kernels are the only fused operations and
+// every kernel can be compared bit for bit with the scalar restatement used by the tests.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/brdae.h"
+
+#if defined(__CUDACC__)
+#define BRDAE_HD __device__ __forceinline__
+#define BRDAE_D __device__ __forceinline__
+#define BRDAE_CX __host__ __device__ constexpr
+#else
+#define BRDAE_HD inline
+#define BRDAE_D inline
+#define BRDAE_CX constexpr
+#endif
+
+namespace brdae {
+
+constexpr double RC0 = 0x1.3d8b64657caeap-3, RC1 = 0x1.4a36c0803a6dfp-1;
+constexpr double RE0 = -0x1.418fd8baffe05p+3, RE1 = 0x1.61d41b2d54580p+0, RE2 = -0x1.5555555555555p-2;
+constexpr double MU_REAL = 0x1.d1a48d83e731dp+1;
+constexpr double MU_CR = 0x1.572db93e0c672p+1, MU_CI = -0x1.86747f2c3fcb6p+1;
+constexpr double T00 = 0x1.82d23845d677bp-4, T01 = -0x1.214a74c403bf7p-3, T02 = 0x1.ebff91a6d688ep-6;
+constexpr double T10 = 0x1.0037de70aa1edp-2, T11 = 0x1.a20e91e20b551p-3, T12 = -0x1.8821fa2a36dedp-2;
+constexpr double TI00 = 0x1.0b70201a79c46p+2, TI01 = 0x1.4f8c15da84e86p-2, TI02 = 0x1.0bf7ff59d56efp-1;
+constexpr double TI10 = -0x1.0b70201a79c46p+2, TI11 = -0x1.4f8c15da84e86p-2, TI12 = 0x1.e810014c55221p-2;
+constexpr double TI20 = 0x1.017885a24a7f2p-1, TI21 = -0x1.4934e6fcaa598p+1, TI22 = 0x1.312c0cf7bdfd1p-1;
+constexpr double P00 = 0x1.418fd8baffe05p+3, P01 = -0x1.9a12ce7b30915p+4, P02 = 0x1.f295c43b61425p+3;
+constexpr double P10 = -0x1.61d41b2d54580p+0, P11 = 0x1.497af24bb677ep+3, P12 = -0x1.1d406ee60becfp+3;
+constexpr double P20 = 0x1.5555555555555p-2, P21 = -0x1.5555555555555p+1, P22 = 0x1.aaaaaaaaaaaabp+1;
+
+// (T W)_i for one component: fma chain over the stages 0,1,2; T[2] = (1, 1, 0)
+template <int I>
+BRDAE_HD double stage_z(double w0, double w1, double w2) {
+    if (I == 0) return fma(T02, w2, fma(T01, w1, T00 * w0));
+    if (I == 1) return fma(T12, w2, fma(T11, w1, T10 * w0));
+    return w0 + w1;
+}
+BRDAE_HD double stage_c(int i) { return i == 0 ? RC0 : (i == 1 ? RC1 : 1.0); }
+
+// finite test that reads the same on host and device (false for NaN and +-inf)
+BRDAE_HD bool is_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
+BRDAE_HD double hpow(double h, int e) { return e == 0 ? 1.0 : (e == 1 ? h : h * h); }
+
+// predict_factor, radauDAE.py:52-98; x**0.25 = sqrt(sqrt(x))
+BRDAE_HD double gustafsson(double h_abs, double h_abs_old, double err, double err_old, bool hist,
+                           bool predictive) {
+    double mult = 1.0;
+    if (predictive && hist && err != 0.0) mult = h_abs / h_abs_old * sqrt(sqrt(err_old / err));
+    double base = 1.0 / sqrt(sqrt(err));
+    return (mult < 1.0 ? mult : 1.0) * base;
+}
+
+// kernel-side view of one call: everything uniform across the ensemble lives here (constant bank)
+struct SolveArgs {
+    int64_t B;
+    int32_t T;
+    int32_t n;  // runtime state size (npendulum); equals Prob::N for the small problems
+    const double *y0, *params, *t_eval;
+    double *y_eval;
+    int32_t *n_eval;
+    double *t_final, *y_final;
+    int32_t *status, *counters;
+    unsigned long long *work_counter;
+    double *scratch;  // per-CTA global scratch (K2)
+    double t0, tb, dir, rtol;
+    double h0, max_step, newton_tol, nonconv_factor, safety_factor, min_factor, max_factor, jac_recompute;
+    double rsq3n, rsqn, rsq_nondiff;
+    int64_t nmax_step;
+    int32_t maxit, nmax_bad;
+    int32_t scale_residuals, scale_newton_norm, scale_error, zero_algebraic_error;
+    int32_t always_2nd, predictive_controller, predictive_newton, extrapolate, all_newton, constant_dt;
+    int32_t has_jac_const;
+    // small-problem (n <= BRDAE_NMAX_SMALL) uniform vectors; K2 reads its own from global memory
+    double atol[BRDAE_NMAX_SMALL];
+    int32_t var_index[BRDAE_NMAX_SMALL];
+    double mass[BRDAE_NMAX_SMALL * BRDAE_NMAX_SMALL];
+    double jac_const[BRDAE_NMAX_SMALL * BRDAE_NMAX_SMALL];
+    // large-problem uniform vectors (device pointers, K2)
+    const double *atol_dev;
+    const int32_t *var_index_dev;
+};
+
+enum : int { CN_NFEV = 0, CN_NJEV, CN_NLU, CN_NSTEP, CN_NACC, CN_NREJ, CN_NFAIL, CN_NSOLVE, CN_NSOLVE_ERR, CN_COUNT };
+
+}  // namespace brdae

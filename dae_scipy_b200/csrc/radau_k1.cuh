@@ -1,0 +1,661 @@
+// radau_k1.cuh -- K1: thread-per-system batched RadauDAE for small systems (N <= 8), sm_100a.
+//
+// One lane integrates one system at a time; a persistent grid pulls system indices from a
+// global work counter (warp-aggregated atomicAdd: ballot/popc/shfl), so lanes whose trajectory
+// is finished, failed or short are refilled at once instead of idling until the slowest lane
+// of the warp is done.
+//
+// The reference's nested loops (radauDAE.py:564 `while not step_accepted`, :591 `while not
+// converged`, :846 Newton `for`) are flattened into a per-lane phase machine.  Every trip of
+// the warp loop each live lane performs exactly ONE simplified-Newton iteration (the dominant
+// cost); step prologue, attempt set-up, LU factorisation and error estimate / controller are
+// predicated blocks before and after it, so divergent lanes re-converge on the expensive phase.
+//
+// Storage (N = 5): the real and complex LU factors (3 N^2 doubles), f(t,y), y_old, the dense
+// output coefficients Q (3N) and the point (t_J, y_J) the Jacobian was last evaluated at live in
+// shared memory, lane-strided ([slot][lane]: conflict-free 8-byte accesses); y, W and all
+// controller scalars live in registers.  The Jacobian itself is never stored: it is
+// re-materialised from (t_J, y_J) when a factorisation needs it, which reproduces the
+// reference's "stale J, new h" refactorisations (radauDAE.py:594-613 with self.J kept) exactly.
+//
+// Reference map: prologue :516-562, attempt :564-588, factorisation :594-613, Newton :793-949,
+// non-convergence :635-658, error estimate :669-711, accept/reject :713-739, epilogue :742-784,
+// dense output :951-982, driver / t_eval slicing :1079-1157 (scipy ivp.py:659-732).
+#pragma once
+#include "problems.cuh"
+
+namespace brdae {
+
+enum : int { PH_IDLE = 0, PH_STEP, PH_ATTEMPT, PH_NEWTON_INIT, PH_NEWTON, PH_ERREST, PH_EXIT };
+
+// lane-strided shared-memory slots of one lane
+template <int STRIDE>
+struct Slots {
+    double *base;
+    BRDAE_HD double &operator()(int e) const { return base[e * STRIDE]; }
+};
+
+// ---- LU of the spec, fully unrolled, in registers -------------------------------------------
+// Right-looking elimination, partial pivoting on |a| (first maximum), only the active columns
+// are swapped (multipliers stay where they were computed), reciprocal pivot on the diagonal.
+// Returns the pivot rows packed 3 bits each.
+template <int N>
+BRDAE_HD unsigned lu_real_regs(double (&A)[N][N]) {
+    unsigned piv = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int p = k;
+        double best = fabs(A[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            double v = fabs(A[r][k]);
+            if (v > best) { best = v; p = r; }
+        }
+        piv |= (unsigned)p << (3 * k);
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {  // branch-free row exchange: keeps A in registers
+            const bool sw = (p == r);
+#pragma unroll
+            for (int c = k; c < N; ++c) {
+                const double u = A[k][c], v = A[r][c];
+                A[k][c] = sw ? v : u; A[r][c] = sw ? u : v;
+            }
+        }
+        double rcp = 1.0 / A[k][k];
+        A[k][k] = rcp;
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            double l = A[r][k] * rcp;
+            A[r][k] = l;
+#pragma unroll
+            for (int c = k + 1; c < N; ++c) A[r][c] = fma(-l, A[k][c], A[r][c]);
+        }
+    }
+    return piv;
+}
+// complex: pivot on |re|+|im| (BLAS izamax), reciprocal pivot conj(p)/|p|^2
+template <int N>
+BRDAE_HD unsigned lu_cplx_regs(double (&R)[N][N], double (&I)[N][N]) {
+    unsigned piv = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int p = k;
+        double best = fabs(R[k][k]) + fabs(I[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            double v = fabs(R[r][k]) + fabs(I[r][k]);
+            if (v > best) { best = v; p = r; }
+        }
+        piv |= (unsigned)p << (3 * k);
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            const bool sw = (p == r);
+#pragma unroll
+            for (int c = k; c < N; ++c) {
+                const double u = R[k][c], v = R[r][c], ui = I[k][c], vi = I[r][c];
+                R[k][c] = sw ? v : u; R[r][c] = sw ? u : v;
+                I[k][c] = sw ? vi : ui; I[r][c] = sw ? ui : vi;
+            }
+        }
+        const double pr = R[k][k], pi = I[k][k];
+        const double invd = 1.0 / fma(pr, pr, pi * pi);
+        const double qr = pr * invd, qi = -(pi * invd);
+        R[k][k] = qr; I[k][k] = qi;
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            const double ar = R[r][k], ai = I[r][k];
+            const double lr = fma(ar, qr, -(ai * qi));
+            const double li = fma(ar, qi, ai * qr);
+            R[r][k] = lr; I[r][k] = li;
+#pragma unroll
+            for (int c = k + 1; c < N; ++c) {
+                const double ur = R[k][c], ui = I[k][c];
+                double xr = R[r][c], xi = I[r][c];
+                xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
+                xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
+                R[r][c] = xr; I[r][c] = xi;
+            }
+        }
+    }
+    return piv;
+}
+
+// ---- triangular solves streaming the factors from lane-strided shared memory ----------------
+template <int N, class S>
+BRDAE_HD void solve_real_sm(const S &sm, int base, unsigned piv, double (&b)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int p = (piv >> (3 * k)) & 7;
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            const bool sw = (p == r);
+            const double u = b[k], v = b[r];
+            b[k] = sw ? v : u; b[r] = sw ? u : v;
+        }
+        const double bk = b[k];
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) b[r] = fma(-sm(base + r * N + k), bk, b[r]);
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+        double s = b[k];
+#pragma unroll
+        for (int c = k + 1; c < N; ++c) s = fma(-sm(base + k * N + c), b[c], s);
+        b[k] = s * sm(base + k * N + k);
+    }
+}
+template <int N, class S>
+BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, unsigned piv, double (&br)[N], double (&bi)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int p = (piv >> (3 * k)) & 7;
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            const bool sw = (p == r);
+            const double u = br[k], v = br[r], ui = bi[k], vi = bi[r];
+            br[k] = sw ? v : u; br[r] = sw ? u : v;
+            bi[k] = sw ? vi : ui; bi[r] = sw ? ui : vi;
+        }
+        const double xr = br[k], xi = bi[k];
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            const double lr = sm(base_r + r * N + k), li = sm(base_i + r * N + k);
+            double yr = br[r], yi = bi[r];
+            yr = fma(-lr, xr, yr); yr = fma(li, xi, yr);
+            yi = fma(-lr, xi, yi); yi = fma(-li, xr, yi);
+            br[r] = yr; bi[r] = yi;
+        }
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+        double sr = br[k], si = bi[k];
+#pragma unroll
+        for (int c = k + 1; c < N; ++c) {
+            const double ur = sm(base_r + k * N + c), ui = sm(base_i + k * N + c);
+            sr = fma(-ur, br[c], sr); sr = fma(ui, bi[c], sr);
+            si = fma(-ur, bi[c], si); si = fma(-ui, br[c], si);
+        }
+        const double qr = sm(base_r + k * N + k), qi = sm(base_i + k * N + k);
+        br[k] = fma(sr, qr, -(si * qi));
+        bi[k] = fma(sr, qi, si * qr);
+    }
+}
+
+template <class Prob>
+struct K1Layout {
+    static constexpr int N = Prob::N;
+    static constexpr int S_LUR = 0;
+    static constexpr int S_LCR = N * N;
+    static constexpr int S_LCI = 2 * N * N;
+    static constexpr int S_F = 3 * N * N;
+    static constexpr int S_YOLD = S_F + N;
+    static constexpr int S_Q = S_YOLD + N;
+    static constexpr int S_YJ = S_Q + 3 * N;
+    static constexpr int S_TJ = S_YJ + N;
+    static constexpr int SLOTS = S_TJ + 1;
+};
+
+// warp-level helpers; the host build (tests/host_sim) runs a "warp" of one lane
+#if defined(__CUDA_ARCH__)
+BRDAE_D bool warp_all(bool x) { return __all_sync(0xffffffffu, x); }
+BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
+    const unsigned need = __ballot_sync(0xffffffffu, want);
+    long long idx = -1;
+    if (need) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(need) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (want) idx = (long long)(base + __popc(need & ((1u << lane) - 1u)));
+    }
+    return idx;
+}
+#else
+inline bool warp_all(bool x) { return x; }
+inline long long fetch_system(bool want, unsigned long long *counter) { return want ? (long long)((*counter)++) : -1; }
+#endif
+
+// The per-lane integrator.  `sm` addresses this lane's shared-memory slots.
+template <class Prob, class Mass, class S>
+BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
+    constexpr int N = Prob::N;
+    using L = K1Layout<Prob>;
+    typename Prob::P prm;
+
+    // ---- lane state ---------------------------------------------------------------------
+    int phase = PH_IDLE;
+    long long idx = -1;
+    double t = 0, y[N];
+    double h_abs_state = 0, h_abs_old_state = 0, err_old_state = 0;
+    bool hist_state = false, current_jac = true, lu_valid = false, have_sol = false;
+    double h_sol = 1, t_sol_old = 0, inv_h_lu = 1.0;
+    unsigned piv_r = 0, piv_c = 0;
+    int cnt[CN_COUNT];
+    int ei = 0;
+    long long nsteps = 0;
+    // step scope
+    double min_step = 0, h_abs = 0, h_abs_old = 0, err_old = 0;
+    bool hist = false, rejected = false;
+    // attempt scope
+    double h = 0, t_new = 0, inv_ns[N], mr = 0, mcr = 0, mci = 0;
+    // Newton scope
+    double W[3][N];
+    int k = 0, nbad = 0, n_iter = 0;
+    double dwn_old = 0, rate = 0, safety = 0;
+    bool have_old = false, have_rate = false;
+#pragma unroll
+    for (int c = 0; c < N; ++c) { y[c] = 0; inv_ns[c] = 0; W[0][c] = W[1][c] = W[2][c] = 0; }
+#pragma unroll
+    for (int q = 0; q < CN_COUNT; ++q) cnt[q] = 0;
+
+    const int MAXIT = a.maxit;
+    const double dir = a.dir;
+
+    for (;;) {
+        // ================= refill idle lanes =================================================
+        {
+            const long long got = fetch_system(phase == PH_IDLE, a.work_counter);
+            if (phase == PH_IDLE) {
+                if (got >= a.B) phase = PH_EXIT;
+                else {
+                    idx = got;
+                    Prob::load(prm, a.params, a.B, idx);
+                    t = a.t0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) y[c] = a.y0[(int64_t)c * a.B + idx];
+                    double f0[N];
+                    Prob::rhs(prm, t, y, f0);                            // :304
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { sm(L::S_F + c) = f0[c]; sm(L::S_YJ + c) = y[c]; }
+                    sm(L::S_TJ) = t;                                     // J0 = jac(t0, y0) :483
+#pragma unroll
+                    for (int q = 0; q < CN_COUNT; ++q) cnt[q] = 0;
+                    cnt[CN_NFEV] = 1;
+                    cnt[CN_NJEV] = a.has_jac_const ? 0 : 1;
+                    h_abs_state = a.h0;
+                    hist_state = false; current_jac = true; lu_valid = false; have_sol = false;
+                    inv_h_lu = 1.0; ei = 0; nsteps = 0;
+                    phase = PH_STEP;
+                    if (t == a.tb) {  // OdeSolver.step corner case (scipy base.py:193-198)
+                        for (; ei < a.T; ++ei)
+#pragma unroll
+                            for (int c = 0; c < N; ++c) a.y_eval[((int64_t)ei * N + c) * a.B + idx] = y[c];
+                        a.n_eval[idx] = ei; a.t_final[idx] = t; a.status[idx] = BRDAE_STATUS_FINISHED;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) a.y_final[(int64_t)c * a.B + idx] = y[c];
+#pragma unroll
+                        for (int q = 0; q < CN_COUNT; ++q) a.counters[(int64_t)q * a.B + idx] = cnt[q];
+                        phase = PH_IDLE;
+                    }
+                }
+            }
+        }
+        if (warp_all(phase == PH_EXIT)) break;
+
+        int finish_status = 1;  // 1 = still running
+
+        // ================= step prologue :516-562 ============================================
+        if (phase == PH_STEP) {
+            ++nsteps;
+            if (a.nmax_step > 0 && nsteps > a.nmax_step) finish_status = BRDAE_STATUS_NMAX_STEP;
+            else {
+                cnt[CN_NSTEP]++;
+                min_step = fmax(1e-20, 10 * fabs(nextafter(t, dir * INFINITY) - t));
+                h_abs_old = h_abs_old_state; err_old = err_old_state; hist = hist_state;
+                if (h_abs_state > a.max_step) { h_abs = a.max_step; hist = false; }
+                else if (h_abs_state < min_step) { h_abs = min_step; hist = false; }
+                else h_abs = h_abs_state;
+                if (fabs(a.tb - (t + dir * h_abs)) < 1e-2 * h_abs) { h_abs = fabs(a.tb - t); lu_valid = false; }
+                rejected = false;
+                phase = PH_ATTEMPT;
+            }
+        }
+        // ================= attempt set-up :564-588 ===========================================
+        if (phase == PH_ATTEMPT) {
+            if (h_abs < min_step) finish_status = BRDAE_STATUS_TOO_SMALL_STEP;
+            else {
+                h = h_abs * dir;
+                t_new = t + h;
+                if (dir * (t_new - a.tb) > 0) t_new = a.tb;
+                h = t_new - t;
+                h_abs = fabs(h);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const int ve = a.var_index[c] > 1 ? a.var_index[c] - 1 : 0;
+                    const double hp = a.scale_newton_norm ? hpow(h, ve) : 1.0;
+                    inv_ns[c] = hp / (a.atol[c] + fabs(y[c]) * a.rtol);
+                }
+                mr = MU_REAL / h; mcr = MU_CR / h; mci = MU_CI / h;
+                phase = PH_NEWTON_INIT;
+            }
+        }
+        // ================= (re)factorisation + starting guess :580-583, :594-613 ==============
+        if (phase == PH_NEWTON_INIT) {
+            if (!lu_valid) {
+                if (a.scale_residuals) inv_h_lu = 1.0 / h;
+                double J[N][N];
+                if (a.has_jac_const) {
+#pragma unroll
+                    for (int r = 0; r < N; ++r)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) J[r][c] = a.jac_const[r * N + c];
+                } else {
+                    double yJ[N];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) yJ[c] = sm(L::S_YJ + c);
+                    Prob::jac(prm, sm(L::S_TJ), yJ, J);
+                }
+                {
+                    double A[N][N];
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        const double hs = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            const double v = Mass::nz(r, c) ? fma(mr, Mass::get(prm, a, r, c), -J[r][c]) : -J[r][c];
+                            A[r][c] = hs * v;
+                        }
+                    }
+                    piv_r = lu_real_regs<N>(A);
+#pragma unroll
+                    for (int r = 0; r < N; ++r)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) sm(L::S_LUR + r * N + c) = A[r][c];
+                }
+                {
+                    double R[N][N], I[N][N];
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        const double hs = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            const bool nz = Mass::nz(r, c);
+                            const double m = nz ? Mass::get(prm, a, r, c) : 0.0;
+                            const double v = nz ? fma(mcr, m, -J[r][c]) : -J[r][c];
+                            R[r][c] = hs * v;
+                            I[r][c] = nz ? hs * (mci * m) : 0.0;
+                        }
+                    }
+                    piv_c = lu_cplx_regs<N>(R, I);
+#pragma unroll
+                    for (int r = 0; r < N; ++r)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) { sm(L::S_LCR + r * N + c) = R[r][c]; sm(L::S_LCI + r * N + c) = I[r][c]; }
+                }
+                cnt[CN_NLU]++;
+                lu_valid = true;
+            }
+            // W = TI Z0, Z0 from the previous step's cubic evaluated beyond its interval
+            if (!have_sol || !a.extrapolate) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) { W[0][c] = 0.0; W[1][c] = 0.0; W[2][c] = 0.0; }
+            } else {
+                double x[3], x2[3], x3[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double tt = t + h * stage_c(i);
+                    x[i] = (tt - t_sol_old) / h_sol;
+                    x2[i] = x[i] * x[i];
+                    x3[i] = x2[i] * x[i];
+                }
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const double q0 = sm(L::S_Q + 3 * c), q1 = sm(L::S_Q + 3 * c + 1), q2 = sm(L::S_Q + 3 * c + 2);
+                    const double yo = sm(L::S_YOLD + c);
+                    double z[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        double v = q0 * x[i];
+                        v = fma(q1, x2[i], v);
+                        v = fma(q2, x3[i], v);
+                        v = v + yo;
+                        z[i] = v - y[c];
+                    }
+                    W[0][c] = fma(TI02, z[2], fma(TI01, z[1], TI00 * z[0]));
+                    W[1][c] = fma(TI12, z[2], fma(TI11, z[1], TI10 * z[0]));
+                    W[2][c] = fma(TI22, z[2], fma(TI21, z[1], TI20 * z[0]));
+                }
+            }
+            k = 0; nbad = 0; have_old = false; have_rate = false; rate = 0; dwn_old = 0;
+            phase = PH_NEWTON;
+        }
+        // ================= one simplified-Newton iteration :846-940 ==========================
+        if (phase == PH_NEWTON) {
+            double fr[N], fcr[N], fci[N];
+            bool finite = true;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double Y[N], F[N];
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const double z = (i == 0) ? stage_z<0>(W[0][c], W[1][c], W[2][c])
+                                   : (i == 1) ? stage_z<1>(W[0][c], W[1][c], W[2][c])
+                                              : stage_z<2>(W[0][c], W[1][c], W[2][c]);
+                    Y[c] = y[c] + z;
+                }
+                Prob::rhs(prm, t + h * stage_c(i), Y, F);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const double Fv = F[c];
+                    finite = finite && is_finite(Fv);
+                    if (i == 0) { fr[c] = TI00 * Fv; fcr[c] = TI10 * Fv; fci[c] = TI20 * Fv; }
+                    else if (i == 1) { fr[c] = fma(TI01, Fv, fr[c]); fcr[c] = fma(TI11, Fv, fcr[c]); fci[c] = fma(TI21, Fv, fci[c]); }
+                    else { fr[c] = fma(TI02, Fv, fr[c]); fcr[c] = fma(TI12, Fv, fcr[c]); fci[c] = fma(TI22, Fv, fci[c]); }
+                }
+            }
+            cnt[CN_NFEV] += 3;
+            int outcome = 0;  // 0 continue, 1 converged, 2 stop (not converged)
+            bool update_old = true;
+            if (!finite) outcome = 2;
+            else {
+                double mw0[N], mw1[N], mw2[N];
+                mass_mv<Mass>(prm, a, W[0], mw0);
+                mass_mv<Mass>(prm, a, W[1], mw1);
+                mass_mv<Mass>(prm, a, W[2], mw2);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const double hs = (a.scale_residuals && a.var_index[c] >= 1) ? inv_h_lu : 1.0;
+                    double ar = fr[c], br = fcr[c], bi = fci[c];
+                    if (!mass_row_empty<Mass, N>(c)) {
+                        ar = fma(-mr, mw0[c], ar);
+                        br = fma(-mcr, mw1[c], br); br = fma(mci, mw2[c], br);
+                        bi = fma(-mcr, mw2[c], bi); bi = fma(-mci, mw1[c], bi);
+                    }
+                    fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
+                }
+                solve_real_sm<N>(sm, L::S_LUR, piv_r, fr);
+                solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, piv_c, fcr, fci);
+                cnt[CN_NSOLVE]++;
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < N; ++c) { const double v = fr[c] * inv_ns[c]; s = fma(v, v, s); }
+#pragma unroll
+                for (int c = 0; c < N; ++c) { const double v = fcr[c] * inv_ns[c]; s = fma(v, v, s); }
+#pragma unroll
+                for (int c = 0; c < N; ++c) { const double v = fci[c] * inv_ns[c]; s = fma(v, v, s); }
+                const double dwn = sqrt(s) * a.rsq3n;
+#pragma unroll
+                for (int c = 0; c < N; ++c) { W[0][c] += fr[c]; W[1][c] += fcr[c]; W[2][c] += fci[c]; }
+                double dw_true = 0, dw_true_max = 0;
+                if (have_old) {
+                    rate = dwn / dwn_old; have_rate = true;
+                    const double inv1 = 1.0 / (1.0 - rate);
+                    dw_true = rate * inv1 * dwn;
+                    double rp = rate;
+                    for (int e = 1; e < MAXIT - k; ++e) rp *= rate;
+                    dw_true_max = rp * inv1 * dwn;
+                }
+                if (dwn < a.newton_tol) outcome = 1;
+                else if (have_rate) {
+                    bool fall = true;
+                    if (rate >= 1) {
+                        if (rate < 100 && nbad < a.nmax_bad) { nbad++; update_old = false; fall = false; }
+                        else if (!a.all_newton) { outcome = 2; fall = false; }
+                    }
+                    if (fall) {
+                        if (dw_true < a.newton_tol) outcome = 1;
+                        else if (dw_true_max > a.newton_tol && a.predictive_newton) {
+                            if (nbad < a.nmax_bad) { nbad++; update_old = false; }
+                            else if (!a.all_newton) outcome = 2;
+                        }
+                    }
+                }
+                if (outcome == 0 && update_old) { dwn_old = dwn; have_old = true; }
+            }
+            if (outcome == 0) {
+                ++k;
+                if (k >= MAXIT) { outcome = 2; n_iter = MAXIT; }
+            } else n_iter = k + 1;
+            if (outcome != 0) {
+                safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);   // :631
+                if (outcome == 1) phase = PH_ERREST;
+                else if (current_jac) {                                            // :650-658
+                    cnt[CN_NFAIL]++;
+                    h_abs *= a.nonconv_factor;
+                    lu_valid = false;
+                    phase = PH_ATTEMPT;
+                } else {                                                            // :643-647
+#pragma unroll
+                    for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
+                    sm(L::S_TJ) = t;
+                    cnt[CN_NJEV]++;
+                    current_jac = true; lu_valid = false;
+                    phase = PH_NEWTON_INIT;
+                }
+            }
+        }
+        // ================= error estimate, accept/reject, epilogue :660-784 ===================
+        if (phase == PH_ERREST) {
+            double Z[3][N];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                Z[0][c] = stage_z<0>(W[0][c], W[1][c], W[2][c]);
+                Z[1][c] = stage_z<1>(W[0][c], W[1][c], W[2][c]);
+                Z[2][c] = stage_z<2>(W[0][c], W[1][c], W[2][c]);
+            }
+            double error_norm = 0.0;
+            bool accepted = true;
+            if (!a.constant_dt) {
+                double ze[N], inv_es[N], mze[N], err[N];
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    double v = Z[0][c] * RE0;
+                    v = fma(Z[1][c], RE1, v);
+                    v = fma(Z[2][c], RE2, v);
+                    ze[c] = v / h;
+                    const double ynew = y[c] + Z[2][c];
+                    const int ve = a.var_index[c] > 1 ? a.var_index[c] - 1 : 0;
+                    const double hp = a.scale_error ? hpow(h, ve) : 1.0;
+                    inv_es[c] = hp / (a.atol[c] + fmax(fabs(y[c]), fabs(ynew)) * a.rtol);
+                }
+                mass_mv<Mass>(prm, a, ze, mze);
+#pragma unroll
+                for (int c = 0; c < N; ++c) err[c] = sm(L::S_F + c) + mze[c];
+                for (int pass = 0;; ++pass) {
+                    solve_real_sm<N>(sm, L::S_LUR, piv_r, err);   // rhs NOT scaled by hscale
+                    cnt[CN_NSOLVE_ERR]++;
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        if (a.zero_algebraic_error && a.var_index[c] != 0) err[c] = 0.0;
+                        else { const double v = err[c] * inv_es[c]; s = fma(v, v, s); }
+                    }
+                    error_norm = sqrt(s) * (a.zero_algebraic_error ? a.rsq_nondiff : a.rsqn);
+                    if (pass == 1 || !(error_norm > 1 && (a.always_2nd || rejected))) break;
+                    double Y[N], F[N];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) Y[c] = y[c] + err[c];
+                    Prob::rhs(prm, t, Y, F);
+                    cnt[CN_NFEV]++;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) err[c] = F[c] + mze[c];
+                }
+                if (error_norm > 1) {                                               // :713-733
+                    const double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller);
+                    h_abs *= fmax(a.min_factor, safety * factor);
+                    lu_valid = false; rejected = true; cnt[CN_NREJ]++;
+                    accepted = false;
+                    phase = PH_ATTEMPT;
+                } else cnt[CN_NACC]++;
+            }
+            if (accepted) {                                                         // :742-784
+                const bool has_jac_fn = !a.has_jac_const;
+                const bool recompute = has_jac_fn && n_iter > 2 && have_rate && rate > a.jac_recompute;
+                double factor;
+                if (a.constant_dt) factor = a.max_step / h_abs;
+                else factor = fmin(a.max_factor, safety * gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller));
+                if (!recompute && factor < 1.2) factor = 1; else lu_valid = false;
+                double fnew[N];
+#pragma unroll
+                for (int c = 0; c < N; ++c) { sm(L::S_YOLD + c) = y[c]; y[c] = y[c] + Z[2][c]; }
+                Prob::rhs(prm, t_new, y, fnew);
+                cnt[CN_NFEV]++;
+#pragma unroll
+                for (int c = 0; c < N; ++c) sm(L::S_F + c) = fnew[c];
+                if (recompute) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
+                    sm(L::S_TJ) = t_new;
+                    cnt[CN_NJEV]++;
+                    current_jac = true;
+                } else if (has_jac_fn) current_jac = false;
+                h_abs_old_state = h_abs_state; err_old_state = error_norm; hist_state = true;
+                h_abs_state = h_abs * factor;
+                double Q[N][3];
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    Q[c][0] = fma(Z[2][c], P20, fma(Z[1][c], P10, Z[0][c] * P00));
+                    Q[c][1] = fma(Z[2][c], P21, fma(Z[1][c], P11, Z[0][c] * P01));
+                    Q[c][2] = fma(Z[2][c], P22, fma(Z[1][c], P12, Z[0][c] * P02));
+                    sm(L::S_Q + 3 * c) = Q[c][0]; sm(L::S_Q + 3 * c + 1) = Q[c][1]; sm(L::S_Q + 3 * c + 2) = Q[c][2];
+                }
+                t_sol_old = t; h_sol = t_new - t; have_sol = true;
+                t = t_new;
+                // driver: t_eval points inside (t_old, t]  (searchsorted side='right', ivp.py:711-729)
+                while (ei < a.T) {
+                    const double te = a.t_eval[ei];
+                    if (!(dir > 0 ? te <= t : te >= t)) break;
+                    const double x = (te - t_sol_old) / h_sol;
+                    const double x2 = x * x, x3 = x2 * x;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        double v = Q[c][0] * x;
+                        v = fma(Q[c][1], x2, v);
+                        v = fma(Q[c][2], x3, v);
+                        a.y_eval[((int64_t)ei * N + c) * a.B + idx] = v + sm(L::S_YOLD + c);
+                    }
+                    ++ei;
+                }
+                if (dir * (t - a.tb) >= 0) finish_status = BRDAE_STATUS_FINISHED;
+                else phase = PH_STEP;
+            }
+        }
+        // ================= retire a finished / failed system ==================================
+        if (finish_status != 1) {
+            const double qnan = NAN;
+            for (int e = ei; e < a.T; ++e)
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.y_eval[((int64_t)e * N + c) * a.B + idx] = qnan;
+            a.n_eval[idx] = ei;
+            a.t_final[idx] = t;
+#pragma unroll
+            for (int c = 0; c < N; ++c) a.y_final[(int64_t)c * a.B + idx] = y[c];
+            a.status[idx] = finish_status;
+#pragma unroll
+            for (int q = 0; q < CN_COUNT; ++q) a.counters[(int64_t)q * a.B + idx] = cnt[q];
+            phase = PH_IDLE;
+        }
+    }
+}
+
+#if defined(__CUDACC__)
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k1_kernel(const __grid_constant__ SolveArgs a) {
+    extern __shared__ double k1_smem[];
+    Slots<BLOCK> sm{k1_smem + threadIdx.x};
+    k1_lane_loop<Prob, Mass>(a, sm);
+}
+#endif
+
+}  // namespace brdae

@@ -1,0 +1,75 @@
+"""Seeded synthetic ensembles for the BASELINE.json configurations.
+
+Every generator returns a dict with the arguments of `solve_ivp_batched`:
+`problem, t_span, y0 [B,n], params [B,p] | None, t_eval, options` — numpy only, so that the
+GPU path, the oracles and the bench all integrate exactly the same inputs.
+The first `k` systems of an ensemble do not depend on B (the draws are made for the whole
+requested size with `numpy.random.default_rng(seed)` and are sliced), which is what lets a
+parity subsample of a 1M-system run be re-integrated on the CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import problems as P
+
+
+def pendulum_ensemble(B, t_end=2.0, n_t_eval=21, seed=0, index=3, rtol=1e-6, atol=1e-6, first_step=1e-2):
+    """C2: index-3 pendulum, theta0 ~ U(0.1, 3.0), theta_dot0 ~ U(-1, 1), r0 = m = 1, g = 9.81."""
+    rng = np.random.default_rng(seed)
+    draws = rng.random((B, 2))
+    theta0 = 0.1 + 2.9 * draws[:, 0]
+    thetad0 = -1.0 + 2.0 * draws[:, 1]
+    name = f"pendulum{index}"
+    prob = P.PROBLEMS[name]
+    return dict(problem=name, t_span=(0.0, float(t_end)), y0=P.pendulum_initial_state(theta0, thetad0),
+                params=prob.default_params(B), t_eval=np.linspace(0.0, t_end, n_t_eval),
+                options=dict(rtol=rtol, atol=atol, first_step=first_step, mass_matrix="problem",
+                             var_index=prob.var_index_array()))
+
+
+def robertson_ensemble(B, t_end=5e6, n_t_eval=16, seed=1, rtol=1e-6, atol=1e-8):
+    """C3: Robertson DAE, k_i = k_i0 * 10**U(-0.5, 0.5)."""
+    rng = np.random.default_rng(seed)
+    k0 = np.array([0.04, 1e4, 3e7])
+    params = k0[None, :] * 10.0 ** (rng.random((B, 3)) - 0.5)
+    prob = P.PROBLEMS["robertson"]
+    t_eval = np.logspace(-5, np.log10(t_end), n_t_eval)
+    t_eval[-1] = min(t_eval[-1], t_end)
+    return dict(problem="robertson", t_span=(0.0, float(t_end)), y0=P.robertson_initial_state(B),
+                params=params, t_eval=t_eval,
+                options=dict(rtol=rtol, atol=atol, first_step=1e-8, max_bad_ite=0, scale_newton_norm=False,
+                             mass_matrix="problem", var_index=prob.var_index_array()))
+
+
+def transistor_ensemble(B, t_end=0.2, n_t_eval=21, seed=2):
+    """C4: transistor amplifier, C1..C3 and R0..R5 each scaled by 10**U(-0.1, 0.1); script options
+    of transistor_amplifier.py:78-88."""
+    rng = np.random.default_rng(seed)
+    prob = P.PROBLEMS["transistor"]
+    params = prob.default_params(B)
+    params[:, :9] *= 10.0 ** (0.2 * rng.random((B, 9)) - 0.1)
+    return dict(problem="transistor", t_span=(0.0, float(t_end)), y0=P.transistor_initial_state(params),
+                params=params, t_eval=np.linspace(0.0, t_end, n_t_eval),
+                options=dict(rtol=1e-5, atol=1e-5, first_step=1e-8, scale_residuals=False,
+                             scale_newton_norm=False, scale_error=True, zero_algebraic_error=False,
+                             max_bad_ite=1, mass_matrix="problem", var_index=None))
+
+
+def npendulum_ensemble(B, n_nodes=20, n_t_eval=21, seed=3, t_end=None):
+    """C5: n-pendulum chain, initial_angle ~ U(pi/8, 3pi/8); script options of
+    recursive_pendulum.py:233-246 with the analytic Jacobian."""
+    rng = np.random.default_rng(seed)
+    ang = np.pi / 8 + (np.pi / 4) * rng.random(B)
+    prob = P.PROBLEMS["npendulum"]
+    tf = prob.t_span[1] if t_end is None else float(t_end)
+    n = 5 * n_nodes
+    return dict(problem="npendulum", t_span=(0.0, tf), y0=P.npendulum_initial_state(n_nodes, ang), params=None,
+                t_eval=np.linspace(0.0, tf, n_t_eval),
+                options=dict(rtol=1e-5, atol=1e-5, first_step=1e-3, max_step=prob.t_span[1] / 10, max_newton_ite=7,
+                             max_bad_ite=2, scale_residuals=True, scale_newton_norm=True, scale_error=True,
+                             mass_matrix="problem", var_index=prob.var_index_array(n)))
+
+
+ENSEMBLES = {"pendulum": pendulum_ensemble, "robertson": robertson_ensemble,
+             "transistor": transistor_ensemble, "npendulum": npendulum_ensemble}
