@@ -1,0 +1,74 @@
+"""Multi-GPU sharding of an ensemble: one process per GPU, torch.distributed for the plumbing.
+
+The systems of an ensemble are independent: there is no exchange step during
+the integration, so the ensemble is partitioned across ranks and every rank runs the
+single-GPU path on its shard.  Collectives are used only after the kernels: an `all_reduce`
+of the summed counters / status histogram, and — on request — a `gather` of the per-system
+results onto rank 0 (NCCL over NVLink when the backend is nccl; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(B: int, world_size: int, rank: int):
+    """Contiguous, balanced partition of range(B): the first B % world_size ranks get one more."""
+    base, rem = divmod(int(B), int(world_size))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def shard_ensemble(ens: dict, world_size: int, rank: int) -> dict:
+    """Slice the batch-sized entries (y0, params) of an ensemble description for this rank."""
+    B = ens["y0"].shape[0]
+    lo, hi = shard_bounds(B, world_size, rank)
+    out = dict(ens)
+    out["y0"] = ens["y0"][lo:hi]
+    out["params"] = None if ens["params"] is None else ens["params"][lo:hi]
+    out["shard"] = (lo, hi)
+    return out
+
+
+def reduce_statistics(counters_sum, status_hist, dist=None, device=None):
+    """Sum the per-rank statistics vectors over all ranks (all_reduce SUM).  `counters_sum` is the
+    int64 [9] sum of the per-system counters of the local shard, `status_hist` an int64 [4] vector
+    (finished, too-small-step, lu-failed, nmax-step)."""
+    import torch
+    vec = torch.cat([torch.as_tensor(counters_sum, dtype=torch.int64).reshape(-1),
+                     torch.as_tensor(status_hist, dtype=torch.int64).reshape(-1)])
+    if device is not None:
+        vec = vec.to(device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return vec[:9].clone(), vec[9:].clone()
+
+
+def gather_results(local: dict, B_total: int, dist, dst: int = 0):
+    """Gather per-system result tensors of all shards onto rank `dst`, restoring ensemble order.
+
+    `local` maps name -> tensor whose LAST axis is the local system axis (kernel SoA layout,
+    e.g. y_eval [T, n, B_local], status [B_local]).  Shards may differ by one system, so each is
+    padded to the largest shard before `dist.gather`.  Returns the dict of gathered tensors on
+    `dst` and None elsewhere."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [shard_bounds(B_total, world, r) for r in range(world)]
+    maxlen = max(hi - lo for lo, hi in sizes)
+    out = {} if rank == dst else None
+    for name, ten in local.items():
+        pad = maxlen - ten.shape[-1]
+        send = ten if pad == 0 else torch.nn.functional.pad(ten, (0, pad))
+        send = send.contiguous()
+        bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+        dist.gather(send, gather_list=bufs, dst=dst)
+        if rank == dst:
+            out[name] = torch.cat([b[..., :hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=-1)
+    return out
+
+
+def status_histogram(status):
+    """[finished, too-small-step, lu-failed, nmax-step] counts of a status vector."""
+    import torch
+    s = status if isinstance(status, torch.Tensor) else torch.as_tensor(np.asarray(status))
+    return torch.stack([(s == 0).sum(), (s == -1).sum(), (s == -2).sum(), (s == 2).sum()]).to(torch.int64)

@@ -1,0 +1,57 @@
+"""Algorithmic FLOP and byte model of the hot path, evaluated from the
+per-system counters the kernels return — never from a profiler.
+
+Counting rule: +, -, *, /, sqrt and each libm call count 1; an FMA counts 2; complex multiply 6,
+complex add 2.  Dense size n, z = nnz(M):
+    F_LU   = 5 (2/3 n^3 - 1/2 n^2 - 1/6 n)      real + complex factorisation (complex = 4 x real)
+    F_form = 5 n^2 + 3 z                          forming both iteration matrices
+    F_newt = (2n^2 - n) + 4 (2n^2 - n) + 60 n + 6 z   one simplified-Newton iteration (without its 3 RHS)
+    F_err  = 2 n^2 + 15 n + 2 z                   one error estimate
+    FLOPs  = nfev F_f + njev F_J + nlu (F_form + F_LU) + nlusolve F_newt + nlusolve_err F_err
+             + naccpt 15 n + n_out (6 n + 3)
+For the banded CTA-per-system kernel 2/3 n^3 becomes 2 N kl (kl + ku) and 2 n^2 becomes
+2 N (2 kl + ku) with kl = 9, ku = 7.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# per right-hand-side / Jacobian evaluation; n-pendulum figures are per node
+F_RHS = {"pendulum3": 12, "pendulum2": 12, "pendulum1": 20, "robertson": 15, "transistor": 22, "npendulum": 17}
+F_JAC = {"pendulum3": 4, "pendulum2": 4, "pendulum1": 12, "robertson": 8, "transistor": 12, "npendulum": 30}
+MASS_NNZ = {"pendulum3": 4, "pendulum2": 4, "pendulum1": 4, "robertson": 2, "transistor": 9}
+
+
+def flop_constants(problem: str, n: int):
+    if problem == "npendulum":
+        nodes = n // 5
+        kl, ku = 9, 7
+        z = 4 * nodes
+        lu_real = 2 * n * kl * (kl + ku)
+        solve_real = 2 * n * (2 * kl + ku)
+        f_lu = 5 * lu_real
+        f_form = 5 * n * (kl + ku + 1) + 3 * z
+        f_newt = 5 * solve_real + 60 * n + 6 * z
+        f_err = solve_real + 15 * n + 2 * z
+        return dict(F_f=F_RHS[problem] * nodes, F_J=F_JAC[problem] * nodes, F_LU=f_lu, F_form=f_form,
+                    F_newt=f_newt, F_err=f_err)
+    z = MASS_NNZ[problem]
+    f_lu = 5 * (2 / 3 * n ** 3 - n ** 2 / 2 - n / 6)
+    return dict(F_f=F_RHS[problem], F_J=F_JAC[problem], F_LU=f_lu, F_form=5 * n * n + 3 * z,
+                F_newt=(2 * n * n - n) + 4 * (2 * n * n - n) + 60 * n + 6 * z,
+                F_err=2 * n * n + 15 * n + 2 * z)
+
+
+def algorithmic_flops(problem: str, n: int, counter_sums, n_out_total: int) -> float:
+    """counter_sums: the 9 counters summed over the ensemble, in _abi.COUNTER_NAMES order."""
+    c = flop_constants(problem, n)
+    nfev, njev, nlu, _nstep, naccpt, _nrej, _nfail, nsolve, nsolve_err = [float(x) for x in counter_sums]
+    return (nfev * c["F_f"] + njev * c["F_J"] + nlu * (c["F_form"] + c["F_LU"]) + nsolve * c["F_newt"]
+            + nsolve_err * c["F_err"] + naccpt * 15 * n + float(n_out_total) * (6 * n + 3))
+
+
+def algorithmic_bytes(n: int, n_params: int, T: int, B: int) -> float:
+    """HBM bytes a launch must move: y0 + params in; y_eval, t_final, y_final, status, n_eval,
+    counters out."""
+    per_sys = 8 * (n + n_params) + 8 * n * T + 8 * (n + 1) + 4 * (2 + 9)
+    return float(per_sys) * B

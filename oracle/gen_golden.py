@@ -1,0 +1,201 @@
+"""ORACLE (test infrastructure) — generate tests/golden/*.npz by running THE REFERENCE ITSELF.
+
+Run in the build container, where /root/reference is mounted:
+    python oracle/gen_golden.py
+It imports `scipyDAE.radauDAE.RadauDAE` from /root/reference and drives it with
+`scipy.integrate.solve_ivp(method=RadauDAE)` exactly like the reference scripts do
+(tests/pendulum.py:266-280, tests/robertson.py:105-116, tests/transistor_amplifier.py:78-88,
+tests/recursive_pendulum.py:233-246), on the seeded ensembles of dae_scipy_b200.ensembles.  The
+right-hand sides are the parametrised restatements of oracle/problems_numpy.py (checked in
+tests/test_oracle_numpy.py to return the same bits as the reference closures) and the Jacobians
+are the analytic ones, so that every implementation is handed the same Jacobian.
+
+Each fixture stores inputs (y0, params, t_eval, options) and the reference outputs
+(y [B, n, T], status, the nine counters).  Nothing is copied from the reference sources.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+warnings.filterwarnings("ignore")
+
+from scipy.integrate import solve_ivp  # noqa: E402
+from scipyDAE.radauDAE import RadauDAE  # noqa: E402  (the reference)
+
+from dae_scipy_b200 import ensembles  # noqa: E402  (numpy-only input generators)
+from oracle import problems_numpy as prob  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def build_system(problem, p, n=None):
+    if problem.startswith("pendulum"):
+        return prob.pendulum(int(problem[-1]), *p)
+    if problem == "robertson":
+        return prob.robertson(*p)
+    if problem == "transistor":
+        return prob.transistor(*p)
+    if problem == "npendulum":
+        return prob.npendulum(n // 5)
+    raise ValueError(problem)
+
+
+def run_reference_with_counters(ens, over=None):
+    """Same as run_reference but steps the solver object directly (the loop of scipy ivp.py:659-732)
+    to read nstep/naccpt/nrejct/nfailed/_nlusolve/_nlusolve_errorest from it."""
+    opts = dict(ens["options"])
+    opts.update(over or {})
+    mm = opts.pop("mass_matrix")
+    vi = opts.pop("var_index")
+    nmax_step = opts.pop("nmax_step", np.inf)
+    B, n = ens["y0"].shape
+    te = np.asarray(ens["t_eval"], dtype=float)
+    T = te.size
+    t0, tf = ens["t_span"]
+    y = np.full((B, n, T), np.nan)
+    status = np.zeros(B, dtype=np.int32)
+    n_eval = np.zeros(B, dtype=np.int32)
+    counters = np.zeros((B, 9), dtype=np.int32)
+    y_final = np.zeros((B, n))
+    t_final = np.zeros(B)
+    for i in range(B):
+        p = ens["params"][i] if ens["params"] is not None else ()
+        fun, jac, mass, _ = build_system(ens["problem"], p, n)
+        if not isinstance(mm, str):
+            mass = mm
+        with contextlib.redirect_stdout(io.StringIO()):
+            solver = RadauDAE(fun, t0, np.array(ens["y0"][i], dtype=float), tf, jac=jac, mass_matrix=mass,
+                              var_index=None if vi is None else np.asarray(vi, dtype=float), **opts)
+            ei = 0
+            st = None
+            nsteps = 0
+            while st is None:
+                nsteps += 1
+                if nsteps > nmax_step:
+                    st = 2
+                    break
+                solver.step()
+                if solver.status == 'finished':
+                    st = 0
+                elif solver.status == 'failed':
+                    st = -1
+                    break
+                t = solver.t
+                if tf > t0:
+                    ei_new = int(np.searchsorted(te, t, side='right'))
+                    pts = te[ei:ei_new]
+                else:
+                    # user order is decreasing: points >= t
+                    ei_new = ei
+                    while ei_new < T and te[ei_new] >= t:
+                        ei_new += 1
+                    pts = te[ei:ei_new]
+                if pts.size:
+                    y[i, :, ei:ei_new] = solver.dense_output()(pts)
+                    ei = ei_new
+        n_eval[i] = ei
+        status[i] = st
+        counters[i] = [solver.nfev, solver.njev, solver.nlu, solver.nstep, solver.naccpt, solver.nrejct,
+                       solver.nfailed, solver._nlusolve, solver._nlusolve_errorest]
+        y_final[i] = solver.y
+        t_final[i] = solver.t
+    return dict(y=y, status=status, n_eval=n_eval, counters=counters, y_final=y_final, t_final=t_final)
+
+
+def save(name, ens, over=None):
+    out = run_reference_with_counters(ens, over)
+    opts = dict(ens["options"])
+    opts.update(over or {})
+    vi = opts.pop("var_index")
+    mm = opts.pop("mass_matrix")
+    meta = dict(problem=ens["problem"], t_span=list(ens["t_span"]),
+                options={k: (v if not isinstance(v, (np.floating, np.integer)) else v.item()) for k, v in opts.items()},
+                mass_matrix=mm if isinstance(mm, str) else "array")
+    arrays = dict(y0=ens["y0"], t_eval=np.asarray(ens["t_eval"], dtype=float),
+                  var_index=np.zeros(0, dtype=np.int32) if vi is None else np.asarray(vi, dtype=np.int32),
+                  has_var_index=np.array(vi is not None), meta=np.array(json.dumps(meta)), **out)
+    if ens["params"] is not None:
+        arrays["params"] = ens["params"]
+    if not isinstance(mm, str):
+        arrays["mass"] = np.asarray(mm, dtype=float)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **arrays)
+    c = out["counters"]
+    print(f"{name}: B={ens['y0'].shape[0]} status {np.bincount(out['status'] + 1).tolist()} "
+          f"mean acc/rej/fail {c[:, 4].mean():.1f}/{c[:, 5].mean():.1f}/{c[:, 6].mean():.1f}")
+
+
+def single(problem, y0, params, t_span, t_eval, options):
+    return dict(problem=problem, t_span=tuple(t_span), y0=np.atleast_2d(np.asarray(y0, dtype=float)),
+                params=None if params is None else np.atleast_2d(np.asarray(params, dtype=float)),
+                t_eval=np.asarray(t_eval, dtype=float), options=options)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    E = ensembles
+    from dae_scipy_b200 import problems as P
+    # --- well-conditioned known answers of SURVEY 4.2 (G1, G2, G3)
+    pend = P.PROBLEMS["pendulum3"]
+    save("g1_pendulum3_single", single("pendulum3", prob.pendulum_ic(np.pi / 4, 0.), pend.param_defaults, (0, 2),
+                                       np.linspace(0, 2, 21),
+                                       dict(rtol=1e-6, atol=1e-6, first_step=1e-2, mass_matrix="problem",
+                                            var_index=pend.var_index_array())))
+    rob = P.PROBLEMS["robertson"]
+    save("g2_robertson_single", single("robertson", prob.ROBERTSON_Y0, rob.param_defaults, (0, 40), [0.4, 4., 40.],
+                                       dict(rtol=1e-6, atol=1e-8, first_step=1e-8, max_bad_ite=0,
+                                            scale_newton_norm=False, mass_matrix="problem",
+                                            var_index=rob.var_index_array())))
+    tra = E.transistor_ensemble(1, t_end=0.2)
+    tra["params"] = P.PROBLEMS["transistor"].default_params(1)
+    tra["y0"] = P.transistor_initial_state(tra["params"])
+    save("g3_transistor_single", tra)
+    # --- reference script configurations
+    save("script_pendulum3", single("pendulum3", prob.pendulum_ic(np.pi / 2, 0., r0=3.), (1.0, 9.81, 3.0), (0, 10),
+                                    np.linspace(0, 10, 51),
+                                    dict(rtol=1e-8, atol=1e-8, newton_tol=1e-2, mass_matrix="problem",
+                                         var_index=pend.var_index_array())))
+    save("script_robertson", single("robertson", prob.ROBERTSON_Y0, rob.param_defaults, (0, 5e6),
+                                    np.logspace(-5, np.log10(5e6), 16).clip(max=5e6),
+                                    dict(rtol=1e-3, atol=1e-4, first_step=1e-8, max_newton_ite=6, max_bad_ite=0,
+                                         scale_residuals=True, scale_newton_norm=False, scale_error=True,
+                                         mass_matrix="problem", var_index=rob.var_index_array())))
+    # --- seeded ensembles (first systems of the BASELINE configurations)
+    save("ens_pendulum3_tend2", E.pendulum_ensemble(64, t_end=2.0))
+    save("ens_pendulum3_tend10", E.pendulum_ensemble(16, t_end=10.0))
+    save("ens_pendulum2_tend2", E.pendulum_ensemble(16, index=2))
+    save("ens_pendulum1_tend2", E.pendulum_ensemble(16, index=1))
+    save("ens_robertson", E.robertson_ensemble(32))
+    save("ens_transistor_t0p05", E.transistor_ensemble(8, t_end=0.05))
+    # --- option surface / edge cases on the pendulum
+    e = E.pendulum_ensemble(8, t_end=1.0)
+    save("opt_pendulum3_controller_off", e, dict(bUsePredictiveController=False, bAlwaysApply2ndEstimate=False,
+                                                 bUsePredictiveNewtonStoppingCriterion=False, zero_algebraic_error=True,
+                                                 max_newton_ite=8, rtol=1e-4))
+    save("opt_pendulum3_no_scaling", e, dict(scale_residuals=False, scale_newton_norm=False, scale_error=False,
+                                             bUseExtrapolatedGuess=False, rtol=1e-4, first_step=1e-3))
+    save("opt_pendulum3_max_step", e, dict(max_step=0.02))
+    save("opt_pendulum3_default_first_step", E.pendulum_ensemble(8, t_end=0.25), dict(first_step=None))
+    save("opt_pendulum3_nmax_step", e, dict(nmax_step=25))
+    save("opt_pendulum3_dense_mass", e, dict(mass_matrix=np.diag([1., 1., 1., 1., 0.]) * 2.0))
+    back = E.pendulum_ensemble(8, t_end=1.0)
+    back["t_span"] = (1.0, 0.0)
+    back["t_eval"] = np.linspace(1.0, 0.0, 11)
+    save("opt_pendulum3_backward", back)
+    # --- n-pendulum chains (dense analytic Jacobian handed to the reference)
+    save("ens_npendulum_n4", E.npendulum_ensemble(3, n_nodes=4))
+    save("ens_npendulum_n10", E.npendulum_ensemble(2, n_nodes=10))
+    save("ens_npendulum_n20", E.npendulum_ensemble(2, n_nodes=20))
+
+
+if __name__ == "__main__":
+    main()

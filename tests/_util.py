@@ -1,0 +1,172 @@
+"""Shared helpers of the test-suite: golden fixtures, the three CPU checkers and the parity rule."""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+HAVE_REFERENCE = os.path.isdir("/root/reference/scipyDAE")
+
+# parity tolerance of BASELINE.json north_star: every trajectory within 10*rtol (scaled by atol)
+# of the reference at each t_eval point
+PARITY_FACTOR = 10.0
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    opts = dict(meta["options"])
+    opts["var_index"] = z["var_index"] if bool(z["has_var_index"]) else None
+    opts["mass_matrix"] = z["mass"] if "mass" in z.files else meta["mass_matrix"]
+    ens = dict(problem=meta["problem"], t_span=tuple(meta["t_span"]), y0=z["y0"],
+               params=z["params"] if "params" in z.files else None, t_eval=z["t_eval"], options=opts)
+    ref = {k: z[k] for k in ("y", "status", "n_eval", "counters", "y_final", "t_final")}
+    return ens, ref
+
+
+def scaled_error(y, y_ref, rtol, atol):
+    """max over everything of |y - y_ref| / (atol + rtol |y_ref|); NaN pattern must agree."""
+    assert y.shape == y_ref.shape
+    nan_a, nan_b = np.isnan(y), np.isnan(y_ref)
+    assert np.array_equal(nan_a, nan_b), "different sets of reached t_eval points"
+    atol = np.asarray(atol, dtype=float)
+    if atol.ndim == 1:
+        atol = atol[None, :, None]
+    err = np.abs(y - y_ref) / (atol + rtol * np.abs(y_ref))
+    return float(np.nanmax(err)) if np.isfinite(err).any() else 0.0
+
+
+def count_agreement(c, c_ref):
+    """fraction of systems whose (naccpt, nrejct, nfailed) are identical"""
+    return float((c[:, 4:7] == c_ref[:, 4:7]).all(axis=1).mean())
+
+
+# ------------------------------------------------------------------ checker 1: C oracle
+def run_c_oracle(ens, nthreads=0, **over):
+    from oracle import c_oracle
+    opts = dict(ens["options"])
+    opts.update(over)
+    mm = opts.pop("mass_matrix")
+    B = ens["y0"].shape[0]
+    params = ens["params"] if ens["params"] is not None else np.zeros((B, 0))
+    r = c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"], params, t_eval=ens["t_eval"],
+                             mass_matrix=None if isinstance(mm, str) else (np.eye(ens["y0"].shape[1]) if mm is None else mm),
+                             nthreads=nthreads, **opts)
+    return dict(y=r.y, status=r.status, n_eval=r.n_eval, counters=r.counters, y_final=r.y_final, t_final=r.t_final)
+
+
+# ------------------------------------------------------------------ checker 2: numpy oracle
+def run_numpy_oracle(ens, **over):
+    from oracle import radau_numpy as orc, problems_numpy as prob
+    opts = dict(ens["options"])
+    opts.update(over)
+    mm = opts.pop("mass_matrix")
+    vi = opts.pop("var_index")
+    B, n = ens["y0"].shape
+    T = len(ens["t_eval"])
+    out = dict(y=np.full((B, n, T), np.nan), status=np.zeros(B, np.int32), n_eval=np.zeros(B, np.int32),
+               counters=np.zeros((B, 9), np.int32), y_final=np.zeros((B, n)), t_final=np.zeros(B))
+    for i in range(B):
+        p = ens["params"][i] if ens["params"] is not None else ()
+        name = ens["problem"]
+        if name.startswith("pendulum"):
+            fun, jac, mass, _ = prob.pendulum(int(name[-1]), *p)
+        elif name == "robertson":
+            fun, jac, mass, _ = prob.robertson(*p)
+        elif name == "transistor":
+            fun, jac, mass, _ = prob.transistor(*p)
+        else:
+            fun, jac, mass, _ = prob.npendulum(n // 5)
+        if not isinstance(mm, str):
+            mass = mm
+        r = orc.solve(fun, ens["t_span"], ens["y0"][i], jac=jac, mass_matrix=mass,
+                      var_index=None if vi is None else np.asarray(vi, dtype=float), t_eval=ens["t_eval"], **opts)
+        k = r.y.shape[1]
+        out["y"][i, :, :k] = r.y
+        out["n_eval"][i] = k
+        out["status"][i] = r.status
+        out["counters"][i] = r.counters.as_array()
+        out["y_final"][i] = r.y_final
+        out["t_final"][i] = r.t_final
+    return out
+
+
+# ------------------------------------------------------------------ kernel source on the CPU
+_sim = None
+
+
+def run_kernel_source_on_cpu(ens, **over):
+    """tests/host_sim: the K1 kernel SOURCE compiled for the host, one lane."""
+    global _sim
+    import dae_scipy_b200 as br
+    from dae_scipy_b200 import _abi
+    if _sim is None:
+        _sim = C.CDLL(os.path.join(ROOT, "tests", "host_sim", "libk1_host_sim.so"))
+        _sim.sim_solve.restype = C.c_int
+        _sim.sim_solve.argtypes = [C.POINTER(_abi.BrdaeBatch), C.POINTER(_abi.BrdaeOptions)]
+    opts = dict(ens["options"])
+    opts.update(over)
+    y0 = np.ascontiguousarray(ens["y0"], dtype=np.float64)
+    B, n = y0.shape
+    hb = br.prepare(ens["problem"], ens["t_span"], y0.shape, t_eval=ens["t_eval"], **opts)
+    T = hb.t_eval.size
+    y0s = np.ascontiguousarray(y0.T)
+    ps = np.ascontiguousarray(ens["params"].T) if ens["params"] is not None else None
+    out = {"y_eval": np.empty((max(T, 1), n, B)), "n_eval": np.empty(B, np.int32), "t_final": np.empty(B),
+           "y_final": np.empty((n, B)), "status": np.empty(B, np.int32), "counters": np.empty((9, B), np.int32)}
+    ptr = {k: v.ctypes.data for k, v in out.items()}
+    ptr.update(y0=y0s.ctypes.data, params=ps.ctypes.data if ps is not None else None,
+               t_eval=hb.t_eval.ctypes.data if T else None)
+    b = hb.struct(ptr)
+    rc = _sim.sim_solve(C.byref(b), C.byref(hb.options))
+    assert rc == 0, f"sim_solve returned {rc}"
+    return dict(y=np.ascontiguousarray(out["y_eval"][:T].transpose(2, 1, 0)), status=out["status"],
+                n_eval=out["n_eval"], counters=np.ascontiguousarray(out["counters"].T),
+                y_final=np.ascontiguousarray(out["y_final"].T), t_final=out["t_final"])
+
+
+# ------------------------------------------------------------------ the product (GPU)
+def run_gpu(ens, host_api=False, **over):
+    import dae_scipy_b200 as br
+    opts = dict(ens["options"])
+    opts.update(over)
+    if host_api:
+        r = br.solve_ivp_batched_host(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], **opts)
+        return dict(y=np.ascontiguousarray(r["y"]), status=r["status"], n_eval=r["n_eval"],
+                    counters=np.ascontiguousarray(r["counters"]), y_final=np.ascontiguousarray(r["y_final"]),
+                    t_final=r["t_final"])
+    import torch
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], **opts)
+    torch.cuda.synchronize()
+    o = res.numpy()
+    return dict(y=o["y"], status=o["status"], n_eval=o["n_eval"], counters=o["counters"], y_final=o["y_final"],
+                t_final=o["t_final"])
+
+
+def assert_bit_identical(a, b, what=""):
+    for k in ("status", "n_eval", "counters"):
+        assert np.array_equal(a[k], b[k]), f"{what}: {k} differ"
+    for k in ("y", "y_final", "t_final"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), f"{what}: {k} not bit-identical"
+
+
+def well_conditioned(name):
+    """Fixtures on which the reference itself is reproducible under rounding noise:
+    step counts must then be identical, not just statistically close."""
+    return name in ("g1_pendulum3_single", "g2_robertson_single", "ens_pendulum3_tend2", "ens_pendulum2_tend2",
+                    "ens_pendulum1_tend2", "opt_pendulum3_max_step", "opt_pendulum3_nmax_step",
+                    "opt_pendulum3_dense_mass", "opt_pendulum3_backward", "opt_pendulum3_controller_off",
+                    "ens_npendulum_n4", "ens_npendulum_n10", "ens_npendulum_n20", "script_robertson")

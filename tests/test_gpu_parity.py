@@ -1,0 +1,175 @@
+"""GPU parity tests (run on the B200 box): the CUDA kernels, called through the C ABI, against
+  (1) the scalar C oracle on the same seeded inputs          -> bit-identical (FP64, same spec);
+      the transistor RHS uses sin/exp whose device libm differs from glibc by <= 2 ulp, so it is
+      held to the north_star tolerance instead;
+  (2) the committed fixtures the reference itself produced   -> every t_eval value within
+      10*(atol + rtol*|y_ref|) and identical accepted/rejected/failed counts for >= 99 % of the
+      systems on the well-conditioned configurations (BASELINE.json north_star);
+  (3) size-independent properties at BASELINE.json's full ensemble sizes.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import dae_scipy_b200 as br
+from _util import (PARITY_FACTOR, assert_bit_identical, count_agreement, golden_names, load_golden,
+                   run_c_oracle, run_gpu, scaled_error, well_conditioned)
+
+pytestmark = pytest.mark.gpu
+E = br.ensembles
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dae_scipy_b200 import _abi
+    _abi.load()                      # fails loudly if libbrdae.so is missing
+
+
+# ---------------------------------------------------------------- (1) against the C oracle
+@pytest.mark.parametrize("case,make,over", [
+    ("pendulum3_t2_4096", lambda: E.pendulum_ensemble(4096), {}),
+    ("pendulum3_t10_512", lambda: E.pendulum_ensemble(512, t_end=10.0), {}),
+    ("pendulum2_1024", lambda: E.pendulum_ensemble(1024, index=2), {}),
+    ("pendulum1_1024", lambda: E.pendulum_ensemble(1024, index=1), {}),
+    ("robertson_4096", lambda: E.robertson_ensemble(4096), {}),
+    ("robertson_script_tol", lambda: E.robertson_ensemble(1024), dict(rtol=1e-3, atol=1e-4)),
+    ("pendulum3_default_first_step", lambda: E.pendulum_ensemble(256, t_end=0.5), dict(first_step=None)),
+    ("pendulum3_dense_mass", lambda: E.pendulum_ensemble(256), dict(mass_matrix=np.diag([1., 1, 1, 1, 0]) * 1.5)),
+    ("pendulum3_identity_mass", lambda: E.pendulum_ensemble(64, t_end=0.2), dict(mass_matrix=None, var_index=None)),
+    ("pendulum3_failing", lambda: E.pendulum_ensemble(256), dict(
+        bUseExtrapolatedGuess=False, scale_residuals=False, scale_newton_norm=False, scale_error=False,
+        bPerformAllNewtonIterations=True, newton_tol=1e-3, rtol=1e-4)),
+    ("pendulum3_controller_off", lambda: E.pendulum_ensemble(256), dict(
+        zero_algebraic_error=True, bAlwaysApply2ndEstimate=False, bUsePredictiveController=False,
+        bUsePredictiveNewtonStoppingCriterion=False, max_newton_ite=8, rtol=1e-4)),
+    ("pendulum3_nmax_step", lambda: E.pendulum_ensemble(256), dict(nmax_step=40)),
+    ("pendulum3_max_step", lambda: E.pendulum_ensemble(256), dict(max_step=0.02)),
+    ("pendulum3_constant_dt", lambda: E.pendulum_ensemble(64, t_end=0.5), dict(constant_dt=True, max_step=0.01, first_step=0.01, newton_tol=1e-8)),
+    ("robertson_vector_atol", lambda: E.robertson_ensemble(256), dict(atol=np.array([1e-8, 1e-12, 1e-8]))),
+    ("ragged_sizes_1", lambda: E.pendulum_ensemble(1), {}),
+    ("ragged_sizes_33", lambda: E.pendulum_ensemble(33), {}),
+    ("ragged_sizes_129", lambda: E.robertson_ensemble(129), {}),
+])
+def test_gpu_bit_identical_to_c_oracle(case, make, over):
+    ens = make()
+    assert_bit_identical(run_gpu(ens, **over), run_c_oracle(ens, **over), case)
+
+
+def test_gpu_constant_jacobian_mode():
+    ens = E.pendulum_ensemble(32, t_end=0.3)
+    J = np.array([[0, 0, 1., 0, 0], [0, 0, 0, 1., 0], [-5., 0, 0, 0, -0.5], [0, -5., 0, 0, 0.8], [1., -1.6, 0, 0, 0]])
+    assert_bit_identical(run_gpu(ens, jac=J), run_c_oracle(ens, jac_const=J), "constant jac")
+
+
+def test_gpu_backward_integration_and_t0_equals_tbound():
+    ens = E.pendulum_ensemble(64)
+    ens["t_span"], ens["t_eval"] = (2.0, 0.0), np.linspace(2.0, 0.0, 9)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "backward")
+    ens = E.pendulum_ensemble(16)
+    ens["t_span"], ens["t_eval"] = (1.0, 1.0), np.array([1.0])
+    ens["options"] = dict(ens["options"], first_step=None)
+    out = run_gpu(ens)
+    assert (out["status"] == 0).all() and np.array_equal(out["y"][:, :, 0], ens["y0"])
+
+
+def test_gpu_transistor_within_tolerance_of_c_oracle():
+    ens = E.transistor_ensemble(64, t_end=0.02)
+    g, c = run_gpu(ens), run_c_oracle(ens)
+    assert np.array_equal(g["status"], c["status"]) and np.array_equal(g["n_eval"], c["n_eval"])
+    assert scaled_error(g["y"], c["y"], 1e-5, 1e-5) <= PARITY_FACTOR
+
+
+def test_empty_ensemble_and_no_t_eval():
+    ens = E.pendulum_ensemble(8)
+    out = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"][:0], ens["params"][:0], t_eval=ens["t_eval"],
+                               **ens["options"]).numpy()
+    assert out["y"].shape == (0, 5, 21) and out["status"].shape == (0,)
+    out = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=None, **ens["options"]).numpy()
+    ref = run_c_oracle(dict(ens, t_eval=np.empty(0)))
+    assert out["y"].shape == (8, 5, 0) and np.array_equal(out["y_final"], ref["y_final"])
+    assert np.array_equal(out["t_final"], np.full(8, 2.0))
+
+
+def test_host_buffer_entry_equals_device_entry():
+    ens = E.pendulum_ensemble(777)
+    assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "brdae_solve_host vs brdae_solve")
+
+
+def test_invalid_y0_raises_like_scipy():
+    ens = E.pendulum_ensemble(4)
+    y0 = ens["y0"].copy()
+    y0[2, 1] = np.nan
+    with pytest.raises(ValueError, match="must be finite"):
+        br.solve_ivp_batched(ens["problem"], ens["t_span"], y0, ens["params"], t_eval=ens["t_eval"], **ens["options"])
+
+
+# ---------------------------------------------------------------- (2) against the reference fixtures
+@pytest.mark.parametrize("name", [n for n in golden_names() if "npendulum" not in n])
+def test_gpu_against_reference_fixture(name):
+    ens, ref = load_golden(name)
+    out = run_gpu(ens)
+    assert np.array_equal(out["status"], ref["status"]), "per-system status differs from the reference"
+    rtol, atol = ens["options"]["rtol"], ens["options"]["atol"]
+    if well_conditioned(name):
+        assert np.array_equal(out["n_eval"], ref["n_eval"])
+        err = scaled_error(out["y"], ref["y"], rtol, atol)
+        assert err <= PARITY_FACTOR, f"max |dy|/(atol+rtol|y|) = {err:.3g}"
+        assert count_agreement(out["counters"], ref["counters"]) >= 0.99
+    else:   # rounding-chaotic configurations: statistical agreement only
+        fin = ref["status"] == 0
+        if fin.any():
+            d = np.abs(out["y"][fin][:, :4] - ref["y"][fin][:, :4]) / (1.0 + np.abs(ref["y"][fin][:, :4]))
+            assert np.nanmax(d) < 5e-3
+            tot, tot_ref = out["counters"][fin, 3].sum(), ref["counters"][fin, 3].sum()
+            assert abs(int(tot) - int(tot_ref)) <= 0.1 * tot_ref
+
+
+# ---------------------------------------------------------------- (3) properties at full size
+def test_full_size_pendulum_ensemble_properties():
+    """BASELINE configs[1]: 1,048,576 index-3 pendulums to t_end = 2."""
+    import torch
+    B = 1 << 20
+    ens = E.pendulum_ensemble(B)
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], **ens["options"])
+    torch.cuda.synchronize()
+    assert bool((res.status == 0).all()) and bool((res.n_eval == 21).all())
+    y = res.y                                                   # [B, 5, 21]
+    assert bool(torch.isfinite(y).all())
+    # the position constraint x^2 + y^2 = r0^2 is enforced to the tolerance at every output point
+    c = (y[:, 0] ** 2 + y[:, 1] ** 2 - 1.0).abs().max().item()
+    assert c < 1e-4
+    # energy  E = (vx^2+vy^2)/2 + g y  is conserved by the exact flow
+    en = 0.5 * (y[:, 2] ** 2 + y[:, 3] ** 2) + 9.81 * y[:, 1]
+    assert (en - en[:, :1]).abs().max().item() < 5e-4
+    # t_eval[0] == t0 returns the initial state exactly (x = 0 in the cubic)
+    assert torch.equal(y[:, :, 0].cpu(), torch.as_tensor(ens["y0"]))
+    # parity subsample: the first 2048 systems of the 1M run are bit-identical to the CPU oracle
+    k = 2048
+    sub = dict(ens, y0=ens["y0"][:k], params=ens["params"][:k])
+    ref = run_c_oracle(sub)
+    assert np.array_equal(y[:k].cpu().numpy(), ref["y"])
+    assert np.array_equal(res.counters[:, :k].t().cpu().numpy(), ref["counters"])
+    # order independence: a permuted ensemble gives the permuted results, bit for bit
+    perm = np.random.default_rng(0).permutation(8192)
+    sub = dict(ens, y0=ens["y0"][:8192][perm], params=ens["params"][:8192][perm])
+    out = run_gpu(sub)
+    assert np.array_equal(out["y"], y[:8192].cpu().numpy()[perm])
+
+
+def test_full_size_robertson_ensemble_properties():
+    """BASELINE configs[2] on one GPU: 4,194,304 rate-constant sets to t = 5e6 (1/8 of it here
+    keeps the run short; the bench covers the full size)."""
+    import torch
+    B = 1 << 19
+    ens = E.robertson_ensemble(B)
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], **ens["options"])
+    torch.cuda.synchronize()
+    assert bool((res.status == 0).all())
+    y = res.y
+    # mass conservation y0 + y1 + y2 = 1 (the algebraic equation) at every output
+    assert (y.sum(dim=1) - 1.0).abs().max().item() < 1e-6
+    assert bool((y > -1e-6).all())
+    k = 1024
+    ref = run_c_oracle(dict(ens, y0=ens["y0"][:k], params=ens["params"][:k]))
+    assert np.array_equal(y[:k].cpu().numpy(), ref["y"])

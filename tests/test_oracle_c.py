@@ -1,0 +1,74 @@
+"""The scalar C restatement (oracle/radau_ref.c) pinned to the reference: every committed
+reference fixture within the parity tolerance (10*(atol + rtol|y|)) with identical step counts
+on the well-conditioned configurations; the chaotic ones only statistically."""
+import numpy as np
+import pytest
+
+from _util import (PARITY_FACTOR, count_agreement, golden_names, load_golden, run_c_oracle,
+                   run_numpy_oracle, scaled_error, well_conditioned)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_c_oracle_against_reference_fixture(name):
+    ens, ref = load_golden(name)
+    out = run_c_oracle(ens)
+    assert np.array_equal(out["status"], ref["status"]), "per-system status differs from the reference"
+    rtol, atol = ens["options"]["rtol"], ens["options"]["atol"]
+    if well_conditioned(name):
+        assert np.array_equal(out["n_eval"], ref["n_eval"])
+        err = scaled_error(out["y"], ref["y"], rtol, atol)
+        assert err <= PARITY_FACTOR, f"max |dy|/(atol+rtol|y|) = {err:.3g} > {PARITY_FACTOR}"
+        assert count_agreement(out["counters"], ref["counters"]) >= 0.99
+        # the cheap counters follow from identical control flow
+        assert (out["counters"][:, 3] == ref["counters"][:, 3]).mean() >= 0.99
+    else:
+        # rounding-chaotic configurations: positions/velocities stay close, step totals within 10 %
+        fin = (ref["status"] == 0)
+        if fin.any():
+            n_cmp = min(4, out["y"].shape[1])
+            d = np.abs(out["y"][fin][:, :n_cmp] - ref["y"][fin][:, :n_cmp])
+            scale = 1.0 + np.abs(ref["y"][fin][:, :n_cmp])
+            assert np.nanmax(d / scale) < 5e-3
+            tot, tot_ref = out["counters"][fin, 3].sum(), ref["counters"][fin, 3].sum()
+            assert abs(tot - tot_ref) <= 0.1 * tot_ref
+
+
+def test_c_oracle_matches_numpy_oracle_on_a_fresh_ensemble():
+    """Independent of the fixtures: a seeded ensemble not used anywhere else."""
+    import dae_scipy_b200 as br
+    ens = br.ensembles.pendulum_ensemble(24, t_end=1.5, seed=77)
+    a, b = run_c_oracle(ens), run_numpy_oracle(ens)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["n_eval"], b["n_eval"])
+    assert scaled_error(a["y"], b["y"], 1e-6, 1e-6) <= PARITY_FACTOR
+    assert count_agreement(a["counters"], b["counters"]) >= 0.95
+
+
+def test_c_oracle_rhs_and_jacobian_equal_numpy_restatement():
+    from oracle import c_oracle, problems_numpy as prob
+    rng = np.random.default_rng(3)
+    for name, builder, p in (("pendulum3", prob.pendulum(3, 1.3, 9.81, 0.9), [1.3, 9.81, 0.9]),
+                             ("pendulum2", prob.pendulum(2, 1.3, 9.81, 0.9), [1.3, 9.81, 0.9]),
+                             ("pendulum1", prob.pendulum(1, 1.3, 9.81, 0.9), [1.3, 9.81, 0.9]),
+                             ("robertson", prob.robertson(0.05, 2e4, 1e7), [0.05, 2e4, 1e7])):
+        f, j = builder[0], builder[1]
+        y = rng.standard_normal(5 if name.startswith("pend") else 3)
+        fc, Jc = c_oracle.eval_rhs_jac(name, p, 0.2, y)
+        assert np.array_equal(fc, f(0.2, y)) and np.array_equal(Jc, j(0.2, y))
+    d = prob.TRANSISTOR_DEFAULTS
+    pv = [d[k] for k in prob.TRANSISTOR_ORDER]
+    f, j, _, _ = prob.transistor()
+    y = prob.transistor_y0() + 0.01 * rng.standard_normal(5)
+    fc, Jc = c_oracle.eval_rhs_jac("transistor", pv, 0.0021, y)
+    assert np.allclose(fc, f(0.0021, y), rtol=1e-14, atol=0) and np.allclose(Jc, j(0.0021, y), rtol=1e-13, atol=0)
+    for n in (2, 6):
+        f, j, _, _ = prob.npendulum(n)
+        x = prob.npendulum_ic(n, 0.5) + 0.02 * rng.standard_normal(5 * n)
+        fc, Jc = c_oracle.eval_rhs_jac("npendulum", [], 0.0, x)
+        assert np.allclose(fc, f(0., x), rtol=1e-14, atol=1e-14) and np.allclose(Jc, j(0., x), rtol=1e-13, atol=1e-13)
+
+
+def test_c_oracle_is_thread_count_invariant():
+    import dae_scipy_b200 as br
+    ens = br.ensembles.robertson_ensemble(40)
+    a, b = run_c_oracle(ens, nthreads=1), run_c_oracle(ens, nthreads=4)
+    assert np.array_equal(a["y"], b["y"], equal_nan=True) and np.array_equal(a["counters"], b["counters"])
