@@ -136,12 +136,13 @@ BRDAE_HD void solve_real_sm(const S &sm, int base, unsigned piv, double (&b)[N])
 #pragma unroll
         for (int r = k + 1; r < N; ++r) b[r] = fma(-sm(base + r * N + k), bk, b[r]);
     }
+    // back substitution, column oriented (x_k final once the columns > k have been applied)
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-        double s = b[k];
+        const double xk = b[k] * sm(base + k * N + k);
+        b[k] = xk;
 #pragma unroll
-        for (int c = k + 1; c < N; ++c) s = fma(-sm(base + k * N + c), b[c], s);
-        b[k] = s * sm(base + k * N + k);
+        for (int r = 0; r < k; ++r) b[r] = fma(-sm(base + r * N + k), xk, b[r]);
     }
 }
 template <int N, class S>
@@ -168,16 +169,19 @@ BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, unsigned piv, d
     }
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-        double sr = br[k], si = bi[k];
-#pragma unroll
-        for (int c = k + 1; c < N; ++c) {
-            const double ur = sm(base_r + k * N + c), ui = sm(base_i + k * N + c);
-            sr = fma(-ur, br[c], sr); sr = fma(ui, bi[c], sr);
-            si = fma(-ur, bi[c], si); si = fma(-ui, br[c], si);
-        }
         const double qr = sm(base_r + k * N + k), qi = sm(base_i + k * N + k);
-        br[k] = fma(sr, qr, -(si * qi));
-        bi[k] = fma(sr, qi, si * qr);
+        const double sr = br[k], si = bi[k];
+        const double xr = fma(sr, qr, -(si * qi));
+        const double xi = fma(sr, qi, si * qr);
+        br[k] = xr; bi[k] = xi;
+#pragma unroll
+        for (int r = 0; r < k; ++r) {
+            const double ur = sm(base_r + r * N + k), ui = sm(base_i + r * N + k);
+            double yr = br[r], yi = bi[r];
+            yr = fma(-ur, xr, yr); yr = fma(ui, xi, yr);
+            yi = fma(-ur, xi, yi); yi = fma(-ui, xr, yi);
+            br[r] = yr; bi[r] = yi;
+        }
     }
 }
 

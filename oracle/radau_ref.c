@@ -311,11 +311,12 @@ static void solve_real(const lu_pair *L, double *b) {
         double bk = b[k];
         for (int r = k + 1; r <= rmax; ++r) b[r] = fma(-A[r * n + k], bk, b[r]);
     }
+    /* back substitution, column oriented: x_k is final once columns > k have been applied */
     for (int k = n - 1; k >= 0; --k) {
-        int cmax = imin(n - 1, k + L->ku + L->kl);
-        double s = b[k];
-        for (int c = k + 1; c <= cmax; ++c) s = fma(-A[k * n + c], b[c], s);
-        b[k] = s * A[k * n + k];
+        int rmin = k - (L->ku + L->kl); if (rmin < 0) rmin = 0;
+        double xk = b[k] * A[k * n + k];
+        b[k] = xk;
+        for (int r = rmin; r < k; ++r) b[r] = fma(-A[r * n + k], xk, b[r]);
     }
 }
 /* complex: pivot on |re|+|im| (BLAS izamax), reciprocal pivot = conj(p)/|p|^2 */
@@ -376,16 +377,19 @@ static void solve_cplx(const lu_pair *L, double *br, double *bi) {
         }
     }
     for (int k = n - 1; k >= 0; --k) {
-        int cmax = imin(n - 1, k + L->ku + L->kl);
-        double sr = br[k], si = bi[k];
-        for (int c = k + 1; c <= cmax; ++c) {
-            double ur = R[k * n + c], ui = I[k * n + c];
-            sr = fma(-ur, br[c], sr); sr = fma(ui, bi[c], sr);
-            si = fma(-ur, bi[c], si); si = fma(-ui, br[c], si);
-        }
+        int rmin = k - (L->ku + L->kl); if (rmin < 0) rmin = 0;
         double qr = R[k * n + k], qi = I[k * n + k];
-        br[k] = fma(sr, qr, -(si * qi));
-        bi[k] = fma(sr, qi, si * qr);
+        double sr = br[k], si = bi[k];
+        double xr = fma(sr, qr, -(si * qi));
+        double xi = fma(sr, qi, si * qr);
+        br[k] = xr; bi[k] = xi;
+        for (int r = rmin; r < k; ++r) {
+            double ur = R[r * n + k], ui = I[r * n + k];
+            double yr = br[r], yi = bi[r];
+            yr = fma(-ur, xr, yr); yr = fma(ui, xi, yr);
+            yi = fma(-ur, xi, yi); yi = fma(-ui, xr, yi);
+            br[r] = yr; bi[r] = yi;
+        }
     }
 }
 
