@@ -6,17 +6,23 @@
 // of the warp is done.
 //
 // The reference's nested loops (radauDAE.py:564 `while not step_accepted`, :591 `while not
-// converged`, :846 Newton `for`) are flattened into a per-lane phase machine.  Every trip of
-// the warp loop each live lane performs exactly ONE simplified-Newton iteration (the dominant
-// cost); step prologue, attempt set-up, LU factorisation and error estimate / controller are
-// predicated blocks before and after it, so divergent lanes re-converge on the expensive phase.
+// converged`, :846 Newton `for`) are flattened into a per-lane state machine with three
+// expensive states -- FACTOR (iteration matrices + both LUs), NEWTON (one simplified-Newton
+// iteration) and ERREST (error estimate, accept/reject, controller, dense output) -- and one
+// cheap one (SETUP: step prologue, attempt set-up, starting guess).  Every trip of the warp
+// loop the warp votes (ballot/popc) and executes ONLY the expensive block most lanes wait for,
+// with exactly those lanes: the dispatch branch is warp-uniform, so a block is never executed
+// for the sake of one straggler, and the lanes of a warp fall into a common
+// FACTOR, NEWTON x k, ERREST cadence by themselves.
 //
 // Storage (N = 5): the real and complex LU factors (3 N^2 doubles), f(t,y), y_old, the dense
 // output coefficients Q (3N) and the point (t_J, y_J) the Jacobian was last evaluated at live in
-// shared memory, lane-strided ([slot][lane]: conflict-free 8-byte accesses); y, W and all
+// shared memory, lane-strided ([slot][lane]: conflict-free 8-byte accesses); y, W and the
 // controller scalars live in registers.  The Jacobian itself is never stored: it is
 // re-materialised from (t_J, y_J) when a factorisation needs it, which reproduces the
 // reference's "stale J, new h" refactorisations (radauDAE.py:594-613 with self.J kept) exactly.
+// The LUs are computed left-looking, one column at a time in registers against the finished
+// columns in shared memory, so a factorisation needs N (2N complex) live values instead of N^2.
 //
 // Reference map: prologue :516-562, attempt :564-588, factorisation :594-613, Newton :793-949,
 // non-convergence :635-658, error estimate :669-711, accept/reject :713-739, epilogue :742-784,
@@ -26,7 +32,9 @@
 
 namespace brdae {
 
-enum : int { PH_IDLE = 0, PH_STEP, PH_ATTEMPT, PH_NEWTON_INIT, PH_NEWTON, PH_ERREST, PH_EXIT };
+enum : int { ST_IDLE = 0, ST_SETUP, ST_FACTOR, ST_NEWTON, ST_ERREST, ST_EXIT };
+// what a lane entering SETUP still has to do
+enum : int { SETUP_STEP = 0, SETUP_ATTEMPT = 1, SETUP_GUESS = 2 };
 
 // lane-strided shared-memory slots of one lane
 template <int STRIDE>
@@ -35,87 +43,110 @@ struct Slots {
     BRDAE_HD double &operator()(int e) const { return base[e * STRIDE]; }
 };
 
-// ---- LU of the spec, fully unrolled, in registers -------------------------------------------
-// Right-looking elimination, partial pivoting on |a| (first maximum), only the active columns
-// are swapped (multipliers stay where they were computed), reciprocal pivot on the diagonal.
+// ---- LU of the spec, left-looking, one column at a time ------------------------------------
+// Same arithmetic as a right-looking elimination with partial pivoting on |a| (first maximum)
+// where only the active columns are exchanged and the reciprocal pivot is stored on the
+// diagonal: element (r,k) receives its updates -l(r,j) u(j,k), j = 0,1,.. in the same order.
+// `column(k, col)` fills col[r] = A[r][k]; finished columns are read back from shared memory.
 // Returns the pivot rows packed 3 bits each.
-template <int N>
-BRDAE_HD unsigned lu_real_regs(double (&A)[N][N]) {
+template <int N, class S, class ColFn>
+BRDAE_HD unsigned lu_real_left(const S &sm, int base, ColFn &&column) {
     unsigned piv = 0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
+        double col[N];
+        column(k, col);
+#pragma unroll
+        for (int j = 0; j < k; ++j) {
+            const int pj = (piv >> (3 * j)) & 7;
+#pragma unroll
+            for (int r = j + 1; r < N; ++r) {  // branch-free exchange keeps the column in registers
+                const bool sw = (pj == r);
+                const double u = col[j], v = col[r];
+                col[j] = sw ? v : u; col[r] = sw ? u : v;
+            }
+            const double cj = col[j];
+#pragma unroll
+            for (int r = j + 1; r < N; ++r) col[r] = fma(-sm(base + r * N + j), cj, col[r]);
+        }
         int p = k;
-        double best = fabs(A[k][k]);
+        double best = fabs(col[k]);
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
-            double v = fabs(A[r][k]);
+            const double v = fabs(col[r]);
             if (v > best) { best = v; p = r; }
         }
         piv |= (unsigned)p << (3 * k);
 #pragma unroll
-        for (int r = k + 1; r < N; ++r) {  // branch-free row exchange: keeps A in registers
-            const bool sw = (p == r);
-#pragma unroll
-            for (int c = k; c < N; ++c) {
-                const double u = A[k][c], v = A[r][c];
-                A[k][c] = sw ? v : u; A[r][c] = sw ? u : v;
-            }
-        }
-        double rcp = 1.0 / A[k][k];
-        A[k][k] = rcp;
-#pragma unroll
         for (int r = k + 1; r < N; ++r) {
-            double l = A[r][k] * rcp;
-            A[r][k] = l;
-#pragma unroll
-            for (int c = k + 1; c < N; ++c) A[r][c] = fma(-l, A[k][c], A[r][c]);
+            const bool sw = (p == r);
+            const double u = col[k], v = col[r];
+            col[k] = sw ? v : u; col[r] = sw ? u : v;
         }
+        const double rcp = 1.0 / col[k];
+        col[k] = rcp;
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) col[r] = col[r] * rcp;
+#pragma unroll
+        for (int r = 0; r < N; ++r) sm(base + r * N + k) = col[r];
     }
     return piv;
 }
 // complex: pivot on |re|+|im| (BLAS izamax), reciprocal pivot conj(p)/|p|^2
-template <int N>
-BRDAE_HD unsigned lu_cplx_regs(double (&R)[N][N], double (&I)[N][N]) {
+template <int N, class S, class ColFn>
+BRDAE_HD unsigned lu_cplx_left(const S &sm, int base_r, int base_i, ColFn &&column) {
     unsigned piv = 0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
+        double cr[N], ci[N];
+        column(k, cr, ci);
+#pragma unroll
+        for (int j = 0; j < k; ++j) {
+            const int pj = (piv >> (3 * j)) & 7;
+#pragma unroll
+            for (int r = j + 1; r < N; ++r) {
+                const bool sw = (pj == r);
+                const double u = cr[j], v = cr[r], ui = ci[j], vi = ci[r];
+                cr[j] = sw ? v : u; cr[r] = sw ? u : v;
+                ci[j] = sw ? vi : ui; ci[r] = sw ? ui : vi;
+            }
+            const double ur = cr[j], ui = ci[j];
+#pragma unroll
+            for (int r = j + 1; r < N; ++r) {
+                const double lr = sm(base_r + r * N + j), li = sm(base_i + r * N + j);
+                double xr = cr[r], xi = ci[r];
+                xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
+                xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
+                cr[r] = xr; ci[r] = xi;
+            }
+        }
         int p = k;
-        double best = fabs(R[k][k]) + fabs(I[k][k]);
+        double best = fabs(cr[k]) + fabs(ci[k]);
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
-            double v = fabs(R[r][k]) + fabs(I[r][k]);
+            const double v = fabs(cr[r]) + fabs(ci[r]);
             if (v > best) { best = v; p = r; }
         }
         piv |= (unsigned)p << (3 * k);
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
             const bool sw = (p == r);
-#pragma unroll
-            for (int c = k; c < N; ++c) {
-                const double u = R[k][c], v = R[r][c], ui = I[k][c], vi = I[r][c];
-                R[k][c] = sw ? v : u; R[r][c] = sw ? u : v;
-                I[k][c] = sw ? vi : ui; I[r][c] = sw ? ui : vi;
-            }
+            const double u = cr[k], v = cr[r], ui = ci[k], vi = ci[r];
+            cr[k] = sw ? v : u; cr[r] = sw ? u : v;
+            ci[k] = sw ? vi : ui; ci[r] = sw ? ui : vi;
         }
-        const double pr = R[k][k], pi = I[k][k];
+        const double pr = cr[k], pi = ci[k];
         const double invd = 1.0 / fma(pr, pr, pi * pi);
         const double qr = pr * invd, qi = -(pi * invd);
-        R[k][k] = qr; I[k][k] = qi;
+        cr[k] = qr; ci[k] = qi;
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
-            const double ar = R[r][k], ai = I[r][k];
-            const double lr = fma(ar, qr, -(ai * qi));
-            const double li = fma(ar, qi, ai * qr);
-            R[r][k] = lr; I[r][k] = li;
-#pragma unroll
-            for (int c = k + 1; c < N; ++c) {
-                const double ur = R[k][c], ui = I[k][c];
-                double xr = R[r][c], xi = I[r][c];
-                xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
-                xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
-                R[r][c] = xr; I[r][c] = xi;
-            }
+            const double ar = cr[r], ai = ci[r];
+            cr[r] = fma(ar, qr, -(ai * qi));
+            ci[r] = fma(ar, qi, ai * qr);
         }
+#pragma unroll
+        for (int r = 0; r < N; ++r) { sm(base_r + r * N + k) = cr[r]; sm(base_i + r * N + k) = ci[r]; }
     }
     return piv;
 }
@@ -202,6 +233,9 @@ struct K1Layout {
 // warp-level helpers; the host build (tests/host_sim) runs a "warp" of one lane
 #if defined(__CUDA_ARCH__)
 BRDAE_D bool warp_all(bool x) { return __all_sync(0xffffffffu, x); }
+BRDAE_D bool warp_any(bool x) { return __any_sync(0xffffffffu, x); }
+BRDAE_D int warp_count(bool x) { return __popc(__ballot_sync(0xffffffffu, x)); }
+BRDAE_D void warp_converge() { __syncwarp(); }
 BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
     const unsigned need = __ballot_sync(0xffffffffu, want);
     long long idx = -1;
@@ -217,6 +251,9 @@ BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
 }
 #else
 inline bool warp_all(bool x) { return x; }
+inline bool warp_any(bool x) { return x; }
+inline int warp_count(bool x) { return x ? 1 : 0; }
+inline void warp_converge() {}
 inline long long fetch_system(bool want, unsigned long long *counter) { return want ? (long long)((*counter)++) : -1; }
 #endif
 
@@ -228,7 +265,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
     typename Prob::P prm;
 
     // ---- lane state ---------------------------------------------------------------------
-    int phase = PH_IDLE;
+    int state = ST_IDLE, setup_kind = SETUP_STEP;
     long long idx = -1;
     double t = 0, y[N];
     double h_abs_state = 0, h_abs_old_state = 0, err_old_state = 0;
@@ -257,11 +294,12 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
     const double dir = a.dir;
 
     for (;;) {
+        int finish_status = 1;  // 1 = still running
         // ================= refill idle lanes =================================================
-        {
-            const long long got = fetch_system(phase == PH_IDLE, a.work_counter);
-            if (phase == PH_IDLE) {
-                if (got >= a.B) phase = PH_EXIT;
+        if (warp_any(state == ST_IDLE)) {
+            const long long got = fetch_system(state == ST_IDLE, a.work_counter);
+            if (state == ST_IDLE) {
+                if (got >= a.B) state = ST_EXIT;
                 else {
                     idx = got;
                     Prob::load(prm, a.params, a.B, idx);
@@ -280,63 +318,29 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                     h_abs_state = a.h0;
                     hist_state = false; current_jac = true; lu_valid = false; have_sol = false;
                     inv_h_lu = 1.0; ei = 0; nsteps = 0;
-                    phase = PH_STEP;
+                    state = ST_SETUP; setup_kind = SETUP_STEP;
                     if (t == a.tb) {  // OdeSolver.step corner case (scipy base.py:193-198)
                         for (; ei < a.T; ++ei)
 #pragma unroll
                             for (int c = 0; c < N; ++c) a.y_eval[((int64_t)ei * N + c) * a.B + idx] = y[c];
-                        a.n_eval[idx] = ei; a.t_final[idx] = t; a.status[idx] = BRDAE_STATUS_FINISHED;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) a.y_final[(int64_t)c * a.B + idx] = y[c];
-#pragma unroll
-                        for (int q = 0; q < CN_COUNT; ++q) a.counters[(int64_t)q * a.B + idx] = cnt[q];
-                        phase = PH_IDLE;
+                        finish_status = BRDAE_STATUS_FINISHED;
+                        state = ST_IDLE;
                     }
                 }
             }
+            if (warp_all(state == ST_EXIT)) break;
         }
-        if (warp_all(phase == PH_EXIT)) break;
+        warp_converge();
 
-        int finish_status = 1;  // 1 = still running
+        // ================= vote: run the expensive block most lanes are waiting for ===========
+        const int nF = warp_count(state == ST_FACTOR);
+        const int nN = warp_count(state == ST_NEWTON);
+        const int nE = warp_count(state == ST_ERREST);
+        const int run = (nN > 0 && nN >= nE && nN >= nF) ? ST_NEWTON : ((nE > 0 && nE >= nF) ? ST_ERREST : (nF > 0 ? ST_FACTOR : ST_IDLE));
 
-        // ================= step prologue :516-562 ============================================
-        if (phase == PH_STEP) {
-            ++nsteps;
-            if (a.nmax_step > 0 && nsteps > a.nmax_step) finish_status = BRDAE_STATUS_NMAX_STEP;
-            else {
-                cnt[CN_NSTEP]++;
-                min_step = fmax(1e-20, 10 * fabs(nextafter(t, dir * INFINITY) - t));
-                h_abs_old = h_abs_old_state; err_old = err_old_state; hist = hist_state;
-                if (h_abs_state > a.max_step) { h_abs = a.max_step; hist = false; }
-                else if (h_abs_state < min_step) { h_abs = min_step; hist = false; }
-                else h_abs = h_abs_state;
-                if (fabs(a.tb - (t + dir * h_abs)) < 1e-2 * h_abs) { h_abs = fabs(a.tb - t); lu_valid = false; }
-                rejected = false;
-                phase = PH_ATTEMPT;
-            }
-        }
-        // ================= attempt set-up :564-588 ===========================================
-        if (phase == PH_ATTEMPT) {
-            if (h_abs < min_step) finish_status = BRDAE_STATUS_TOO_SMALL_STEP;
-            else {
-                h = h_abs * dir;
-                t_new = t + h;
-                if (dir * (t_new - a.tb) > 0) t_new = a.tb;
-                h = t_new - t;
-                h_abs = fabs(h);
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const int ve = a.var_index[c] > 1 ? a.var_index[c] - 1 : 0;
-                    const double hp = a.scale_newton_norm ? hpow(h, ve) : 1.0;
-                    inv_ns[c] = hp / (a.atol[c] + fabs(y[c]) * a.rtol);
-                }
-                mr = MU_REAL / h; mcr = MU_CR / h; mci = MU_CI / h;
-                phase = PH_NEWTON_INIT;
-            }
-        }
-        // ================= (re)factorisation + starting guess :580-583, :594-613 ==============
-        if (phase == PH_NEWTON_INIT) {
-            if (!lu_valid) {
+        // ================= (re)factorisation :594-613 =========================================
+        if (run == ST_FACTOR) {
+            if (state == ST_FACTOR) {
                 if (a.scale_residuals) inv_h_lu = 1.0 / h;
                 double J[N][N];
                 if (a.has_jac_const) {
@@ -350,305 +354,335 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                     for (int c = 0; c < N; ++c) yJ[c] = sm(L::S_YJ + c);
                     Prob::jac(prm, sm(L::S_TJ), yJ, J);
                 }
-                {
-                    double A[N][N];
+                double hs[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) hs[r] = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
+                piv_r = lu_real_left<N>(sm, L::S_LUR, [&](int kc, double (&col)[N]) {
 #pragma unroll
                     for (int r = 0; r < N; ++r) {
-                        const double hs = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) {
-                            const double v = Mass::nz(r, c) ? fma(mr, Mass::get(prm, a, r, c), -J[r][c]) : -J[r][c];
-                            A[r][c] = hs * v;
-                        }
+                        const double v = Mass::nz(r, kc) ? fma(mr, Mass::get(prm, a, r, kc), -J[r][kc]) : -J[r][kc];
+                        col[r] = hs[r] * v;
                     }
-                    piv_r = lu_real_regs<N>(A);
-#pragma unroll
-                    for (int r = 0; r < N; ++r)
-#pragma unroll
-                        for (int c = 0; c < N; ++c) sm(L::S_LUR + r * N + c) = A[r][c];
-                }
-                {
-                    double R[N][N], I[N][N];
+                });
+                piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, [&](int kc, double (&cr)[N], double (&ci)[N]) {
 #pragma unroll
                     for (int r = 0; r < N; ++r) {
-                        const double hs = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) {
-                            const bool nz = Mass::nz(r, c);
-                            const double m = nz ? Mass::get(prm, a, r, c) : 0.0;
-                            const double v = nz ? fma(mcr, m, -J[r][c]) : -J[r][c];
-                            R[r][c] = hs * v;
-                            I[r][c] = nz ? hs * (mci * m) : 0.0;
-                        }
+                        const bool nz = Mass::nz(r, kc);
+                        const double m = nz ? Mass::get(prm, a, r, kc) : 0.0;
+                        const double v = nz ? fma(mcr, m, -J[r][kc]) : -J[r][kc];
+                        cr[r] = hs[r] * v;
+                        ci[r] = nz ? hs[r] * (mci * m) : 0.0;
                     }
-                    piv_c = lu_cplx_regs<N>(R, I);
-#pragma unroll
-                    for (int r = 0; r < N; ++r)
-#pragma unroll
-                        for (int c = 0; c < N; ++c) { sm(L::S_LCR + r * N + c) = R[r][c]; sm(L::S_LCI + r * N + c) = I[r][c]; }
-                }
+                });
                 cnt[CN_NLU]++;
                 lu_valid = true;
+                state = ST_NEWTON;
             }
-            // W = TI Z0, Z0 from the previous step's cubic evaluated beyond its interval
-            if (!have_sol || !a.extrapolate) {
-#pragma unroll
-                for (int c = 0; c < N; ++c) { W[0][c] = 0.0; W[1][c] = 0.0; W[2][c] = 0.0; }
-            } else {
-                double x[3], x2[3], x3[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double tt = t + h * stage_c(i);
-                    x[i] = (tt - t_sol_old) / h_sol;
-                    x2[i] = x[i] * x[i];
-                    x3[i] = x2[i] * x[i];
-                }
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const double q0 = sm(L::S_Q + 3 * c), q1 = sm(L::S_Q + 3 * c + 1), q2 = sm(L::S_Q + 3 * c + 2);
-                    const double yo = sm(L::S_YOLD + c);
-                    double z[3];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        double v = q0 * x[i];
-                        v = fma(q1, x2[i], v);
-                        v = fma(q2, x3[i], v);
-                        v = v + yo;
-                        z[i] = v - y[c];
-                    }
-                    W[0][c] = fma(TI02, z[2], fma(TI01, z[1], TI00 * z[0]));
-                    W[1][c] = fma(TI12, z[2], fma(TI11, z[1], TI10 * z[0]));
-                    W[2][c] = fma(TI22, z[2], fma(TI21, z[1], TI20 * z[0]));
-                }
-            }
-            k = 0; nbad = 0; have_old = false; have_rate = false; rate = 0; dwn_old = 0;
-            phase = PH_NEWTON;
         }
         // ================= one simplified-Newton iteration :846-940 ==========================
-        if (phase == PH_NEWTON) {
-            double fr[N], fcr[N], fci[N];
-            bool finite = true;
+        else if (run == ST_NEWTON) {
+            if (state == ST_NEWTON) {
+                double fr[N], fcr[N], fci[N];
+                bool finite = true;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double Y[N], F[N];
+                for (int i = 0; i < 3; ++i) {
+                    double Y[N], F[N];
 #pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const double z = (i == 0) ? stage_z<0>(W[0][c], W[1][c], W[2][c])
-                                   : (i == 1) ? stage_z<1>(W[0][c], W[1][c], W[2][c])
-                                              : stage_z<2>(W[0][c], W[1][c], W[2][c]);
-                    Y[c] = y[c] + z;
-                }
-                Prob::rhs(prm, t + h * stage_c(i), Y, F);
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const double Fv = F[c];
-                    finite = finite && is_finite(Fv);
-                    if (i == 0) { fr[c] = TI00 * Fv; fcr[c] = TI10 * Fv; fci[c] = TI20 * Fv; }
-                    else if (i == 1) { fr[c] = fma(TI01, Fv, fr[c]); fcr[c] = fma(TI11, Fv, fcr[c]); fci[c] = fma(TI21, Fv, fci[c]); }
-                    else { fr[c] = fma(TI02, Fv, fr[c]); fcr[c] = fma(TI12, Fv, fcr[c]); fci[c] = fma(TI22, Fv, fci[c]); }
-                }
-            }
-            cnt[CN_NFEV] += 3;
-            int outcome = 0;  // 0 continue, 1 converged, 2 stop (not converged)
-            bool update_old = true;
-            if (!finite) outcome = 2;
-            else {
-                double mw0[N], mw1[N], mw2[N];
-                mass_mv<Mass>(prm, a, W[0], mw0);
-                mass_mv<Mass>(prm, a, W[1], mw1);
-                mass_mv<Mass>(prm, a, W[2], mw2);
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const double hs = (a.scale_residuals && a.var_index[c] >= 1) ? inv_h_lu : 1.0;
-                    double ar = fr[c], br = fcr[c], bi = fci[c];
-                    if (!mass_row_empty<Mass, N>(c)) {
-                        ar = fma(-mr, mw0[c], ar);
-                        br = fma(-mcr, mw1[c], br); br = fma(mci, mw2[c], br);
-                        bi = fma(-mcr, mw2[c], bi); bi = fma(-mci, mw1[c], bi);
+                    for (int c = 0; c < N; ++c) {
+                        const double z = (i == 0) ? stage_z<0>(W[0][c], W[1][c], W[2][c])
+                                       : (i == 1) ? stage_z<1>(W[0][c], W[1][c], W[2][c])
+                                                  : stage_z<2>(W[0][c], W[1][c], W[2][c]);
+                        Y[c] = y[c] + z;
                     }
-                    fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
-                }
-                solve_real_sm<N>(sm, L::S_LUR, piv_r, fr);
-                solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, piv_c, fcr, fci);
-                cnt[CN_NSOLVE]++;
-                double s = 0.0;
+                    Prob::rhs(prm, t + h * stage_c(i), Y, F);
 #pragma unroll
-                for (int c = 0; c < N; ++c) { const double v = fr[c] * inv_ns[c]; s = fma(v, v, s); }
-#pragma unroll
-                for (int c = 0; c < N; ++c) { const double v = fcr[c] * inv_ns[c]; s = fma(v, v, s); }
-#pragma unroll
-                for (int c = 0; c < N; ++c) { const double v = fci[c] * inv_ns[c]; s = fma(v, v, s); }
-                const double dwn = sqrt(s) * a.rsq3n;
-#pragma unroll
-                for (int c = 0; c < N; ++c) { W[0][c] += fr[c]; W[1][c] += fcr[c]; W[2][c] += fci[c]; }
-                double dw_true = 0, dw_true_max = 0;
-                if (have_old) {
-                    rate = dwn / dwn_old; have_rate = true;
-                    const double inv1 = 1.0 / (1.0 - rate);
-                    dw_true = rate * inv1 * dwn;
-                    double rp = rate;
-                    for (int e = 1; e < MAXIT - k; ++e) rp *= rate;
-                    dw_true_max = rp * inv1 * dwn;
-                }
-                if (dwn < a.newton_tol) outcome = 1;
-                else if (have_rate) {
-                    bool fall = true;
-                    if (rate >= 1) {
-                        if (rate < 100 && nbad < a.nmax_bad) { nbad++; update_old = false; fall = false; }
-                        else if (!a.all_newton) { outcome = 2; fall = false; }
+                    for (int c = 0; c < N; ++c) {
+                        const double Fv = F[c];
+                        finite = finite && is_finite(Fv);
+                        if (i == 0) { fr[c] = TI00 * Fv; fcr[c] = TI10 * Fv; fci[c] = TI20 * Fv; }
+                        else if (i == 1) { fr[c] = fma(TI01, Fv, fr[c]); fcr[c] = fma(TI11, Fv, fcr[c]); fci[c] = fma(TI21, Fv, fci[c]); }
+                        else { fr[c] = fma(TI02, Fv, fr[c]); fcr[c] = fma(TI12, Fv, fcr[c]); fci[c] = fma(TI22, Fv, fci[c]); }
                     }
-                    if (fall) {
-                        if (dw_true < a.newton_tol) outcome = 1;
-                        else if (dw_true_max > a.newton_tol && a.predictive_newton) {
-                            if (nbad < a.nmax_bad) { nbad++; update_old = false; }
-                            else if (!a.all_newton) outcome = 2;
+                }
+                cnt[CN_NFEV] += 3;
+                int outcome = 0;  // 0 continue, 1 converged, 2 stop (not converged)
+                bool update_old = true;
+                if (!finite) outcome = 2;
+                else {
+                    double mw0[N], mw1[N], mw2[N];
+                    mass_mv<Mass>(prm, a, W[0], mw0);
+                    mass_mv<Mass>(prm, a, W[1], mw1);
+                    mass_mv<Mass>(prm, a, W[2], mw2);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        const double hs = (a.scale_residuals && a.var_index[c] >= 1) ? inv_h_lu : 1.0;
+                        double ar = fr[c], br = fcr[c], bi = fci[c];
+                        if (!mass_row_empty<Mass, N>(c)) {
+                            ar = fma(-mr, mw0[c], ar);
+                            br = fma(-mcr, mw1[c], br); br = fma(mci, mw2[c], br);
+                            bi = fma(-mcr, mw2[c], bi); bi = fma(-mci, mw1[c], bi);
+                        }
+                        fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
+                    }
+                    solve_real_sm<N>(sm, L::S_LUR, piv_r, fr);
+                    solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, piv_c, fcr, fci);
+                    cnt[CN_NSOLVE]++;
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { const double v = fr[c] * inv_ns[c]; s = fma(v, v, s); }
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { const double v = fcr[c] * inv_ns[c]; s = fma(v, v, s); }
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { const double v = fci[c] * inv_ns[c]; s = fma(v, v, s); }
+                    const double dwn = sqrt(s) * a.rsq3n;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { W[0][c] += fr[c]; W[1][c] += fcr[c]; W[2][c] += fci[c]; }
+                    double dw_true = 0, dw_true_max = 0;
+                    if (have_old) {
+                        rate = dwn / dwn_old; have_rate = true;
+                        const double inv1 = 1.0 / (1.0 - rate);
+                        dw_true = rate * inv1 * dwn;
+                        double rp = rate;
+                        for (int e = 1; e < MAXIT - k; ++e) rp *= rate;
+                        dw_true_max = rp * inv1 * dwn;
+                    }
+                    if (dwn < a.newton_tol) outcome = 1;
+                    else if (have_rate) {
+                        bool fall = true;
+                        if (rate >= 1) {
+                            if (rate < 100 && nbad < a.nmax_bad) { nbad++; update_old = false; fall = false; }
+                            else if (!a.all_newton) { outcome = 2; fall = false; }
+                        }
+                        if (fall) {
+                            if (dw_true < a.newton_tol) outcome = 1;
+                            else if (dw_true_max > a.newton_tol && a.predictive_newton) {
+                                if (nbad < a.nmax_bad) { nbad++; update_old = false; }
+                                else if (!a.all_newton) outcome = 2;
+                            }
                         }
                     }
+                    if (outcome == 0 && update_old) { dwn_old = dwn; have_old = true; }
                 }
-                if (outcome == 0 && update_old) { dwn_old = dwn; have_old = true; }
-            }
-            if (outcome == 0) {
-                ++k;
-                if (k >= MAXIT) { outcome = 2; n_iter = MAXIT; }
-            } else n_iter = k + 1;
-            if (outcome != 0) {
-                safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);   // :631
-                if (outcome == 1) phase = PH_ERREST;
-                else if (current_jac) {                                            // :650-658
-                    cnt[CN_NFAIL]++;
-                    h_abs *= a.nonconv_factor;
-                    lu_valid = false;
-                    phase = PH_ATTEMPT;
-                } else {                                                            // :643-647
+                if (outcome == 0) {
+                    ++k;
+                    if (k >= MAXIT) { outcome = 2; n_iter = MAXIT; }
+                } else n_iter = k + 1;
+                if (outcome != 0) {
+                    safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);   // :631
+                    if (outcome == 1) state = ST_ERREST;
+                    else if (current_jac) {                                            // :650-658
+                        cnt[CN_NFAIL]++;
+                        h_abs *= a.nonconv_factor;
+                        lu_valid = false;
+                        state = ST_SETUP; setup_kind = SETUP_ATTEMPT;
+                    } else {                                                            // :643-647
 #pragma unroll
-                    for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
-                    sm(L::S_TJ) = t;
-                    cnt[CN_NJEV]++;
-                    current_jac = true; lu_valid = false;
-                    phase = PH_NEWTON_INIT;
+                        for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
+                        sm(L::S_TJ) = t;
+                        cnt[CN_NJEV]++;
+                        current_jac = true; lu_valid = false;
+                        state = ST_SETUP; setup_kind = SETUP_GUESS;
+                    }
                 }
             }
         }
         // ================= error estimate, accept/reject, epilogue :660-784 ===================
-        if (phase == PH_ERREST) {
-            double Z[3][N];
-#pragma unroll
-            for (int c = 0; c < N; ++c) {
-                Z[0][c] = stage_z<0>(W[0][c], W[1][c], W[2][c]);
-                Z[1][c] = stage_z<1>(W[0][c], W[1][c], W[2][c]);
-                Z[2][c] = stage_z<2>(W[0][c], W[1][c], W[2][c]);
-            }
-            double error_norm = 0.0;
-            bool accepted = true;
-            if (!a.constant_dt) {
-                double ze[N], inv_es[N], mze[N], err[N];
+        else if (run == ST_ERREST) {
+            if (state == ST_ERREST) {
+                double Z[3][N];
 #pragma unroll
                 for (int c = 0; c < N; ++c) {
-                    double v = Z[0][c] * RE0;
-                    v = fma(Z[1][c], RE1, v);
-                    v = fma(Z[2][c], RE2, v);
-                    ze[c] = v / h;
-                    const double ynew = y[c] + Z[2][c];
-                    const int ve = a.var_index[c] > 1 ? a.var_index[c] - 1 : 0;
-                    const double hp = a.scale_error ? hpow(h, ve) : 1.0;
-                    inv_es[c] = hp / (a.atol[c] + fmax(fabs(y[c]), fabs(ynew)) * a.rtol);
+                    Z[0][c] = stage_z<0>(W[0][c], W[1][c], W[2][c]);
+                    Z[1][c] = stage_z<1>(W[0][c], W[1][c], W[2][c]);
+                    Z[2][c] = stage_z<2>(W[0][c], W[1][c], W[2][c]);
                 }
-                mass_mv<Mass>(prm, a, ze, mze);
-#pragma unroll
-                for (int c = 0; c < N; ++c) err[c] = sm(L::S_F + c) + mze[c];
-                for (int pass = 0;; ++pass) {
-                    solve_real_sm<N>(sm, L::S_LUR, piv_r, err);   // rhs NOT scaled by hscale
-                    cnt[CN_NSOLVE_ERR]++;
-                    double s = 0.0;
+                double error_norm = 0.0;
+                bool accepted = true;
+                if (!a.constant_dt) {
+                    double ze[N], inv_es[N], mze[N], err[N];
 #pragma unroll
                     for (int c = 0; c < N; ++c) {
-                        if (a.zero_algebraic_error && a.var_index[c] != 0) err[c] = 0.0;
-                        else { const double v = err[c] * inv_es[c]; s = fma(v, v, s); }
+                        double v = Z[0][c] * RE0;
+                        v = fma(Z[1][c], RE1, v);
+                        v = fma(Z[2][c], RE2, v);
+                        ze[c] = v / h;
+                        const double ynew = y[c] + Z[2][c];
+                        const int ve = a.var_index[c] > 1 ? a.var_index[c] - 1 : 0;
+                        const double hp = a.scale_error ? hpow(h, ve) : 1.0;
+                        inv_es[c] = hp / (a.atol[c] + fmax(fabs(y[c]), fabs(ynew)) * a.rtol);
                     }
-                    error_norm = sqrt(s) * (a.zero_algebraic_error ? a.rsq_nondiff : a.rsqn);
-                    if (pass == 1 || !(error_norm > 1 && (a.always_2nd || rejected))) break;
-                    double Y[N], F[N];
+                    mass_mv<Mass>(prm, a, ze, mze);
 #pragma unroll
-                    for (int c = 0; c < N; ++c) Y[c] = y[c] + err[c];
-                    Prob::rhs(prm, t, Y, F);
+                    for (int c = 0; c < N; ++c) err[c] = sm(L::S_F + c) + mze[c];
+                    for (int pass = 0;; ++pass) {
+                        solve_real_sm<N>(sm, L::S_LUR, piv_r, err);   // rhs NOT scaled by hscale
+                        cnt[CN_NSOLVE_ERR]++;
+                        double s = 0.0;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            if (a.zero_algebraic_error && a.var_index[c] != 0) err[c] = 0.0;
+                            else { const double v = err[c] * inv_es[c]; s = fma(v, v, s); }
+                        }
+                        error_norm = sqrt(s) * (a.zero_algebraic_error ? a.rsq_nondiff : a.rsqn);
+                        if (pass == 1 || !(error_norm > 1 && (a.always_2nd || rejected))) break;
+                        double Y[N], F[N];
+#pragma unroll
+                        for (int c = 0; c < N; ++c) Y[c] = y[c] + err[c];
+                        Prob::rhs(prm, t, Y, F);
+                        cnt[CN_NFEV]++;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) err[c] = F[c] + mze[c];
+                    }
+                    if (error_norm > 1) {                                               // :713-733
+                        const double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller);
+                        h_abs *= fmax(a.min_factor, safety * factor);
+                        lu_valid = false; rejected = true; cnt[CN_NREJ]++;
+                        accepted = false;
+                        state = ST_SETUP; setup_kind = SETUP_ATTEMPT;
+                    } else cnt[CN_NACC]++;
+                }
+                if (accepted) {                                                         // :742-784
+                    const bool has_jac_fn = !a.has_jac_const;
+                    const bool recompute = has_jac_fn && n_iter > 2 && have_rate && rate > a.jac_recompute;
+                    double factor;
+                    if (a.constant_dt) factor = a.max_step / h_abs;
+                    else factor = fmin(a.max_factor, safety * gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller));
+                    if (!recompute && factor < 1.2) factor = 1; else lu_valid = false;
+                    double fnew[N];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { sm(L::S_YOLD + c) = y[c]; y[c] = y[c] + Z[2][c]; }
+                    Prob::rhs(prm, t_new, y, fnew);
                     cnt[CN_NFEV]++;
 #pragma unroll
-                    for (int c = 0; c < N; ++c) err[c] = F[c] + mze[c];
-                }
-                if (error_norm > 1) {                                               // :713-733
-                    const double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller);
-                    h_abs *= fmax(a.min_factor, safety * factor);
-                    lu_valid = false; rejected = true; cnt[CN_NREJ]++;
-                    accepted = false;
-                    phase = PH_ATTEMPT;
-                } else cnt[CN_NACC]++;
-            }
-            if (accepted) {                                                         // :742-784
-                const bool has_jac_fn = !a.has_jac_const;
-                const bool recompute = has_jac_fn && n_iter > 2 && have_rate && rate > a.jac_recompute;
-                double factor;
-                if (a.constant_dt) factor = a.max_step / h_abs;
-                else factor = fmin(a.max_factor, safety * gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller));
-                if (!recompute && factor < 1.2) factor = 1; else lu_valid = false;
-                double fnew[N];
+                    for (int c = 0; c < N; ++c) sm(L::S_F + c) = fnew[c];
+                    if (recompute) {
 #pragma unroll
-                for (int c = 0; c < N; ++c) { sm(L::S_YOLD + c) = y[c]; y[c] = y[c] + Z[2][c]; }
-                Prob::rhs(prm, t_new, y, fnew);
-                cnt[CN_NFEV]++;
-#pragma unroll
-                for (int c = 0; c < N; ++c) sm(L::S_F + c) = fnew[c];
-                if (recompute) {
-#pragma unroll
-                    for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
-                    sm(L::S_TJ) = t_new;
-                    cnt[CN_NJEV]++;
-                    current_jac = true;
-                } else if (has_jac_fn) current_jac = false;
-                h_abs_old_state = h_abs_state; err_old_state = error_norm; hist_state = true;
-                h_abs_state = h_abs * factor;
-                double Q[N][3];
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    Q[c][0] = fma(Z[2][c], P20, fma(Z[1][c], P10, Z[0][c] * P00));
-                    Q[c][1] = fma(Z[2][c], P21, fma(Z[1][c], P11, Z[0][c] * P01));
-                    Q[c][2] = fma(Z[2][c], P22, fma(Z[1][c], P12, Z[0][c] * P02));
-                    sm(L::S_Q + 3 * c) = Q[c][0]; sm(L::S_Q + 3 * c + 1) = Q[c][1]; sm(L::S_Q + 3 * c + 2) = Q[c][2];
-                }
-                t_sol_old = t; h_sol = t_new - t; have_sol = true;
-                t = t_new;
-                // driver: t_eval points inside (t_old, t]  (searchsorted side='right', ivp.py:711-729)
-                while (ei < a.T) {
-                    const double te = a.t_eval[ei];
-                    if (!(dir > 0 ? te <= t : te >= t)) break;
-                    const double x = (te - t_sol_old) / h_sol;
-                    const double x2 = x * x, x3 = x2 * x;
+                        for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
+                        sm(L::S_TJ) = t_new;
+                        cnt[CN_NJEV]++;
+                        current_jac = true;
+                    } else if (has_jac_fn) current_jac = false;
+                    h_abs_old_state = h_abs_state; err_old_state = error_norm; hist_state = true;
+                    h_abs_state = h_abs * factor;
+                    double Q[N][3];
 #pragma unroll
                     for (int c = 0; c < N; ++c) {
-                        double v = Q[c][0] * x;
-                        v = fma(Q[c][1], x2, v);
-                        v = fma(Q[c][2], x3, v);
-                        a.y_eval[((int64_t)ei * N + c) * a.B + idx] = v + sm(L::S_YOLD + c);
+                        Q[c][0] = fma(Z[2][c], P20, fma(Z[1][c], P10, Z[0][c] * P00));
+                        Q[c][1] = fma(Z[2][c], P21, fma(Z[1][c], P11, Z[0][c] * P01));
+                        Q[c][2] = fma(Z[2][c], P22, fma(Z[1][c], P12, Z[0][c] * P02));
+                        sm(L::S_Q + 3 * c) = Q[c][0]; sm(L::S_Q + 3 * c + 1) = Q[c][1]; sm(L::S_Q + 3 * c + 2) = Q[c][2];
                     }
-                    ++ei;
+                    t_sol_old = t; h_sol = t_new - t; have_sol = true;
+                    t = t_new;
+                    // driver: t_eval points inside (t_old, t]  (searchsorted side='right', ivp.py:711-729)
+                    while (ei < a.T) {
+                        const double te = a.t_eval[ei];
+                        if (!(dir > 0 ? te <= t : te >= t)) break;
+                        const double x = (te - t_sol_old) / h_sol;
+                        const double x2 = x * x, x3 = x2 * x;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            double v = Q[c][0] * x;
+                            v = fma(Q[c][1], x2, v);
+                            v = fma(Q[c][2], x3, v);
+                            a.y_eval[((int64_t)ei * N + c) * a.B + idx] = v + sm(L::S_YOLD + c);
+                        }
+                        ++ei;
+                    }
+                    if (dir * (t - a.tb) >= 0) finish_status = BRDAE_STATUS_FINISHED;
+                    else { state = ST_SETUP; setup_kind = SETUP_STEP; }
                 }
-                if (dir * (t - a.tb) >= 0) finish_status = BRDAE_STATUS_FINISHED;
-                else phase = PH_STEP;
+            }
+        }
+        warp_converge();
+
+        // ================= cheap set-up: prologue :516-562, attempt :564-588, guess :580-583 ===
+        if (warp_any(state == ST_SETUP && finish_status == 1)) {
+            if (state == ST_SETUP && finish_status == 1) {
+                if (setup_kind == SETUP_STEP) {
+                    ++nsteps;
+                    if (a.nmax_step > 0 && nsteps > a.nmax_step) finish_status = BRDAE_STATUS_NMAX_STEP;
+                    else {
+                        cnt[CN_NSTEP]++;
+                        min_step = fmax(1e-20, 10 * fabs(nextafter(t, dir * INFINITY) - t));
+                        h_abs_old = h_abs_old_state; err_old = err_old_state; hist = hist_state;
+                        if (h_abs_state > a.max_step) { h_abs = a.max_step; hist = false; }
+                        else if (h_abs_state < min_step) { h_abs = min_step; hist = false; }
+                        else h_abs = h_abs_state;
+                        if (fabs(a.tb - (t + dir * h_abs)) < 1e-2 * h_abs) { h_abs = fabs(a.tb - t); lu_valid = false; }
+                        rejected = false;
+                    }
+                }
+                if (finish_status == 1 && setup_kind <= SETUP_ATTEMPT) {
+                    if (h_abs < min_step) finish_status = BRDAE_STATUS_TOO_SMALL_STEP;
+                    else {
+                        h = h_abs * dir;
+                        t_new = t + h;
+                        if (dir * (t_new - a.tb) > 0) t_new = a.tb;
+                        h = t_new - t;
+                        h_abs = fabs(h);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            const int ve = a.var_index[c] > 1 ? a.var_index[c] - 1 : 0;
+                            const double hp = a.scale_newton_norm ? hpow(h, ve) : 1.0;
+                            inv_ns[c] = hp / (a.atol[c] + fabs(y[c]) * a.rtol);
+                        }
+                        mr = MU_REAL / h; mcr = MU_CR / h; mci = MU_CI / h;
+                    }
+                }
+                if (finish_status == 1) {
+                    // W = TI Z0, Z0 from the previous step's cubic evaluated beyond its interval
+                    if (!have_sol || !a.extrapolate) {
+#pragma unroll
+                        for (int c = 0; c < N; ++c) { W[0][c] = 0.0; W[1][c] = 0.0; W[2][c] = 0.0; }
+                    } else {
+                        double x[3], x2[3], x3[3];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const double tt = t + h * stage_c(i);
+                            x[i] = (tt - t_sol_old) / h_sol;
+                            x2[i] = x[i] * x[i];
+                            x3[i] = x2[i] * x[i];
+                        }
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            const double q0 = sm(L::S_Q + 3 * c), q1 = sm(L::S_Q + 3 * c + 1), q2 = sm(L::S_Q + 3 * c + 2);
+                            const double yo = sm(L::S_YOLD + c);
+                            double z[3];
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                double v = q0 * x[i];
+                                v = fma(q1, x2[i], v);
+                                v = fma(q2, x3[i], v);
+                                v = v + yo;
+                                z[i] = v - y[c];
+                            }
+                            W[0][c] = fma(TI02, z[2], fma(TI01, z[1], TI00 * z[0]));
+                            W[1][c] = fma(TI12, z[2], fma(TI11, z[1], TI10 * z[0]));
+                            W[2][c] = fma(TI22, z[2], fma(TI21, z[1], TI20 * z[0]));
+                        }
+                    }
+                    k = 0; nbad = 0; have_old = false; have_rate = false; rate = 0; dwn_old = 0;
+                    state = lu_valid ? ST_NEWTON : ST_FACTOR;
+                }
             }
         }
         // ================= retire a finished / failed system ==================================
-        if (finish_status != 1) {
-            const double qnan = NAN;
-            for (int e = ei; e < a.T; ++e)
+        if (warp_any(finish_status != 1)) {
+            if (finish_status != 1) {
+                const double qnan = NAN;
+                for (int e = ei; e < a.T; ++e)
 #pragma unroll
-                for (int c = 0; c < N; ++c) a.y_eval[((int64_t)e * N + c) * a.B + idx] = qnan;
-            a.n_eval[idx] = ei;
-            a.t_final[idx] = t;
+                    for (int c = 0; c < N; ++c) a.y_eval[((int64_t)e * N + c) * a.B + idx] = qnan;
+                a.n_eval[idx] = ei;
+                a.t_final[idx] = t;
 #pragma unroll
-            for (int c = 0; c < N; ++c) a.y_final[(int64_t)c * a.B + idx] = y[c];
-            a.status[idx] = finish_status;
+                for (int c = 0; c < N; ++c) a.y_final[(int64_t)c * a.B + idx] = y[c];
+                a.status[idx] = finish_status;
 #pragma unroll
-            for (int q = 0; q < CN_COUNT; ++q) a.counters[(int64_t)q * a.B + idx] = cnt[q];
-            phase = PH_IDLE;
+                for (int q = 0; q < CN_COUNT; ++q) a.counters[(int64_t)q * a.B + idx] = cnt[q];
+                state = ST_IDLE;
+            }
         }
     }
 }
