@@ -5,7 +5,7 @@
 
 namespace brdae {
 
-template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS>
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE = false>
 int k1_launch(const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
     constexpr int smem = K1Layout<Prob>::SLOTS * BLOCK * (int)sizeof(double);
     int64_t want = (a.B + BLOCK - 1) / BLOCK;
@@ -14,7 +14,7 @@ int k1_launch(const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool g
     if (grid < 1) grid = 1;
     if (g) { g->grid = grid; g->block = BLOCK; g->smem = smem; }
     if (geom_only) return BRDAE_OK;
-    auto kern = k1_kernel<Prob, Mass, BLOCK, MIN_BLOCKS>;
+    auto kern = k1_kernel<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BRDAE_ERR_CUDA;
     kern<<<grid, BLOCK, smem, s>>>(a);
     return cudaPeekAtLastError() == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;

@@ -7,7 +7,7 @@ template <int INDEX>
 static int go(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
     using Prob = Pendulum<INDEX>;
     if (dense_mass) return k1_launch<Prob, MassDense<5>, 128, 2>(a, sms, s, g, geom_only);
-    return k1_launch<Prob, typename Prob::Mass, 128, 2>(a, sms, s, g, geom_only);
+    return k1_launch<Prob, typename Prob::Mass, 256, 1, true>(a, sms, s, g, geom_only);
 }
 
 int k1_pendulum(int index, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {

@@ -235,6 +235,10 @@ struct K1Layout {
 BRDAE_D bool warp_all(bool x) { return __all_sync(0xffffffffu, x); }
 BRDAE_D bool warp_any(bool x) { return __any_sync(0xffffffffu, x); }
 BRDAE_D int warp_count(bool x) { return __popc(__ballot_sync(0xffffffffu, x)); }
+// vote scope: one warp, or the whole CTA (all warps then run the same block at the same time and
+// share its instruction-cache lines)
+template <bool CTA_WIDE>
+BRDAE_D int vote_count(bool x) { return CTA_WIDE ? __syncthreads_count(x) : warp_count(x); }
 BRDAE_D void warp_converge() { __syncwarp(); }
 BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
     const unsigned need = __ballot_sync(0xffffffffu, want);
@@ -253,12 +257,14 @@ BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
 inline bool warp_all(bool x) { return x; }
 inline bool warp_any(bool x) { return x; }
 inline int warp_count(bool x) { return x ? 1 : 0; }
+template <bool CTA_WIDE>
+inline int vote_count(bool x) { return x ? 1 : 0; }
 inline void warp_converge() {}
 inline long long fetch_system(bool want, unsigned long long *counter) { return want ? (long long)((*counter)++) : -1; }
 #endif
 
 // The per-lane integrator.  `sm` addresses this lane's shared-memory slots.
-template <class Prob, class Mass, class S>
+template <class Prob, class Mass, bool CTA_WIDE, class S>
 BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
     constexpr int N = Prob::N;
     using L = K1Layout<Prob>;
@@ -328,14 +334,15 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                     }
                 }
             }
-            if (warp_all(state == ST_EXIT)) break;
+            if (!CTA_WIDE && warp_all(state == ST_EXIT)) break;
         }
         warp_converge();
+        if (CTA_WIDE && vote_count<CTA_WIDE>(state != ST_EXIT) == 0) break;
 
         // ================= vote: run the expensive block most lanes are waiting for ===========
-        const int nF = warp_count(state == ST_FACTOR);
-        const int nN = warp_count(state == ST_NEWTON);
-        const int nE = warp_count(state == ST_ERREST);
+        const int nF = vote_count<CTA_WIDE>(state == ST_FACTOR);
+        const int nN = vote_count<CTA_WIDE>(state == ST_NEWTON);
+        const int nE = vote_count<CTA_WIDE>(state == ST_ERREST);
         const int run = (nN > 0 && nN >= nE && nN >= nF) ? ST_NEWTON : ((nE > 0 && nE >= nF) ? ST_ERREST : (nF > 0 ? ST_FACTOR : ST_IDLE));
 
         // ================= (re)factorisation :594-613 =========================================
@@ -688,11 +695,11 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
 }
 
 #if defined(__CUDACC__)
-template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS>
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k1_kernel(const __grid_constant__ SolveArgs a) {
     extern __shared__ double k1_smem[];
     Slots<BLOCK> sm{k1_smem + threadIdx.x};
-    k1_lane_loop<Prob, Mass>(a, sm);
+    k1_lane_loop<Prob, Mass, CTA_WIDE>(a, sm);
 }
 #endif
 

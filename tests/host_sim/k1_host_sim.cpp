@@ -17,7 +17,7 @@ template <class Prob, class Mass>
 static void run(const SolveArgs &a) {
     std::vector<double> slots(K1Layout<Prob>::SLOTS, 0.0);
     Slots<1> sm{slots.data()};
-    k1_lane_loop<Prob, Mass>(a, sm);
+    k1_lane_loop<Prob, Mass, false>(a, sm);
 }
 
 template <class Prob>
