@@ -11,7 +11,7 @@ import math
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrdae.so")
+LIB_PATH = os.environ.get("BRDAE_LIB") or os.path.join(_HERE, "libbrdae.so")   # BRDAE_LIB: tuning builds
 
 COUNTER_NAMES = ("nfev", "njev", "nlu", "nstep", "naccpt", "nrejct", "nfailed", "nlusolve",
                  "nlusolve_errorest")

@@ -53,6 +53,28 @@ def _compile(src, force, hdr_mtime, log):
     return obj, r.stderr
 
 
+def build_variant(tag: str, defines: dict) -> str:
+    """Tuning helper: build a second library `libbrdae_<tag>.so` with extra -D macros (objects in
+    build/<tag>/); select it at run time with BRDAE_LIB=<path>."""
+    objdir = os.path.join(OBJDIR, tag)
+    os.makedirs(objdir, exist_ok=True)
+    lib = os.path.join(HERE, f"libbrdae_{tag}.so")
+    dflags = [f"-D{k}={v}" for k, v in defines.items()]
+
+    def one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        r = subprocess.run([_nvcc(), *NVCC_FLAGS, *dflags, "-c", os.path.join(CSRC, src), "-o", obj],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr)
+        return obj
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, SOURCES))
+    subprocess.run([_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"],
+                   check=True)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     hdr = _newest_header_mtime()

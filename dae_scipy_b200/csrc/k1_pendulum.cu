@@ -1,13 +1,24 @@
 // k1_pendulum.cu -- K1 instantiations for the single pendulum, index 3 / 2 / 1.
 #include "k1_launch.cuh"
 
+// launch geometry (overridable for tuning experiments)
+#ifndef K1_PEND_BLOCK
+#define K1_PEND_BLOCK 256
+#endif
+#ifndef K1_PEND_MINB
+#define K1_PEND_MINB 1
+#endif
+#ifndef K1_PEND_CTAWIDE
+#define K1_PEND_CTAWIDE true
+#endif
+
 namespace brdae {
 
 template <int INDEX>
 static int go(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
     using Prob = Pendulum<INDEX>;
-    if (dense_mass) return k1_launch<Prob, MassDense<5>, 128, 2>(a, sms, s, g, geom_only);
-    return k1_launch<Prob, typename Prob::Mass, 256, 1, true>(a, sms, s, g, geom_only);
+    if (dense_mass) return k1_launch<Prob, MassDense<5>, K1_PEND_BLOCK, K1_PEND_MINB, K1_PEND_CTAWIDE>(a, sms, s, g, geom_only);
+    return k1_launch<Prob, typename Prob::Mass, K1_PEND_BLOCK, K1_PEND_MINB, K1_PEND_CTAWIDE>(a, sms, s, g, geom_only);
 }
 
 int k1_pendulum(int index, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {

@@ -5,8 +5,8 @@
 namespace brdae {
 
 int k1_transistor(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
-    if (dense_mass) return k1_launch<Transistor, MassDense<5>, 128, 2>(a, sms, s, g, geom_only);
-    return k1_launch<Transistor, Transistor::Mass, 128, 2>(a, sms, s, g, geom_only);
+    if (dense_mass) return k1_launch<Transistor, MassDense<5>, 256, 1, true>(a, sms, s, g, geom_only);
+    return k1_launch<Transistor, Transistor::Mass, 256, 1, true>(a, sms, s, g, geom_only);
 }
 
 }  // namespace brdae

@@ -35,6 +35,16 @@ constexpr double P00 = 0x1.418fd8baffe05p+3, P01 = -0x1.9a12ce7b30915p+4, P02 = 
 constexpr double P10 = -0x1.61d41b2d54580p+0, P11 = 0x1.497af24bb677ep+3, P12 = -0x1.1d406ee60becfp+3;
 constexpr double P20 = 0x1.5555555555555p-2, P21 = -0x1.5555555555555p+1, P22 = 0x1.aaaaaaaaaaaabp+1;
 
+// the same transforms as tables, for loops that are deliberately not unrolled
+#if defined(__CUDACC__)
+#define BRDAE_TABLE __constant__ const double
+#else
+#define BRDAE_TABLE static const double
+#endif
+BRDAE_TABLE kStageT[3][3] = {{T00, T01, T02}, {T10, T11, T12}, {1.0, 1.0, 0.0}};
+BRDAE_TABLE kStageTI[3][3] = {{TI00, TI01, TI02}, {TI10, TI11, TI12}, {TI20, TI21, TI22}};
+BRDAE_TABLE kStageC[3] = {RC0, RC1, 1.0};
+
 // (T W)_i for one component: fma chain over the stages 0,1,2; T[2] = (1, 1, 0)
 template <int I>
 BRDAE_HD double stage_z(double w0, double w1, double w2) {

@@ -237,8 +237,24 @@ BRDAE_D bool warp_any(bool x) { return __any_sync(0xffffffffu, x); }
 BRDAE_D int warp_count(bool x) { return __popc(__ballot_sync(0xffffffffu, x)); }
 // vote scope: one warp, or the whole CTA (all warps then run the same block at the same time and
 // share its instruction-cache lines)
+// one vote per trip: how many lanes are alive / wait for FACTOR / NEWTON / ERREST.  CTA-wide votes
+// cost a single barrier: every warp posts its four ballot counts (packed 4 x 16 bit) into a
+// double-buffered shared slot, and after the barrier every thread sums the slots.
+struct Votes { int alive, nF, nN, nE; };
 template <bool CTA_WIDE>
-BRDAE_D int vote_count(bool x) { return CTA_WIDE ? __syncthreads_count(x) : warp_count(x); }
+BRDAE_D Votes vote(int state, unsigned trip) {
+    const int a = warp_count(state != ST_EXIT), f = warp_count(state == ST_FACTOR);
+    const int n = warp_count(state == ST_NEWTON), e = warp_count(state == ST_ERREST);
+    if (!CTA_WIDE) return Votes{a, f, n, e};
+    __shared__ unsigned long long posted[2][32];
+    const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0)
+        posted[trip & 1][warp] = (unsigned long long)a | ((unsigned long long)f << 16) | ((unsigned long long)n << 32) | ((unsigned long long)e << 48);
+    __syncthreads();
+    unsigned long long sum = 0;
+    for (int w = 0; w < nwarps; ++w) sum += posted[trip & 1][w];
+    return Votes{(int)(sum & 0xffff), (int)((sum >> 16) & 0xffff), (int)((sum >> 32) & 0xffff), (int)(sum >> 48)};
+}
 BRDAE_D void warp_converge() { __syncwarp(); }
 BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
     const unsigned need = __ballot_sync(0xffffffffu, want);
@@ -257,8 +273,11 @@ BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
 inline bool warp_all(bool x) { return x; }
 inline bool warp_any(bool x) { return x; }
 inline int warp_count(bool x) { return x ? 1 : 0; }
+struct Votes { int alive, nF, nN, nE; };
 template <bool CTA_WIDE>
-inline int vote_count(bool x) { return x ? 1 : 0; }
+inline Votes vote(int state, unsigned) {
+    return Votes{state != ST_EXIT, state == ST_FACTOR, state == ST_NEWTON, state == ST_ERREST};
+}
 inline void warp_converge() {}
 inline long long fetch_system(bool want, unsigned long long *counter) { return want ? (long long)((*counter)++) : -1; }
 #endif
@@ -276,7 +295,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
     double t = 0, y[N];
     double h_abs_state = 0, h_abs_old_state = 0, err_old_state = 0;
     bool hist_state = false, current_jac = true, lu_valid = false, have_sol = false;
-    double h_sol = 1, t_sol_old = 0, inv_h_lu = 1.0;
+    double inv_h_sol = 1, t_sol_old = 0, inv_h_lu = 1.0;
     unsigned piv_r = 0, piv_c = 0;
     int cnt[CN_COUNT];
     int ei = 0;
@@ -285,7 +304,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
     double min_step = 0, h_abs = 0, h_abs_old = 0, err_old = 0;
     bool hist = false, rejected = false;
     // attempt scope
-    double h = 0, t_new = 0, inv_ns[N], mr = 0, mcr = 0, mci = 0;
+    double h = 0, inv_h = 0, t_new = 0, inv_ns[N], mr = 0, mcr = 0, mci = 0;
     // Newton scope
     double W[3][N];
     int k = 0, nbad = 0, n_iter = 0;
@@ -298,6 +317,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
 
     const int MAXIT = a.maxit;
     const double dir = a.dir;
+    unsigned trip = 0;
 
     for (;;) {
         int finish_status = 1;  // 1 = still running
@@ -337,18 +357,17 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
             if (!CTA_WIDE && warp_all(state == ST_EXIT)) break;
         }
         warp_converge();
-        if (CTA_WIDE && vote_count<CTA_WIDE>(state != ST_EXIT) == 0) break;
 
         // ================= vote: run the expensive block most lanes are waiting for ===========
-        const int nF = vote_count<CTA_WIDE>(state == ST_FACTOR);
-        const int nN = vote_count<CTA_WIDE>(state == ST_NEWTON);
-        const int nE = vote_count<CTA_WIDE>(state == ST_ERREST);
+        const Votes v = vote<CTA_WIDE>(state, trip++);
+        if (CTA_WIDE && v.alive == 0) break;
+        const int nF = v.nF, nN = v.nN, nE = v.nE;
         const int run = (nN > 0 && nN >= nE && nN >= nF) ? ST_NEWTON : ((nE > 0 && nE >= nF) ? ST_ERREST : (nF > 0 ? ST_FACTOR : ST_IDLE));
 
         // ================= (re)factorisation :594-613 =========================================
         if (run == ST_FACTOR) {
             if (state == ST_FACTOR) {
-                if (a.scale_residuals) inv_h_lu = 1.0 / h;
+                if (a.scale_residuals) inv_h_lu = inv_h;
                 double J[N][N];
                 if (a.has_jac_const) {
 #pragma unroll
@@ -389,26 +408,26 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
         // ================= one simplified-Newton iteration :846-940 ==========================
         else if (run == ST_NEWTON) {
             if (state == ST_NEWTON) {
+                // the three stages run as a rolled loop (instruction-cache footprint); coefficients
+                // come from constant tables.  Values are those of the unrolled form: the first
+                // accumulation fma(a, F, 0) equals a*F, and (T W)_2 = fma(0, W2, fma(1, W1, 1*W0)) = W0 + W1.
                 double fr[N], fcr[N], fci[N];
                 bool finite = true;
 #pragma unroll
+                for (int c = 0; c < N; ++c) { fr[c] = 0.0; fcr[c] = 0.0; fci[c] = 0.0; }
+#pragma unroll 1
                 for (int i = 0; i < 3; ++i) {
+                    const double t0c = kStageT[i][0], t1c = kStageT[i][1], t2c = kStageT[i][2];
+                    const double a0 = kStageTI[0][i], a1 = kStageTI[1][i], a2 = kStageTI[2][i];
                     double Y[N], F[N];
 #pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        const double z = (i == 0) ? stage_z<0>(W[0][c], W[1][c], W[2][c])
-                                       : (i == 1) ? stage_z<1>(W[0][c], W[1][c], W[2][c])
-                                                  : stage_z<2>(W[0][c], W[1][c], W[2][c]);
-                        Y[c] = y[c] + z;
-                    }
-                    Prob::rhs(prm, t + h * stage_c(i), Y, F);
+                    for (int c = 0; c < N; ++c) Y[c] = y[c] + fma(t2c, W[2][c], fma(t1c, W[1][c], t0c * W[0][c]));
+                    Prob::rhs(prm, t + h * kStageC[i], Y, F);
 #pragma unroll
                     for (int c = 0; c < N; ++c) {
                         const double Fv = F[c];
                         finite = finite && is_finite(Fv);
-                        if (i == 0) { fr[c] = TI00 * Fv; fcr[c] = TI10 * Fv; fci[c] = TI20 * Fv; }
-                        else if (i == 1) { fr[c] = fma(TI01, Fv, fr[c]); fcr[c] = fma(TI11, Fv, fcr[c]); fci[c] = fma(TI21, Fv, fci[c]); }
-                        else { fr[c] = fma(TI02, Fv, fr[c]); fcr[c] = fma(TI12, Fv, fcr[c]); fci[c] = fma(TI22, Fv, fci[c]); }
+                        fr[c] = fma(a0, Fv, fr[c]); fcr[c] = fma(a1, Fv, fcr[c]); fci[c] = fma(a2, Fv, fci[c]);
                     }
                 }
                 cnt[CN_NFEV] += 3;
@@ -512,7 +531,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                         double v = Z[0][c] * RE0;
                         v = fma(Z[1][c], RE1, v);
                         v = fma(Z[2][c], RE2, v);
-                        ze[c] = v / h;
+                        ze[c] = v * inv_h;
                         const double ynew = y[c] + Z[2][c];
                         const int ve = a.var_index[c] > 1 ? a.var_index[c] - 1 : 0;
                         const double hp = a.scale_error ? hpow(h, ve) : 1.0;
@@ -579,13 +598,13 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                         Q[c][2] = fma(Z[2][c], P22, fma(Z[1][c], P12, Z[0][c] * P02));
                         sm(L::S_Q + 3 * c) = Q[c][0]; sm(L::S_Q + 3 * c + 1) = Q[c][1]; sm(L::S_Q + 3 * c + 2) = Q[c][2];
                     }
-                    t_sol_old = t; h_sol = t_new - t; have_sol = true;
+                    t_sol_old = t; inv_h_sol = inv_h; have_sol = true;
                     t = t_new;
                     // driver: t_eval points inside (t_old, t]  (searchsorted side='right', ivp.py:711-729)
                     while (ei < a.T) {
                         const double te = a.t_eval[ei];
                         if (!(dir > 0 ? te <= t : te >= t)) break;
-                        const double x = (te - t_sol_old) / h_sol;
+                        const double x = (te - t_sol_old) * inv_h_sol;
                         const double x2 = x * x, x3 = x2 * x;
 #pragma unroll
                         for (int c = 0; c < N; ++c) {
@@ -634,7 +653,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                             const double hp = a.scale_newton_norm ? hpow(h, ve) : 1.0;
                             inv_ns[c] = hp / (a.atol[c] + fabs(y[c]) * a.rtol);
                         }
-                        mr = MU_REAL / h; mcr = MU_CR / h; mci = MU_CI / h;
+                        inv_h = 1.0 / h;   // the one division by h of an attempt
+                        mr = MU_REAL * inv_h; mcr = MU_CR * inv_h; mci = MU_CI * inv_h;
                     }
                 }
                 if (finish_status == 1) {
@@ -647,7 +667,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
                             const double tt = t + h * stage_c(i);
-                            x[i] = (tt - t_sol_old) / h_sol;
+                            x[i] = (tt - t_sol_old) * inv_h_sol;
                             x2[i] = x[i] * x[i];
                             x3[i] = x2[i] * x[i];
                         }

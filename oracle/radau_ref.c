@@ -11,7 +11,7 @@
  * reference is not even bit-reproducible against itself across OpenBLAS kernel families).
  * This restatement therefore fixes ONE explicit evaluation order -- right-looking LU with
  * partial pivoting and reciprocal pivots, fma() where written, x**0.25 as sqrt(sqrt(x)),
- * divisions by the Newton/error scales done as multiplications by a reciprocal, norms as
+ * divisions by the Newton/error scales and by h done as multiplications by a reciprocal, norms as
  * sqrt(sum)*rsqrt(size) -- so that an independent implementation of the same spec (the CUDA
  * kernels) can be compared with it BIT FOR BIT, while this file itself is pinned to the
  * reference statistically (tests/test_oracle_c.py: every t_eval value within the parity
@@ -513,7 +513,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
     if (has_jac_fn) { prob_jac(pc, t, w->y, w->J); cnt[C_NJEV] = 1; } /* :483-484 */
     else memcpy(w->J, jac_const, sizeof(double) * n * n);
     int current_jac = 1, lu_valid = 0, have_sol = 0;
-    double h_sol = 0, t_sol_old = 0, inv_h_lu = 1.0;
+    double inv_h_sol = 0, t_sol_old = 0, inv_h_lu = 1.0;
     int status = 1; /* running */
     int ei = 0;     /* next t_eval index */
     int64_t nsteps = 0;
@@ -538,7 +538,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
         if (fabs(tb - (t + dir * h_abs)) < 1e-2 * h_abs) { h_abs = fabs(tb - t); lu_valid = 0; }
         int rejected = 0, accepted = 0;
         int n_iter = 0;
-        double rate = 0, h = 0, t_new = t, error_norm = 0, safety = 0;
+        double rate = 0, h = 0, inv_h = 0, t_new = t, error_norm = 0, safety = 0;
         int have_rate = 0;
 
         while (!accepted) {
@@ -548,6 +548,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
             if (dir * (t_new - tb) > 0) t_new = tb;
             h = t_new - t;
             h_abs = fabs(h);
+            inv_h = 1.0 / h; /* the one division by h of an attempt; mu/h, Z.E/h and x/h use it */
             /* Newton scale, :585-588, kept as a reciprocal */
             for (int c = 0; c < n; ++c) {
                 int ve = var_index[c] > 1 ? var_index[c] - 1 : 0;
@@ -561,7 +562,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 else {
                     for (int i = 0; i < 3; ++i) {
                         double tt = t + h * RC[i];
-                        double x = (tt - t_sol_old) / h_sol;
+                        double x = (tt - t_sol_old) * inv_h_sol;
                         double p2 = x * x, p3 = p2 * x;
                         for (int c = 0; c < n; ++c) {
                             double v = w->Q[c * 3 + 0] * x;
@@ -579,10 +580,10 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                         }
                 }
                 if (!lu_valid) { /* :594-613 */
-                    if (o->scale_residuals) inv_h_lu = 1.0 / h;
+                    if (o->scale_residuals) inv_h_lu = inv_h;
                     for (int c = 0; c < n; ++c)
                         w->hs[c] = (o->scale_residuals && var_index[c] >= 1) ? inv_h_lu : 1.0;
-                    double mr = MU_REAL / h, mcr = MU_CR / h, mci = MU_CI / h;
+                    double mr = MU_REAL * inv_h, mcr = MU_CR * inv_h, mci = MU_CI * inv_h;
                     for (int r = 0; r < n; ++r)
                         for (int c = 0; c < n; ++c) {
                             double m = w->M[r * n + c], j = w->J[r * n + c], s = w->hs[r];
@@ -596,7 +597,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     lu_valid = 1;
                 }
                 /* ------------- simplified Newton, :793-949 */
-                double mr = MU_REAL / h, mcr = MU_CR / h, mci = MU_CI / h;
+                double mr = MU_REAL * inv_h, mcr = MU_CR * inv_h, mci = MU_CI * inv_h;
                 double dwn_old = 0;
                 int have_old = 0, nbad = 0, k;
                 have_rate = 0; rate = 0;
@@ -684,7 +685,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 double v = w->Z[c] * RE[0];
                 v = fma(w->Z[n + c], RE[1], v);
                 v = fma(w->Z[2 * n + c], RE[2], v);
-                w->ze[c] = v / h;
+                w->ze[c] = v * inv_h;
                 double ynew = w->y[c] + w->Z[2 * n + c];
                 int ve = var_index[c] > 1 ? var_index[c] - 1 : 0;
                 double hp = o->scale_error ? hpow(h, ve) : 1.0;
@@ -733,12 +734,12 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 v = fma(w->Z[n + c], RP[1][j], v);
                 w->Q[c * 3 + j] = fma(w->Z[2 * n + c], RP[2][j], v);
             }
-        t_sol_old = t; h_sol = t_new - t; have_sol = 1;
+        t_sol_old = t; inv_h_sol = inv_h; have_sol = 1;
         t = t_new;
         /* ---------------- driver: finished? t_eval points inside (t_old, t] */
         if (dir * (t - tb) >= 0) status = ST_FINISHED;
         while (ei < T && (dir > 0 ? t_eval[ei] <= t : t_eval[ei] >= t)) {
-            double x = (t_eval[ei] - t_sol_old) / h_sol;
+            double x = (t_eval[ei] - t_sol_old) * inv_h_sol;
             double p2 = x * x, p3 = p2 * x;
             for (int c = 0; c < n; ++c) {
                 double v = w->Q[c * 3 + 0] * x;
