@@ -1,13 +1,661 @@
-// k2_npendulum.cu -- placeholder translation unit until the CTA-per-system banded kernel lands.
+// k2_npendulum.cu -- K2: CTA-per-system batched RadauDAE for the recursive n-pendulum chain
+// (reference problem scipyDAE/tests/recursive_pendulum.py:93-127; N = 5 n unknowns interleaved
+// (x, y, vx, vy, lambda) per node, index 3, mass diag(1,1,1,1,0) per node), sm_100a.
+//
+// One CTA integrates one rope at a time (persistent CTAs pull rope indices from the global work
+// counter).  All vectors of the step -- y, f, y_old, the dense-output coefficients Q, the
+// transformed stage values W, the Newton residuals/increments -- live in shared memory; the
+// iteration matrices are BANDED (Jacobian lower bandwidth 9, upper 7) and are stored,
+// factored and solved in LAPACK-style band storage with room for pivoting fill (2 kl + ku + 1 = 26
+// entries per row): the real factor in shared memory, the complex one in shared memory when it
+// fits (n <= 50) and otherwise in an L2-resident per-CTA slice of the workspace.
+//
+// Parallelism inside the CTA: right-hand side, Jacobian assembly and every vector operation run
+// node-parallel over all threads; the two banded LUs (and the two triangular solves of each
+// Newton iteration) run concurrently, the real system on warp 0 and the complex one on warp 1,
+// each column step spread over the lanes (pivot search by shuffle arg-max, row exchange,
+// multipliers and the (kl x (kl+ku)) rank-1 update).  Arithmetic follows the same contract as the
+// thread-per-system kernels (right-looking elimination, first-maximum partial pivoting, reciprocal
+// pivots, column-oriented substitutions, fma where written), restricted to the band -- the entries
+// outside it are exact zeros -- with norms accumulated as 32 interleaved chains folded by a
+// shuffle tree.
+//
+// Reference map: same as radau_k1.cuh (radauDAE.py:515-791, 793-949, 951-982, 1079-1157).
+#include <cuda_runtime.h>
+
 #include "kernels.cuh"
 
 namespace brdae {
 
-size_t k2_scratch_bytes(int, int) { return 0; }
+namespace {
 
-int k2_npendulum(bool, const SolveArgs &, const brdae_batch *, int, cudaStream_t, LaunchGeom *g, bool) {
-    if (g) { g->grid = 0; g->block = 0; g->smem = 0; }
-    return BRDAE_ERR_UNSUPPORTED;
+constexpr int KL = 9, KU = 7, WB = 2 * KL + KU + 1;  // band storage width (26)
+constexpr int K2_BLOCK = 128;
+constexpr double GRAV = 9.81;
+
+struct K2Cfg {
+    int complex_in_smem;          // complex LU factors in shared memory?
+    size_t scratch_stride;        // doubles per CTA in the global scratch
+};
+
+__device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+#define AB(ab, r, c) (ab)[(r) * WB + ((c) - (r) + KL)]
+
+// ---- banded LU, one warp, real ---------------------------------------------------------------
+__device__ void lu_band_real(double *ab, int *piv, int N) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < N; ++k) {
+        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + KU + KL);
+        double v = -1.0;
+        int idx = k + lane;
+        if (idx <= rmax) v = fabs(AB(ab, idx, k));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double v2 = __shfl_down_sync(0xffffffffu, v, off);
+            const int i2 = __shfl_down_sync(0xffffffffu, idx, off);
+            if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+        }
+        const int p = __shfl_sync(0xffffffffu, idx, 0);
+        if (lane == 0) piv[k] = p;
+        if (p != k) {
+            const int c = k + lane;
+            if (c <= cmax) { const double u = AB(ab, k, c); AB(ab, k, c) = AB(ab, p, c); AB(ab, p, c) = u; }
+        }
+        __syncwarp();
+        const double rcp = 1.0 / AB(ab, k, k);
+        __syncwarp();
+        if (lane == 0) AB(ab, k, k) = rcp;
+        if (lane < rmax - k) { const int r = k + 1 + lane; AB(ab, r, k) = AB(ab, r, k) * rcp; }
+        __syncwarp();
+        const int nr = rmax - k, nc = cmax - k;
+        for (int e = lane; e < nr * nc; e += 32) {
+            const int r = k + 1 + e / nc, c = k + 1 + e % nc;
+            AB(ab, r, c) = fma(-AB(ab, r, k), AB(ab, k, c), AB(ab, r, c));
+        }
+        __syncwarp();
+    }
+}
+// complex, pivot on |re| + |im|
+__device__ void lu_band_cplx(double *ar, double *ai, int *piv, int N) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < N; ++k) {
+        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + KU + KL);
+        double v = -1.0;
+        int idx = k + lane;
+        if (idx <= rmax) v = fabs(AB(ar, idx, k)) + fabs(AB(ai, idx, k));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double v2 = __shfl_down_sync(0xffffffffu, v, off);
+            const int i2 = __shfl_down_sync(0xffffffffu, idx, off);
+            if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+        }
+        const int p = __shfl_sync(0xffffffffu, idx, 0);
+        if (lane == 0) piv[k] = p;
+        if (p != k) {
+            const int c = k + lane;
+            if (c <= cmax) {
+                double u = AB(ar, k, c); AB(ar, k, c) = AB(ar, p, c); AB(ar, p, c) = u;
+                u = AB(ai, k, c); AB(ai, k, c) = AB(ai, p, c); AB(ai, p, c) = u;
+            }
+        }
+        __syncwarp();
+        const double pr = AB(ar, k, k), pi = AB(ai, k, k);
+        const double invd = 1.0 / fma(pr, pr, pi * pi);
+        const double qr = pr * invd, qi = -(pi * invd);
+        __syncwarp();
+        if (lane == 0) { AB(ar, k, k) = qr; AB(ai, k, k) = qi; }
+        if (lane < rmax - k) {
+            const int r = k + 1 + lane;
+            const double xr = AB(ar, r, k), xi = AB(ai, r, k);
+            AB(ar, r, k) = fma(xr, qr, -(xi * qi));
+            AB(ai, r, k) = fma(xr, qi, xi * qr);
+        }
+        __syncwarp();
+        const int nr = rmax - k, nc = cmax - k;
+        for (int e = lane; e < nr * nc; e += 32) {
+            const int r = k + 1 + e / nc, c = k + 1 + e % nc;
+            const double lr = AB(ar, r, k), li = AB(ai, r, k), ur = AB(ar, k, c), ui = AB(ai, k, c);
+            double xr = AB(ar, r, c), xi = AB(ai, r, c);
+            xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
+            xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
+            AB(ar, r, c) = xr; AB(ai, r, c) = xi;
+        }
+        __syncwarp();
+    }
+}
+// ---- banded triangular solves, one warp each ---------------------------------------------------
+__device__ void solve_band_real(const double *ab, const int *piv, double *b, int N) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < N; ++k) {
+        const int p = piv[k], rmax = imin(N - 1, k + KL);
+        if (p != k && lane == 0) { const double u = b[k]; b[k] = b[p]; b[p] = u; }
+        __syncwarp();
+        const double bk = b[k];
+        if (lane < rmax - k) { const int r = k + 1 + lane; b[r] = fma(-AB(ab, r, k), bk, b[r]); }
+        __syncwarp();
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        const int rmin = imax(0, k - (KU + KL));
+        const double xk = b[k] * AB(ab, k, k);
+        __syncwarp();
+        if (lane == 0) b[k] = xk;
+        if (lane < k - rmin) { const int r = rmin + lane; b[r] = fma(-AB(ab, r, k), xk, b[r]); }
+        __syncwarp();
+    }
+}
+__device__ void solve_band_cplx(const double *ar, const double *ai, const int *piv, double *br, double *bi, int N) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < N; ++k) {
+        const int p = piv[k], rmax = imin(N - 1, k + KL);
+        if (p != k && lane == 0) {
+            double u = br[k]; br[k] = br[p]; br[p] = u;
+            u = bi[k]; bi[k] = bi[p]; bi[p] = u;
+        }
+        __syncwarp();
+        const double xr = br[k], xi = bi[k];
+        if (lane < rmax - k) {
+            const int r = k + 1 + lane;
+            const double lr = AB(ar, r, k), li = AB(ai, r, k);
+            double yr = br[r], yi = bi[r];
+            yr = fma(-lr, xr, yr); yr = fma(li, xi, yr);
+            yi = fma(-lr, xi, yi); yi = fma(-li, xr, yi);
+            br[r] = yr; bi[r] = yi;
+        }
+        __syncwarp();
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        const int rmin = imax(0, k - (KU + KL));
+        const double qr = AB(ar, k, k), qi = AB(ai, k, k);
+        const double sr = br[k], si = bi[k];
+        const double xr = fma(sr, qr, -(si * qi));
+        const double xi = fma(sr, qi, si * qr);
+        __syncwarp();
+        if (lane == 0) { br[k] = xr; bi[k] = xi; }
+        if (lane < k - rmin) {
+            const int r = rmin + lane;
+            const double ur = AB(ar, r, k), ui = AB(ai, r, k);
+            double yr = br[r], yi = bi[r];
+            yr = fma(-ur, xr, yr); yr = fma(ui, xi, yr);
+            yi = fma(-ur, xi, yi); yi = fma(-ui, xr, yi);
+            br[r] = yr; bi[r] = yi;
+        }
+        __syncwarp();
+    }
+}
+
+// sum of squares of v[e] * s[e mod N], e < m, by warp 0: 32 interleaved chains + shuffle tree.
+// The result is left in *out (shared); callers __syncthreads() before reading it.
+__device__ void sumsq_scaled(const double *v, const double *s, int N, int m, double *out) {
+    if (threadIdx.x < 32) {
+        double p = 0.0;
+        for (int e = threadIdx.x; e < m; e += 32) { const double x = v[e] * s[e % N]; p = fma(x, x, p); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) p = p + __shfl_down_sync(0xffffffffu, p, off);
+        if (threadIdx.x == 0) *out = p;
+    }
+}
+
+struct Rope {           // shared-memory views of one CTA
+    int N, nn;
+    double *y, *f, *yold, *yJ, *Q, *W, *R, *inv_ns, *inv_es, *Yt, *Ft, *ze, *err, *aa, *bb;
+    double *mass_m, *inv_m, *r0s, *atol, *red;
+    int *vidx, *pivr, *pivc;
+    double *lur, *lcr, *lci;
+};
+
+// f = rhs(Y): recursive_pendulum.py:93-118.  Node-parallel, two phases (the (i+1) term).
+__device__ void rope_rhs(const Rope &s, const double *Y, double *F) {
+    for (int i = threadIdx.x; i < s.nn; i += blockDim.x) {
+        const double *q = Y + 5 * i;
+        const double dx = (i == 0) ? q[0] : q[0] - q[-5];
+        const double dy = (i == 0) ? q[1] : q[1] - q[-4];
+        const double rs = dx * dx + dy * dy;
+        s.aa[i] = q[4] * dx / rs;
+        s.bb[i] = q[4] * dy / rs;
+        F[5 * i + 4] = rs - s.r0s[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < s.nn; i += blockDim.x) {
+        const double *q = Y + 5 * i;
+        double *o = F + 5 * i;
+        o[0] = q[2];
+        o[1] = q[3];
+        if (i == s.nn - 1) {
+            o[2] = s.inv_m[i] * s.aa[i];
+            o[3] = s.inv_m[i] * (s.bb[i] - s.mass_m[i] * GRAV);
+        } else {
+            o[2] = s.inv_m[i] * (s.aa[i] - s.aa[i + 1]);
+            o[3] = s.inv_m[i] * (s.bb[i] - s.bb[i + 1] - s.mass_m[i] * GRAV);
+        }
+    }
+    __syncthreads();
+}
+
+struct NodeJac { double adx, ady, bdx, bdy, al, bl, dx, dy; };
+__device__ __forceinline__ NodeJac node_jac(const double *X, int i) {
+    const double *q = X + 5 * i;
+    NodeJac j;
+    j.dx = (i == 0) ? q[0] : q[0] - q[-5];
+    j.dy = (i == 0) ? q[1] : q[1] - q[-4];
+    const double rs = j.dx * j.dx + j.dy * j.dy, l = q[4], rs2 = rs * rs;
+    j.adx = l * (rs - 2 * j.dx * j.dx) / rs2;
+    j.ady = l * (-2 * j.dx * j.dy) / rs2;
+    j.bdy = l * (rs - 2 * j.dy * j.dy) / rs2;
+    j.bdx = j.ady;
+    j.al = j.dx / rs;
+    j.bl = j.dy / rs;
+    return j;
+}
+
+// iteration matrices hscale (mu/h M - J) in band storage, then both LUs (radauDAE.py:594-613)
+__device__ void rope_factor(const Rope &s, const SolveArgs &a, double mr, double mcr, double mci, double inv_h_lu) {
+    const int N = s.N;
+    for (int e = threadIdx.x; e < N * WB; e += blockDim.x) { s.lur[e] = 0.0; s.lcr[e] = 0.0; s.lci[e] = 0.0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < s.nn; i += blockDim.x) {
+        const NodeJac me = node_jac(s.yJ, i);
+        const int r = 5 * i;
+        const double im = s.inv_m[i];
+        auto hs = [&](int row) { return (a.scale_residuals && s.vidx[row] >= 1) ? inv_h_lu : 1.0; };
+        // put(row, col, mass entry, jac entry)
+        auto put = [&](int row, int col, double m, double jv) {
+            const double h = hs(row);
+            AB(s.lur, row, col) = h * fma(mr, m, -jv);
+            AB(s.lcr, row, col) = h * fma(mcr, m, -jv);
+            AB(s.lci, row, col) = h * (mci * m);
+        };
+        put(r, r, 1.0, 0.0); put(r + 1, r + 1, 1.0, 0.0); put(r + 2, r + 2, 1.0, 0.0); put(r + 3, r + 3, 1.0, 0.0);
+        put(r, r + 2, 0.0, 1.0);
+        put(r + 1, r + 3, 0.0, 1.0);
+        double j20 = im * me.adx, j21 = im * me.ady, j30 = im * me.bdx, j31 = im * me.bdy;
+        if (i < s.nn - 1) {
+            const NodeJac nx = node_jac(s.yJ, i + 1);
+            j20 = j20 + im * nx.adx; j21 = j21 + im * nx.ady; j30 = j30 + im * nx.bdx; j31 = j31 + im * nx.bdy;
+            put(r + 2, r + 5, 0.0, -(im * nx.adx)); put(r + 2, r + 6, 0.0, -(im * nx.ady)); put(r + 2, r + 9, 0.0, -(im * nx.al));
+            put(r + 3, r + 5, 0.0, -(im * nx.bdx)); put(r + 3, r + 6, 0.0, -(im * nx.bdy)); put(r + 3, r + 9, 0.0, -(im * nx.bl));
+        }
+        put(r + 2, r, 0.0, j20); put(r + 2, r + 1, 0.0, j21); put(r + 2, r + 4, 0.0, im * me.al);
+        put(r + 3, r, 0.0, j30); put(r + 3, r + 1, 0.0, j31); put(r + 3, r + 4, 0.0, im * me.bl);
+        put(r + 4, r, 0.0, 2 * me.dx); put(r + 4, r + 1, 0.0, 2 * me.dy);
+        if (i > 0) {
+            put(r + 2, r - 5, 0.0, -(im * me.adx)); put(r + 2, r - 4, 0.0, -(im * me.ady));
+            put(r + 3, r - 5, 0.0, -(im * me.bdx)); put(r + 3, r - 4, 0.0, -(im * me.bdy));
+            put(r + 4, r - 5, 0.0, -2 * me.dx); put(r + 4, r - 4, 0.0, -2 * me.dy);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) lu_band_real(s.lur, s.pivr, N);
+    else if (warp == 1) lu_band_cplx(s.lcr, s.lci, s.pivc, N);
+    __syncthreads();
+}
+
+template <int I>
+__device__ __forceinline__ double zstage(const double *W, int N, int c) { return stage_z<I>(W[c], W[N + c], W[2 * N + c]); }
+
+__global__ void __launch_bounds__(K2_BLOCK, 1) k2_kernel(const __grid_constant__ SolveArgs a, const K2Cfg cfg) {
+    extern __shared__ double sm[];
+    __shared__ long long next_idx;
+    const int N = a.n, nn = N / 5, tid = threadIdx.x, nthr = blockDim.x;
+    Rope s;
+    s.N = N; s.nn = nn;
+    double *p = sm;
+    s.y = p; p += N; s.f = p; p += N; s.yold = p; p += N; s.yJ = p; p += N;
+    s.Q = p; p += 3 * N; s.W = p; p += 3 * N; s.R = p; p += 3 * N;
+    s.inv_ns = p; p += N; s.inv_es = p; p += N; s.Yt = p; p += N; s.Ft = p; p += N; s.ze = p; p += N; s.err = p; p += N;
+    s.aa = p; p += nn; s.bb = p; p += nn; s.mass_m = p; p += nn; s.inv_m = p; p += nn; s.r0s = p; p += nn;
+    s.atol = p; p += N; s.red = p; p += 8;
+    s.lur = p; p += (size_t)N * WB;
+    if (cfg.complex_in_smem) { s.lcr = p; p += (size_t)N * WB; s.lci = p; p += (size_t)N * WB; }
+    else { s.lcr = a.scratch + (size_t)blockIdx.x * cfg.scratch_stride; s.lci = s.lcr + (size_t)N * WB; }
+    s.vidx = reinterpret_cast<int *>(p); s.pivr = s.vidx + N; s.pivc = s.pivr + N;
+
+    for (int c = tid; c < N; c += nthr) { s.atol[c] = a.atol_dev[c]; s.vidx[c] = a.var_index_dev[c]; }
+    for (int i = tid; i < nn; i += nthr) {       // recursive_pendulum.py:63-73
+        const double m = (i == nn - 1) ? 1.0 : 1.0 / (nn - 1);
+        const double r0 = 2.0 / nn;
+        s.mass_m[i] = m; s.inv_m[i] = 1 / m; s.r0s[i] = r0 * r0;
+    }
+    __syncthreads();
+
+    const int MAXIT = a.maxit;
+    const double dir = a.dir;
+    double *Z = s.R;   // the stage values Z = T W reuse the residual buffer once Newton is over
+
+    for (;;) {
+        if (tid == 0) next_idx = (long long)atomicAdd(a.work_counter, 1ull);
+        __syncthreads();
+        const long long idx = next_idx;
+        __syncthreads();
+        if (idx >= a.B) break;
+
+        int cnt[CN_COUNT];
+#pragma unroll
+        for (int q = 0; q < CN_COUNT; ++q) cnt[q] = 0;
+        double t = a.t0;
+        for (int c = tid; c < N; c += nthr) { const double v = a.y0[(int64_t)c * a.B + idx]; s.y[c] = v; s.yJ[c] = v; }
+        __syncthreads();
+        rope_rhs(s, s.y, s.f);
+        cnt[CN_NFEV] = 1; cnt[CN_NJEV] = 1;
+        double h_abs_state = a.h0, h_abs_old_state = 0, err_old_state = 0;
+        bool hist_state = false, current_jac = true, lu_valid = false, have_sol = false;
+        double inv_h_sol = 0, t_sol_old = 0, inv_h_lu = 1.0;
+        int status = 1, ei = 0;
+        long long nsteps = 0;
+
+        if (t == a.tb) {
+            for (; ei < a.T; ++ei)
+                for (int c = tid; c < N; c += nthr) a.y_eval[((int64_t)ei * N + c) * a.B + idx] = s.y[c];
+            status = BRDAE_STATUS_FINISHED;
+        }
+
+        while (status == 1) {
+            ++nsteps;
+            if (a.nmax_step > 0 && nsteps > a.nmax_step) { status = BRDAE_STATUS_NMAX_STEP; break; }
+            cnt[CN_NSTEP]++;
+            const double min_step = fmax(1e-20, 10 * fabs(nextafter(t, dir * INFINITY) - t));
+            double h_abs, h_abs_old = h_abs_old_state, err_old = err_old_state;
+            bool hist = hist_state;
+            if (h_abs_state > a.max_step) { h_abs = a.max_step; hist = false; }
+            else if (h_abs_state < min_step) { h_abs = min_step; hist = false; }
+            else h_abs = h_abs_state;
+            if (fabs(a.tb - (t + dir * h_abs)) < 1e-2 * h_abs) { h_abs = fabs(a.tb - t); lu_valid = false; }
+            bool rejected = false, accepted = false, have_rate = false;
+            int n_iter = 0;
+            double rate = 0, h = 0, inv_h = 0, t_new = t, error_norm = 0, safety = 0;
+
+            while (!accepted) {
+                if (h_abs < min_step) { status = BRDAE_STATUS_TOO_SMALL_STEP; break; }
+                h = h_abs * dir;
+                t_new = t + h;
+                if (dir * (t_new - a.tb) > 0) t_new = a.tb;
+                h = t_new - t;
+                h_abs = fabs(h);
+                inv_h = 1.0 / h;
+                for (int c = tid; c < N; c += nthr) {
+                    const int ve = s.vidx[c] > 1 ? s.vidx[c] - 1 : 0;
+                    const double hp = a.scale_newton_norm ? hpow(h, ve) : 1.0;
+                    s.inv_ns[c] = hp / (s.atol[c] + fabs(s.y[c]) * a.rtol);
+                }
+                const double mr = MU_REAL * inv_h, mcr = MU_CR * inv_h, mci = MU_CI * inv_h;
+                bool converged = false;
+                for (;;) {
+                    // starting guess W = TI Z0 (:580-583)
+                    if (!have_sol || !a.extrapolate) {
+                        for (int e = tid; e < 3 * N; e += nthr) s.W[e] = 0.0;
+                    } else {
+                        double x[3], x2[3], x3[3];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const double tt = t + h * stage_c(i);
+                            x[i] = (tt - t_sol_old) * inv_h_sol; x2[i] = x[i] * x[i]; x3[i] = x2[i] * x[i];
+                        }
+                        for (int c = tid; c < N; c += nthr) {
+                            const double q0 = s.Q[3 * c], q1 = s.Q[3 * c + 1], q2 = s.Q[3 * c + 2], yo = s.yold[c];
+                            double z[3];
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                double v = q0 * x[i];
+                                v = fma(q1, x2[i], v);
+                                v = fma(q2, x3[i], v);
+                                v = v + yo;
+                                z[i] = v - s.y[c];
+                            }
+                            s.W[c] = fma(TI02, z[2], fma(TI01, z[1], TI00 * z[0]));
+                            s.W[N + c] = fma(TI12, z[2], fma(TI11, z[1], TI10 * z[0]));
+                            s.W[2 * N + c] = fma(TI22, z[2], fma(TI21, z[1], TI20 * z[0]));
+                        }
+                    }
+                    __syncthreads();
+                    if (!lu_valid) {
+                        if (a.scale_residuals) inv_h_lu = inv_h;
+                        rope_factor(s, a, mr, mcr, mci, inv_h_lu);
+                        cnt[CN_NLU]++;
+                        lu_valid = true;
+                    }
+                    // simplified Newton (:793-949)
+                    double dwn_old = 0;
+                    bool have_old = false;
+                    int nbad = 0, k;
+                    have_rate = false; rate = 0; converged = false;
+                    for (k = 0; k < MAXIT; ++k) {
+                        bool finite = true;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            for (int c = tid; c < N; c += nthr) {
+                                const double z = (i == 0) ? zstage<0>(s.W, N, c) : (i == 1) ? zstage<1>(s.W, N, c) : zstage<2>(s.W, N, c);
+                                s.Yt[c] = s.y[c] + z;
+                            }
+                            __syncthreads();
+                            rope_rhs(s, s.Yt, s.Ft);
+                            const double a0 = (i == 0) ? TI00 : (i == 1) ? TI01 : TI02;
+                            const double a1 = (i == 0) ? TI10 : (i == 1) ? TI11 : TI12;
+                            const double a2 = (i == 0) ? TI20 : (i == 1) ? TI21 : TI22;
+                            for (int c = tid; c < N; c += nthr) {
+                                const double Fv = s.Ft[c];
+                                finite = finite && is_finite(Fv);
+                                if (i == 0) { s.R[c] = a0 * Fv; s.R[N + c] = a1 * Fv; s.R[2 * N + c] = a2 * Fv; }
+                                else { s.R[c] = fma(a0, Fv, s.R[c]); s.R[N + c] = fma(a1, Fv, s.R[N + c]); s.R[2 * N + c] = fma(a2, Fv, s.R[2 * N + c]); }
+                            }
+                            __syncthreads();
+                        }
+                        cnt[CN_NFEV] += 3;
+                        if (!__syncthreads_and(finite)) break;
+                        for (int c = tid; c < N; c += nthr) {
+                            const double hs = (a.scale_residuals && s.vidx[c] >= 1) ? inv_h_lu : 1.0;
+                            double ar = s.R[c], br = s.R[N + c], bi = s.R[2 * N + c];
+                            if (c % 5 != 4) {        // mass diag(1,1,1,1,0): M W = W on these rows
+                                const double w0 = s.W[c], w1 = s.W[N + c], w2 = s.W[2 * N + c];
+                                ar = fma(-mr, w0, ar);
+                                br = fma(-mcr, w1, br); br = fma(mci, w2, br);
+                                bi = fma(-mcr, w2, bi); bi = fma(-mci, w1, bi);
+                            }
+                            s.R[c] = ar * hs; s.R[N + c] = br * hs; s.R[2 * N + c] = bi * hs;
+                        }
+                        __syncthreads();
+                        if ((tid >> 5) == 0) solve_band_real(s.lur, s.pivr, s.R, N);
+                        else if ((tid >> 5) == 1) solve_band_cplx(s.lcr, s.lci, s.pivc, s.R + N, s.R + 2 * N, N);
+                        __syncthreads();
+                        cnt[CN_NSOLVE]++;
+                        sumsq_scaled(s.R, s.inv_ns, N, 3 * N, s.red);
+                        __syncthreads();
+                        const double dwn = sqrt(s.red[0]) * a.rsq3n;
+                        for (int e = tid; e < 3 * N; e += nthr) s.W[e] += s.R[e];
+                        __syncthreads();
+                        double dw_true = 0, dw_true_max = 0;
+                        if (have_old) {
+                            rate = dwn / dwn_old; have_rate = true;
+                            const double inv1 = 1.0 / (1.0 - rate);
+                            dw_true = rate * inv1 * dwn;
+                            double rp = rate;
+                            for (int e = 1; e < MAXIT - k; ++e) rp *= rate;
+                            dw_true_max = rp * inv1 * dwn;
+                        }
+                        if (dwn < a.newton_tol) { converged = true; break; }
+                        if (have_rate) {
+                            if (rate >= 1) {
+                                if (rate < 100 && nbad < a.nmax_bad) { nbad++; continue; }
+                                if (!a.all_newton) break;
+                            }
+                            if (dw_true < a.newton_tol) { converged = true; break; }
+                            if (dw_true_max > a.newton_tol && a.predictive_newton) {
+                                if (nbad < a.nmax_bad) { nbad++; continue; }
+                                if (!a.all_newton) break;
+                            }
+                        }
+                        dwn_old = dwn; have_old = true;
+                    }
+                    n_iter = (k < MAXIT) ? k + 1 : MAXIT;
+                    safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);
+                    if (converged) break;
+                    if (current_jac) break;
+                    for (int c = tid; c < N; c += nthr) s.yJ[c] = s.y[c];     // J = jac(t, y) (:643)
+                    __syncthreads();
+                    cnt[CN_NJEV]++;
+                    current_jac = true; lu_valid = false;
+                }
+                if (!converged) {
+                    cnt[CN_NFAIL]++;
+                    h_abs *= a.nonconv_factor;
+                    lu_valid = false;
+                    continue;
+                }
+                for (int c = tid; c < N; c += nthr) {
+                    const double z0 = zstage<0>(s.W, N, c), z1 = zstage<1>(s.W, N, c), z2 = zstage<2>(s.W, N, c);
+                    Z[c] = z0; Z[N + c] = z1; Z[2 * N + c] = z2;
+                }
+                __syncthreads();
+                if (a.constant_dt) { accepted = true; error_norm = 0; break; }
+                // error estimate (:669-711)
+                for (int c = tid; c < N; c += nthr) {
+                    double v = Z[c] * RE0;
+                    v = fma(Z[N + c], RE1, v);
+                    v = fma(Z[2 * N + c], RE2, v);
+                    const double zev = v * inv_h;
+                    const double ynew = s.y[c] + Z[2 * N + c];
+                    const int ve = s.vidx[c] > 1 ? s.vidx[c] - 1 : 0;
+                    const double hp = a.scale_error ? hpow(h, ve) : 1.0;
+                    s.inv_es[c] = hp / (s.atol[c] + fmax(fabs(s.y[c]), fabs(ynew)) * a.rtol);
+                    s.ze[c] = (c % 5 != 4) ? zev : 0.0;              // M . ZE
+                    s.err[c] = s.f[c] + s.ze[c];
+                }
+                __syncthreads();
+                for (int pass = 0;; ++pass) {
+                    if ((tid >> 5) == 0) solve_band_real(s.lur, s.pivr, s.err, N);   // rhs NOT scaled by hscale
+                    __syncthreads();
+                    cnt[CN_NSOLVE_ERR]++;
+                    if (a.zero_algebraic_error) {
+                        for (int c = tid; c < N; c += nthr) if (s.vidx[c] != 0) s.err[c] = 0.0;
+                        __syncthreads();
+                    }
+                    sumsq_scaled(s.err, s.inv_es, N, N, s.red);
+                    __syncthreads();
+                    error_norm = sqrt(s.red[0]) * (a.zero_algebraic_error ? a.rsq_nondiff : a.rsqn);
+                    __syncthreads();
+                    if (pass == 1 || !(error_norm > 1 && (a.always_2nd || rejected))) break;
+                    for (int c = tid; c < N; c += nthr) s.Yt[c] = s.y[c] + s.err[c];
+                    __syncthreads();
+                    rope_rhs(s, s.Yt, s.Ft);
+                    cnt[CN_NFEV]++;
+                    for (int c = tid; c < N; c += nthr) s.err[c] = s.Ft[c] + s.ze[c];
+                    __syncthreads();
+                }
+                if (error_norm > 1) {
+                    const double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller);
+                    h_abs *= fmax(a.min_factor, safety * factor);
+                    lu_valid = false; rejected = true; cnt[CN_NREJ]++;
+                } else { cnt[CN_NACC]++; accepted = true; }
+            }
+            if (status != 1) break;
+            // epilogue (:742-784)
+            const bool recompute = n_iter > 2 && have_rate && rate > a.jac_recompute;
+            double factor;
+            if (a.constant_dt) factor = a.max_step / h_abs;
+            else factor = fmin(a.max_factor, safety * gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller));
+            if (!recompute && factor < 1.2) factor = 1; else lu_valid = false;
+            for (int c = tid; c < N; c += nthr) {
+                const double yo = s.y[c];
+                s.yold[c] = yo;
+                s.y[c] = yo + Z[2 * N + c];
+                s.Q[3 * c] = fma(Z[2 * N + c], P20, fma(Z[N + c], P10, Z[c] * P00));
+                s.Q[3 * c + 1] = fma(Z[2 * N + c], P21, fma(Z[N + c], P11, Z[c] * P01));
+                s.Q[3 * c + 2] = fma(Z[2 * N + c], P22, fma(Z[N + c], P12, Z[c] * P02));
+            }
+            __syncthreads();
+            rope_rhs(s, s.y, s.f);
+            cnt[CN_NFEV]++;
+            if (recompute) {
+                for (int c = tid; c < N; c += nthr) s.yJ[c] = s.y[c];
+                __syncthreads();
+                cnt[CN_NJEV]++;
+                current_jac = true;
+            } else current_jac = false;
+            h_abs_old_state = h_abs_state; err_old_state = error_norm; hist_state = true;
+            h_abs_state = h_abs * factor;
+            t_sol_old = t; inv_h_sol = inv_h; have_sol = true;
+            t = t_new;
+            if (dir * (t - a.tb) >= 0) status = BRDAE_STATUS_FINISHED;
+            while (ei < a.T) {
+                const double te = a.t_eval[ei];
+                if (!(dir > 0 ? te <= t : te >= t)) break;
+                const double x = (te - t_sol_old) * inv_h_sol;
+                const double x2 = x * x, x3 = x2 * x;
+                for (int c = tid; c < N; c += nthr) {
+                    double v = s.Q[3 * c] * x;
+                    v = fma(s.Q[3 * c + 1], x2, v);
+                    v = fma(s.Q[3 * c + 2], x3, v);
+                    a.y_eval[((int64_t)ei * N + c) * a.B + idx] = v + s.yold[c];
+                }
+                ++ei;
+            }
+        }
+        // retire
+        for (int e = ei; e < a.T; ++e)
+            for (int c = tid; c < N; c += nthr) a.y_eval[((int64_t)e * N + c) * a.B + idx] = NAN;
+        for (int c = tid; c < N; c += nthr) a.y_final[(int64_t)c * a.B + idx] = s.y[c];
+        if (tid == 0) {
+            a.n_eval[idx] = ei; a.t_final[idx] = t; a.status[idx] = status;
+#pragma unroll
+            for (int q = 0; q < CN_COUNT; ++q) a.counters[(int64_t)q * a.B + idx] = cnt[q];
+        }
+        __syncthreads();
+    }
+}
+
+size_t k2_smem_doubles(int N, bool complex_in_smem) {
+    const int nn = N / 5;
+    size_t d = 4 * (size_t)N + 9 * (size_t)N + 6 * (size_t)N + 5 * (size_t)nn + N + 8 + (size_t)N * WB;
+    if (complex_in_smem) d += 2 * (size_t)N * WB;
+    d += (3 * (size_t)N * sizeof(int) + 7) / 8 + 1;
+    return d;
+}
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;
+bool k2_complex_fits(int N) { return k2_smem_doubles(N, true) * 8 <= kSmemBudget; }
+constexpr size_t kHeaderBytes = 256;
+
+}  // namespace
+
+// workspace layout after the 256-byte work counter: atol[N] | var_index[N] (int32, padded) | per-CTA complex LU
+size_t k2_scratch_bytes(int n, int sms) {
+    size_t bytes = sizeof(double) * n + ((sizeof(int32_t) * n + 7) / 8) * 8;
+    if (!k2_complex_fits(n)) bytes += (size_t)(sms > 0 ? sms : 148) * 2 * n * WB * sizeof(double);
+    return bytes;
+}
+
+int k2_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, int sms, cudaStream_t stream, LaunchGeom *g,
+                 bool geom_only) {
+    const int N = a_in.n;
+    if (N <= 0 || N % 5 != 0 || N < 10) return BRDAE_ERR_BAD_ARGUMENT;
+    const bool cfits = k2_complex_fits(N);
+    const size_t smem = k2_smem_doubles(N, cfits) * 8;
+    if (smem > kSmemBudget) return BRDAE_ERR_UNSUPPORTED;          // more than ~170 nodes
+    const int nsm = sms > 0 ? sms : 148;
+    int per_sm = (int)(kSmemBudget / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t grid = (int64_t)nsm * per_sm;
+    if (!cfits) grid = nsm;
+    if (a_in.B < grid) grid = a_in.B > 0 ? a_in.B : 1;
+    if (g) { g->grid = (int)grid; g->block = K2_BLOCK; g->smem = (int)smem; }
+    if (geom_only) return BRDAE_OK;
+    if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;   // band kernel: the problem's own M and J only
+    SolveArgs a = a_in;
+    char *ws = reinterpret_cast<char *>(a.work_counter) + kHeaderBytes;
+    double *atol_d = reinterpret_cast<double *>(ws);
+    int32_t *vidx_d = reinterpret_cast<int32_t *>(ws + sizeof(double) * N);
+    double *scratch = reinterpret_cast<double *>(ws + sizeof(double) * N + ((sizeof(int32_t) * N + 7) / 8) * 8);
+    if (cudaMemcpyAsync(atol_d, b->atol, sizeof(double) * N, cudaMemcpyHostToDevice, stream) != cudaSuccess) return BRDAE_ERR_CUDA;
+    if (b->var_index) {
+        if (cudaMemcpyAsync(vidx_d, b->var_index, sizeof(int32_t) * N, cudaMemcpyHostToDevice, stream) != cudaSuccess) return BRDAE_ERR_CUDA;
+    } else if (cudaMemsetAsync(vidx_d, 0, sizeof(int32_t) * N, stream) != cudaSuccess) return BRDAE_ERR_CUDA;
+    a.atol_dev = atol_d; a.var_index_dev = vidx_d; a.scratch = scratch;
+    K2Cfg cfg;
+    cfg.complex_in_smem = cfits ? 1 : 0;
+    cfg.scratch_stride = (size_t)2 * N * WB;
+    if (cudaFuncSetAttribute(k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BRDAE_ERR_CUDA;
+    k2_kernel<<<(int)grid, K2_BLOCK, smem, stream>>>(a, cfg);
+    return cudaPeekAtLastError() == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;
 }
 
 }  // namespace brdae

@@ -409,6 +409,24 @@ static void mass_mv(int n, const double *M, const int *mlo, const int *mhi, cons
     }
 }
 
+/* sum of squares of v[0..m-1].  Small systems (thread-per-system kernels, n <= 8): one fma chain in
+ * index order.  Large systems (CTA-per-system kernel): 32 interleaved partial chains (entry e goes
+ * to chain e mod 32, in increasing e) folded by the binary tree 16, 8, 4, 2, 1 -- the order a warp
+ * reduction produces. */
+static double sum_squares(const double *v, int m, int lanes32) {
+    if (!lanes32) {
+        double s = 0;
+        for (int e = 0; e < m; ++e) s = fma(v[e], v[e], s);
+        return s;
+    }
+    double p[32];
+    for (int j = 0; j < 32; ++j) p[j] = 0.0;
+    for (int e = 0; e < m; ++e) p[e & 31] = fma(v[e], v[e], p[e & 31]);
+    for (int off = 16; off >= 1; off >>= 1)
+        for (int j = 0; j < off; ++j) p[j] = p[j] + p[j + off];
+    return p[0];
+}
+
 static double hpow(double h, int e) { return e == 0 ? 1.0 : (e == 1 ? h : h * h); }
 
 /* predict_factor, radauDAE.py:52-98 */
@@ -423,7 +441,7 @@ static double gustafsson(double h_abs, double h_abs_old, double err, double err_
 typedef struct {
     int n;
     double *y, *f, *yold, *Q /*[n][3]*/, *W /*[3][n]*/, *Z /*[3][n]*/, *F, *J, *M;
-    double *fr, *fcr, *fci, *mw0, *mw1, *mw2, *inv_ns, *inv_es, *ze, *err, *tmp, *hs;
+    double *fr, *fcr, *fci, *mw0, *mw1, *mw2, *inv_ns, *inv_es, *ze, *err, *tmp, *hs, *sq;
     int *mlo, *mhi;
     lu_pair lu;
 } work;
@@ -439,7 +457,7 @@ static void work_alloc(work *w, int n) {
     w->fr = xcalloc(N, 8); w->fcr = xcalloc(N, 8); w->fci = xcalloc(N, 8);
     w->mw0 = xcalloc(N, 8); w->mw1 = xcalloc(N, 8); w->mw2 = xcalloc(N, 8);
     w->inv_ns = xcalloc(N, 8); w->inv_es = xcalloc(N, 8); w->ze = xcalloc(N, 8);
-    w->err = xcalloc(N, 8); w->tmp = xcalloc(N, 8); w->hs = xcalloc(N, 8);
+    w->err = xcalloc(N, 8); w->tmp = xcalloc(N, 8); w->hs = xcalloc(N, 8); w->sq = xcalloc(3 * N, 8);
     w->mlo = xcalloc(N, sizeof(int)); w->mhi = xcalloc(N, sizeof(int));
     w->lu.n = n;
     w->lu.lr = xcalloc(N * N, 8); w->lu.lcr = xcalloc(N * N, 8); w->lu.lci = xcalloc(N * N, 8);
@@ -449,7 +467,7 @@ static void work_free(work *w) {
     free(w->y); free(w->f); free(w->yold); free(w->Q); free(w->W); free(w->Z); free(w->F);
     free(w->J); free(w->M); free(w->fr); free(w->fcr); free(w->fci); free(w->mw0); free(w->mw1);
     free(w->mw2); free(w->inv_ns); free(w->inv_es); free(w->ze); free(w->err); free(w->tmp);
-    free(w->hs); free(w->mlo); free(w->mhi);
+    free(w->hs); free(w->sq); free(w->mlo); free(w->mhi);
     free(w->lu.lr); free(w->lu.lcr); free(w->lu.lci); free(w->lu.pr); free(w->lu.pc);
 }
 
@@ -634,11 +652,12 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     solve_real(&w->lu, w->fr);
                     solve_cplx(&w->lu, w->fcr, w->fci);
                     cnt[C_NSOLVE]++;
-                    double s = 0;
-                    for (int c = 0; c < n; ++c) { double v = w->fr[c] * w->inv_ns[c]; s = fma(v, v, s); }
-                    for (int c = 0; c < n; ++c) { double v = w->fcr[c] * w->inv_ns[c]; s = fma(v, v, s); }
-                    for (int c = 0; c < n; ++c) { double v = w->fci[c] * w->inv_ns[c]; s = fma(v, v, s); }
-                    double dwn = sqrt(s) * rsq3n;
+                    for (int c = 0; c < n; ++c) {
+                        w->sq[c] = w->fr[c] * w->inv_ns[c];
+                        w->sq[n + c] = w->fcr[c] * w->inv_ns[c];
+                        w->sq[2 * n + c] = w->fci[c] * w->inv_ns[c];
+                    }
+                    double dwn = sqrt(sum_squares(w->sq, 3 * n, n > 8)) * rsq3n;
                     for (int c = 0; c < n; ++c) {
                         w->W[c] += w->fr[c]; w->W[n + c] += w->fcr[c]; w->W[2 * n + c] += w->fci[c];
                     }
@@ -701,12 +720,11 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 }
                 solve_real(&w->lu, w->err);    /* rhs deliberately NOT scaled by hscale */
                 cnt[C_NSOLVE_ERR]++;
-                double s = 0;
                 for (int c = 0; c < n; ++c) {
-                    if (o->zero_algebraic_error && var_index[c] != 0) { w->err[c] = 0.0; continue; }
-                    double v = w->err[c] * w->inv_es[c]; s = fma(v, v, s);
+                    if (o->zero_algebraic_error && var_index[c] != 0) { w->err[c] = 0.0; w->sq[c] = 0.0; continue; }
+                    w->sq[c] = w->err[c] * w->inv_es[c];
                 }
-                error_norm = sqrt(s) * (o->zero_algebraic_error ? rsqdiff : rsqn);
+                error_norm = sqrt(sum_squares(w->sq, n, n > 8)) * (o->zero_algebraic_error ? rsqdiff : rsqn);
                 if (!(error_norm > 1 && (o->always_2nd_estimate || rejected))) break;
             }
             if (error_norm > 1) {                                                   /* :713-733 */

@@ -56,6 +56,28 @@ def test_gpu_bit_identical_to_c_oracle(case, make, over):
     assert_bit_identical(run_gpu(ens, **over), run_c_oracle(ens, **over), case)
 
 
+@pytest.mark.parametrize("nodes,B,over", [
+    (2, 5, {}), (4, 7, {}), (10, 6, {}), (20, 4, {}),
+    (4, 3, dict(nmax_step=30)), (6, 3, dict(rtol=1e-3, atol=1e-3, max_step=np.inf)),
+    (3, 4, dict(zero_algebraic_error=True, bAlwaysApply2ndEstimate=False, bUsePredictiveController=False)),
+    (5, 3, dict(scale_residuals=False, scale_newton_norm=False, scale_error=False, bUseExtrapolatedGuess=False)),
+])
+def test_gpu_npendulum_bit_identical_to_c_oracle(nodes, B, over):
+    """K2 (CTA-per-system, banded LU in shared memory) against the dense scalar oracle."""
+    ens = E.npendulum_ensemble(B, n_nodes=nodes)
+    assert_bit_identical(run_gpu(ens, **over), run_c_oracle(ens, **over), f"npendulum n={nodes}")
+
+
+def test_gpu_npendulum_large_chain_complex_factor_in_global_scratch():
+    ens = E.npendulum_ensemble(2, n_nodes=100, t_end=0.5)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "npendulum n=100")
+
+
+def test_gpu_npendulum_more_ropes_than_ctas():
+    ens = E.npendulum_ensemble(700, n_nodes=4, t_end=0.4)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "npendulum 700 ropes")
+
+
 def test_gpu_constant_jacobian_mode():
     ens = E.pendulum_ensemble(32, t_end=0.3)
     J = np.array([[0, 0, 1., 0, 0], [0, 0, 0, 1., 0], [-5., 0, 0, 0, -0.5], [0, -5., 0, 0, 0.8], [1., -1.6, 0, 0, 0]])
@@ -105,7 +127,7 @@ def test_invalid_y0_raises_like_scipy():
 
 
 # ---------------------------------------------------------------- (2) against the reference fixtures
-@pytest.mark.parametrize("name", [n for n in golden_names() if "npendulum" not in n])
+@pytest.mark.parametrize("name", golden_names())
 def test_gpu_against_reference_fixture(name):
     ens, ref = load_golden(name)
     out = run_gpu(ens)
