@@ -36,6 +36,9 @@ WORKLOADS = {
     "pendulum3_1M_tend10": ("pendulum", dict(t_end=10.0, n_t_eval=21), 1 << 20),
     "robertson_4M": ("robertson", dict(), 1 << 22),
     "transistor_256k": ("transistor", dict(t_end=0.2), 1 << 18),
+    "npendulum_n20_16k": ("npendulum", dict(n_nodes=20), 1 << 14),
+    "npendulum_n50_16k": ("npendulum", dict(n_nodes=50), 1 << 14),
+    "npendulum_n100_16k": ("npendulum", dict(n_nodes=100), 1 << 14),
 }
 
 
@@ -110,6 +113,8 @@ def _cpu_worker(args):
                 fun, jac, mass, vi = prob.robertson(*params[i])
             elif problem == "transistor":
                 fun, jac, mass, vi = prob.transistor(*params[i])
+            elif problem == "npendulum":
+                fun, jac, mass, vi = prob.npendulum(y0s.shape[1] // 5)
             else:
                 raise ValueError(problem)
             r = orc.solve(fun, t_span, y0s[i], jac=jac, mass_matrix=mass,
@@ -124,7 +129,7 @@ def cpu_reference_rate(ens, n_systems, cores):
     cores, on the first `n_systems` systems of the ensemble."""
     import multiprocessing as mp
     y0 = ens["y0"][:n_systems]
-    params = ens["params"][:n_systems]
+    params = ens["params"][:n_systems] if ens["params"] is not None else np.zeros((n_systems, 0))
     chunks = [c for c in np.array_split(np.arange(n_systems), cores) if c.size]
     jobs = [(ens["problem"], y0[c], params[c], ens["t_span"], ens["t_eval"], ens["options"]) for c in chunks]
     ctx = mp.get_context("fork")
@@ -202,14 +207,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # weak scaling: every rank owns its own B-system ensemble (seed offset by rank)
-    seed = {"pendulum": 0, "robertson": 1, "transistor": 2}[gen_key] + 1000 * rank
+    seed = {"pendulum": 0, "robertson": 1, "transistor": 2, "npendulum": 3}[gen_key] + 1000 * rank
     ens = br.ensembles.ENSEMBLES[gen_key](B, seed=seed, **gen_kw)
     prob = br.get_problem(ens["problem"])
     n, T, npar = ens["y0"].shape[1], len(ens["t_eval"]), prob.n_params
 
     # inputs resident in HBM before the timed region
     y0_d = torch.as_tensor(ens["y0"]).to(dev)
-    par_d = torch.as_tensor(ens["params"]).to(dev)
+    par_d = torch.as_tensor(ens["params"]).to(dev) if ens["params"] is not None else None
     stream = torch.cuda.current_stream(dev)
 
     def one_pass():
@@ -266,7 +271,7 @@ def main():
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                 "peak_source": "measured in this run: dependent-chain DFMA probe (brdae_fp64_peak_probe)",
-                "kernel": "k1_kernel<Pendulum<3>,MassDiag01>" if gen_key == "pendulum" else f"k1_kernel<{gen_key}>",
+                "kernel": {"pendulum": "k1_kernel<Pendulum<3>,MassDiag01>", "npendulum": "k2_kernel"}.get(gen_key, f"k1_kernel<{gen_key}>"),
                 "kernel_ms": kms, "flops_per_launch": fl, "flops_per_trajectory": fl / B,
                 "hbm": {"algorithmic_bytes": abytes, "achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak,
                         "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src}}
@@ -277,7 +282,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         y0_h = torch.as_tensor(ens["y0"]).pin_memory().numpy()
-        par_h = torch.as_tensor(ens["params"]).pin_memory().numpy()
+        par_h = torch.as_tensor(ens["params"]).pin_memory().numpy() if ens["params"] is not None else None
         for _ in range(2):
             br.solve_ivp_batched_host(ens["problem"], ens["t_span"], y0_h, par_h, t_eval=ens["t_eval"], **ens["options"])
         barrier()
