@@ -64,20 +64,23 @@ BRDAE_CX bool mass_row_empty(int r) {
 template <int INDEX>
 struct Pendulum {
     static constexpr int N = 5, NP = 3;
-    struct P { double m, g, r0; };
+    // im = 1/m and r0s = r0*r0 are formed once per system (the contract multiplies by 1/m where the
+    // reference divides by m; identical for the reference's m = 1)
+    struct P { double im, g, r0s; };
     using Mass = MassDiag01<5, 0x0Fu>;  // pendulum.py:139-140
     static BRDAE_HD void load(P &p, const double *params, int64_t B, int64_t i) {
-        p.m = params[i]; p.g = params[B + i]; p.r0 = params[2 * B + i];
+        const double r0 = params[2 * B + i];
+        p.im = 1.0 / params[i]; p.g = params[B + i]; p.r0s = r0 * r0;
     }
     static BRDAE_HD void rhs(const P &p, double, const double (&X)[5], double (&f)[5]) {
         const double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
         f[0] = vx;
         f[1] = vy;
-        f[2] = -x * l / p.m;
-        f[3] = -p.g - (y * l) / p.m;
-        if (INDEX == 3) f[4] = x * x + y * y - p.r0 * p.r0;
+        f[2] = -x * l * p.im;
+        f[3] = -p.g - (y * l) * p.im;
+        if (INDEX == 3) f[4] = x * x + y * y - p.r0s;
         else if (INDEX == 2) f[4] = x * vx + y * vy;
-        else f[4] = l * (x * x + y * y) / p.m + p.g * y - (vx * vx + vy * vy);
+        else f[4] = l * (x * x + y * y) * p.im + p.g * y - (vx * vx + vy * vy);
     }
     static BRDAE_HD void jac(const P &p, double, const double (&X)[5], double (&J)[5][5]) {
         const double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
@@ -87,13 +90,13 @@ struct Pendulum {
             for (int c = 0; c < 5; ++c) J[r][c] = 0.0;
         J[0][2] = 1.0;
         J[1][3] = 1.0;
-        J[2][0] = -l / p.m; J[2][4] = -x / p.m;
-        J[3][1] = -l / p.m; J[3][4] = -y / p.m;
+        J[2][0] = -l * p.im; J[2][4] = -x * p.im;
+        J[3][1] = -l * p.im; J[3][4] = -y * p.im;
         if (INDEX == 3) { J[4][0] = 2 * x; J[4][1] = 2 * y; }
         else if (INDEX == 2) { J[4][0] = vx; J[4][1] = vy; J[4][2] = x; J[4][3] = y; }
         else {
-            J[4][0] = 2 * x * l / p.m; J[4][1] = 2 * y * l / p.m + p.g; J[4][2] = -2 * vx;
-            J[4][3] = -2 * vy; J[4][4] = (x * x + y * y) / p.m;
+            J[4][0] = 2 * x * l * p.im; J[4][1] = 2 * y * l * p.im + p.g; J[4][2] = -2 * vx;
+            J[4][3] = -2 * vy; J[4][4] = (x * x + y * y) * p.im;
         }
     }
 };
@@ -121,7 +124,9 @@ struct Robertson {
 // ---------------------------------------------------------------- transistor amplifier
 struct Transistor {
     static constexpr int N = 5, NP = 12;
-    struct P { double C1, C2, C3, R0, R1, R2, R3, R4, R5, Ub, Ua, w; };
+    // conductances and the constant source terms are formed once per system (the contract multiplies
+    // by 1/R where the reference divides by R)
+    struct P { double C1, C2, C3, g0, g12, g3, g4, g5, ub2, ub4, Ua, w; };
     // M = [[C1,-C1,0,0,0],[-C1,C1,0,0,0],[0,0,C2,0,0],[0,0,0,C3,-C3],[0,0,0,-C3,C3]]
     struct Mass {
         static constexpr int N = 5;
@@ -135,30 +140,33 @@ struct Transistor {
         }
     };
     static BRDAE_HD void load(P &p, const double *q, int64_t B, int64_t i) {
-        p.C1 = q[i]; p.C2 = q[B + i]; p.C3 = q[2 * B + i]; p.R0 = q[3 * B + i]; p.R1 = q[4 * B + i];
-        p.R2 = q[5 * B + i]; p.R3 = q[6 * B + i]; p.R4 = q[7 * B + i]; p.R5 = q[8 * B + i];
-        p.Ub = q[9 * B + i]; p.Ua = q[10 * B + i]; p.w = q[11 * B + i];
+        p.C1 = q[i]; p.C2 = q[B + i]; p.C3 = q[2 * B + i];
+        const double R0 = q[3 * B + i], R1 = q[4 * B + i], R2 = q[5 * B + i], R3 = q[6 * B + i], R4 = q[7 * B + i];
+        const double R5 = q[8 * B + i], Ub = q[9 * B + i];
+        p.g0 = 1 / R0; p.g12 = 1 / R1 + 1 / R2; p.g3 = 1 / R3; p.g4 = 1 / R4; p.g5 = 1 / R5;
+        p.ub2 = Ub / R2; p.ub4 = Ub / R4;
+        p.Ua = q[10 * B + i]; p.w = q[11 * B + i];
     }
     static BRDAE_HD void rhs(const P &p, double t, const double (&y)[5], double (&f)[5]) {
         const double Ue = p.Ua * sin(p.w * t);
-        const double fT = 1e-6 * (exp((y[1] - y[2]) / 0.026) - 1);
-        f[0] = (Ue - y[0]) / p.R0;
-        f[1] = p.Ub / p.R2 - y[1] * (1 / p.R1 + 1 / p.R2) - 0.01 * fT;
-        f[2] = fT - y[2] / p.R3;
-        f[3] = p.Ub / p.R4 - y[3] / p.R4 - 0.99 * fT;
-        f[4] = -y[4] / p.R5;
+        const double fT = 1e-6 * (exp((y[1] - y[2]) * (1 / 0.026)) - 1);
+        f[0] = (Ue - y[0]) * p.g0;
+        f[1] = p.ub2 - y[1] * p.g12 - 0.01 * fT;
+        f[2] = fT - y[2] * p.g3;
+        f[3] = p.ub4 - y[3] * p.g4 - 0.99 * fT;
+        f[4] = -y[4] * p.g5;
     }
     static BRDAE_HD void jac(const P &p, double, const double (&y)[5], double (&J)[5][5]) {
-        const double df = 1e-6 * exp((y[1] - y[2]) / 0.026) / 0.026;
+        const double df = 1e-6 * exp((y[1] - y[2]) * (1 / 0.026)) * (1 / 0.026);
 #pragma unroll
         for (int r = 0; r < 5; ++r)
 #pragma unroll
             for (int c = 0; c < 5; ++c) J[r][c] = 0.0;
-        J[0][0] = -1 / p.R0;
-        J[1][1] = -(1 / p.R1 + 1 / p.R2) - 0.01 * df; J[1][2] = 0.01 * df;
-        J[2][1] = df; J[2][2] = -df - 1 / p.R3;
-        J[3][1] = -0.99 * df; J[3][2] = 0.99 * df; J[3][3] = -1 / p.R4;
-        J[4][4] = -1 / p.R5;
+        J[0][0] = -p.g0;
+        J[1][1] = -p.g12 - 0.01 * df; J[1][2] = 0.01 * df;
+        J[2][1] = df; J[2][2] = -df - p.g3;
+        J[3][1] = -0.99 * df; J[3][2] = 0.99 * df; J[3][3] = -p.g4;
+        J[4][4] = -p.g5;
     }
 };
 

@@ -44,72 +44,87 @@ struct Slots {
 };
 
 // ---- LU of the spec, left-looking, one column at a time ------------------------------------
-// Same arithmetic as a right-looking elimination with partial pivoting on |a| (first maximum)
-// where only the active columns are exchanged and the reciprocal pivot is stored on the
-// diagonal: element (r,k) receives its updates -l(r,j) u(j,k), j = 0,1,.. in the same order.
-// `column(k, col)` fills col[r] = A[r][k]; finished columns are read back from shared memory.
-// Returns the pivot rows packed 3 bits each.
+// Same arithmetic as a right-looking elimination with partial pivoting on |a| (first maximum) and
+// reciprocal pivots: element (row, k) receives its updates -l(row,j) u(j,k), j = 0,1,.. in the same
+// order.  Bookkeeping is LAPACK's: rows are kept in CURRENT (pivoted) order, the multipliers move
+// with their rows, and the row permutation is a packed 3-bit table.  A permuted access is a
+// dynamically addressed shared-memory load -- free there, while a dynamic REGISTER index would cost
+// a chain of selects per element (the first version spent more instructions on selects than on
+// FP64 math).  `column(k, col)` fills col[r] = A[r][k] in original row order; it is parked in the
+// still-unused column k of the factor storage and read back in current row order.
+BRDAE_HD unsigned perm_identity(int n) {
+    unsigned p = 0;
+    for (int i = 0; i < n; ++i) p |= (unsigned)i << (3 * i);
+    return p;
+}
+BRDAE_HD unsigned perm_swap(unsigned perm, int k, int p) {
+    const unsigned fk = (perm >> (3 * k)) & 7u, fp = (perm >> (3 * p)) & 7u;
+    perm &= ~((7u << (3 * k)) | (7u << (3 * p)));
+    return perm | (fp << (3 * k)) | (fk << (3 * p));     // k == p: unchanged
+}
 template <int N, class S, class ColFn>
 BRDAE_HD unsigned lu_real_left(const S &sm, int base, ColFn &&column) {
-    unsigned piv = 0;
+    unsigned perm = perm_identity(N);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        double col[N];
-        column(k, col);
+        double cur[N];
+        {
+            double col[N];
+            column(k, col);
+#pragma unroll
+            for (int r = 0; r < N; ++r) sm(base + r * N + k) = col[r];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) cur[i] = sm(base + (int)((perm >> (3 * i)) & 7u) * N + k);
 #pragma unroll
         for (int j = 0; j < k; ++j) {
-            const int pj = (piv >> (3 * j)) & 7;
+            const double cj = cur[j];
 #pragma unroll
-            for (int r = j + 1; r < N; ++r) {  // branch-free exchange keeps the column in registers
-                const bool sw = (pj == r);
-                const double u = col[j], v = col[r];
-                col[j] = sw ? v : u; col[r] = sw ? u : v;
-            }
-            const double cj = col[j];
-#pragma unroll
-            for (int r = j + 1; r < N; ++r) col[r] = fma(-sm(base + r * N + j), cj, col[r]);
+            for (int r = j + 1; r < N; ++r) cur[r] = fma(-sm(base + r * N + j), cj, cur[r]);
         }
         int p = k;
-        double best = fabs(col[k]);
+        double best = fabs(cur[k]), pv = cur[k];
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
-            const double v = fabs(col[r]);
-            if (v > best) { best = v; p = r; }
+            const double v = fabs(cur[r]);
+            const bool g = v > best;
+            best = g ? v : best; p = g ? r : p; pv = g ? cur[r] : pv;
         }
-        piv |= (unsigned)p << (3 * k);
+        const double rcp = 1.0 / pv;
 #pragma unroll
-        for (int r = k + 1; r < N; ++r) {
-            const bool sw = (p == r);
-            const double u = col[k], v = col[r];
-            col[k] = sw ? v : u; col[r] = sw ? u : v;
+        for (int i = 0; i < N; ++i) sm(base + i * N + k) = (i < k) ? cur[i] : cur[i] * rcp;
+        if (k < N - 1) {     // exchange rows k and p of the finished columns and of this one
+#pragma unroll
+            for (int j = 0; j <= k; ++j) {
+                const double u = sm(base + k * N + j), v = sm(base + p * N + j);
+                sm(base + k * N + j) = v; sm(base + p * N + j) = u;
+            }
+            perm = perm_swap(perm, k, p);
         }
-        const double rcp = 1.0 / col[k];
-        col[k] = rcp;
-#pragma unroll
-        for (int r = k + 1; r < N; ++r) col[r] = col[r] * rcp;
-#pragma unroll
-        for (int r = 0; r < N; ++r) sm(base + r * N + k) = col[r];
+        sm(base + k * N + k) = rcp;
     }
-    return piv;
+    return perm;
 }
 // complex: pivot on |re|+|im| (BLAS izamax), reciprocal pivot conj(p)/|p|^2
 template <int N, class S, class ColFn>
 BRDAE_HD unsigned lu_cplx_left(const S &sm, int base_r, int base_i, ColFn &&column) {
-    unsigned piv = 0;
+    unsigned perm = perm_identity(N);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         double cr[N], ci[N];
-        column(k, cr, ci);
+        {
+            double colr[N], coli[N];
+            column(k, colr, coli);
+#pragma unroll
+            for (int r = 0; r < N; ++r) { sm(base_r + r * N + k) = colr[r]; sm(base_i + r * N + k) = coli[r]; }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int src = (int)((perm >> (3 * i)) & 7u) * N + k;
+            cr[i] = sm(base_r + src); ci[i] = sm(base_i + src);
+        }
 #pragma unroll
         for (int j = 0; j < k; ++j) {
-            const int pj = (piv >> (3 * j)) & 7;
-#pragma unroll
-            for (int r = j + 1; r < N; ++r) {
-                const bool sw = (pj == r);
-                const double u = cr[j], v = cr[r], ui = ci[j], vi = ci[r];
-                cr[j] = sw ? v : u; cr[r] = sw ? u : v;
-                ci[j] = sw ? vi : ui; ci[r] = sw ? ui : vi;
-            }
             const double ur = cr[j], ui = ci[j];
 #pragma unroll
             for (int r = j + 1; r < N; ++r) {
@@ -121,48 +136,48 @@ BRDAE_HD unsigned lu_cplx_left(const S &sm, int base_r, int base_i, ColFn &&colu
             }
         }
         int p = k;
-        double best = fabs(cr[k]) + fabs(ci[k]);
+        double best = fabs(cr[k]) + fabs(ci[k]), pr = cr[k], pi = ci[k];
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
             const double v = fabs(cr[r]) + fabs(ci[r]);
-            if (v > best) { best = v; p = r; }
+            const bool g = v > best;
+            best = g ? v : best; p = g ? r : p; pr = g ? cr[r] : pr; pi = g ? ci[r] : pi;
         }
-        piv |= (unsigned)p << (3 * k);
-#pragma unroll
-        for (int r = k + 1; r < N; ++r) {
-            const bool sw = (p == r);
-            const double u = cr[k], v = cr[r], ui = ci[k], vi = ci[r];
-            cr[k] = sw ? v : u; cr[r] = sw ? u : v;
-            ci[k] = sw ? vi : ui; ci[r] = sw ? ui : vi;
-        }
-        const double pr = cr[k], pi = ci[k];
         const double invd = 1.0 / fma(pr, pr, pi * pi);
         const double qr = pr * invd, qi = -(pi * invd);
-        cr[k] = qr; ci[k] = qi;
 #pragma unroll
-        for (int r = k + 1; r < N; ++r) {
-            const double ar = cr[r], ai = ci[r];
-            cr[r] = fma(ar, qr, -(ai * qi));
-            ci[r] = fma(ar, qi, ai * qr);
+        for (int i = 0; i < N; ++i) {
+            if (i < k) { sm(base_r + i * N + k) = cr[i]; sm(base_i + i * N + k) = ci[i]; }
+            else {
+                sm(base_r + i * N + k) = fma(cr[i], qr, -(ci[i] * qi));
+                sm(base_i + i * N + k) = fma(cr[i], qi, ci[i] * qr);
+            }
         }
+        if (k < N - 1) {
 #pragma unroll
-        for (int r = 0; r < N; ++r) { sm(base_r + r * N + k) = cr[r]; sm(base_i + r * N + k) = ci[r]; }
+            for (int j = 0; j <= k; ++j) {
+                const double u = sm(base_r + k * N + j), v = sm(base_r + p * N + j);
+                sm(base_r + k * N + j) = v; sm(base_r + p * N + j) = u;
+                const double ui = sm(base_i + k * N + j), vi = sm(base_i + p * N + j);
+                sm(base_i + k * N + j) = vi; sm(base_i + p * N + j) = ui;
+            }
+            perm = perm_swap(perm, k, p);
+        }
+        sm(base_r + k * N + k) = qr; sm(base_i + k * N + k) = qi;
     }
-    return piv;
+    return perm;
 }
 
 // ---- triangular solves streaming the factors from lane-strided shared memory ----------------
+// b is put into pivoted order by a round trip through N scratch slots (dynamic load address).
 template <int N, class S>
-BRDAE_HD void solve_real_sm(const S &sm, int base, unsigned piv, double (&b)[N]) {
+BRDAE_HD void solve_real_sm(const S &sm, int base, int scratch, unsigned perm, double (&b)[N]) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) sm(scratch + c) = b[c];
+#pragma unroll
+    for (int i = 0; i < N; ++i) b[i] = sm(scratch + (int)((perm >> (3 * i)) & 7u));
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const int p = (piv >> (3 * k)) & 7;
-#pragma unroll
-        for (int r = k + 1; r < N; ++r) {
-            const bool sw = (p == r);
-            const double u = b[k], v = b[r];
-            b[k] = sw ? v : u; b[r] = sw ? u : v;
-        }
         const double bk = b[k];
 #pragma unroll
         for (int r = k + 1; r < N; ++r) b[r] = fma(-sm(base + r * N + k), bk, b[r]);
@@ -177,17 +192,17 @@ BRDAE_HD void solve_real_sm(const S &sm, int base, unsigned piv, double (&b)[N])
     }
 }
 template <int N, class S>
-BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, unsigned piv, double (&br)[N], double (&bi)[N]) {
+BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, unsigned perm, double (&br)[N], double (&bi)[N]) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) sm(scratch + c) = br[c];
+#pragma unroll
+    for (int i = 0; i < N; ++i) br[i] = sm(scratch + (int)((perm >> (3 * i)) & 7u));
+#pragma unroll
+    for (int c = 0; c < N; ++c) sm(scratch + c) = bi[c];
+#pragma unroll
+    for (int i = 0; i < N; ++i) bi[i] = sm(scratch + (int)((perm >> (3 * i)) & 7u));
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const int p = (piv >> (3 * k)) & 7;
-#pragma unroll
-        for (int r = k + 1; r < N; ++r) {
-            const bool sw = (p == r);
-            const double u = br[k], v = br[r], ui = bi[k], vi = bi[r];
-            br[k] = sw ? v : u; br[r] = sw ? u : v;
-            bi[k] = sw ? vi : ui; bi[r] = sw ? ui : vi;
-        }
         const double xr = br[k], xi = bi[k];
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
@@ -227,7 +242,8 @@ struct K1Layout {
     static constexpr int S_Q = S_YOLD + N;
     static constexpr int S_YJ = S_Q + 3 * N;
     static constexpr int S_TJ = S_YJ + N;
-    static constexpr int SLOTS = S_TJ + 1;
+    static constexpr int S_B = S_TJ + 1;          // N scratch slots: right-hand sides on their way into pivoted order
+    static constexpr int SLOTS = S_B + N;
 };
 
 // warp-level helpers; the host build (tests/host_sim) runs a "warp" of one lane
@@ -450,8 +466,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                         }
                         fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
                     }
-                    solve_real_sm<N>(sm, L::S_LUR, piv_r, fr);
-                    solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, piv_c, fcr, fci);
+                    solve_real_sm<N>(sm, L::S_LUR, L::S_B, piv_r, fr);
+                    solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
                     cnt[CN_NSOLVE]++;
                     double s = 0.0;
 #pragma unroll
@@ -541,7 +557,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
 #pragma unroll
                     for (int c = 0; c < N; ++c) err[c] = sm(L::S_F + c) + mze[c];
                     for (int pass = 0;; ++pass) {
-                        solve_real_sm<N>(sm, L::S_LUR, piv_r, err);   // rhs NOT scaled by hscale
+                        solve_real_sm<N>(sm, L::S_LUR, L::S_B, piv_r, err);   // rhs NOT scaled by hscale
                         cnt[CN_NSOLVE_ERR]++;
                         double s = 0.0;
 #pragma unroll

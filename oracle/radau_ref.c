@@ -81,30 +81,31 @@ typedef struct {
 /* pendulum.py:130-148 (index 3), :151-166 (index 2), :169-184 (index 1); p = (m, g, r0) */
 static void pend_rhs(const prob_ctx *c, double t, const double *X, double *f) {
     (void)t;
-    double m = c->p[0], g = c->p[1], r0 = c->p[2];
+    /* contract: multiply by im = 1/m where the reference divides by m (identical for m = 1) */
+    double im = 1.0 / c->p[0], g = c->p[1], r0 = c->p[2];
     double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
     f[0] = vx;
     f[1] = vy;
-    f[2] = -x * l / m;
-    f[3] = -g - (y * l) / m;
+    f[2] = -x * l * im;
+    f[3] = -g - (y * l) * im;
     if (c->problem == PB_PENDULUM3) f[4] = x * x + y * y - r0 * r0;
     else if (c->problem == PB_PENDULUM2) f[4] = x * vx + y * vy;
-    else f[4] = l * (x * x + y * y) / m + g * y - (vx * vx + vy * vy);
+    else f[4] = l * (x * x + y * y) * im + g * y - (vx * vx + vy * vy);
 }
 static void pend_jac(const prob_ctx *c, double t, const double *X, double *J) {
     (void)t;
-    double m = c->p[0], g = c->p[1];
+    double im = 1.0 / c->p[0], g = c->p[1];
     double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
     memset(J, 0, 25 * sizeof(double));
     J[0 * 5 + 2] = 1.0;
     J[1 * 5 + 3] = 1.0;
-    J[2 * 5 + 0] = -l / m; J[2 * 5 + 4] = -x / m;
-    J[3 * 5 + 1] = -l / m; J[3 * 5 + 4] = -y / m;
+    J[2 * 5 + 0] = -l * im; J[2 * 5 + 4] = -x * im;
+    J[3 * 5 + 1] = -l * im; J[3 * 5 + 4] = -y * im;
     if (c->problem == PB_PENDULUM3) { J[4 * 5 + 0] = 2 * x; J[4 * 5 + 1] = 2 * y; }
     else if (c->problem == PB_PENDULUM2) { J[20] = vx; J[21] = vy; J[22] = x; J[23] = y; }
     else {
-        J[20] = 2 * x * l / m; J[21] = 2 * y * l / m + g; J[22] = -2 * vx; J[23] = -2 * vy;
-        J[24] = (x * x + y * y) / m;
+        J[20] = 2 * x * l * im; J[21] = 2 * y * l * im + g; J[22] = -2 * vx; J[23] = -2 * vy;
+        J[24] = (x * x + y * y) * im;
     }
 }
 /* robertson.py:80-87; p = (k1,k2,k3) */
@@ -125,26 +126,29 @@ static void rob_jac(const prob_ctx *c, double t, const double *y, double *J) {
 /* transistor_amplifier.py:33-56; p = (C1,C2,C3,R0,R1,R2,R3,R4,R5,Ub,Ua,w) */
 static void tra_rhs(const prob_ctx *c, double t, const double *y, double *f) {
     const double *p = c->p;
+    /* contract: conductances 1/R formed once; multiply where the reference divides */
     double R0 = p[3], R1 = p[4], R2 = p[5], R3 = p[6], R4 = p[7], R5 = p[8], Ub = p[9];
+    double g0 = 1 / R0, g12 = 1 / R1 + 1 / R2, g3 = 1 / R3, g4 = 1 / R4, g5 = 1 / R5, ub2 = Ub / R2, ub4 = Ub / R4;
     double Ue = p[10] * sin(p[11] * t);
-    double fT = 1e-6 * (exp((y[1] - y[2]) / 0.026) - 1);
-    f[0] = (Ue - y[0]) / R0;
-    f[1] = Ub / R2 - y[1] * (1 / R1 + 1 / R2) - 0.01 * fT;
-    f[2] = fT - y[2] / R3;
-    f[3] = Ub / R4 - y[3] / R4 - 0.99 * fT;
-    f[4] = -y[4] / R5;
+    double fT = 1e-6 * (exp((y[1] - y[2]) * (1 / 0.026)) - 1);
+    f[0] = (Ue - y[0]) * g0;
+    f[1] = ub2 - y[1] * g12 - 0.01 * fT;
+    f[2] = fT - y[2] * g3;
+    f[3] = ub4 - y[3] * g4 - 0.99 * fT;
+    f[4] = -y[4] * g5;
 }
 static void tra_jac(const prob_ctx *c, double t, const double *y, double *J) {
     (void)t;
     const double *p = c->p;
     double R0 = p[3], R1 = p[4], R2 = p[5], R3 = p[6], R4 = p[7], R5 = p[8];
-    double df = 1e-6 * exp((y[1] - y[2]) / 0.026) / 0.026;
+    double g0 = 1 / R0, g12 = 1 / R1 + 1 / R2, g3 = 1 / R3, g4 = 1 / R4, g5 = 1 / R5;
+    double df = 1e-6 * exp((y[1] - y[2]) * (1 / 0.026)) * (1 / 0.026);
     memset(J, 0, 25 * sizeof(double));
-    J[0] = -1 / R0;
-    J[6] = -(1 / R1 + 1 / R2) - 0.01 * df; J[7] = 0.01 * df;
-    J[11] = df; J[12] = -df - 1 / R3;
-    J[16] = -0.99 * df; J[17] = 0.99 * df; J[18] = -1 / R4;
-    J[24] = -1 / R5;
+    J[0] = -g0;
+    J[6] = -g12 - 0.01 * df; J[7] = 0.01 * df;
+    J[11] = df; J[12] = -df - g3;
+    J[16] = -0.99 * df; J[17] = 0.99 * df; J[18] = -g4;
+    J[24] = -g5;
 }
 static void tra_mass(const double *p, double *M) {
     double C1 = p[0], C2 = p[1], C3 = p[2];
@@ -481,6 +485,13 @@ static void stage_Z(int n, const double *W, int i, double *z) {
     }
 }
 
+/* Optional event trace of ONE system (single-threaded use only): 'F' factorisation pair, 'N' Newton
+ * iteration, 'E' error estimate + accept/reject, one char per event.  Used by the scheduling
+ * study in profiles/tools/sched_sim.py. */
+static char *g_trace = NULL;
+static int g_trace_cap = 0, g_trace_len = 0;
+static void trace_ev(char c) { if (g_trace && g_trace_len < g_trace_cap) g_trace[g_trace_len++] = c; }
+
 /* Integrate one system.  Layout of the batch arrays is SoA: element (row, sys) at row*B+sys. */
 static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, const double *mass_in,
                           const double *jac_const, const int *var_index, const double *atol,
@@ -612,6 +623,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     lu_real(&w->lu);
                     lu_cplx(&w->lu);
                     cnt[C_NLU]++;
+                    trace_ev('F');
                     lu_valid = 1;
                 }
                 /* ------------- simplified Newton, :793-949 */
@@ -639,6 +651,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                         }
                     }
                     cnt[C_NFEV] += 3;
+                    trace_ev('N');
                     if (!finite) break;
                     mass_mv(n, w->M, w->mlo, w->mhi, w->W, w->mw0);
                     mass_mv(n, w->M, w->mlo, w->mhi, w->W + n, w->mw1);
@@ -698,6 +711,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 continue;
             }
             for (int i = 0; i < 3; ++i) stage_Z(n, w->W, i, w->Z + i * n);
+            trace_ev('E');
             if (o->constant_dt) { accepted = 1; error_norm = 0; break; }
             /* ------------- error estimate, :669-711 */
             for (int c = 0; c < n; ++c) {
@@ -775,6 +789,24 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
     for (int c = 0; c < n; ++c) y_final[(int64_t)c * B + sys] = w->y[c];
     status_out[sys] = status;
     for (int k = 0; k < C_COUNT; ++k) counters[(int64_t)k * B + sys] = cnt[k];
+}
+
+/* Event trace of system `sys` of a batch (see trace_ev); returns the number of events. */
+int orc_solve(int problem, int n, int n_params, int64_t B, const double *y0, const double *params,
+              const double *mass, const double *jac_const, const int32_t *var_index,
+              const double *atol, double rtol, double t0, double t_bound, const double *t_eval,
+              int T, const orc_options *opts, double *y_eval, int32_t *n_eval, double *t_final,
+              double *y_final, int32_t *status, int32_t *counters, int nthreads);
+int orc_trace(int problem, int n, int n_params, const double *y0, const double *params, const int32_t *var_index,
+              const double *atol, double rtol, double t0, double t_bound, const orc_options *opts, char *buf, int cap) {
+    double *ye = NULL, tf, *yf = malloc(sizeof(double) * n);
+    int32_t ne, st, cn[C_COUNT];
+    g_trace = buf; g_trace_cap = cap; g_trace_len = 0;
+    orc_solve(problem, n, n_params, 1, y0, params, NULL, NULL, var_index, atol, rtol, t0, t_bound, NULL, 0, opts, ye, &ne,
+              &tf, yf, &st, cn, 1);
+    g_trace = NULL;
+    free(yf);
+    return g_trace_len;
 }
 
 /* Batch entry.  All pointers are host pointers; SoA layouts as in include/brdae.h.

@@ -46,14 +46,20 @@ def test_c_oracle_matches_numpy_oracle_on_a_fresh_ensemble():
 def test_c_oracle_rhs_and_jacobian_equal_numpy_restatement():
     from oracle import c_oracle, problems_numpy as prob
     rng = np.random.default_rng(3)
-    for name, builder, p in (("pendulum3", prob.pendulum(3, 1.3, 9.81, 0.9), [1.3, 9.81, 0.9]),
-                             ("pendulum2", prob.pendulum(2, 1.3, 9.81, 0.9), [1.3, 9.81, 0.9]),
-                             ("pendulum1", prob.pendulum(1, 1.3, 9.81, 0.9), [1.3, 9.81, 0.9]),
+    # the reference's m = 1 (and any power of two): same bits; other masses: the contract multiplies by 1/m
+    for name, builder, p in (("pendulum3", prob.pendulum(3, 1.0, 9.81, 0.9), [1.0, 9.81, 0.9]),
+                             ("pendulum2", prob.pendulum(2, 2.0, 9.81, 0.9), [2.0, 9.81, 0.9]),
+                             ("pendulum1", prob.pendulum(1, 1.0, 9.81, 0.9), [1.0, 9.81, 0.9]),
                              ("robertson", prob.robertson(0.05, 2e4, 1e7), [0.05, 2e4, 1e7])):
         f, j = builder[0], builder[1]
         y = rng.standard_normal(5 if name.startswith("pend") else 3)
         fc, Jc = c_oracle.eval_rhs_jac(name, p, 0.2, y)
         assert np.array_equal(fc, f(0.2, y)) and np.array_equal(Jc, j(0.2, y))
+    for idx in (3, 2, 1):
+        f, j, _, _ = prob.pendulum(idx, 1.3, 9.81, 0.9)
+        y = rng.standard_normal(5)
+        fc, Jc = c_oracle.eval_rhs_jac(f"pendulum{idx}", [1.3, 9.81, 0.9], 0.2, y)
+        assert np.allclose(fc, f(0.2, y), rtol=4e-16, atol=0) and np.allclose(Jc, j(0.2, y), rtol=4e-16, atol=0)
     d = prob.TRANSISTOR_DEFAULTS
     pv = [d[k] for k in prob.TRANSISTOR_ORDER]
     f, j, _, _ = prob.transistor()
