@@ -144,6 +144,12 @@ def load(path: str | None = None):
     lib.brdae_launch_info.restype = C.c_int
     lib.brdae_launch_info.argtypes = [C.POINTER(BrdaeBatch), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.brdae_solve_host_rows.restype = C.c_int
+    lib.brdae_solve_host_rows.argtypes = [C.POINTER(BrdaeBatch), C.POINTER(BrdaeOptions)]
+    lib.brdae_alloc_pinned.restype = C.c_int
+    lib.brdae_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.brdae_free_pinned.restype = C.c_int
+    lib.brdae_free_pinned.argtypes = [C.c_void_p]
     lib.brdae_fp64_peak_probe.restype = C.c_int
     lib.brdae_fp64_peak_probe.argtypes = [C.c_double, C.POINTER(C.c_double), C.c_void_p]
     if path is None:
@@ -153,7 +159,8 @@ def load(path: str | None = None):
 
 EXPORTED_SYMBOLS = ("brdae_abi_version", "brdae_strerror", "brdae_problem_lookup",
                     "brdae_default_options", "brdae_workspace_bytes", "brdae_solve",
-                    "brdae_solve_host", "brdae_launch_info", "brdae_fp64_peak_probe")
+                    "brdae_solve_host", "brdae_solve_host_rows", "brdae_launch_info", "brdae_fp64_peak_probe",
+                    "brdae_alloc_pinned", "brdae_free_pinned")
 
 
 def check(rc: int, what: str = "brdae call"):

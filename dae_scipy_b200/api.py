@@ -303,37 +303,81 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     return res
 
 
-def solve_ivp_batched_host(problem, t_span, y0, params=None, *, t_eval=None, **options):
-    """Same call with numpy arrays in and out, through `brdae_solve_host` (the library does the
-    device allocation and the copies).  This is the entry a numpy/scipy user of the reference
-    binds to; it is what bench.py times as the end-to-end path."""
+class PinnedArray:
+    """numpy array over page-locked host memory from brdae_alloc_pinned (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = _abi.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _abi.check(self._lib.brdae_alloc_pinned(max(self.nbytes, 1), C.byref(p)), "brdae_alloc_pinned")
+        self._ptr = p
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self._lib.brdae_free_pinned(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
+def host_buffers(n, B, T, n_params=0, pinned=True):
+    """Reusable result buffers for `solve_ivp_batched_host(..., buffers=...)` in the row-per-system
+    layout (`y` [B, n, T], `y_final` [B, n], `counters` [B, 9], ...), page-locked when `pinned`
+    (PCIe-rate copies, no first-touch page faults on every call)."""
+    spec = {"y": ((B, n, max(T, 1)), np.float64), "n_eval": ((B,), np.int32), "t_final": ((B,), np.float64),
+            "y_final": ((B, n), np.float64), "status": ((B,), np.int32), "counters": ((B, _abi.NCOUNTERS), np.int32)}
+    bufs, keep = {}, []
+    for k, (shape, dt) in spec.items():
+        if pinned:
+            pa = PinnedArray(shape, dt)
+            keep.append(pa)
+            bufs[k] = pa.array
+        else:
+            bufs[k] = np.empty(shape, dtype=dt)
+    bufs["_owners"] = keep
+    bufs["_shape"] = (n, B, T)
+    return bufs
+
+
+def solve_ivp_batched_host(problem, t_span, y0, params=None, *, t_eval=None, buffers=None, **options):
+    """Same call with numpy arrays in and out, through `brdae_solve_host_rows`: `y0` [B, n] and
+    `params` [B, p] are handed to the library as they are (row per system), results come back as
+    `y` [B, n, T] etc.; device allocation, copies and the layout permutations happen inside the
+    library.  This is the entry a numpy/scipy user of the reference binds to and what bench.py
+    times as the end-to-end path.  `buffers` (from `host_buffers`) lets repeated calls reuse
+    page-locked result arrays; the returned arrays are then views of those buffers."""
     lib = _abi.load()
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     hb = prepare(problem, t_span, y0.shape, t_eval=t_eval, params=params, **options)
     prob, n, B, T = hb.problem, hb.n, hb.B, hb.t_eval.size
-    y0_soa = np.ascontiguousarray(y0.T)
+    if not np.isfinite(y0).all():
+        raise ValueError("All components of the initial state `y0` must be finite.")
+    if buffers is None:
+        buffers = host_buffers(n, B, T, prob.n_params, pinned=False)
+    out = buffers
+    if out["_shape"] != (n, B, T):
+        raise ValueError("`buffers` were made for another problem size.")
+    par = None
     if prob.n_params:
-        p = prob.default_params(B) if params is None else np.asarray(params, dtype=np.float64)
-        if p.shape != (B, prob.n_params):
+        par = prob.default_params(B) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        if par.shape != (B, prob.n_params):
             raise ValueError(f"`params` must have shape {(B, prob.n_params)}.")
-        par_soa = np.ascontiguousarray(p.T)
-    else:
-        par_soa = None
-    out = {"y_eval": np.empty((max(T, 1), n, B)), "n_eval": np.empty(B, dtype=np.int32),
-           "t_final": np.empty(B), "y_final": np.empty((n, B)), "status": np.empty(B, dtype=np.int32),
-           "counters": np.empty((_abi.NCOUNTERS, B), dtype=np.int32)}
-    ptr = {k: v.ctypes.data for k, v in out.items()}
-    ptr.update({"y0": y0_soa.ctypes.data, "params": par_soa.ctypes.data if par_soa is not None else None,
-                "t_eval": hb.t_eval.ctypes.data if T else None})
-    if not T:
-        ptr["y_eval"] = None
+    ptr = {"y0": y0.ctypes.data, "params": par.ctypes.data if par is not None else None,
+           "t_eval": hb.t_eval.ctypes.data if T else None, "y_eval": out["y"].ctypes.data if T else None,
+           "n_eval": out["n_eval"].ctypes.data, "t_final": out["t_final"].ctypes.data,
+           "y_final": out["y_final"].ctypes.data, "status": out["status"].ctypes.data,
+           "counters": out["counters"].ctypes.data}
     batch = hb.struct(ptr)
-    _abi.check(lib.brdae_solve_host(C.byref(batch), C.byref(hb.options)), "brdae_solve_host")
-    res = {"t": hb.t_eval, "y": out["y_eval"][:T].transpose(2, 1, 0), "n_eval": out["n_eval"],
-           "status": out["status"], "success": out["status"] >= 0, "t_final": out["t_final"],
-           "y_final": out["y_final"].T, "counters": out["counters"].T}
+    _abi.check(lib.brdae_solve_host_rows(C.byref(batch), C.byref(hb.options)), "brdae_solve_host_rows")
+    res = {"t": hb.t_eval, "y": out["y"][:, :, :T], "n_eval": out["n_eval"], "status": out["status"],
+           "success": out["status"] >= 0, "t_final": out["t_final"], "y_final": out["y_final"],
+           "counters": out["counters"]}
     for i, name in enumerate(_abi.COUNTER_NAMES):
-        res[name] = out["counters"][i]
+        res[name] = out["counters"][:, i]
     return res
 
 

@@ -98,6 +98,10 @@ int brdae_solve(const brdae_batch *b, const brdae_options *o, void *workspace, s
 
 #define CK(x) do { if ((x) != cudaSuccess) { rc = BRDAE_ERR_CUDA; goto done; } } while (0)
 
+// Host-buffer form: stream-ordered allocation from the device's default memory pool (kept warm
+// between calls by a high release threshold, so repeated calls do not pay cudaMalloc/cudaFree),
+// H2D of the inputs, the solve, D2H of every result, one synchronisation at the end.  Pinned host
+// buffers make the copies run at PCIe speed; pageable ones work but are staged by the driver.
 int brdae_solve_host(const brdae_batch *hb, const brdae_options *o) {
     int rc = validate(hb, o);
     if (rc != BRDAE_OK) return rc;
@@ -110,27 +114,34 @@ int brdae_solve_host(const brdae_batch *hb, const brdae_options *o) {
     void *ws = nullptr;
     cudaStream_t s = nullptr;
     size_t wsb = 0;
-    CK(cudaStreamCreate(&s));
-    CK(cudaMalloc(&dy0, sizeof(double) * n * B));
+    int dev = 0;
+    cudaMemPool_t pool;
+    CK(cudaGetDevice(&dev));
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CK(cudaMallocAsync(&dy0, sizeof(double) * n * B, s));
     CK(cudaMemcpyAsync(dy0, hb->y0, sizeof(double) * n * B, cudaMemcpyHostToDevice, s));
     if (np > 0) {
-        CK(cudaMalloc(&dpar, sizeof(double) * np * B));
+        CK(cudaMallocAsync(&dpar, sizeof(double) * np * B, s));
         CK(cudaMemcpyAsync(dpar, hb->params, sizeof(double) * np * B, cudaMemcpyHostToDevice, s));
     }
     if (T > 0) {
-        CK(cudaMalloc(&dte, sizeof(double) * T));
+        CK(cudaMallocAsync(&dte, sizeof(double) * T, s));
         CK(cudaMemcpyAsync(dte, hb->t_eval, sizeof(double) * T, cudaMemcpyHostToDevice, s));
-        CK(cudaMalloc(&dye, sizeof(double) * (size_t)T * n * B));
+        CK(cudaMallocAsync(&dye, sizeof(double) * (size_t)T * n * B, s));
     }
-    CK(cudaMalloc(&dtf, sizeof(double) * B));
-    CK(cudaMalloc(&dyf, sizeof(double) * n * B));
-    CK(cudaMalloc(&dne, sizeof(int32_t) * B));
-    CK(cudaMalloc(&dst, sizeof(int32_t) * B));
-    CK(cudaMalloc(&dcn, sizeof(int32_t) * BRDAE_NCOUNTERS * B));
+    CK(cudaMallocAsync(&dtf, sizeof(double) * B, s));
+    CK(cudaMallocAsync(&dyf, sizeof(double) * n * B, s));
+    CK(cudaMallocAsync(&dne, sizeof(int32_t) * B, s));
+    CK(cudaMallocAsync(&dst, sizeof(int32_t) * B, s));
+    CK(cudaMallocAsync(&dcn, sizeof(int32_t) * BRDAE_NCOUNTERS * B, s));
     d.y0 = dy0; d.params = dpar; d.t_eval = dte; d.y_eval = dye; d.t_final = dtf; d.y_final = dyf;
     d.n_eval = dne; d.status = dst; d.counters = dcn;
     wsb = brdae_workspace_bytes(&d, o);
-    CK(cudaMalloc(&ws, wsb));
+    CK(cudaMallocAsync(&ws, wsb, s));
     rc = brdae_solve(&d, o, ws, wsb, s);
     if (rc != BRDAE_OK) goto done;
     if (T > 0) CK(cudaMemcpyAsync(hb->y_eval, dye, sizeof(double) * (size_t)T * n * B, cudaMemcpyDeviceToHost, s));
@@ -139,13 +150,98 @@ int brdae_solve_host(const brdae_batch *hb, const brdae_options *o) {
     CK(cudaMemcpyAsync(hb->n_eval, dne, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(hb->status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(hb->counters, dcn, sizeof(int32_t) * BRDAE_NCOUNTERS * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
 done:
-    cudaFree(dy0); cudaFree(dpar); cudaFree(dte); cudaFree(dye); cudaFree(dtf); cudaFree(dyf);
-    cudaFree(dne); cudaFree(dst); cudaFree(dcn); cudaFree(ws);
-    if (s) cudaStreamDestroy(s);
+    if (s) {
+        void *bufs[] = {dy0, dpar, dte, dye, dtf, dyf, dne, dst, dcn, ws};
+        for (void *q : bufs) if (q) cudaFreeAsync(q, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess && rc == BRDAE_OK) rc = BRDAE_ERR_CUDA;
+        cudaStreamDestroy(s);
+    }
     return rc;
 }
+
+// Row-per-system form (the layout a caller coming from per-system solve_ivp calls holds):
+// y0 [B][n], params [B][p] in; y_eval [B][n][T], y_final [B][n], counters [B][9] out.  The
+// rows <-> SoA permutations run on the device (layout.cu), so the host never transposes.
+int brdae_solve_host_rows(const brdae_batch *hb, const brdae_options *o) {
+    int rc = validate(hb, o);
+    if (rc != BRDAE_OK) return rc;
+    const int64_t B = hb->n_systems;
+    if (B == 0) return BRDAE_OK;
+    const int n = hb->n, T = hb->n_t_eval, np = hb->n_params;
+    brdae_batch d = *hb;
+    double *stage = nullptr, *dy0 = nullptr, *dpar = nullptr, *dte = nullptr, *dye = nullptr, *dye_rows = nullptr;
+    double *dtf = nullptr, *dyf = nullptr, *dyf_rows = nullptr;
+    int32_t *dne = nullptr, *dst = nullptr, *dcn = nullptr, *dcn_rows = nullptr;
+    void *ws = nullptr;
+    cudaStream_t s = nullptr;
+    size_t wsb = 0;
+    int dev = 0;
+    cudaMemPool_t pool;
+    const int64_t in_rows = (int64_t)(n > np ? n : np);
+    CK(cudaGetDevice(&dev));
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CK(cudaMallocAsync(&stage, sizeof(double) * in_rows * B, s));
+    CK(cudaMallocAsync(&dy0, sizeof(double) * n * B, s));
+    CK(cudaMemcpyAsync(stage, hb->y0, sizeof(double) * n * B, cudaMemcpyHostToDevice, s));
+    permute_f64(stage, dy0, B, n, n, B, 1, 0, 0, s);                      // [B][n] -> [n][B]
+    if (np > 0) {
+        CK(cudaMallocAsync(&dpar, sizeof(double) * np * B, s));
+        CK(cudaMemcpyAsync(stage, hb->params, sizeof(double) * np * B, cudaMemcpyHostToDevice, s));
+        permute_f64(stage, dpar, B, np, np, B, 1, 0, 0, s);
+    }
+    if (T > 0) {
+        CK(cudaMallocAsync(&dte, sizeof(double) * T, s));
+        CK(cudaMemcpyAsync(dte, hb->t_eval, sizeof(double) * T, cudaMemcpyHostToDevice, s));
+        CK(cudaMallocAsync(&dye, sizeof(double) * (size_t)T * n * B, s));
+        CK(cudaMallocAsync(&dye_rows, sizeof(double) * (size_t)T * n * B, s));
+    }
+    CK(cudaMallocAsync(&dtf, sizeof(double) * B, s));
+    CK(cudaMallocAsync(&dyf, sizeof(double) * n * B, s));
+    CK(cudaMallocAsync(&dyf_rows, sizeof(double) * n * B, s));
+    CK(cudaMallocAsync(&dne, sizeof(int32_t) * B, s));
+    CK(cudaMallocAsync(&dst, sizeof(int32_t) * B, s));
+    CK(cudaMallocAsync(&dcn, sizeof(int32_t) * BRDAE_NCOUNTERS * B, s));
+    CK(cudaMallocAsync(&dcn_rows, sizeof(int32_t) * BRDAE_NCOUNTERS * B, s));
+    d.y0 = dy0; d.params = dpar; d.t_eval = dte; d.y_eval = dye; d.t_final = dtf; d.y_final = dyf;
+    d.n_eval = dne; d.status = dst; d.counters = dcn;
+    wsb = brdae_workspace_bytes(&d, o);
+    CK(cudaMallocAsync(&ws, wsb, s));
+    rc = brdae_solve(&d, o, ws, wsb, s);
+    if (rc != BRDAE_OK) goto done;
+    if (T > 0) {   // [T][n][B] -> [B][n][T], one (T x B) plane per unknown
+        permute_f64(dye, dye_rows, T, B, (int64_t)n * B, (int64_t)n * T, n, B, T, s);
+        CK(cudaMemcpyAsync(hb->y_eval, dye_rows, sizeof(double) * (size_t)T * n * B, cudaMemcpyDeviceToHost, s));
+    }
+    permute_f64(dyf, dyf_rows, n, B, B, n, 1, 0, 0, s);                   // [n][B] -> [B][n]
+    permute_i32(dcn, dcn_rows, BRDAE_NCOUNTERS, B, B, BRDAE_NCOUNTERS, 1, 0, 0, s);
+    CK(cudaMemcpyAsync(hb->y_final, dyf_rows, sizeof(double) * n * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hb->counters, dcn_rows, sizeof(int32_t) * BRDAE_NCOUNTERS * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hb->t_final, dtf, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hb->n_eval, dne, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hb->status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+    if (cudaGetLastError() != cudaSuccess) rc = BRDAE_ERR_CUDA;
+done:
+    if (s) {
+        void *bufs[] = {stage, dy0, dpar, dte, dye, dye_rows, dtf, dyf, dyf_rows, dne, dst, dcn, dcn_rows, ws};
+        for (void *q : bufs) if (q) cudaFreeAsync(q, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess && rc == BRDAE_OK) rc = BRDAE_ERR_CUDA;
+        cudaStreamDestroy(s);
+    }
+    return rc;
+}
+
+// Page-locked host memory for callers without their own allocator (numpy users): copies from and
+// to such buffers run at full PCIe rate and do not pay first-touch page faults on every call.
+int brdae_alloc_pinned(size_t bytes, void **ptr) {
+    if (!ptr) return BRDAE_ERR_BAD_ARGUMENT;
+    return cudaMallocHost(ptr, bytes ? bytes : 1) == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;
+}
+int brdae_free_pinned(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA; }
 
 int brdae_fp64_peak_probe(double ms_target, double *flops, void *cuda_stream) {
     if (!flops) return BRDAE_ERR_BAD_ARGUMENT;

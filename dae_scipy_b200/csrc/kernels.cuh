@@ -22,6 +22,13 @@ int k1_transistor(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, 
 int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 size_t k2_scratch_bytes(int n, int sms);
 
+// layout.cu: dst[z*dst_zs + c*dst_rs + r] = src[z*src_zs + r*src_rs + c] for r < R, c < C, z < Z
+// (rows <-> structure-of-arrays permutations of the host-buffer entry points)
+void permute_f64(const double *src, double *dst, int64_t R, int64_t C, int64_t src_rs, int64_t dst_rs, int Z,
+                 int64_t src_zs, int64_t dst_zs, cudaStream_t s);
+void permute_i32(const int32_t *src, int32_t *dst, int64_t R, int64_t C, int64_t src_rs, int64_t dst_rs, int Z,
+                 int64_t src_zs, int64_t dst_zs, cudaStream_t s);
+
 int fp64_peak_probe(double ms_target, double *flops, cudaStream_t s, int sms);
 
 }  // namespace brdae

@@ -131,6 +131,16 @@ int brdae_solve(const brdae_batch *batch, const brdae_options *opts, void *works
  * numpy arrays binds to. */
 int brdae_solve_host(const brdae_batch *host_batch, const brdae_options *opts);
 
+/* Host-buffer call in the row-per-system layout a per-system solve_ivp user already holds:
+ * y0 [B][n], params [B][n_params] in; y_eval [B][n][T] (OdeResult.y per system), y_final [B][n],
+ * counters [B][BRDAE_NCOUNTERS] out; n_eval, t_final, status [B].  The permutations to and from
+ * the kernels' structure-of-arrays layout are done on the device. */
+int brdae_solve_host_rows(const brdae_batch *host_batch_rows, const brdae_options *opts);
+
+/* Page-locked host buffers for callers of brdae_solve_host (cudaMallocHost / cudaFreeHost). */
+int brdae_alloc_pinned(size_t bytes, void **ptr);
+int brdae_free_pinned(void *ptr);
+
 /* Launch geometry chosen for a batch, for reporting (grid, block, dynamic shared memory bytes). */
 int brdae_launch_info(const brdae_batch *batch, int32_t *grid, int32_t *block, int32_t *smem_bytes);
 

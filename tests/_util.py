@@ -145,9 +145,9 @@ def run_gpu(ens, host_api=False, **over):
     opts.update(over)
     if host_api:
         r = br.solve_ivp_batched_host(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], **opts)
-        return dict(y=np.ascontiguousarray(r["y"]), status=r["status"], n_eval=r["n_eval"],
+        return dict(y=np.ascontiguousarray(r["y"]), status=r["status"].copy(), n_eval=r["n_eval"].copy(),
                     counters=np.ascontiguousarray(r["counters"]), y_final=np.ascontiguousarray(r["y_final"]),
-                    t_final=r["t_final"])
+                    t_final=r["t_final"].copy())
     import torch
     res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], **opts)
     torch.cuda.synchronize()

@@ -114,8 +114,20 @@ def test_empty_ensemble_and_no_t_eval():
 
 
 def test_host_buffer_entry_equals_device_entry():
+    """brdae_solve_host_rows (row-per-system host buffers, device-side permutations) vs brdae_solve."""
     ens = E.pendulum_ensemble(777)
-    assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "brdae_solve_host vs brdae_solve")
+    assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "brdae_solve_host_rows vs brdae_solve")
+    ens = E.robertson_ensemble(70001)      # odd size, more than one tile in every direction
+    assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "robertson rows")
+    ens = E.npendulum_ensemble(5, n_nodes=4, t_end=0.3)
+    assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "npendulum rows")
+    # reused page-locked buffers, and the SoA host entry
+    ens = E.pendulum_ensemble(300)
+    bufs = br.host_buffers(5, 300, 21, 3, pinned=True)
+    r1 = br.solve_ivp_batched_host(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"],
+                                   buffers=bufs, **ens["options"])
+    ref = run_gpu(ens)
+    assert np.array_equal(r1["y"], ref["y"]) and np.array_equal(r1["counters"], ref["counters"])
 
 
 def test_invalid_y0_raises_like_scipy():
