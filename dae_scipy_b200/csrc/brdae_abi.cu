@@ -163,75 +163,123 @@ done:
 // Row-per-system form (the layout a caller coming from per-system solve_ivp calls holds):
 // y0 [B][n], params [B][p] in; y_eval [B][n][T], y_final [B][n], counters [B][9] out.  The
 // rows <-> SoA permutations run on the device (layout.cu), so the host never transposes.
+// Large ensembles are pipelined in chunks over two streams and two sets of device buffers: the
+// device-to-host copy of chunk c (the bulk of the PCIe traffic) overlaps the integration of chunk
+// c+1.  A row-per-system slice is contiguous in host memory, so every copy stays one memcpy.
+namespace {
+struct RowsChunkBufs {
+    double *stage = nullptr, *y0 = nullptr, *par = nullptr, *ye = nullptr, *ye_rows = nullptr, *tf = nullptr, *yf = nullptr,
+           *yf_rows = nullptr;
+    int32_t *ne = nullptr, *st = nullptr, *cn = nullptr, *cn_rows = nullptr;
+    void *ws = nullptr;
+    cudaEvent_t done = nullptr, freed = nullptr;
+};
+}  // namespace
+
 int brdae_solve_host_rows(const brdae_batch *hb, const brdae_options *o) {
     int rc = validate(hb, o);
     if (rc != BRDAE_OK) return rc;
     const int64_t B = hb->n_systems;
     if (B == 0) return BRDAE_OK;
     const int n = hb->n, T = hb->n_t_eval, np = hb->n_params;
-    brdae_batch d = *hb;
-    double *stage = nullptr, *dy0 = nullptr, *dpar = nullptr, *dte = nullptr, *dye = nullptr, *dye_rows = nullptr;
-    double *dtf = nullptr, *dyf = nullptr, *dyf_rows = nullptr;
-    int32_t *dne = nullptr, *dst = nullptr, *dcn = nullptr, *dcn_rows = nullptr;
-    void *ws = nullptr;
-    cudaStream_t s = nullptr;
+    const int64_t in_rows = (int64_t)(n > np ? n : np);
+    // chunking: about a quarter of a million systems per chunk, at most 8 chunks
+    int nchunks = (int)(B / 262144);
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 8) nchunks = 8;
+    const int64_t Bc = (B + nchunks - 1) / nchunks;
+    const int nsets = nchunks > 1 ? 2 : 1;
+    RowsChunkBufs cb[2];
+    double *dte = nullptr;
+    cudaStream_t s = nullptr, s_copy = nullptr;
     size_t wsb = 0;
     int dev = 0;
     cudaMemPool_t pool;
-    const int64_t in_rows = (int64_t)(n > np ? n : np);
     CK(cudaGetDevice(&dev));
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    CK(cudaMallocAsync(&stage, sizeof(double) * in_rows * B, s));
-    CK(cudaMallocAsync(&dy0, sizeof(double) * n * B, s));
-    CK(cudaMemcpyAsync(stage, hb->y0, sizeof(double) * n * B, cudaMemcpyHostToDevice, s));
-    permute_f64(stage, dy0, B, n, n, B, 1, 0, 0, s);                      // [B][n] -> [n][B]
-    if (np > 0) {
-        CK(cudaMallocAsync(&dpar, sizeof(double) * np * B, s));
-        CK(cudaMemcpyAsync(stage, hb->params, sizeof(double) * np * B, cudaMemcpyHostToDevice, s));
-        permute_f64(stage, dpar, B, np, np, B, 1, 0, 0, s);
-    }
+    CK(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
     if (T > 0) {
         CK(cudaMallocAsync(&dte, sizeof(double) * T, s));
         CK(cudaMemcpyAsync(dte, hb->t_eval, sizeof(double) * T, cudaMemcpyHostToDevice, s));
-        CK(cudaMallocAsync(&dye, sizeof(double) * (size_t)T * n * B, s));
-        CK(cudaMallocAsync(&dye_rows, sizeof(double) * (size_t)T * n * B, s));
     }
-    CK(cudaMallocAsync(&dtf, sizeof(double) * B, s));
-    CK(cudaMallocAsync(&dyf, sizeof(double) * n * B, s));
-    CK(cudaMallocAsync(&dyf_rows, sizeof(double) * n * B, s));
-    CK(cudaMallocAsync(&dne, sizeof(int32_t) * B, s));
-    CK(cudaMallocAsync(&dst, sizeof(int32_t) * B, s));
-    CK(cudaMallocAsync(&dcn, sizeof(int32_t) * BRDAE_NCOUNTERS * B, s));
-    CK(cudaMallocAsync(&dcn_rows, sizeof(int32_t) * BRDAE_NCOUNTERS * B, s));
-    d.y0 = dy0; d.params = dpar; d.t_eval = dte; d.y_eval = dye; d.t_final = dtf; d.y_final = dyf;
-    d.n_eval = dne; d.status = dst; d.counters = dcn;
-    wsb = brdae_workspace_bytes(&d, o);
-    CK(cudaMallocAsync(&ws, wsb, s));
-    rc = brdae_solve(&d, o, ws, wsb, s);
-    if (rc != BRDAE_OK) goto done;
-    if (T > 0) {   // [T][n][B] -> [B][n][T], one (T x B) plane per unknown
-        permute_f64(dye, dye_rows, T, B, (int64_t)n * B, (int64_t)n * T, n, B, T, s);
-        CK(cudaMemcpyAsync(hb->y_eval, dye_rows, sizeof(double) * (size_t)T * n * B, cudaMemcpyDeviceToHost, s));
+    {
+        brdae_batch probe = *hb;
+        probe.n_systems = Bc;
+        wsb = brdae_workspace_bytes(&probe, o);
     }
-    permute_f64(dyf, dyf_rows, n, B, B, n, 1, 0, 0, s);                   // [n][B] -> [B][n]
-    permute_i32(dcn, dcn_rows, BRDAE_NCOUNTERS, B, B, BRDAE_NCOUNTERS, 1, 0, 0, s);
-    CK(cudaMemcpyAsync(hb->y_final, dyf_rows, sizeof(double) * n * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(hb->counters, dcn_rows, sizeof(int32_t) * BRDAE_NCOUNTERS * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(hb->t_final, dtf, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(hb->n_eval, dne, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(hb->status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < nsets; ++k) {
+        RowsChunkBufs &c = cb[k];
+        CK(cudaMallocAsync(&c.stage, sizeof(double) * in_rows * Bc, s));
+        CK(cudaMallocAsync(&c.y0, sizeof(double) * n * Bc, s));
+        if (np > 0) CK(cudaMallocAsync(&c.par, sizeof(double) * np * Bc, s));
+        if (T > 0) {
+            CK(cudaMallocAsync(&c.ye, sizeof(double) * (size_t)T * n * Bc, s));
+            CK(cudaMallocAsync(&c.ye_rows, sizeof(double) * (size_t)T * n * Bc, s));
+        }
+        CK(cudaMallocAsync(&c.tf, sizeof(double) * Bc, s));
+        CK(cudaMallocAsync(&c.yf, sizeof(double) * n * Bc, s));
+        CK(cudaMallocAsync(&c.yf_rows, sizeof(double) * n * Bc, s));
+        CK(cudaMallocAsync(&c.ne, sizeof(int32_t) * Bc, s));
+        CK(cudaMallocAsync(&c.st, sizeof(int32_t) * Bc, s));
+        CK(cudaMallocAsync(&c.cn, sizeof(int32_t) * BRDAE_NCOUNTERS * Bc, s));
+        CK(cudaMallocAsync(&c.cn_rows, sizeof(int32_t) * BRDAE_NCOUNTERS * Bc, s));
+        CK(cudaMallocAsync(&c.ws, wsb, s));
+        CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.freed, cudaEventDisableTiming));
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int64_t b0 = (int64_t)ch * Bc;
+        const int64_t bn = (B - b0 < Bc) ? B - b0 : Bc;
+        if (bn <= 0) break;
+        RowsChunkBufs &c = cb[ch % nsets];
+        if (ch >= nsets) CK(cudaStreamWaitEvent(s, c.freed, 0));           // this set's results have left the device
+        CK(cudaMemcpyAsync(c.stage, hb->y0 + b0 * n, sizeof(double) * n * bn, cudaMemcpyHostToDevice, s));
+        permute_f64(c.stage, c.y0, bn, n, n, bn, 1, 0, 0, s);               // [bn][n] -> [n][bn]
+        if (np > 0) {
+            CK(cudaMemcpyAsync(c.stage, hb->params + b0 * np, sizeof(double) * np * bn, cudaMemcpyHostToDevice, s));
+            permute_f64(c.stage, c.par, bn, np, np, bn, 1, 0, 0, s);
+        }
+        brdae_batch d = *hb;
+        d.n_systems = bn;
+        d.y0 = c.y0; d.params = c.par; d.t_eval = dte; d.y_eval = c.ye; d.t_final = c.tf; d.y_final = c.yf;
+        d.n_eval = c.ne; d.status = c.st; d.counters = c.cn;
+        rc = brdae_solve(&d, o, c.ws, wsb, s);
+        if (rc != BRDAE_OK) goto done;
+        if (T > 0) permute_f64(c.ye, c.ye_rows, T, bn, (int64_t)n * bn, (int64_t)n * T, n, bn, T, s);   // -> [bn][n][T]
+        permute_f64(c.yf, c.yf_rows, n, bn, bn, n, 1, 0, 0, s);
+        permute_i32(c.cn, c.cn_rows, BRDAE_NCOUNTERS, bn, bn, BRDAE_NCOUNTERS, 1, 0, 0, s);
+        CK(cudaEventRecord(c.done, s));
+        CK(cudaStreamWaitEvent(s_copy, c.done, 0));
+        if (T > 0) CK(cudaMemcpyAsync(hb->y_eval + (size_t)b0 * n * T, c.ye_rows, sizeof(double) * (size_t)T * n * bn, cudaMemcpyDeviceToHost, s_copy));
+        CK(cudaMemcpyAsync(hb->y_final + b0 * n, c.yf_rows, sizeof(double) * n * bn, cudaMemcpyDeviceToHost, s_copy));
+        CK(cudaMemcpyAsync(hb->counters + b0 * BRDAE_NCOUNTERS, c.cn_rows, sizeof(int32_t) * BRDAE_NCOUNTERS * bn, cudaMemcpyDeviceToHost, s_copy));
+        CK(cudaMemcpyAsync(hb->t_final + b0, c.tf, sizeof(double) * bn, cudaMemcpyDeviceToHost, s_copy));
+        CK(cudaMemcpyAsync(hb->n_eval + b0, c.ne, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, s_copy));
+        CK(cudaMemcpyAsync(hb->status + b0, c.st, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, s_copy));
+        CK(cudaEventRecord(c.freed, s_copy));
+    }
     if (cudaGetLastError() != cudaSuccess) rc = BRDAE_ERR_CUDA;
 done:
+    if (s_copy && cudaStreamSynchronize(s_copy) != cudaSuccess && rc == BRDAE_OK) rc = BRDAE_ERR_CUDA;
     if (s) {
-        void *bufs[] = {stage, dy0, dpar, dte, dye, dye_rows, dtf, dyf, dyf_rows, dne, dst, dcn, dcn_rows, ws};
-        for (void *q : bufs) if (q) cudaFreeAsync(q, s);
+        for (int k = 0; k < 2; ++k) {
+            RowsChunkBufs &c = cb[k];
+            void *bufs[] = {c.stage, c.y0, c.par, c.ye, c.ye_rows, c.tf, c.yf, c.yf_rows, c.ne, c.st, c.cn, c.cn_rows, c.ws};
+            for (void *q : bufs) if (q) cudaFreeAsync(q, s);
+        }
+        if (dte) cudaFreeAsync(dte, s);
         if (cudaStreamSynchronize(s) != cudaSuccess && rc == BRDAE_OK) rc = BRDAE_ERR_CUDA;
+        for (int k = 0; k < 2; ++k) {
+            if (cb[k].done) cudaEventDestroy(cb[k].done);
+            if (cb[k].freed) cudaEventDestroy(cb[k].freed);
+        }
         cudaStreamDestroy(s);
     }
+    if (s_copy) cudaStreamDestroy(s_copy);
     return rc;
 }
 

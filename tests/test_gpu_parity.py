@@ -121,6 +121,8 @@ def test_host_buffer_entry_equals_device_entry():
     assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "robertson rows")
     ens = E.npendulum_ensemble(5, n_nodes=4, t_end=0.3)
     assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "npendulum rows")
+    ens = E.robertson_ensemble(3 * 262144 + 12345, t_end=10.0, n_t_eval=5)   # pipelined in 3 chunks, last one ragged
+    assert_bit_identical(run_gpu(ens, host_api=True), run_gpu(ens), "chunked rows")
     # reused page-locked buffers, and the SoA host entry
     ens = E.pendulum_ensemble(300)
     bufs = br.host_buffers(5, 300, 21, 3, pinned=True)
