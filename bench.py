@@ -107,16 +107,7 @@ def _cpu_worker(args):
     done = 0
     with contextlib.redirect_stdout(io.StringIO()):
         for i in range(y0s.shape[0]):
-            if problem.startswith("pendulum"):
-                fun, jac, mass, vi = prob.pendulum(int(problem[-1]), *params[i])
-            elif problem == "robertson":
-                fun, jac, mass, vi = prob.robertson(*params[i])
-            elif problem == "transistor":
-                fun, jac, mass, vi = prob.transistor(*params[i])
-            elif problem == "npendulum":
-                fun, jac, mass, vi = prob.npendulum(y0s.shape[1] // 5)
-            else:
-                raise ValueError(problem)
+            fun, jac, mass, vi = prob.build(problem, params[i], y0s.shape[1])
             r = orc.solve(fun, t_span, y0s[i], jac=jac, mass_matrix=mass,
                           var_index=None if var_index is None else np.asarray(var_index, dtype=float),
                           t_eval=t_eval, **opts)

@@ -17,6 +17,8 @@ static const ProblemInfo kProblems[] = {
     {"pendulum3", BRDAE_PENDULUM3, 5, 3}, {"pendulum2", BRDAE_PENDULUM2, 5, 3},
     {"pendulum1", BRDAE_PENDULUM1, 5, 3}, {"robertson", BRDAE_ROBERTSON, 3, 3},
     {"transistor", BRDAE_TRANSISTOR, 5, 12}, {"npendulum", BRDAE_NPENDULUM, 0, 0},
+    {"robertson_ode", BRDAE_ROBERTSON_ODE, 3, 3}, {"jay", BRDAE_JAY, 5, 1},
+    {"polydae2", BRDAE_POLYDAE2, 2, 5}, {"linear7", BRDAE_LINEAR7, 7, 7},
 };
 
 inline const ProblemInfo *find_problem(int32_t id) {

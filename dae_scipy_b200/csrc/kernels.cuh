@@ -18,6 +18,7 @@ int launch_solver(int problem, bool dense_mass, const SolveArgs &a, const brdae_
 int k1_pendulum(int index, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 int k1_robertson(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 int k1_transistor(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+int k1_extra(int problem, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 // CTA-per-system banded kernel for the n-pendulum chain (k2_npendulum.cu)
 int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 size_t k2_scratch_bytes(int n, int sms);

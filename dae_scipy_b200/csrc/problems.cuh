@@ -170,4 +170,105 @@ struct Transistor {
     }
 };
 
+// ---------------------------------------------------------------- Robertson, ODE formulation
+// robertson.py:69-77; used by the reference's DAE-vs-ODE cross-check (:249-251)
+struct RobertsonODE {
+    static constexpr int N = 3, NP = 3;
+    struct P { double k1, k2, k3; };
+    using Mass = MassDiag01<3, 0x7u>;
+    static BRDAE_HD void load(P &p, const double *params, int64_t B, int64_t i) {
+        p.k1 = params[i]; p.k2 = params[B + i]; p.k3 = params[2 * B + i];
+    }
+    static BRDAE_HD void rhs(const P &p, double, const double (&y)[3], double (&f)[3]) {
+        f[0] = -p.k1 * y[0] + p.k2 * y[1] * y[2];
+        f[1] = p.k1 * y[0] - p.k2 * y[1] * y[2] - p.k3 * (y[1] * y[1]);
+        f[2] = p.k3 * (y[1] * y[1]);
+    }
+    static BRDAE_HD void jac(const P &p, double, const double (&y)[3], double (&J)[3][3]) {
+        J[0][0] = -p.k1; J[0][1] = p.k2 * y[2]; J[0][2] = p.k2 * y[1];
+        J[1][0] = p.k1; J[1][1] = -p.k2 * y[2] - 2 * p.k3 * y[1]; J[1][2] = -p.k2 * y[1];
+        J[2][0] = 0; J[2][1] = 2 * p.k3 * y[1]; J[2][2] = 0;
+    }
+};
+
+// ---------------------------------------------------------------- Jay 1995 index-3 DAE
+// jay_dae.py:22-68; parameter: nonlinear-multiplier flag.  Analytic Jacobian (FD in the reference).
+struct Jay {
+    static constexpr int N = 5, NP = 1;
+    struct P { double nonlinear; };
+    using Mass = MassDiag01<5, 0x0Fu>;
+    static BRDAE_HD void load(P &p, const double *params, int64_t, int64_t i) { p.nonlinear = params[i]; }
+    static BRDAE_HD void rhs(const P &p, double, const double (&y)[5], double (&f)[5]) {
+        const double y1 = y[0], y2 = y[1], z1 = y[2], z2 = y[3], la = y[4];
+        f[0] = 2 * y1 * y2 * z1 * z2;
+        f[1] = -y1 * y2 * (z2 * z2);
+        f[2] = (y1 * y2 + z1 * z2) * la;
+        if (p.nonlinear != 0.0) f[3] = -y1 * (y2 * y2) * (z2 * z2 * z2) * (la * la);
+        else f[3] = -y1 * (y2 * y2) * (z2 * z2) * la;
+        f[4] = y1 * (y2 * y2) - 1.0;
+    }
+    static BRDAE_HD void jac(const P &p, double, const double (&y)[5], double (&J)[5][5]) {
+        const double y1 = y[0], y2 = y[1], z1 = y[2], z2 = y[3], la = y[4];
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) J[r][c] = 0.0;
+        J[0][0] = 2 * y2 * z1 * z2; J[0][1] = 2 * y1 * z1 * z2; J[0][2] = 2 * y1 * y2 * z2; J[0][3] = 2 * y1 * y2 * z1;
+        J[1][0] = -y2 * (z2 * z2); J[1][1] = -y1 * (z2 * z2); J[1][3] = -2 * y1 * y2 * z2;
+        J[2][0] = y2 * la; J[2][1] = y1 * la; J[2][2] = z2 * la; J[2][3] = z1 * la; J[2][4] = y1 * y2 + z1 * z2;
+        if (p.nonlinear != 0.0) {
+            J[3][0] = -(y2 * y2) * (z2 * z2 * z2) * (la * la); J[3][1] = -2 * y1 * y2 * (z2 * z2 * z2) * (la * la);
+            J[3][3] = -3 * y1 * (y2 * y2) * (z2 * z2) * (la * la); J[3][4] = -2 * y1 * (y2 * y2) * (z2 * z2 * z2) * la;
+        } else {
+            J[3][0] = -(y2 * y2) * (z2 * z2) * la; J[3][1] = -2 * y1 * y2 * (z2 * z2) * la;
+            J[3][3] = -2 * y1 * (y2 * y2) * z2 * la; J[3][4] = -y1 * (y2 * y2) * (z2 * z2);
+        }
+        J[4][0] = y2 * y2; J[4][1] = 2 * y1 * y2;
+    }
+};
+
+// ---------------------------------------------------------------- polynomial index-2 DAE
+// validation_dense_output.py:23-59 with p = 2: y' = P'(t) + (z - y), 0 = y - P(t);
+// parameters (a4, a3, a2, a1, a0), Horner evaluation
+struct PolyDAE2 {
+    static constexpr int N = 2, NP = 5;
+    struct P { double a[5]; };
+    using Mass = MassDiag01<2, 0x1u>;
+    static BRDAE_HD void load(P &p, const double *params, int64_t B, int64_t i) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p.a[k] = params[k * B + i];
+    }
+    static BRDAE_HD void rhs(const P &p, double t, const double (&x)[2], double (&f)[2]) {
+        const double Pv = (((p.a[0] * t + p.a[1]) * t + p.a[2]) * t + p.a[3]) * t + p.a[4];
+        const double dP = ((4 * p.a[0] * t + 3 * p.a[1]) * t + 2 * p.a[2]) * t + p.a[3];
+        f[0] = dP + (x[1] - x[0]);
+        f[1] = x[0] - Pv;
+    }
+    static BRDAE_HD void jac(const P &, double, const double (&)[2], double (&J)[2][2]) {
+        J[0][0] = -1; J[0][1] = 1; J[1][0] = 1; J[1][1] = 0;
+    }
+};
+
+// ---------------------------------------------------------------- linear ODE (mass-matrix check)
+// linear_ODE_with_mass_matrix.py:32-39: f = c * x componentwise, 7 unknowns, parameters c[7]
+struct Linear7 {
+    static constexpr int N = 7, NP = 7;
+    struct P { double c[7]; };
+    using Mass = MassDiag01<7, 0x7Fu>;
+    static BRDAE_HD void load(P &p, const double *params, int64_t B, int64_t i) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) p.c[k] = params[k * B + i];
+    }
+    static BRDAE_HD void rhs(const P &p, double, const double (&x)[7], double (&f)[7]) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) f[k] = p.c[k] * x[k];
+    }
+    static BRDAE_HD void jac(const P &p, double, const double (&)[7], double (&J)[7][7]) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) J[r][c] = (r == c) ? p.c[r] : 0.0;
+    }
+};
+
 }  // namespace brdae

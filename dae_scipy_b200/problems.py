@@ -45,6 +45,16 @@ class Problem:
             return M
         if self.name == "robertson":
             return np.array([[1., 0., 0.], [0., 1., 0.], [0., 0., 0.]])
+        if self.name == "robertson_ode":
+            return np.eye(3)
+        if self.name == "jay":
+            M = np.eye(5)
+            M[-1, -1] = 0
+            return M
+        if self.name == "polydae2":
+            return np.array([[1., 0.], [0., 0.]])
+        if self.name == "linear7":
+            return np.eye(7)
         if self.name == "transistor":
             p = np.asarray(self.param_defaults if params is None else params, dtype=np.float64)
             C1, C2, C3 = p[0], p[1], p[2]
@@ -73,6 +83,11 @@ PROBLEMS = {
                           (1e-6, 2e-6, 3e-6, 1e3, 9e3, 9e3, 9e3, 9e3, 9e3, 6.0, 0.4, 200 * np.pi),
                           (0, 0, 0, 0, 0), (0.0, 1.0), per_system_mass=True),
     "npendulum": Problem("npendulum", 5, 0, (), (), (), (0.0, 2 * (2 * np.pi * np.sqrt(2.0 / 9.81)))),
+    # known-answer problems of the reference's own checks
+    "robertson_ode": Problem("robertson_ode", 6, 3, ("k1", "k2", "k3"), (0.04, 1e4, 3e7), (0, 0, 0), (0.0, 5e6)),
+    "jay": Problem("jay", 7, 5, ("nonlinear",), (1.0,), (0, 0, 0, 0, 3), (0.0, 0.1)),
+    "polydae2": Problem("polydae2", 8, 2, ("a4", "a3", "a2", "a1", "a0"), (0.0, 0.0, 0.0, 1.0, 0.0), (0, 2), (0.0, 2.0)),
+    "linear7": Problem("linear7", 9, 7, tuple(f"c{k}" for k in range(7)), (1.0,) * 7, (0,) * 7, (0.0, 1.0)),
 }
 
 

@@ -37,7 +37,11 @@ enum {
     BRDAE_ROBERTSON = 3, /* tests/robertson.py:78-87   params (k1, k2, k3)          n=3 */
     BRDAE_TRANSISTOR = 4, /* tests/transistor_amplifier.py:33-56
                              params (C1,C2,C3,R0,R1,R2,R3,R4,R5,Ub,Ua,w)           n=5 */
-    BRDAE_NPENDULUM = 5  /* tests/recursive_pendulum.py:93-127, no params, n = 5*nodes */
+    BRDAE_NPENDULUM = 5, /* tests/recursive_pendulum.py:93-127, no params, n = 5*nodes */
+    BRDAE_ROBERTSON_ODE = 6, /* tests/robertson.py:69-77 (ODE form), params (k1,k2,k3)   n=3 */
+    BRDAE_JAY = 7,       /* tests/jay_dae.py:22-68, params (nonlinear flag)             n=5 */
+    BRDAE_POLYDAE2 = 8,  /* tests/validation_dense_output.py:23-59 (p=2), params a4..a0 n=2 */
+    BRDAE_LINEAR7 = 9    /* tests/linear_ODE_with_mass_matrix.py:32-39, params c[7]     n=7 */
 };
 
 /* per-system status, same meaning as OdeResult.status (radauDAE.py:986-989, 1087-1091) */

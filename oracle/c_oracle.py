@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libradau_oracle.so")
 
 PROBLEM_IDS = {"pendulum3": 0, "pendulum2": 1, "pendulum1": 2, "robertson": 3, "transistor": 4,
-               "npendulum": 5}
+               "npendulum": 5, "robertson_ode": 6, "jay": 7, "polydae2": 8, "linear7": 9}
 COUNTER_NAMES = ("nfev", "njev", "nlu", "nstep", "naccpt", "nrejct", "nfailed", "nlusolve",
                  "nlusolve_err")
 

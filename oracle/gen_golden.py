@@ -39,15 +39,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 def build_system(problem, p, n=None):
-    if problem.startswith("pendulum"):
-        return prob.pendulum(int(problem[-1]), *p)
-    if problem == "robertson":
-        return prob.robertson(*p)
-    if problem == "transistor":
-        return prob.transistor(*p)
-    if problem == "npendulum":
-        return prob.npendulum(n // 5)
-    raise ValueError(problem)
+    return prob.build(problem, p, n)
 
 
 def run_reference_with_counters(ens, over=None):
@@ -191,6 +183,36 @@ def main():
     back["t_span"] = (1.0, 0.0)
     back["t_eval"] = np.linspace(1.0, 0.0, 11)
     save("opt_pendulum3_backward", back)
+    # --- the reference's own known-answer problems, analytic Jacobians
+    jay_opts = dict(rtol=1e-3, atol=1e-4, first_step=1e-5, max_newton_ite=6, min_factor=0.2, max_factor=10,
+                    zero_algebraic_error=True, scale_residuals=False, scale_newton_norm=False, scale_error=True,
+                    max_bad_ite=1, bUsePredictiveNewtonStoppingCriterion=False, mass_matrix="problem",
+                    var_index=np.array([0, 0, 0, 0, 3]))                       # jay_dae.py:76-101
+    save("kat_jay", dict(problem="jay", t_span=(0.0, 0.1), y0=np.ones((2, 5)), params=np.array([[1.0], [0.0]]),
+                         t_eval=np.linspace(0, 0.1, 11), options=jay_opts))
+    poly_opts = dict(rtol=1e-4, atol=1e-5, first_step=0.25, max_step=0.25, min_factor=0.2, max_factor=10, max_newton_ite=6,
+                     zero_algebraic_error=True, scale_residuals=True, scale_newton_norm=False, scale_error=True,
+                     max_bad_ite=2, bUsePredictiveNewtonStoppingCriterion=False, bPerformAllNewtonIterations=True,
+                     mass_matrix="problem", var_index=np.array([0, 2]))        # validation_dense_output.py:77-105
+    a_full = np.array([0.01, 0.02, .05, -0.1, -0.4, 0.5, 1., 2.])
+    P_rows, y0_rows = [], []
+    for deg in range(0, 5):
+        a = np.flip(np.flip(a_full)[:deg + 1])
+        a5 = np.concatenate([np.zeros(5 - a.size), a])
+        P_rows.append(a5); y0_rows.append([a[-1], a[-1]])
+    save("kat_polydae2", dict(problem="polydae2", t_span=(0.0, 2.0), y0=np.array(y0_rows), params=np.array(P_rows),
+                              t_eval=np.linspace(0, 2, 41), options=poly_opts))
+    lin_opts = dict(rtol=1e-10, atol=1e-10, var_index=None)                    # linear_ODE_with_mass_matrix.py:26-48
+    eig = prob.LINEAR7_EIG
+    save("kat_linear7_with_mass", dict(problem="linear7", t_span=(0.0, 1.0), y0=np.ones((1, 7)), params=np.ones((1, 7)),
+                                       t_eval=np.array([0.5, 1.0]), options=dict(lin_opts, mass_matrix=np.diag(1 / eig))))
+    save("kat_linear7_without_mass", dict(problem="linear7", t_span=(0.0, 1.0), y0=np.ones((1, 7)), params=eig[None, :],
+                                          t_eval=np.array([0.5, 1.0]), options=dict(lin_opts, mass_matrix=np.eye(7))))
+    rob_script = dict(rtol=1e-3, atol=1e-4, first_step=1e-8, max_newton_ite=6, max_bad_ite=0, scale_residuals=True,
+                      scale_newton_norm=False, scale_error=True)                # robertson.py:105-132
+    save("kat_robertson_ode", dict(problem="robertson_ode", t_span=(0.0, 5e6), y0=prob.ROBERTSON_Y0[None, :],
+                                   params=np.array([[0.04, 1e4, 3e7]]), t_eval=np.array([1.0, 1e3, 5e6]),
+                                   options=dict(rob_script, mass_matrix="problem", var_index=np.array([0, 0, 0]))))
     # --- n-pendulum chains (dense analytic Jacobian handed to the reference)
     save("ens_npendulum_n4", E.npendulum_ensemble(3, n_nodes=4))
     save("ens_npendulum_n10", E.npendulum_ensemble(2, n_nodes=10))

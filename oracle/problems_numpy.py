@@ -105,7 +105,95 @@ def robertson(k1=0.04, k2=1e4, k3=3e7):
     return fun, jac, mass, np.array([0, 0, 1])
 
 
+def robertson_ode(k1=0.04, k2=1e4, k3=3e7):
+    """ODE formulation, robertson.py:69-77 (third equation y2' = k3 y1^2, identity mass)."""
+    mass = np.eye(3)
+
+    def fun(t, y):
+        return np.array([-k1 * y[0] + k2 * y[1] * y[2],
+                         k1 * y[0] - k2 * y[1] * y[2] - k3 * (y[1] ** 2),
+                         k3 * (y[1] ** 2)])
+
+    def jac(t, y):
+        return np.array([[-k1, k2 * y[2], k2 * y[1]],
+                         [k1, -k2 * y[2] - 2 * k3 * y[1], -k2 * y[1]],
+                         [0., 2 * k3 * y[1], 0.], ])
+    return fun, jac, mass, np.array([0, 0, 0])
+
+
 ROBERTSON_Y0 = np.array([1., 0., 0.])
+
+
+# ------------------------------------------------------------------------- Jay 1995
+def jay(nonlinear=1.0):
+    """Index-3 DAE of Jay 1995, jay_dae.py:22-68 (y1, y2, z1, z2, lambda).  The reference has no
+    analytic Jacobian (finite differences); the one below is checked by complex step in the tests."""
+    nl = bool(nonlinear)
+    mass = np.eye(5)
+    mass[-1, -1] = 0
+
+    def fun(t, y):
+        y1, y2, z1, z2, la = y
+        if nl:
+            dy3 = -y1 * (y2 ** 2) * (z2 ** 3) * (la ** 2)
+        else:
+            dy3 = -y1 * (y2 ** 2) * (z2 ** 2) * la
+        return np.array([2 * y1 * y2 * z1 * z2, -y1 * y2 * (z2 ** 2), (y1 * y2 + z1 * z2) * la, dy3,
+                         y1 * y2 ** 2 - 1.0], dtype=y.dtype)
+
+    def jac(t, y):
+        y1, y2, z1, z2, la = y
+        J = np.zeros((5, 5))
+        J[0] = [2 * y2 * z1 * z2, 2 * y1 * z1 * z2, 2 * y1 * y2 * z2, 2 * y1 * y2 * z1, 0.]
+        J[1] = [-y2 * (z2 ** 2), -y1 * (z2 ** 2), 0., -2 * y1 * y2 * z2, 0.]
+        J[2] = [y2 * la, y1 * la, z2 * la, z1 * la, y1 * y2 + z1 * z2]
+        if nl:
+            J[3] = [-(y2 ** 2) * (z2 ** 3) * (la ** 2), -2 * y1 * y2 * (z2 ** 3) * (la ** 2), 0.,
+                    -3 * y1 * (y2 ** 2) * (z2 ** 2) * (la ** 2), -2 * y1 * (y2 ** 2) * (z2 ** 3) * la]
+        else:
+            J[3] = [-(y2 ** 2) * (z2 ** 2) * la, -2 * y1 * y2 * (z2 ** 2) * la, 0., -2 * y1 * (y2 ** 2) * z2 * la,
+                    -y1 * (y2 ** 2) * (z2 ** 2)]
+        J[4] = [y2 ** 2, 2 * y1 * y2, 0., 0., 0.]
+        return J
+    return fun, jac, mass, np.array([0, 0, 0, 0, 3])
+
+
+JAY_Y0 = np.ones(5)
+
+
+# ------------------------------------------------------------------------- polynomial index-2 DAE
+def polydae2(a4=0., a3=0., a2=0., a1=1., a0=0.):
+    """validation_dense_output.py:23-59 with p = 2: y' = P'(t) + (z - y), 0 = y - P(t), where
+    P(t) = a4 t^4 + ... + a0 (highest power first, like np.polyval)."""
+    a = np.array([a4, a3, a2, a1, a0], dtype=float)
+    der = np.array([4 * a4, 3 * a3, 2 * a2, a1], dtype=float)
+    mass = np.eye(2)
+    mass[-1, -1] = 0
+
+    def fun(t, x):
+        y, z = x
+        return np.array([np.polyval(der, t) + (z - y), y - np.polyval(a, t)])
+
+    def jac(t, x):
+        return np.array([[-1., 1.], [1., 0.]])
+    return fun, jac, mass, np.array([0, 2])
+
+
+# ------------------------------------------------------------------------- linear ODE with mass
+def linear7(*c):
+    """linear_ODE_with_mass_matrix.py:32-39: f(t, x) = c * x componentwise (c = 1 with the mass matrix
+    diag(1/eig), c = eig without)."""
+    c = np.array(c if c else np.ones(7), dtype=float)
+
+    def fun(t, x):
+        return c * x
+
+    def jac(t, x):
+        return np.diag(c)
+    return fun, jac, np.eye(7), np.zeros(7, dtype=int)
+
+
+LINEAR7_EIG = np.array([float(i) * (-1) ** (i) for i in range(1, 8)])
 
 
 # --------------------------------------------------------------------------- transistor
@@ -261,3 +349,26 @@ def npendulum(n):
         var_index[3 + i * 5] = 2
         var_index[4 + i * 5] = 3
     return fun, jac, np.diag(diag_mass), var_index
+
+
+# --------------------------------------------------------------------------- registry
+def build(problem, params=(), n=None):
+    """(fun, jac, mass, var_index) of one system of `problem` with its parameter vector."""
+    params = tuple(float(x) for x in params)
+    if problem.startswith("pendulum"):
+        return pendulum(int(problem[-1]), *params)
+    if problem == "robertson":
+        return robertson(*params)
+    if problem == "robertson_ode":
+        return robertson_ode(*params)
+    if problem == "transistor":
+        return transistor(*params)
+    if problem == "npendulum":
+        return npendulum(n // 5)
+    if problem == "jay":
+        return jay(*params)
+    if problem == "polydae2":
+        return polydae2(*params)
+    if problem == "linear7":
+        return linear7(*params)
+    raise ValueError(problem)

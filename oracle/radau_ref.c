@@ -68,7 +68,7 @@ enum { C_NFEV, C_NJEV, C_NLU, C_NSTEP, C_NACC, C_NREJ, C_NFAIL, C_NSOLVE, C_NSOL
 
 /* ---- problems: same parameter vectors as dae_scipy_b200/problems.py ---- */
 enum { PB_PENDULUM3 = 0, PB_PENDULUM2 = 1, PB_PENDULUM1 = 2, PB_ROBERTSON = 3, PB_TRANSISTOR = 4,
-       PB_NPENDULUM = 5 };
+       PB_NPENDULUM = 5, PB_ROBERTSON_ODE = 6, PB_JAY = 7, PB_POLYDAE2 = 8, PB_LINEAR7 = 9 };
 
 typedef struct {
     int problem, n;
@@ -122,6 +122,70 @@ static void rob_jac(const prob_ctx *c, double t, const double *y, double *J) {
     J[0] = -k1; J[1] = k2 * y[2]; J[2] = k2 * y[1];
     J[3] = k1;  J[4] = -k2 * y[2] - 2 * k3 * y[1]; J[5] = -k2 * y[1];
     J[6] = 1; J[7] = 1; J[8] = 1;
+}
+/* robertson.py:69-77 (ODE formulation) */
+static void robode_rhs(const prob_ctx *c, double t, const double *y, double *f) {
+    (void)t;
+    double k1 = c->p[0], k2 = c->p[1], k3 = c->p[2];
+    f[0] = -k1 * y[0] + k2 * y[1] * y[2];
+    f[1] = k1 * y[0] - k2 * y[1] * y[2] - k3 * (y[1] * y[1]);
+    f[2] = k3 * (y[1] * y[1]);
+}
+static void robode_jac(const prob_ctx *c, double t, const double *y, double *J) {
+    (void)t;
+    double k1 = c->p[0], k2 = c->p[1], k3 = c->p[2];
+    J[0] = -k1; J[1] = k2 * y[2]; J[2] = k2 * y[1];
+    J[3] = k1;  J[4] = -k2 * y[2] - 2 * k3 * y[1]; J[5] = -k2 * y[1];
+    J[6] = 0; J[7] = 2 * k3 * y[1]; J[8] = 0;
+}
+/* jay_dae.py:22-45; p = (nonlinear flag) */
+static void jay_rhs(const prob_ctx *c, double t, const double *y, double *f) {
+    (void)t;
+    double y1 = y[0], y2 = y[1], z1 = y[2], z2 = y[3], la = y[4];
+    f[0] = 2 * y1 * y2 * z1 * z2;
+    f[1] = -y1 * y2 * (z2 * z2);
+    f[2] = (y1 * y2 + z1 * z2) * la;
+    if (c->p[0] != 0.0) f[3] = -y1 * (y2 * y2) * (z2 * z2 * z2) * (la * la);
+    else f[3] = -y1 * (y2 * y2) * (z2 * z2) * la;
+    f[4] = y1 * (y2 * y2) - 1.0;
+}
+static void jay_jac(const prob_ctx *c, double t, const double *y, double *J) {
+    (void)t;
+    double y1 = y[0], y2 = y[1], z1 = y[2], z2 = y[3], la = y[4];
+    memset(J, 0, 25 * sizeof(double));
+    J[0] = 2 * y2 * z1 * z2; J[1] = 2 * y1 * z1 * z2; J[2] = 2 * y1 * y2 * z2; J[3] = 2 * y1 * y2 * z1;
+    J[5] = -y2 * (z2 * z2); J[6] = -y1 * (z2 * z2); J[8] = -2 * y1 * y2 * z2;
+    J[10] = y2 * la; J[11] = y1 * la; J[12] = z2 * la; J[13] = z1 * la; J[14] = y1 * y2 + z1 * z2;
+    if (c->p[0] != 0.0) {
+        J[15] = -(y2 * y2) * (z2 * z2 * z2) * (la * la); J[16] = -2 * y1 * y2 * (z2 * z2 * z2) * (la * la);
+        J[18] = -3 * y1 * (y2 * y2) * (z2 * z2) * (la * la); J[19] = -2 * y1 * (y2 * y2) * (z2 * z2 * z2) * la;
+    } else {
+        J[15] = -(y2 * y2) * (z2 * z2) * la; J[16] = -2 * y1 * y2 * (z2 * z2) * la;
+        J[18] = -2 * y1 * (y2 * y2) * z2 * la; J[19] = -y1 * (y2 * y2) * (z2 * z2);
+    }
+    J[20] = y2 * y2; J[21] = 2 * y1 * y2;
+}
+/* validation_dense_output.py:23-59, p = 2; params (a4,a3,a2,a1,a0), Horner evaluation */
+static void poly_rhs(const prob_ctx *c, double t, const double *x, double *f) {
+    const double *a = c->p;
+    double P = (((a[0] * t + a[1]) * t + a[2]) * t + a[3]) * t + a[4];
+    double dP = ((4 * a[0] * t + 3 * a[1]) * t + 2 * a[2]) * t + a[3];
+    f[0] = dP + (x[1] - x[0]);
+    f[1] = x[0] - P;
+}
+static void poly_jac(const prob_ctx *c, double t, const double *x, double *J) {
+    (void)c; (void)t; (void)x;
+    J[0] = -1; J[1] = 1; J[2] = 1; J[3] = 0;
+}
+/* linear_ODE_with_mass_matrix.py:32-39: f = c * x, params c[7] */
+static void lin_rhs(const prob_ctx *c, double t, const double *x, double *f) {
+    (void)t;
+    for (int k = 0; k < 7; ++k) f[k] = c->p[k] * x[k];
+}
+static void lin_jac(const prob_ctx *c, double t, const double *x, double *J) {
+    (void)t; (void)x;
+    memset(J, 0, 49 * sizeof(double));
+    for (int k = 0; k < 7; ++k) J[k * 7 + k] = c->p[k];
 }
 /* transistor_amplifier.py:33-56; p = (C1,C2,C3,R0,R1,R2,R3,R4,R5,Ub,Ua,w) */
 static void tra_rhs(const prob_ctx *c, double t, const double *y, double *f) {
@@ -237,6 +301,10 @@ static void prob_rhs(const prob_ctx *c, double t, const double *y, double *f) {
     case PB_ROBERTSON: rob_rhs(c, t, y, f); break;
     case PB_TRANSISTOR: tra_rhs(c, t, y, f); break;
     case PB_NPENDULUM: npe_rhs(c, t, y, f); break;
+    case PB_ROBERTSON_ODE: robode_rhs(c, t, y, f); break;
+    case PB_JAY: jay_rhs(c, t, y, f); break;
+    case PB_POLYDAE2: poly_rhs(c, t, y, f); break;
+    case PB_LINEAR7: lin_rhs(c, t, y, f); break;
     default: pend_rhs(c, t, y, f);
     }
 }
@@ -245,6 +313,10 @@ static void prob_jac(const prob_ctx *c, double t, const double *y, double *J) {
     case PB_ROBERTSON: rob_jac(c, t, y, J); break;
     case PB_TRANSISTOR: tra_jac(c, t, y, J); break;
     case PB_NPENDULUM: npe_jac(c, t, y, J); break;
+    case PB_ROBERTSON_ODE: robode_jac(c, t, y, J); break;
+    case PB_JAY: jay_jac(c, t, y, J); break;
+    case PB_POLYDAE2: poly_jac(c, t, y, J); break;
+    case PB_LINEAR7: lin_jac(c, t, y, J); break;
     default: pend_jac(c, t, y, J);
     }
 }
@@ -255,6 +327,10 @@ int orc_problem_dims(int problem, int *n, int *n_params) {
     case PB_ROBERTSON: *n = 3; *n_params = 3; return 0;
     case PB_TRANSISTOR: *n = 5; *n_params = 12; return 0;
     case PB_NPENDULUM: *n = -1; *n_params = 0; return 0; /* n = 5*nodes given by the caller */
+    case PB_ROBERTSON_ODE: *n = 3; *n_params = 3; return 0;
+    case PB_JAY: *n = 5; *n_params = 1; return 0;
+    case PB_POLYDAE2: *n = 2; *n_params = 5; return 0;
+    case PB_LINEAR7: *n = 7; *n_params = 7; return 0;
     }
     return -1;
 }
@@ -521,8 +597,9 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
     else { /* pendulum.py:139-140, robertson.py:78, recursive_pendulum.py:120-127: identity with a
               zero on the rows of the algebraic unknowns (last of 5 / last of 3) */
         memset(w->M, 0, sizeof(double) * n * n);
-        int blk = (pc->problem == PB_ROBERTSON) ? 3 : 5;
-        for (int c = 0; c < n; ++c) w->M[c * n + c] = (c % blk == blk - 1) ? 0.0 : 1.0;
+        int blk = (pc->problem == PB_ROBERTSON) ? 3 : (pc->problem == PB_POLYDAE2) ? 2 : 5;
+        int identity = (pc->problem == PB_ROBERTSON_ODE || pc->problem == PB_LINEAR7);
+        for (int c = 0; c < n; ++c) w->M[c * n + c] = (!identity && c % blk == blk - 1) ? 0.0 : 1.0;
     }
     for (int r = 0; r < n; ++r) {
         int lo = n, hi = -1;

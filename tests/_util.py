@@ -81,15 +81,7 @@ def run_numpy_oracle(ens, **over):
                counters=np.zeros((B, 9), np.int32), y_final=np.zeros((B, n)), t_final=np.zeros(B))
     for i in range(B):
         p = ens["params"][i] if ens["params"] is not None else ()
-        name = ens["problem"]
-        if name.startswith("pendulum"):
-            fun, jac, mass, _ = prob.pendulum(int(name[-1]), *p)
-        elif name == "robertson":
-            fun, jac, mass, _ = prob.robertson(*p)
-        elif name == "transistor":
-            fun, jac, mass, _ = prob.transistor(*p)
-        else:
-            fun, jac, mass, _ = prob.npendulum(n // 5)
+        fun, jac, mass, _ = prob.build(ens["problem"], p, n)
         if not isinstance(mm, str):
             mass = mm
         r = orc.solve(fun, ens["t_span"], ens["y0"][i], jac=jac, mass_matrix=mass,
@@ -169,4 +161,5 @@ def well_conditioned(name):
     return name in ("g1_pendulum3_single", "g2_robertson_single", "ens_pendulum3_tend2", "ens_pendulum2_tend2",
                     "ens_pendulum1_tend2", "opt_pendulum3_max_step", "opt_pendulum3_nmax_step",
                     "opt_pendulum3_dense_mass", "opt_pendulum3_backward", "opt_pendulum3_controller_off",
-                    "ens_npendulum_n4", "ens_npendulum_n10", "ens_npendulum_n20", "script_robertson")
+                    "ens_npendulum_n4", "ens_npendulum_n10", "ens_npendulum_n20", "script_robertson",
+                    "kat_jay", "kat_polydae2", "kat_linear7_with_mass", "kat_linear7_without_mass", "kat_robertson_ode")

@@ -40,6 +40,10 @@ extern "C" int sim_solve(const brdae_batch *b, const brdae_options *o) {
     case BRDAE_PENDULUM1: run_mass<Pendulum<1>>(dense, a); break;
     case BRDAE_ROBERTSON: run_mass<Robertson>(dense, a); break;
     case BRDAE_TRANSISTOR: run_mass<Transistor>(dense, a); break;
+    case BRDAE_ROBERTSON_ODE: run_mass<RobertsonODE>(dense, a); break;
+    case BRDAE_JAY: run_mass<Jay>(dense, a); break;
+    case BRDAE_POLYDAE2: run_mass<PolyDAE2>(dense, a); break;
+    case BRDAE_LINEAR7: run_mass<Linear7>(dense, a); break;
     default: return BRDAE_ERR_UNSUPPORTED;
     }
     return BRDAE_OK;
