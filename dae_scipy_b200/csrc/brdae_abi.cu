@@ -65,7 +65,8 @@ void brdae_default_options(brdae_options *o) {
 size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *) {
     if (!b) return 0;
     size_t bytes = kCounterBytes;
-    if (b->problem == BRDAE_NPENDULUM) bytes += k2_scratch_bytes(b->n, sm_count());
+    if (b->problem == BRDAE_NPENDULUM)
+        bytes += npendulum_uses_k3(b->n, b->n_systems) ? k3_scratch_bytes(b->n, b->n_systems) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
     return bytes;
 }
 

@@ -23,6 +23,9 @@
 // Reference map: same as radau_k1.cuh (radauDAE.py:515-791, 793-949, 951-982, 1079-1157).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace brdae {
@@ -35,6 +38,7 @@ constexpr double GRAV = 9.81;
 
 struct K2Cfg {
     int complex_in_smem;          // complex LU factors in shared memory?
+    int state_in_global;          // ALL per-rope state in the (L2-resident) global scratch: more ropes in flight
     size_t scratch_stride;        // doubles per CTA in the global scratch
 };
 
@@ -287,27 +291,28 @@ __device__ void rope_factor(const Rope &s, const SolveArgs &a, double mr, double
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     if (warp == 0) lu_band_real(s.lur, s.pivr, N);
-    else if (warp == 1) lu_band_cplx(s.lcr, s.lci, s.pivc, N);
+    if (warp == (blockDim.x > 32 ? 1 : 0)) lu_band_cplx(s.lcr, s.lci, s.pivc, N);   // one-warp CTAs do both in turn
     __syncthreads();
 }
 
 template <int I>
 __device__ __forceinline__ double zstage(const double *W, int N, int c) { return stage_z<I>(W[c], W[N + c], W[2 * N + c]); }
 
-__global__ void __launch_bounds__(K2_BLOCK, 1) k2_kernel(const __grid_constant__ SolveArgs a, const K2Cfg cfg) {
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__ SolveArgs a, const K2Cfg cfg) {
     extern __shared__ double sm[];
     __shared__ long long next_idx;
     const int N = a.n, nn = N / 5, tid = threadIdx.x, nthr = blockDim.x;
     Rope s;
     s.N = N; s.nn = nn;
-    double *p = sm;
+    double *p = cfg.state_in_global ? a.scratch + (size_t)blockIdx.x * cfg.scratch_stride : sm;
     s.y = p; p += N; s.f = p; p += N; s.yold = p; p += N; s.yJ = p; p += N;
     s.Q = p; p += 3 * N; s.W = p; p += 3 * N; s.R = p; p += 3 * N;
     s.inv_ns = p; p += N; s.inv_es = p; p += N; s.Yt = p; p += N; s.Ft = p; p += N; s.ze = p; p += N; s.err = p; p += N;
     s.aa = p; p += nn; s.bb = p; p += nn; s.mass_m = p; p += nn; s.inv_m = p; p += nn; s.r0s = p; p += nn;
     s.atol = p; p += N; s.red = p; p += 8;
     s.lur = p; p += (size_t)N * WB;
-    if (cfg.complex_in_smem) { s.lcr = p; p += (size_t)N * WB; s.lci = p; p += (size_t)N * WB; }
+    if (cfg.complex_in_smem || cfg.state_in_global) { s.lcr = p; p += (size_t)N * WB; s.lci = p; p += (size_t)N * WB; }
     else { s.lcr = a.scratch + (size_t)blockIdx.x * cfg.scratch_stride; s.lci = s.lcr + (size_t)N * WB; }
     s.vidx = reinterpret_cast<int *>(p); s.pivr = s.vidx + N; s.pivc = s.pivr + N;
 
@@ -455,7 +460,7 @@ __global__ void __launch_bounds__(K2_BLOCK, 1) k2_kernel(const __grid_constant__
                         }
                         __syncthreads();
                         if ((tid >> 5) == 0) solve_band_real(s.lur, s.pivr, s.R, N);
-                        else if ((tid >> 5) == 1) solve_band_cplx(s.lcr, s.lci, s.pivc, s.R + N, s.R + 2 * N, N);
+                        if ((tid >> 5) == (nthr > 32 ? 1 : 0)) solve_band_cplx(s.lcr, s.lci, s.pivc, s.R + N, s.R + 2 * N, N);
                         __syncthreads();
                         cnt[CN_NSOLVE]++;
                         sumsq_scaled(s.R, s.inv_ns, N, 3 * N, s.red);
@@ -616,10 +621,29 @@ constexpr size_t kHeaderBytes = 256;
 
 }  // namespace
 
-// workspace layout after the 256-byte work counter: atol[N] | var_index[N] (int32, padded) | per-CTA complex LU
-size_t k2_scratch_bytes(int n, int sms) {
+// workspace layout after the 256-byte work counter: atol[N] | var_index[N] (int32, padded) | per-CTA scratch
+// "global" flavour: 64-thread CTAs whose whole state lives in a per-CTA slice of the workspace (a few
+// hundred MB in total, L2-resident for short chains), so that several times more ropes are in flight
+// per SM than shared memory would allow; chosen for batches that can fill those slots.
+#ifndef K2G_BLOCK_
+#define K2G_BLOCK_ 64
+#endif
+#ifndef K2G_PER_SM_
+#define K2G_PER_SM_ 8
+#endif
+constexpr int K2G_BLOCK = K2G_BLOCK_, K2G_PER_SM = K2G_PER_SM_;
+bool k2_use_global(int64_t B, int sms) {
+    const char *force = std::getenv("BRDAE_K2_STATE");
+    if (force && std::strcmp(force, "smem") == 0) return false;
+    if (force && std::strcmp(force, "global") == 0) return true;
+    return B >= (int64_t)(sms > 0 ? sms : 148) * 4;
+}
+
+size_t k2_scratch_bytes(int n, int sms, int64_t B) {
     size_t bytes = sizeof(double) * n + ((sizeof(int32_t) * n + 7) / 8) * 8;
-    if (!k2_complex_fits(n)) bytes += (size_t)(sms > 0 ? sms : 148) * 2 * n * WB * sizeof(double);
+    const int nsm = sms > 0 ? sms : 148;
+    if (k2_use_global(B, sms)) bytes += (size_t)nsm * K2G_PER_SM * k2_smem_doubles(n, true) * sizeof(double);
+    else if (!k2_complex_fits(n)) bytes += (size_t)nsm * 2 * n * WB * sizeof(double);
     return bytes;
 }
 
@@ -627,17 +651,21 @@ int k2_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, i
                  bool geom_only) {
     const int N = a_in.n;
     if (N <= 0 || N % 5 != 0 || N < 10) return BRDAE_ERR_BAD_ARGUMENT;
-    const bool cfits = k2_complex_fits(N);
-    const size_t smem = k2_smem_doubles(N, cfits) * 8;
-    if (smem > kSmemBudget) return BRDAE_ERR_UNSUPPORTED;          // more than ~170 nodes
     const int nsm = sms > 0 ? sms : 148;
-    int per_sm = (int)(kSmemBudget / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    int64_t grid = (int64_t)nsm * per_sm;
-    if (!cfits) grid = nsm;
+    const bool global_state = k2_use_global(a_in.B, sms);
+    const bool cfits = k2_complex_fits(N);
+    size_t smem = global_state ? 0 : k2_smem_doubles(N, cfits) * 8;
+    if (smem > kSmemBudget) return BRDAE_ERR_UNSUPPORTED;          // more than ~170 nodes in shared-memory mode
+    int64_t grid;
+    if (global_state) grid = (int64_t)nsm * K2G_PER_SM;
+    else {
+        int per_sm = (int)(kSmemBudget / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        grid = cfits ? (int64_t)nsm * per_sm : nsm;
+    }
     if (a_in.B < grid) grid = a_in.B > 0 ? a_in.B : 1;
-    if (g) { g->grid = (int)grid; g->block = K2_BLOCK; g->smem = (int)smem; }
+    if (g) { g->grid = (int)grid; g->block = global_state ? K2G_BLOCK : K2_BLOCK; g->smem = (int)smem; }
     if (geom_only) return BRDAE_OK;
     if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;   // band kernel: the problem's own M and J only
     SolveArgs a = a_in;
@@ -652,9 +680,15 @@ int k2_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, i
     a.atol_dev = atol_d; a.var_index_dev = vidx_d; a.scratch = scratch;
     K2Cfg cfg;
     cfg.complex_in_smem = cfits ? 1 : 0;
-    cfg.scratch_stride = (size_t)2 * N * WB;
-    if (cudaFuncSetAttribute(k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BRDAE_ERR_CUDA;
-    k2_kernel<<<(int)grid, K2_BLOCK, smem, stream>>>(a, cfg);
+    cfg.state_in_global = global_state ? 1 : 0;
+    cfg.scratch_stride = global_state ? k2_smem_doubles(N, true) : (size_t)2 * N * WB;
+    if (global_state) {
+        k2_kernel<K2G_BLOCK, K2G_PER_SM><<<(int)grid, K2G_BLOCK, 0, stream>>>(a, cfg);
+    } else {
+        auto kern = k2_kernel<K2_BLOCK, 1>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BRDAE_ERR_CUDA;
+        kern<<<(int)grid, K2_BLOCK, smem, stream>>>(a, cfg);
+    }
     return cudaPeekAtLastError() == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;
 }
 

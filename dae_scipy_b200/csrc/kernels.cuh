@@ -21,7 +21,12 @@ int k1_transistor(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, 
 int k1_extra(int problem, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 // CTA-per-system banded kernel for the n-pendulum chain (k2_npendulum.cu)
 int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
-size_t k2_scratch_bytes(int n, int sms);
+size_t k2_scratch_bytes(int n, int sms, int64_t B);
+// lane-per-rope kernel for large ensembles of chains (k3_npendulum_lanes.cu)
+int k3_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+size_t k3_scratch_bytes(int n, int64_t B);
+// which chain kernel a batch of B ropes with n unknowns uses (BRDAE_NPENDULUM_KERNEL=k2|k3 overrides)
+bool npendulum_uses_k3(int n, int64_t B);
 
 // layout.cu: dst[z*dst_zs + c*dst_rs + r] = src[z*src_zs + r*src_rs + c] for r < R, c < C, z < Z
 // (rows <-> structure-of-arrays permutations of the host-buffer entry points)

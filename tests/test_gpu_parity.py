@@ -62,10 +62,35 @@ def test_gpu_bit_identical_to_c_oracle(case, make, over):
     (3, 4, dict(zero_algebraic_error=True, bAlwaysApply2ndEstimate=False, bUsePredictiveController=False)),
     (5, 3, dict(scale_residuals=False, scale_newton_norm=False, scale_error=False, bUseExtrapolatedGuess=False)),
 ])
-def test_gpu_npendulum_bit_identical_to_c_oracle(nodes, B, over):
-    """K2 (CTA-per-system, banded LU in shared memory) against the dense scalar oracle."""
+@pytest.mark.parametrize("kernel", ["k2", "k3"])
+def test_gpu_npendulum_bit_identical_to_c_oracle(nodes, B, over, kernel, monkeypatch):
+    """K2 (CTA-per-rope, banded LU in shared memory) and K3 (lane-per-rope, state in global memory)
+    against the dense scalar oracle."""
+    monkeypatch.setenv("BRDAE_NPENDULUM_KERNEL", kernel)
     ens = E.npendulum_ensemble(B, n_nodes=nodes)
-    assert_bit_identical(run_gpu(ens, **over), run_c_oracle(ens, **over), f"npendulum n={nodes}")
+    assert_bit_identical(run_gpu(ens, **over), run_c_oracle(ens, **over), f"npendulum n={nodes} {kernel}")
+
+
+def test_gpu_npendulum_k3_many_ropes_with_refill_and_ragged_warps(monkeypatch):
+    monkeypatch.setenv("BRDAE_NPENDULUM_KERNEL", "k3")
+    ens = E.npendulum_ensemble(1000, n_nodes=4, t_end=0.4)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k3 1000 ropes")
+    ens = E.npendulum_ensemble(3, n_nodes=40, t_end=0.3)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k3 n=40")
+
+
+@pytest.mark.parametrize("state", ["smem", "global"])
+def test_gpu_npendulum_k2_state_placement(state, monkeypatch):
+    """K2 with the rope state in shared memory, and with it in the L2-resident global scratch."""
+    monkeypatch.setenv("BRDAE_K2_STATE", state)
+    ens = E.npendulum_ensemble(40, n_nodes=6, t_end=1.0)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), f"k2 state in {state}")
+
+
+def test_gpu_npendulum_default_kernel_choice_large_batch():
+    ens = E.npendulum_ensemble(1300, n_nodes=2, t_end=0.3)      # enough ropes for the global-state flavour
+    out, ref = run_gpu(ens), run_c_oracle(ens)
+    assert_bit_identical(out, ref, "default choice, 1300 ropes")
 
 
 def test_gpu_npendulum_large_chain_complex_factor_in_global_scratch():
