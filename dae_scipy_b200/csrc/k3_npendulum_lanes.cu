@@ -100,131 +100,254 @@ __device__ __forceinline__ NodeJac node_jac(const Vec &X, int i) {
 }
 
 // ---- banded LU and solves, one lane each, factors in slot-interleaved global memory -----------
+// A lane is alone with its memory latency (there are only B/32 warps), so every loop is written as
+// "issue a batch of independent loads into registers, compute, store": the pivot column, the pivot
+// row and three target rows at a time in the factorisation; a sliding register window of the
+// right-hand side plus a one-column prefetch of the factor in the substitutions.
+constexpr int UW = KU + KL;          // 16 columns right of the pivot
+
 __device__ void lu_band_real(const Vec &ab, const IVec &piv, int N) {
     for (int k = 0; k < N; ++k) {
-        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + KU + KL);
+        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + UW);
+        double cv[KL + 1];                         // pivot column, rows k .. k+9
+#pragma unroll
+        for (int i = 0; i <= KL; ++i) cv[i] = (k + i <= rmax) ? ab[ABI(k + i, k)] : 0.0;
         int p = k;
-        double best = fabs(ab[ABI(k, k)]);
-        for (int r = k + 1; r <= rmax; ++r) {
-            const double v = fabs(ab[ABI(r, k)]);
-            if (v > best) { best = v; p = r; }
+        double best = fabs(cv[0]);
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) {
+            const double v = fabs(cv[i]);
+            if (k + i <= rmax && v > best) { best = v; p = k + i; }
         }
         piv[k] = p;
-        double prow[KU + KL + 1];                 // pivot row, columns k .. k+16, in registers
+        double prow[UW + 1], krow[UW + 1];         // new pivot row (old row p) and old row k, columns k .. k+16
 #pragma unroll
-        for (int j = 0; j <= KU + KL; ++j) {
-            const int c = k + j;
-            if (c <= cmax) {
-                const double u = ab[ABI(p, c)];
-                if (p != k) ab[ABI(p, c)] = ab[ABI(k, c)];
-                prow[j] = u;
-            } else prow[j] = 0.0;
+        for (int j = 0; j <= UW; ++j) {
+            const bool in = (k + j <= cmax);
+            prow[j] = in ? ab[ABI(p, k + j)] : 0.0;
+            krow[j] = in ? ab[ABI(k, k + j)] : 0.0;
         }
         const double rcp = 1.0 / prow[0];
-        ab[ABI(k, k)] = rcp;
         if (p != k) {
 #pragma unroll
-            for (int j = 1; j <= KU + KL; ++j) if (k + j <= cmax) ab[ABI(k, k + j)] = prow[j];
+            for (int j = 0; j <= UW; ++j) if (k + j <= cmax) { ab[ABI(p, k + j)] = krow[j]; ab[ABI(k, k + j)] = prow[j]; }
         }
-        for (int r = k + 1; r <= rmax; ++r) {
-            const double l = ab[ABI(r, k)] * rcp;
-            ab[ABI(r, k)] = l;
+        ab[ABI(k, k)] = rcp;
+        double l[KL + 1];                          // multipliers of rows k+1 .. k+9 (row p now holds old row k)
 #pragma unroll
-            for (int j = 1; j <= KU + KL; ++j) {
-                const int c = k + j;
-                if (c <= cmax) ab[ABI(r, c)] = fma(-l, prow[j], ab[ABI(r, c)]);
-            }
+        for (int i = 1; i <= KL; ++i) {
+            l[i] = ((k + i == p) ? cv[0] : cv[i]) * rcp;
+            if (k + i <= rmax) ab[ABI(k + i, k)] = l[i];
+        }
+#pragma unroll
+        for (int i0 = 1; i0 <= KL; i0 += 3) {      // three target rows per batch
+            double rw[3][UW];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int j = 1; j <= UW; ++j)
+                    rw[q][j - 1] = (k + i0 + q <= rmax && k + j <= cmax) ? ab[ABI(k + i0 + q, k + j)] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int j = 1; j <= UW; ++j)
+                    if (k + i0 + q <= rmax && k + j <= cmax) ab[ABI(k + i0 + q, k + j)] = fma(-l[i0 + q], prow[j], rw[q][j - 1]);
         }
     }
 }
 __device__ void lu_band_cplx(const Vec &ar, const Vec &ai, const IVec &piv, int N) {
     for (int k = 0; k < N; ++k) {
-        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + KU + KL);
+        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + UW);
+        double cvr[KL + 1], cvi[KL + 1];
+#pragma unroll
+        for (int i = 0; i <= KL; ++i) {
+            const bool in = (k + i <= rmax);
+            cvr[i] = in ? ar[ABI(k + i, k)] : 0.0;
+            cvi[i] = in ? ai[ABI(k + i, k)] : 0.0;
+        }
         int p = k;
-        double best = fabs(ar[ABI(k, k)]) + fabs(ai[ABI(k, k)]);
-        for (int r = k + 1; r <= rmax; ++r) {
-            const double v = fabs(ar[ABI(r, k)]) + fabs(ai[ABI(r, k)]);
-            if (v > best) { best = v; p = r; }
+        double best = fabs(cvr[0]) + fabs(cvi[0]);
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) {
+            const double v = fabs(cvr[i]) + fabs(cvi[i]);
+            if (k + i <= rmax && v > best) { best = v; p = k + i; }
         }
         piv[k] = p;
-        double pr_[KU + KL + 1], pi_[KU + KL + 1];
+        double pr_[UW + 1], pi_[UW + 1], kr_[UW + 1], ki_[UW + 1];
 #pragma unroll
-        for (int j = 0; j <= KU + KL; ++j) {
-            const int c = k + j;
-            if (c <= cmax) {
-                const double u = ar[ABI(p, c)], w = ai[ABI(p, c)];
-                if (p != k) { ar[ABI(p, c)] = ar[ABI(k, c)]; ai[ABI(p, c)] = ai[ABI(k, c)]; }
-                pr_[j] = u; pi_[j] = w;
-            } else { pr_[j] = 0.0; pi_[j] = 0.0; }
+        for (int j = 0; j <= UW; ++j) {
+            const bool in = (k + j <= cmax);
+            pr_[j] = in ? ar[ABI(p, k + j)] : 0.0; pi_[j] = in ? ai[ABI(p, k + j)] : 0.0;
+            kr_[j] = in ? ar[ABI(k, k + j)] : 0.0; ki_[j] = in ? ai[ABI(k, k + j)] : 0.0;
         }
         const double invd = 1.0 / fma(pr_[0], pr_[0], pi_[0] * pi_[0]);
         const double qr = pr_[0] * invd, qi = -(pi_[0] * invd);
-        ar[ABI(k, k)] = qr; ai[ABI(k, k)] = qi;
         if (p != k) {
 #pragma unroll
-            for (int j = 1; j <= KU + KL; ++j) if (k + j <= cmax) { ar[ABI(k, k + j)] = pr_[j]; ai[ABI(k, k + j)] = pi_[j]; }
-        }
-        for (int r = k + 1; r <= rmax; ++r) {
-            const double xr0 = ar[ABI(r, k)], xi0 = ai[ABI(r, k)];
-            const double lr = fma(xr0, qr, -(xi0 * qi));
-            const double li = fma(xr0, qi, xi0 * qr);
-            ar[ABI(r, k)] = lr; ai[ABI(r, k)] = li;
-#pragma unroll
-            for (int j = 1; j <= KU + KL; ++j) {
-                const int c = k + j;
-                if (c <= cmax) {
-                    double xr = ar[ABI(r, c)], xi = ai[ABI(r, c)];
-                    xr = fma(-lr, pr_[j], xr); xr = fma(li, pi_[j], xr);
-                    xi = fma(-lr, pi_[j], xi); xi = fma(-li, pr_[j], xi);
-                    ar[ABI(r, c)] = xr; ai[ABI(r, c)] = xi;
+            for (int j = 0; j <= UW; ++j)
+                if (k + j <= cmax) {
+                    ar[ABI(p, k + j)] = kr_[j]; ai[ABI(p, k + j)] = ki_[j];
+                    ar[ABI(k, k + j)] = pr_[j]; ai[ABI(k, k + j)] = pi_[j];
                 }
-            }
+        }
+        ar[ABI(k, k)] = qr; ai[ABI(k, k)] = qi;
+        double lr[KL + 1], li[KL + 1];
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) {
+            const double xr0 = (k + i == p) ? cvr[0] : cvr[i], xi0 = (k + i == p) ? cvi[0] : cvi[i];
+            lr[i] = fma(xr0, qr, -(xi0 * qi));
+            li[i] = fma(xr0, qi, xi0 * qr);
+            if (k + i <= rmax) { ar[ABI(k + i, k)] = lr[i]; ai[ABI(k + i, k)] = li[i]; }
+        }
+#pragma unroll
+        for (int i0 = 1; i0 <= KL; i0 += 3) {
+            double wr[3][UW], wi[3][UW];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int j = 1; j <= UW; ++j) {
+                    const bool in = (k + i0 + q <= rmax && k + j <= cmax);
+                    wr[q][j - 1] = in ? ar[ABI(k + i0 + q, k + j)] : 0.0;
+                    wi[q][j - 1] = in ? ai[ABI(k + i0 + q, k + j)] : 0.0;
+                }
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int j = 1; j <= UW; ++j)
+                    if (k + i0 + q <= rmax && k + j <= cmax) {
+                        double xr = wr[q][j - 1], xi = wi[q][j - 1];
+                        xr = fma(-lr[i0 + q], pr_[j], xr); xr = fma(li[i0 + q], pi_[j], xr);
+                        xi = fma(-lr[i0 + q], pi_[j], xi); xi = fma(-li[i0 + q], pr_[j], xi);
+                        ar[ABI(k + i0 + q, k + j)] = xr; ai[ABI(k + i0 + q, k + j)] = xi;
+                    }
         }
     }
 }
 __device__ void solve_band_real(const Vec &ab, const IVec &piv, const Vec &b, int N) {
-    for (int k = 0; k < N; ++k) {
-        const int p = piv[k], rmax = imin(N - 1, k + KL);
-        double bk = b[k];
-        if (p != k) { const double u = b[p]; b[p] = bk; b[k] = u; bk = u; }
-        for (int r = k + 1; r <= rmax; ++r) b[r] = fma(-ab[ABI(r, k)], bk, b[r]);
+    // forward: window w[i] = b[k+i], i = 0..9; the multipliers of the next column are prefetched
+    {
+        double w[KL + 1], Lc[KL], Ln[KL];
+#pragma unroll
+        for (int i = 0; i <= KL; ++i) w[i] = (i < N) ? b[i] : 0.0;
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) Lc[i - 1] = (i < N) ? ab[ABI(i, 0)] : 0.0;
+        int p = piv[0];
+        for (int k = 0; k < N; ++k) {
+            const int pn = (k + 1 < N) ? piv[k + 1] : 0;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) Ln[i - 1] = (k + 1 + i < N) ? ab[ABI(k + 1 + i, k + 1)] : 0.0;
+            const double bnew = (k + KL + 1 < N) ? b[k + KL + 1] : 0.0;
+            const int d = p - k;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) { const bool sw = (d == i); const double u = w[0], v = w[i]; w[0] = sw ? v : u; w[i] = sw ? u : v; }
+            const double bk = w[0];
+            b[k] = bk;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) w[i] = fma(-Lc[i - 1], bk, w[i]);
+#pragma unroll
+            for (int i = 0; i < KL; ++i) { w[i] = w[i + 1]; Lc[i] = Ln[i]; }
+            w[KL] = bnew;
+            p = pn;
+        }
     }
-    for (int k = N - 1; k >= 0; --k) {
-        const int rmin = imax(0, k - (KU + KL));
-        const double xk = b[k] * ab[ABI(k, k)];
-        b[k] = xk;
-        for (int r = rmin; r < k; ++r) b[r] = fma(-ab[ABI(r, k)], xk, b[r]);
+    // backward, column oriented: window w[j] = b[k-j], j = 0..16
+    {
+        double w[UW + 1], Uc[UW], Un[UW];
+#pragma unroll
+        for (int j = 0; j <= UW; ++j) w[j] = (N - 1 - j >= 0) ? b[N - 1 - j] : 0.0;
+#pragma unroll
+        for (int j = 1; j <= UW; ++j) Uc[j - 1] = (N - 1 - j >= 0) ? ab[ABI(N - 1 - j, N - 1)] : 0.0;
+        double dg = ab[ABI(N - 1, N - 1)];
+        for (int k = N - 1; k >= 0; --k) {
+#pragma unroll
+            for (int j = 1; j <= UW; ++j) Un[j - 1] = (k - 1 - j >= 0) ? ab[ABI(k - 1 - j, k - 1)] : 0.0;
+            const double dgn = (k >= 1) ? ab[ABI(k - 1, k - 1)] : 0.0;
+            const double bnew = (k - UW - 1 >= 0) ? b[k - UW - 1] : 0.0;
+            const double xk = w[0] * dg;
+            b[k] = xk;
+#pragma unroll
+            for (int j = 1; j <= UW; ++j) w[j] = fma(-Uc[j - 1], xk, w[j]);
+#pragma unroll
+            for (int j = 0; j < UW; ++j) { w[j] = w[j + 1]; Uc[j] = Un[j]; }
+            w[UW] = bnew;
+            dg = dgn;
+        }
     }
 }
 __device__ void solve_band_cplx(const Vec &ar, const Vec &ai, const IVec &piv, const Vec &br, const Vec &bi, int N) {
-    for (int k = 0; k < N; ++k) {
-        const int p = piv[k], rmax = imin(N - 1, k + KL);
-        double xr = br[k], xi = bi[k];
-        if (p != k) {
-            const double u = br[p], w = bi[p];
-            br[p] = xr; bi[p] = xi; br[k] = u; bi[k] = w; xr = u; xi = w;
-        }
-        for (int r = k + 1; r <= rmax; ++r) {
-            const double lr = ar[ABI(r, k)], li = ai[ABI(r, k)];
-            double yr = br[r], yi = bi[r];
-            yr = fma(-lr, xr, yr); yr = fma(li, xi, yr);
-            yi = fma(-lr, xi, yi); yi = fma(-li, xr, yi);
-            br[r] = yr; bi[r] = yi;
+    {
+        double wr[KL + 1], wi[KL + 1], Lr[KL], Li[KL], Lrn[KL], Lin[KL];
+#pragma unroll
+        for (int i = 0; i <= KL; ++i) { wr[i] = (i < N) ? br[i] : 0.0; wi[i] = (i < N) ? bi[i] : 0.0; }
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) { Lr[i - 1] = (i < N) ? ar[ABI(i, 0)] : 0.0; Li[i - 1] = (i < N) ? ai[ABI(i, 0)] : 0.0; }
+        int p = piv[0];
+        for (int k = 0; k < N; ++k) {
+            const int pn = (k + 1 < N) ? piv[k + 1] : 0;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) {
+                const bool in = (k + 1 + i < N);
+                Lrn[i - 1] = in ? ar[ABI(k + 1 + i, k + 1)] : 0.0;
+                Lin[i - 1] = in ? ai[ABI(k + 1 + i, k + 1)] : 0.0;
+            }
+            const bool more = (k + KL + 1 < N);
+            const double bnr = more ? br[k + KL + 1] : 0.0, bni = more ? bi[k + KL + 1] : 0.0;
+            const int d = p - k;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) {
+                const bool sw = (d == i);
+                const double u = wr[0], v = wr[i], ui = wi[0], vi = wi[i];
+                wr[0] = sw ? v : u; wr[i] = sw ? u : v; wi[0] = sw ? vi : ui; wi[i] = sw ? ui : vi;
+            }
+            const double xr = wr[0], xi = wi[0];
+            br[k] = xr; bi[k] = xi;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) {
+                double yr = wr[i], yi = wi[i];
+                yr = fma(-Lr[i - 1], xr, yr); yr = fma(Li[i - 1], xi, yr);
+                yi = fma(-Lr[i - 1], xi, yi); yi = fma(-Li[i - 1], xr, yi);
+                wr[i] = yr; wi[i] = yi;
+            }
+#pragma unroll
+            for (int i = 0; i < KL; ++i) { wr[i] = wr[i + 1]; wi[i] = wi[i + 1]; Lr[i] = Lrn[i]; Li[i] = Lin[i]; }
+            wr[KL] = bnr; wi[KL] = bni;
+            p = pn;
         }
     }
-    for (int k = N - 1; k >= 0; --k) {
-        const int rmin = imax(0, k - (KU + KL));
-        const double qr = ar[ABI(k, k)], qi = ai[ABI(k, k)];
-        const double sr = br[k], si = bi[k];
-        const double xr = fma(sr, qr, -(si * qi));
-        const double xi = fma(sr, qi, si * qr);
-        br[k] = xr; bi[k] = xi;
-        for (int r = rmin; r < k; ++r) {
-            const double ur = ar[ABI(r, k)], ui = ai[ABI(r, k)];
-            double yr = br[r], yi = bi[r];
-            yr = fma(-ur, xr, yr); yr = fma(ui, xi, yr);
-            yi = fma(-ur, xi, yi); yi = fma(-ui, xr, yi);
-            br[r] = yr; bi[r] = yi;
+    {
+        double wr[UW + 1], wi[UW + 1], Ur[UW], Ui[UW], Urn[UW], Uin[UW];
+#pragma unroll
+        for (int j = 0; j <= UW; ++j) { const bool in = (N - 1 - j >= 0); wr[j] = in ? br[N - 1 - j] : 0.0; wi[j] = in ? bi[N - 1 - j] : 0.0; }
+#pragma unroll
+        for (int j = 1; j <= UW; ++j) {
+            const bool in = (N - 1 - j >= 0);
+            Ur[j - 1] = in ? ar[ABI(N - 1 - j, N - 1)] : 0.0; Ui[j - 1] = in ? ai[ABI(N - 1 - j, N - 1)] : 0.0;
+        }
+        double qr = ar[ABI(N - 1, N - 1)], qi = ai[ABI(N - 1, N - 1)];
+        for (int k = N - 1; k >= 0; --k) {
+#pragma unroll
+            for (int j = 1; j <= UW; ++j) {
+                const bool in = (k - 1 - j >= 0);
+                Urn[j - 1] = in ? ar[ABI(k - 1 - j, k - 1)] : 0.0; Uin[j - 1] = in ? ai[ABI(k - 1 - j, k - 1)] : 0.0;
+            }
+            const double qrn = (k >= 1) ? ar[ABI(k - 1, k - 1)] : 0.0, qin = (k >= 1) ? ai[ABI(k - 1, k - 1)] : 0.0;
+            const bool more = (k - UW - 1 >= 0);
+            const double bnr = more ? br[k - UW - 1] : 0.0, bni = more ? bi[k - UW - 1] : 0.0;
+            const double sr = wr[0], si = wi[0];
+            const double xr = fma(sr, qr, -(si * qi));
+            const double xi = fma(sr, qi, si * qr);
+            br[k] = xr; bi[k] = xi;
+#pragma unroll
+            for (int j = 1; j <= UW; ++j) {
+                double yr = wr[j], yi = wi[j];
+                yr = fma(-Ur[j - 1], xr, yr); yr = fma(Ui[j - 1], xi, yr);
+                yi = fma(-Ur[j - 1], xi, yi); yi = fma(-Ui[j - 1], xr, yi);
+                wr[j] = yr; wi[j] = yi;
+            }
+#pragma unroll
+            for (int j = 0; j < UW; ++j) { wr[j] = wr[j + 1]; wi[j] = wi[j + 1]; Ur[j] = Urn[j]; Ui[j] = Uin[j]; }
+            wr[UW] = bnr; wi[UW] = bni;
+            qr = qrn; qi = qin;
         }
     }
 }

@@ -163,3 +163,31 @@ def well_conditioned(name):
                     "opt_pendulum3_dense_mass", "opt_pendulum3_backward", "opt_pendulum3_controller_off",
                     "ens_npendulum_n4", "ens_npendulum_n10", "ens_npendulum_n20", "script_robertson",
                     "kat_jay", "kat_polydae2", "kat_linear7_with_mass", "kat_linear7_without_mass", "kat_robertson_ode")
+
+
+def _numpy_oracle_worker(ens):
+    import warnings
+    warnings.filterwarnings("ignore")
+    return run_numpy_oracle(ens)
+
+
+def run_numpy_oracle_parallel(ens, nproc=None):
+    """The reference-equivalent numpy restatement over all host cores (one slice per process)."""
+    import multiprocessing as mp
+    nproc = nproc or min(os.cpu_count() or 1, 32)
+    B = ens["y0"].shape[0]
+    chunks = [c for c in np.array_split(np.arange(B), nproc) if c.size]
+    subs = [dict(ens, y0=ens["y0"][c], params=None if ens["params"] is None else ens["params"][c]) for c in chunks]
+    with mp.get_context("fork").Pool(len(subs)) as pool:
+        outs = pool.map(_numpy_oracle_worker, subs)
+    return {k: np.concatenate([o[k] for o in outs]) for k in outs[0]}
+
+
+def parity_statistics(out, ref, rtol, atol, n_diff):
+    """north_star acceptance numbers: fraction of systems with identical (naccpt, nrejct, nfailed); per-system max
+    of |dy| / (atol + rtol |y_ref|) over the differential unknowns (first n_diff) and over the algebraic ones."""
+    err = np.abs(out["y"] - ref["y"]) / (atol + rtol * np.abs(ref["y"]))
+    return dict(identical_counts=count_agreement(out["counters"], ref["counters"]),
+                status_equal=bool(np.array_equal(out["status"], ref["status"])),
+                diff_err=np.nanmax(err[:, :n_diff, :], axis=(1, 2)),
+                alg_err=np.nanmax(err[:, n_diff:, :], axis=(1, 2)) if err.shape[1] > n_diff else np.zeros(err.shape[0]))
