@@ -9,11 +9,14 @@
 // converged`, :846 Newton `for`) are flattened into a per-lane state machine with three
 // expensive states -- FACTOR (iteration matrices + both LUs), NEWTON (one simplified-Newton
 // iteration) and ERREST (error estimate, accept/reject, controller, dense output) -- and one
-// cheap one (SETUP: step prologue, attempt set-up, starting guess).  Every trip of the warp
-// loop the warp votes (ballot/popc) and executes ONLY the expensive block most lanes wait for,
-// with exactly those lanes: the dispatch branch is warp-uniform, so a block is never executed
-// for the sake of one straggler, and the lanes of a warp fall into a common
-// FACTOR, NEWTON x k, ERREST cadence by themselves.
+// cheap one (SETUP: step prologue, attempt set-up, starting guess).  The blocks are laid out in the
+// order a system walks through them, ERREST -> SETUP -> FACTOR -> NEWTON.  Every trip of the loop the
+// CTA votes once and enters that chain at the expensive block most lanes wait for, running it down to
+// NEWTON: a lane that converged does its error estimate, the next step's set-up, the refactorisation
+// if one is due and its first Newton iteration in a single trip, lanes waiting further down the
+// chain join on the way, and entering at NEWTON skips ERREST and FACTOR for everybody -- a block is
+// never executed for the sake of a straggler.  (A trace-driven simulation of the pendulum ensemble,
+// profiles/tools/sched_sim.py, puts the chain 10 % ahead of running only the majority block.)
 //
 // Storage (N = 5): the real and complex LU factors (3 N^2 doubles), f(t,y), y_old, the dense
 // output coefficients Q (3N) and the point (t_J, y_J) the Jacobian was last evaluated at live in
@@ -46,12 +49,15 @@ struct Slots {
 // ---- LU of the spec, left-looking, one column at a time ------------------------------------
 // Same arithmetic as a right-looking elimination with partial pivoting on |a| (first maximum) and
 // reciprocal pivots: element (row, k) receives its updates -l(row,j) u(j,k), j = 0,1,.. in the same
-// order.  Bookkeeping is LAPACK's: rows are kept in CURRENT (pivoted) order, the multipliers move
-// with their rows, and the row permutation is a packed 3-bit table.  A permuted access is a
-// dynamically addressed shared-memory load -- free there, while a dynamic REGISTER index would cost
-// a chain of selects per element (the first version spent more instructions on selects than on
-// FP64 math).  `column(k, col)` fills col[r] = A[r][k] in original row order; it is parked in the
-// still-unused column k of the factor storage and read back in current row order.
+// order.  Rows are NEVER moved: every row of the factors stays where the matrix row it came from was
+// stored, and the row permutation is a packed 3-bit table (position i of the pivoted order -> original
+// row).  A pivoted access is then a shared-memory load at `row_of(perm, i)`, a dynamic ADDRESS, which
+// is free, while a dynamic REGISTER index would cost a chain of selects per element (the first
+// version spent more instructions on selects than on FP64 math) and physically exchanging the rows
+// (the second version) cost 120 shared-memory accesses per factorisation pair: the kernel is bound by
+// shared-memory bandwidth (2 wavefronts per 8-byte warp access), not by the FP64 pipe.
+// `column(k, col)` fills col[r] = A[r][k] in original row order; it is parked in the still-unused
+// column k of the factor storage and read back in pivoted order.
 BRDAE_HD unsigned perm_identity(int n) {
     unsigned p = 0;
     for (int i = 0; i < n; ++i) p |= (unsigned)i << (3 * i);
@@ -62,25 +68,27 @@ BRDAE_HD unsigned perm_swap(unsigned perm, int k, int p) {
     perm &= ~((7u << (3 * k)) | (7u << (3 * p)));
     return perm | (fp << (3 * k)) | (fk << (3 * p));     // k == p: unchanged
 }
+template <int N>
+BRDAE_HD int row_of(unsigned perm, int i) { return (int)((perm >> (3 * i)) & 7u) * N; }   // slot offset of pivoted row i
+
 template <int N, class S, class ColFn>
 BRDAE_HD unsigned lu_real_left(const S &sm, int base, ColFn &&column) {
     unsigned perm = perm_identity(N);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         double cur[N];
-        {
-            double col[N];
-            column(k, col);
+        column(k, cur);
+        if (k > 0) {
 #pragma unroll
-            for (int r = 0; r < N; ++r) sm(base + r * N + k) = col[r];
+            for (int r = 0; r < N; ++r) sm(base + r * N + k) = cur[r];
+#pragma unroll
+            for (int i = 0; i < N; ++i) cur[i] = sm(base + row_of<N>(perm, i) + k);
         }
-#pragma unroll
-        for (int i = 0; i < N; ++i) cur[i] = sm(base + (int)((perm >> (3 * i)) & 7u) * N + k);
 #pragma unroll
         for (int j = 0; j < k; ++j) {
             const double cj = cur[j];
 #pragma unroll
-            for (int r = j + 1; r < N; ++r) cur[r] = fma(-sm(base + r * N + j), cj, cur[r]);
+            for (int r = j + 1; r < N; ++r) cur[r] = fma(-sm(base + row_of<N>(perm, r) + j), cj, cur[r]);
         }
         int p = k;
         double best = fabs(cur[k]), pv = cur[k];
@@ -92,16 +100,9 @@ BRDAE_HD unsigned lu_real_left(const S &sm, int base, ColFn &&column) {
         }
         const double rcp = 1.0 / pv;
 #pragma unroll
-        for (int i = 0; i < N; ++i) sm(base + i * N + k) = (i < k) ? cur[i] : cur[i] * rcp;
-        if (k < N - 1) {     // exchange rows k and p of the finished columns and of this one
-#pragma unroll
-            for (int j = 0; j <= k; ++j) {
-                const double u = sm(base + k * N + j), v = sm(base + p * N + j);
-                sm(base + k * N + j) = v; sm(base + p * N + j) = u;
-            }
-            perm = perm_swap(perm, k, p);
-        }
-        sm(base + k * N + k) = rcp;
+        for (int i = 0; i < N; ++i) sm(base + row_of<N>(perm, i) + k) = (i < k) ? cur[i] : cur[i] * rcp;
+        perm = perm_swap(perm, k, p);                       // the multipliers stay with their rows
+        sm(base + row_of<N>(perm, k) + k) = rcp;
     }
     return perm;
 }
@@ -112,23 +113,23 @@ BRDAE_HD unsigned lu_cplx_left(const S &sm, int base_r, int base_i, ColFn &&colu
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         double cr[N], ci[N];
-        {
-            double colr[N], coli[N];
-            column(k, colr, coli);
+        column(k, cr, ci);
+        if (k > 0) {
 #pragma unroll
-            for (int r = 0; r < N; ++r) { sm(base_r + r * N + k) = colr[r]; sm(base_i + r * N + k) = coli[r]; }
-        }
+            for (int r = 0; r < N; ++r) { sm(base_r + r * N + k) = cr[r]; sm(base_i + r * N + k) = ci[r]; }
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const int src = (int)((perm >> (3 * i)) & 7u) * N + k;
-            cr[i] = sm(base_r + src); ci[i] = sm(base_i + src);
+            for (int i = 0; i < N; ++i) {
+                const int src = row_of<N>(perm, i) + k;
+                cr[i] = sm(base_r + src); ci[i] = sm(base_i + src);
+            }
         }
 #pragma unroll
         for (int j = 0; j < k; ++j) {
             const double ur = cr[j], ui = ci[j];
 #pragma unroll
             for (int r = j + 1; r < N; ++r) {
-                const double lr = sm(base_r + r * N + j), li = sm(base_i + r * N + j);
+                const int src = row_of<N>(perm, r) + j;
+                const double lr = sm(base_r + src), li = sm(base_i + src);
                 double xr = cr[r], xi = ci[r];
                 xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
                 xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
@@ -147,66 +148,79 @@ BRDAE_HD unsigned lu_cplx_left(const S &sm, int base_r, int base_i, ColFn &&colu
         const double qr = pr * invd, qi = -(pi * invd);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (i < k) { sm(base_r + i * N + k) = cr[i]; sm(base_i + i * N + k) = ci[i]; }
+            const int dst = row_of<N>(perm, i) + k;
+            if (i < k) { sm(base_r + dst) = cr[i]; sm(base_i + dst) = ci[i]; }
             else {
-                sm(base_r + i * N + k) = fma(cr[i], qr, -(ci[i] * qi));
-                sm(base_i + i * N + k) = fma(cr[i], qi, ci[i] * qr);
+                sm(base_r + dst) = fma(cr[i], qr, -(ci[i] * qi));
+                sm(base_i + dst) = fma(cr[i], qi, ci[i] * qr);
             }
         }
-        if (k < N - 1) {
-#pragma unroll
-            for (int j = 0; j <= k; ++j) {
-                const double u = sm(base_r + k * N + j), v = sm(base_r + p * N + j);
-                sm(base_r + k * N + j) = v; sm(base_r + p * N + j) = u;
-                const double ui = sm(base_i + k * N + j), vi = sm(base_i + p * N + j);
-                sm(base_i + k * N + j) = vi; sm(base_i + p * N + j) = ui;
-            }
-            perm = perm_swap(perm, k, p);
-        }
-        sm(base_r + k * N + k) = qr; sm(base_i + k * N + k) = qi;
+        perm = perm_swap(perm, k, p);
+        const int dk = row_of<N>(perm, k) + k;
+        sm(base_r + dk) = qr; sm(base_i + dk) = qi;
     }
     return perm;
 }
 
-// ---- triangular solves streaming the factors from lane-strided shared memory ----------------
-// b is put into pivoted order by a round trip through N scratch slots (dynamic load address).
+// b <- P b (b[i] = b_old[perm_i]): a round trip through N scratch slots with a dynamic load address, or
+// (BRDAE_PERM_SELECT) select chains in registers, which trade 2N shared-memory accesses for ~N^2 selects.
 template <int N, class S>
-BRDAE_HD void solve_real_sm(const S &sm, int base, int scratch, unsigned perm, double (&b)[N]) {
+BRDAE_HD void permute_rhs(const S &sm, int scratch, unsigned perm, double (&b)[N]) {
+#if defined(BRDAE_PERM_SELECT)
+    double o[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) o[c] = b[c];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const unsigned pi = (perm >> (3 * i)) & 7u;
+        double v = o[0];
+#pragma unroll
+        for (int c = 1; c < N; ++c) v = (pi == (unsigned)c) ? o[c] : v;
+        b[i] = v;
+    }
+#else
 #pragma unroll
     for (int c = 0; c < N; ++c) sm(scratch + c) = b[c];
 #pragma unroll
     for (int i = 0; i < N; ++i) b[i] = sm(scratch + (int)((perm >> (3 * i)) & 7u));
+#endif
+}
+// ---- triangular solves streaming the factors from lane-strided shared memory ----------------
+// b is put into pivoted order by a round trip through N scratch slots (dynamic load address).
+template <int N, class S>
+BRDAE_HD void solve_real_sm(const S &sm, int base, int scratch, unsigned perm, double (&b)[N]) {
+    permute_rhs<N>(sm, scratch, perm, b);
+    int ro[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) ro[i] = base + row_of<N>(perm, i);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double bk = b[k];
 #pragma unroll
-        for (int r = k + 1; r < N; ++r) b[r] = fma(-sm(base + r * N + k), bk, b[r]);
+        for (int r = k + 1; r < N; ++r) b[r] = fma(-sm(ro[r] + k), bk, b[r]);
     }
     // back substitution, column oriented (x_k final once the columns > k have been applied)
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-        const double xk = b[k] * sm(base + k * N + k);
+        const double xk = b[k] * sm(ro[k] + k);
         b[k] = xk;
 #pragma unroll
-        for (int r = 0; r < k; ++r) b[r] = fma(-sm(base + r * N + k), xk, b[r]);
+        for (int r = 0; r < k; ++r) b[r] = fma(-sm(ro[r] + k), xk, b[r]);
     }
 }
 template <int N, class S>
 BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, unsigned perm, double (&br)[N], double (&bi)[N]) {
+    permute_rhs<N>(sm, scratch, perm, br);
+    permute_rhs<N>(sm, scratch, perm, bi);
+    int ro[N];
 #pragma unroll
-    for (int c = 0; c < N; ++c) sm(scratch + c) = br[c];
-#pragma unroll
-    for (int i = 0; i < N; ++i) br[i] = sm(scratch + (int)((perm >> (3 * i)) & 7u));
-#pragma unroll
-    for (int c = 0; c < N; ++c) sm(scratch + c) = bi[c];
-#pragma unroll
-    for (int i = 0; i < N; ++i) bi[i] = sm(scratch + (int)((perm >> (3 * i)) & 7u));
+    for (int i = 0; i < N; ++i) ro[i] = row_of<N>(perm, i);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double xr = br[k], xi = bi[k];
 #pragma unroll
         for (int r = k + 1; r < N; ++r) {
-            const double lr = sm(base_r + r * N + k), li = sm(base_i + r * N + k);
+            const double lr = sm(base_r + ro[r] + k), li = sm(base_i + ro[r] + k);
             double yr = br[r], yi = bi[r];
             yr = fma(-lr, xr, yr); yr = fma(li, xi, yr);
             yi = fma(-lr, xi, yi); yi = fma(-li, xr, yi);
@@ -215,14 +229,14 @@ BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, un
     }
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
-        const double qr = sm(base_r + k * N + k), qi = sm(base_i + k * N + k);
+        const double qr = sm(base_r + ro[k] + k), qi = sm(base_i + ro[k] + k);
         const double sr = br[k], si = bi[k];
         const double xr = fma(sr, qr, -(si * qi));
         const double xi = fma(sr, qi, si * qr);
         br[k] = xr; bi[k] = xi;
 #pragma unroll
         for (int r = 0; r < k; ++r) {
-            const double ur = sm(base_r + r * N + k), ui = sm(base_i + r * N + k);
+            const double ur = sm(base_r + ro[r] + k), ui = sm(base_i + ro[r] + k);
             double yr = br[r], yi = bi[r];
             yr = fma(-ur, xr, yr); yr = fma(ui, xi, yr);
             yi = fma(-ur, xi, yi); yi = fma(-ui, xr, yi);
@@ -374,165 +388,20 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
         }
         warp_converge();
 
-        // ================= vote: run the expensive block most lanes are waiting for ===========
+        // ================= vote: where this trip enters the chain ERREST -> SETUP -> FACTOR -> NEWTON ==
+        // The blocks are laid out in the order a system walks through them, and a trip runs the chain
+        // from the block most lanes wait for down to NEWTON: a lane that converged does its error
+        // estimate, the next step's set-up, the refactorisation if one is due and its first Newton
+        // iteration in ONE trip, and lanes already waiting further down the chain join in on the way.
+        // Entering at NEWTON skips ERREST and FACTOR for everybody (they are never run for stragglers).
+        // Lanes in SETUP (a Newton failure of the previous trip) vote with FACTOR, where they are headed.
         const Votes v = vote<CTA_WIDE>(state, trip++);
         if (CTA_WIDE && v.alive == 0) break;
         const int nF = v.nF, nN = v.nN, nE = v.nE;
-        const int run = (nN > 0 && nN >= nE && nN >= nF) ? ST_NEWTON : ((nE > 0 && nE >= nF) ? ST_ERREST : (nF > 0 ? ST_FACTOR : ST_IDLE));
+        const int run = (nN > 0 && nN >= nE && nN >= nF) ? ST_NEWTON : ((nE > 0 && nE >= nF) ? ST_ERREST : ST_FACTOR);
 
-        // ================= (re)factorisation :594-613 =========================================
-        if (run == ST_FACTOR) {
-            if (state == ST_FACTOR) {
-                if (a.scale_residuals) inv_h_lu = inv_h;
-                double J[N][N];
-                if (a.has_jac_const) {
-#pragma unroll
-                    for (int r = 0; r < N; ++r)
-#pragma unroll
-                        for (int c = 0; c < N; ++c) J[r][c] = a.jac_const[r * N + c];
-                } else {
-                    double yJ[N];
-#pragma unroll
-                    for (int c = 0; c < N; ++c) yJ[c] = sm(L::S_YJ + c);
-                    Prob::jac(prm, sm(L::S_TJ), yJ, J);
-                }
-                double hs[N];
-#pragma unroll
-                for (int r = 0; r < N; ++r) hs[r] = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
-                piv_r = lu_real_left<N>(sm, L::S_LUR, [&](int kc, double (&col)[N]) {
-#pragma unroll
-                    for (int r = 0; r < N; ++r) {
-                        const double v = Mass::nz(r, kc) ? fma(mr, Mass::get(prm, a, r, kc), -J[r][kc]) : -J[r][kc];
-                        col[r] = hs[r] * v;
-                    }
-                });
-                piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, [&](int kc, double (&cr)[N], double (&ci)[N]) {
-#pragma unroll
-                    for (int r = 0; r < N; ++r) {
-                        const bool nz = Mass::nz(r, kc);
-                        const double m = nz ? Mass::get(prm, a, r, kc) : 0.0;
-                        const double v = nz ? fma(mcr, m, -J[r][kc]) : -J[r][kc];
-                        cr[r] = hs[r] * v;
-                        ci[r] = nz ? hs[r] * (mci * m) : 0.0;
-                    }
-                });
-                cnt[CN_NLU]++;
-                lu_valid = true;
-                state = ST_NEWTON;
-            }
-        }
-        // ================= one simplified-Newton iteration :846-940 ==========================
-        else if (run == ST_NEWTON) {
-            if (state == ST_NEWTON) {
-                // the three stages as one loop body with table coefficients (unrolled by default).  Values are those of the unrolled form: the first
-                // accumulation fma(a, F, 0) equals a*F, and (T W)_2 = fma(0, W2, fma(1, W1, 1*W0)) = W0 + W1.
-                double fr[N], fcr[N], fci[N];
-                bool finite = true;
-#pragma unroll
-                for (int c = 0; c < N; ++c) { fr[c] = 0.0; fcr[c] = 0.0; fci[c] = 0.0; }
-#if defined(BRDAE_ROLL_STAGES)   // smaller code; measured 1.6 % slower once all warps of an SM share the block
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
-                for (int i = 0; i < 3; ++i) {
-                    const double t0c = kStageT[i][0], t1c = kStageT[i][1], t2c = kStageT[i][2];
-                    const double a0 = kStageTI[0][i], a1 = kStageTI[1][i], a2 = kStageTI[2][i];
-                    double Y[N], F[N];
-#pragma unroll
-                    for (int c = 0; c < N; ++c) Y[c] = y[c] + fma(t2c, W[2][c], fma(t1c, W[1][c], t0c * W[0][c]));
-                    Prob::rhs(prm, t + h * kStageC[i], Y, F);
-#pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        const double Fv = F[c];
-                        finite = finite && is_finite(Fv);
-                        fr[c] = fma(a0, Fv, fr[c]); fcr[c] = fma(a1, Fv, fcr[c]); fci[c] = fma(a2, Fv, fci[c]);
-                    }
-                }
-                cnt[CN_NFEV] += 3;
-                int outcome = 0;  // 0 continue, 1 converged, 2 stop (not converged)
-                bool update_old = true;
-                if (!finite) outcome = 2;
-                else {
-                    double mw0[N], mw1[N], mw2[N];
-                    mass_mv<Mass>(prm, a, W[0], mw0);
-                    mass_mv<Mass>(prm, a, W[1], mw1);
-                    mass_mv<Mass>(prm, a, W[2], mw2);
-#pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        const double hs = (a.scale_residuals && a.var_index[c] >= 1) ? inv_h_lu : 1.0;
-                        double ar = fr[c], br = fcr[c], bi = fci[c];
-                        if (!mass_row_empty<Mass, N>(c)) {
-                            ar = fma(-mr, mw0[c], ar);
-                            br = fma(-mcr, mw1[c], br); br = fma(mci, mw2[c], br);
-                            bi = fma(-mcr, mw2[c], bi); bi = fma(-mci, mw1[c], bi);
-                        }
-                        fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
-                    }
-                    solve_real_sm<N>(sm, L::S_LUR, L::S_B, piv_r, fr);
-                    solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
-                    cnt[CN_NSOLVE]++;
-                    double s = 0.0;
-#pragma unroll
-                    for (int c = 0; c < N; ++c) { const double v = fr[c] * inv_ns[c]; s = fma(v, v, s); }
-#pragma unroll
-                    for (int c = 0; c < N; ++c) { const double v = fcr[c] * inv_ns[c]; s = fma(v, v, s); }
-#pragma unroll
-                    for (int c = 0; c < N; ++c) { const double v = fci[c] * inv_ns[c]; s = fma(v, v, s); }
-                    const double dwn = sqrt(s) * a.rsq3n;
-#pragma unroll
-                    for (int c = 0; c < N; ++c) { W[0][c] += fr[c]; W[1][c] += fcr[c]; W[2][c] += fci[c]; }
-                    double dw_true = 0, dw_true_max = 0;
-                    if (have_old) {
-                        rate = dwn / dwn_old; have_rate = true;
-                        const double inv1 = 1.0 / (1.0 - rate);
-                        dw_true = rate * inv1 * dwn;
-                        double rp = rate;          // rate**(MAXIT-k): uniform trip count, per-lane select
-                        for (int e = 1; e < MAXIT; ++e) rp = (e < MAXIT - k) ? rp * rate : rp;
-                        dw_true_max = rp * inv1 * dwn;
-                    }
-                    if (dwn < a.newton_tol) outcome = 1;
-                    else if (have_rate) {
-                        bool fall = true;
-                        if (rate >= 1) {
-                            if (rate < 100 && nbad < a.nmax_bad) { nbad++; update_old = false; fall = false; }
-                            else if (!a.all_newton) { outcome = 2; fall = false; }
-                        }
-                        if (fall) {
-                            if (dw_true < a.newton_tol) outcome = 1;
-                            else if (dw_true_max > a.newton_tol && a.predictive_newton) {
-                                if (nbad < a.nmax_bad) { nbad++; update_old = false; }
-                                else if (!a.all_newton) outcome = 2;
-                            }
-                        }
-                    }
-                    if (outcome == 0 && update_old) { dwn_old = dwn; have_old = true; }
-                }
-                if (outcome == 0) {
-                    ++k;
-                    if (k >= MAXIT) { outcome = 2; n_iter = MAXIT; }
-                } else n_iter = k + 1;
-                if (outcome != 0) {
-                    safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);   // :631
-                    if (outcome == 1) state = ST_ERREST;
-                    else if (current_jac) {                                            // :650-658
-                        cnt[CN_NFAIL]++;
-                        h_abs *= a.nonconv_factor;
-                        lu_valid = false;
-                        state = ST_SETUP; setup_kind = SETUP_ATTEMPT;
-                    } else {                                                            // :643-647
-#pragma unroll
-                        for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
-                        sm(L::S_TJ) = t;
-                        cnt[CN_NJEV]++;
-                        current_jac = true; lu_valid = false;
-                        state = ST_SETUP; setup_kind = SETUP_GUESS;
-                    }
-                }
-            }
-        }
         // ================= error estimate, accept/reject, epilogue :660-784 ===================
-        else if (run == ST_ERREST) {
+        if (run == ST_ERREST) {
             if (state == ST_ERREST) {
                 double Z[3][N];
 #pragma unroll
@@ -730,6 +599,159 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                 state = ST_IDLE;
             }
         }
+        // ================= (re)factorisation :594-613 =========================================
+        if (run != ST_NEWTON && warp_any(state == ST_FACTOR)) {
+            if (state == ST_FACTOR) {
+                if (a.scale_residuals) inv_h_lu = inv_h;
+                double J[N][N];
+                if (a.has_jac_const) {
+#pragma unroll
+                    for (int r = 0; r < N; ++r)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) J[r][c] = a.jac_const[r * N + c];
+                } else {
+                    double yJ[N];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) yJ[c] = sm(L::S_YJ + c);
+                    Prob::jac(prm, sm(L::S_TJ), yJ, J);
+                }
+                double hs[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) hs[r] = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
+                piv_r = lu_real_left<N>(sm, L::S_LUR, [&](int kc, double (&col)[N]) {
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        const double v = Mass::nz(r, kc) ? fma(mr, Mass::get(prm, a, r, kc), -J[r][kc]) : -J[r][kc];
+                        col[r] = hs[r] * v;
+                    }
+                });
+                piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, [&](int kc, double (&cr)[N], double (&ci)[N]) {
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        const bool nz = Mass::nz(r, kc);
+                        const double m = nz ? Mass::get(prm, a, r, kc) : 0.0;
+                        const double v = nz ? fma(mcr, m, -J[r][kc]) : -J[r][kc];
+                        cr[r] = hs[r] * v;
+                        ci[r] = nz ? hs[r] * (mci * m) : 0.0;
+                    }
+                });
+                cnt[CN_NLU]++;
+                lu_valid = true;
+                state = ST_NEWTON;
+            }
+        }
+        warp_converge();
+        // ================= one simplified-Newton iteration :846-940 ==========================
+        if (warp_any(state == ST_NEWTON)) {
+            if (state == ST_NEWTON) {
+                // the three stages as one loop body with table coefficients (unrolled by default).  Values are those of the unrolled form: the first
+                // accumulation fma(a, F, 0) equals a*F, and (T W)_2 = fma(0, W2, fma(1, W1, 1*W0)) = W0 + W1.
+                double fr[N], fcr[N], fci[N];
+                bool finite = true;
+#pragma unroll
+                for (int c = 0; c < N; ++c) { fr[c] = 0.0; fcr[c] = 0.0; fci[c] = 0.0; }
+#if defined(BRDAE_ROLL_STAGES)   // smaller code; measured 1.6 % slower once all warps of an SM share the block
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+                for (int i = 0; i < 3; ++i) {
+                    const double t0c = kStageT[i][0], t1c = kStageT[i][1], t2c = kStageT[i][2];
+                    const double a0 = kStageTI[0][i], a1 = kStageTI[1][i], a2 = kStageTI[2][i];
+                    double Y[N], F[N];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) Y[c] = y[c] + fma(t2c, W[2][c], fma(t1c, W[1][c], t0c * W[0][c]));
+                    Prob::rhs(prm, t + h * kStageC[i], Y, F);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        const double Fv = F[c];
+                        finite = finite && is_finite(Fv);
+                        fr[c] = fma(a0, Fv, fr[c]); fcr[c] = fma(a1, Fv, fcr[c]); fci[c] = fma(a2, Fv, fci[c]);
+                    }
+                }
+                cnt[CN_NFEV] += 3;
+                int outcome = 0;  // 0 continue, 1 converged, 2 stop (not converged)
+                bool update_old = true;
+                if (!finite) outcome = 2;
+                else {
+                    double mw0[N], mw1[N], mw2[N];
+                    mass_mv<Mass>(prm, a, W[0], mw0);
+                    mass_mv<Mass>(prm, a, W[1], mw1);
+                    mass_mv<Mass>(prm, a, W[2], mw2);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        const double hs = (a.scale_residuals && a.var_index[c] >= 1) ? inv_h_lu : 1.0;
+                        double ar = fr[c], br = fcr[c], bi = fci[c];
+                        if (!mass_row_empty<Mass, N>(c)) {
+                            ar = fma(-mr, mw0[c], ar);
+                            br = fma(-mcr, mw1[c], br); br = fma(mci, mw2[c], br);
+                            bi = fma(-mcr, mw2[c], bi); bi = fma(-mci, mw1[c], bi);
+                        }
+                        fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
+                    }
+                    solve_real_sm<N>(sm, L::S_LUR, L::S_B, piv_r, fr);
+                    solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
+                    cnt[CN_NSOLVE]++;
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { const double v = fr[c] * inv_ns[c]; s = fma(v, v, s); }
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { const double v = fcr[c] * inv_ns[c]; s = fma(v, v, s); }
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { const double v = fci[c] * inv_ns[c]; s = fma(v, v, s); }
+                    const double dwn = sqrt(s) * a.rsq3n;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) { W[0][c] += fr[c]; W[1][c] += fcr[c]; W[2][c] += fci[c]; }
+                    double dw_true = 0, dw_true_max = 0;
+                    if (have_old) {
+                        rate = dwn / dwn_old; have_rate = true;
+                        const double inv1 = 1.0 / (1.0 - rate);
+                        dw_true = rate * inv1 * dwn;
+                        double rp = rate;          // rate**(MAXIT-k): uniform trip count, per-lane select
+                        for (int e = 1; e < MAXIT; ++e) rp = (e < MAXIT - k) ? rp * rate : rp;
+                        dw_true_max = rp * inv1 * dwn;
+                    }
+                    if (dwn < a.newton_tol) outcome = 1;
+                    else if (have_rate) {
+                        bool fall = true;
+                        if (rate >= 1) {
+                            if (rate < 100 && nbad < a.nmax_bad) { nbad++; update_old = false; fall = false; }
+                            else if (!a.all_newton) { outcome = 2; fall = false; }
+                        }
+                        if (fall) {
+                            if (dw_true < a.newton_tol) outcome = 1;
+                            else if (dw_true_max > a.newton_tol && a.predictive_newton) {
+                                if (nbad < a.nmax_bad) { nbad++; update_old = false; }
+                                else if (!a.all_newton) outcome = 2;
+                            }
+                        }
+                    }
+                    if (outcome == 0 && update_old) { dwn_old = dwn; have_old = true; }
+                }
+                if (outcome == 0) {
+                    ++k;
+                    if (k >= MAXIT) { outcome = 2; n_iter = MAXIT; }
+                } else n_iter = k + 1;
+                if (outcome != 0) {
+                    safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);   // :631
+                    if (outcome == 1) state = ST_ERREST;
+                    else if (current_jac) {                                            // :650-658
+                        cnt[CN_NFAIL]++;
+                        h_abs *= a.nonconv_factor;
+                        lu_valid = false;
+                        state = ST_SETUP; setup_kind = SETUP_ATTEMPT;
+                    } else {                                                            // :643-647
+#pragma unroll
+                        for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
+                        sm(L::S_TJ) = t;
+                        cnt[CN_NJEV]++;
+                        current_jac = true; lu_valid = false;
+                        state = ST_SETUP; setup_kind = SETUP_GUESS;
+                    }
+                }
+            }
+        }
+        warp_converge();
     }
 }
 
