@@ -67,6 +67,10 @@ size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *) {
     size_t bytes = kCounterBytes;
     if (b->problem == BRDAE_NPENDULUM)
         bytes += npendulum_uses_k3(b->n, b->n_systems) ? k3_scratch_bytes(b->n, b->n_systems) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
+    else {      // K1: per-CTA slice of cold per-lane state (kernels that keep it in shared memory need none)
+        LaunchGeom g{};
+        if (launch_geometry(b->problem, b->mass != nullptr, b->n, b->n_systems, sm_count(), &g) == BRDAE_OK) bytes += g.scratch_bytes;
+    }
     return bytes;
 }
 

@@ -5,16 +5,17 @@
 
 namespace brdae {
 
-template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE = false>
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE = false, bool COLD_GLOBAL = false>
 int k1_launch(const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
-    constexpr int smem = K1Layout<Prob>::SLOTS * BLOCK * (int)sizeof(double);
+    using L = K1Layout<Prob, COLD_GLOBAL>;
+    constexpr int smem = L::SHARED_SLOTS * BLOCK * (int)sizeof(double);
     int64_t want = (a.B + BLOCK - 1) / BLOCK;
     int64_t cap = (int64_t)(sms > 0 ? sms : 148) * MIN_BLOCKS;  // persistent grid: resident CTAs only
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    if (g) { g->grid = grid; g->block = BLOCK; g->smem = smem; }
+    if (g) { g->grid = grid; g->block = BLOCK; g->smem = smem; g->scratch_bytes = (size_t)grid * BLOCK * L::GLOBAL_SLOTS * sizeof(double); }
     if (geom_only) return BRDAE_OK;
-    auto kern = k1_kernel<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE>;
+    auto kern = k1_kernel<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BRDAE_ERR_CUDA;
     kern<<<grid, BLOCK, smem, s>>>(a);
     return cudaPeekAtLastError() == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;

@@ -665,7 +665,7 @@ int k2_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, i
         grid = cfits ? (int64_t)nsm * per_sm : nsm;
     }
     if (a_in.B < grid) grid = a_in.B > 0 ? a_in.B : 1;
-    if (g) { g->grid = (int)grid; g->block = global_state ? K2G_BLOCK : K2_BLOCK; g->smem = (int)smem; }
+    if (g) { g->grid = (int)grid; g->block = global_state ? K2G_BLOCK : K2_BLOCK; g->smem = (int)smem; g->scratch_bytes = 0; }
     if (geom_only) return BRDAE_OK;
     if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;   // band kernel: the problem's own M and J only
     SolveArgs a = a_in;

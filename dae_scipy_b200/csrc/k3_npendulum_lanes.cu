@@ -778,7 +778,7 @@ int k3_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, i
     const int N = a_in.n;
     if (N < 10 || N % 5 != 0) return BRDAE_ERR_BAD_ARGUMENT;
     const long long G = k3_slots(N, a_in.B);
-    if (g) { g->grid = (int)(G / K3_BLOCK); g->block = K3_BLOCK; g->smem = 0; }
+    if (g) { g->grid = (int)(G / K3_BLOCK); g->block = K3_BLOCK; g->smem = 0; g->scratch_bytes = 0; }
     if (geom_only) return BRDAE_OK;
     if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;
     SolveArgs a = a_in;

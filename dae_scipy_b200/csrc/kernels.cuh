@@ -7,7 +7,7 @@
 
 namespace brdae {
 
-struct LaunchGeom { int grid, block, smem; };
+struct LaunchGeom { int grid, block, smem; size_t scratch_bytes; };   // scratch_bytes: K1 cold-state slice of the workspace
 
 // geometry that launch_solver would use (no launch)
 int launch_geometry(int problem, bool dense_mass, int n, int64_t B, int sms, LaunchGeom *g);

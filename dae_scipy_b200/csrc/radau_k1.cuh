@@ -33,6 +33,13 @@
 #pragma once
 #include "problems.cuh"
 
+#ifndef K1_TEVAL_SHARED
+#define K1_TEVAL_SHARED 256      // output grids up to this many points are staged in shared memory
+#endif
+#ifndef K1_NEWTON_REPS
+#define K1_NEWTON_REPS 2
+#endif
+
 namespace brdae {
 
 enum : int { ST_IDLE = 0, ST_SETUP, ST_FACTOR, ST_NEWTON, ST_ERREST, ST_EXIT };
@@ -163,10 +170,11 @@ BRDAE_HD unsigned lu_cplx_left(const S &sm, int base_r, int base_i, ColFn &&colu
 }
 
 // b <- P b (b[i] = b_old[perm_i]): a round trip through N scratch slots with a dynamic load address, or
-// (BRDAE_PERM_SELECT) select chains in registers, which trade 2N shared-memory accesses for ~N^2 selects.
-template <int N, class S>
+// (SELECT, used by the cold-state layout that has no scratch slots) select chains in registers, which trade
+// 2N shared-memory accesses for ~N^2 selects at the same speed.
+template <int N, bool SELECT, class S>
 BRDAE_HD void permute_rhs(const S &sm, int scratch, unsigned perm, double (&b)[N]) {
-#if defined(BRDAE_PERM_SELECT)
+  if (SELECT) {
     double o[N];
 #pragma unroll
     for (int c = 0; c < N; ++c) o[c] = b[c];
@@ -178,18 +186,18 @@ BRDAE_HD void permute_rhs(const S &sm, int scratch, unsigned perm, double (&b)[N
         for (int c = 1; c < N; ++c) v = (pi == (unsigned)c) ? o[c] : v;
         b[i] = v;
     }
-#else
+  } else {
 #pragma unroll
     for (int c = 0; c < N; ++c) sm(scratch + c) = b[c];
 #pragma unroll
     for (int i = 0; i < N; ++i) b[i] = sm(scratch + (int)((perm >> (3 * i)) & 7u));
-#endif
+  }
 }
 // ---- triangular solves streaming the factors from lane-strided shared memory ----------------
 // b is put into pivoted order by a round trip through N scratch slots (dynamic load address).
-template <int N, class S>
+template <int N, bool SELECT, class S>
 BRDAE_HD void solve_real_sm(const S &sm, int base, int scratch, unsigned perm, double (&b)[N]) {
-    permute_rhs<N>(sm, scratch, perm, b);
+    permute_rhs<N, SELECT>(sm, scratch, perm, b);
     int ro[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) ro[i] = base + row_of<N>(perm, i);
@@ -208,10 +216,10 @@ BRDAE_HD void solve_real_sm(const S &sm, int base, int scratch, unsigned perm, d
         for (int r = 0; r < k; ++r) b[r] = fma(-sm(ro[r] + k), xk, b[r]);
     }
 }
-template <int N, class S>
+template <int N, bool SELECT, class S>
 BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, unsigned perm, double (&br)[N], double (&bi)[N]) {
-    permute_rhs<N>(sm, scratch, perm, br);
-    permute_rhs<N>(sm, scratch, perm, bi);
+    permute_rhs<N, SELECT>(sm, scratch, perm, br);
+    permute_rhs<N, SELECT>(sm, scratch, perm, bi);
     int ro[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) ro[i] = row_of<N>(perm, i);
@@ -245,19 +253,29 @@ BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, un
     }
 }
 
-template <class Prob>
+// Slots of one lane.  HOT: the LU factors (+ N scratch slots for right-hand sides on their way into
+// pivoted order), always in shared memory.  COLD: f(t,y), y_old, the dense-output coefficients Q and the
+// point (t_J, y_J) of the last Jacobian -- touched once or twice per STEP, not per Newton iteration.
+// With COLD_GLOBAL they live in a per-CTA slice of the workspace (coalesced, L2-resident: 31 slots x
+// 148 x 384 lanes = 14 MB) and shared memory holds nothing but the factors: 600 B per lane instead of
+// 928 B, i.e. 12 warps per SM instead of 8.
+template <class Prob, bool COLD_GLOBAL = false>
 struct K1Layout {
     static constexpr int N = Prob::N;
+    static constexpr bool SELECT = COLD_GLOBAL;     // no scratch slots: permute right-hand sides with selects
     static constexpr int S_LUR = 0;
     static constexpr int S_LCR = N * N;
     static constexpr int S_LCI = 2 * N * N;
-    static constexpr int S_F = 3 * N * N;
-    static constexpr int S_YOLD = S_F + N;
-    static constexpr int S_Q = S_YOLD + N;
-    static constexpr int S_YJ = S_Q + 3 * N;
-    static constexpr int S_TJ = S_YJ + N;
-    static constexpr int S_B = S_TJ + 1;          // N scratch slots: right-hand sides on their way into pivoted order
-    static constexpr int SLOTS = S_B + N;
+    static constexpr int S_B = 3 * N * N;
+    static constexpr int HOT = S_B + (SELECT ? 0 : N);
+    static constexpr int C_F = 0;
+    static constexpr int C_YOLD = C_F + N;
+    static constexpr int C_Q = C_YOLD + N;
+    static constexpr int C_YJ = C_Q + 3 * N;
+    static constexpr int C_TJ = C_YJ + N;
+    static constexpr int COLD = C_TJ + 1;
+    static constexpr int SHARED_SLOTS = COLD_GLOBAL ? HOT : HOT + COLD;
+    static constexpr int GLOBAL_SLOTS = COLD_GLOBAL ? COLD : 0;
 };
 
 // warp-level helpers; the host build (tests/host_sim) runs a "warp" of one lane
@@ -312,11 +330,14 @@ inline void warp_converge() {}
 inline long long fetch_system(bool want, unsigned long long *counter) { return want ? (long long)((*counter)++) : -1; }
 #endif
 
-// The per-lane integrator.  `sm` addresses this lane's shared-memory slots.
-template <class Prob, class Mass, bool CTA_WIDE, class S>
-BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
+// The per-lane integrator.  `sm` addresses this lane's hot (shared-memory) slots, `cd` its cold ones.
+// `t_eval` is the output grid as the lanes should read it (the kernel stages short grids in shared
+// memory: the check "is the next output point inside this step" runs after every accepted step, and a
+// global load there put an L2 round trip on the critical path of every ERREST pass).
+template <class Prob, class Mass, bool CTA_WIDE, bool COLD_GLOBAL, class S, class SC>
+BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const double *t_eval) {
     constexpr int N = Prob::N;
-    using L = K1Layout<Prob>;
+    using L = K1Layout<Prob, COLD_GLOBAL>;
     typename Prob::P prm;
 
     // ---- lane state ---------------------------------------------------------------------
@@ -365,8 +386,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                     double f0[N];
                     Prob::rhs(prm, t, y, f0);                            // :304
 #pragma unroll
-                    for (int c = 0; c < N; ++c) { sm(L::S_F + c) = f0[c]; sm(L::S_YJ + c) = y[c]; }
-                    sm(L::S_TJ) = t;                                     // J0 = jac(t0, y0) :483
+                    for (int c = 0; c < N; ++c) { cd(L::C_F + c) = f0[c]; cd(L::C_YJ + c) = y[c]; }
+                    cd(L::C_TJ) = t;                                     // J0 = jac(t0, y0) :483
 #pragma unroll
                     for (int q = 0; q < CN_COUNT; ++q) cnt[q] = 0;
                     cnt[CN_NFEV] = 1;
@@ -427,9 +448,9 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                     }
                     mass_mv<Mass>(prm, a, ze, mze);
 #pragma unroll
-                    for (int c = 0; c < N; ++c) err[c] = sm(L::S_F + c) + mze[c];
+                    for (int c = 0; c < N; ++c) err[c] = cd(L::C_F + c) + mze[c];
                     for (int pass = 0;; ++pass) {
-                        solve_real_sm<N>(sm, L::S_LUR, L::S_B, piv_r, err);   // rhs NOT scaled by hscale
+                        solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, err);   // rhs NOT scaled by hscale
                         cnt[CN_NSOLVE_ERR]++;
                         double s = 0.0;
 #pragma unroll
@@ -464,15 +485,15 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                     if (!recompute && factor < 1.2) factor = 1; else lu_valid = false;
                     double fnew[N];
 #pragma unroll
-                    for (int c = 0; c < N; ++c) { sm(L::S_YOLD + c) = y[c]; y[c] = y[c] + Z[2][c]; }
+                    for (int c = 0; c < N; ++c) { cd(L::C_YOLD + c) = y[c]; y[c] = y[c] + Z[2][c]; }
                     Prob::rhs(prm, t_new, y, fnew);
                     cnt[CN_NFEV]++;
 #pragma unroll
-                    for (int c = 0; c < N; ++c) sm(L::S_F + c) = fnew[c];
+                    for (int c = 0; c < N; ++c) cd(L::C_F + c) = fnew[c];
                     if (recompute) {
 #pragma unroll
-                        for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
-                        sm(L::S_TJ) = t_new;
+                        for (int c = 0; c < N; ++c) cd(L::C_YJ + c) = y[c];
+                        cd(L::C_TJ) = t_new;
                         cnt[CN_NJEV]++;
                         current_jac = true;
                     } else if (has_jac_fn) current_jac = false;
@@ -484,13 +505,13 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                         Q[c][0] = fma(Z[2][c], P20, fma(Z[1][c], P10, Z[0][c] * P00));
                         Q[c][1] = fma(Z[2][c], P21, fma(Z[1][c], P11, Z[0][c] * P01));
                         Q[c][2] = fma(Z[2][c], P22, fma(Z[1][c], P12, Z[0][c] * P02));
-                        sm(L::S_Q + 3 * c) = Q[c][0]; sm(L::S_Q + 3 * c + 1) = Q[c][1]; sm(L::S_Q + 3 * c + 2) = Q[c][2];
+                        cd(L::C_Q + 3 * c) = Q[c][0]; cd(L::C_Q + 3 * c + 1) = Q[c][1]; cd(L::C_Q + 3 * c + 2) = Q[c][2];
                     }
                     t_sol_old = t; inv_h_sol = inv_h; have_sol = true;
                     t = t_new;
                     // driver: t_eval points inside (t_old, t]  (searchsorted side='right', ivp.py:711-729)
                     while (ei < a.T) {
-                        const double te = a.t_eval[ei];
+                        const double te = t_eval[ei];
                         if (!(dir > 0 ? te <= t : te >= t)) break;
                         const double x = (te - t_sol_old) * inv_h_sol;
                         const double x2 = x * x, x3 = x2 * x;
@@ -499,7 +520,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                             double v = Q[c][0] * x;
                             v = fma(Q[c][1], x2, v);
                             v = fma(Q[c][2], x3, v);
-                            a.y_eval[((int64_t)ei * N + c) * a.B + idx] = v + sm(L::S_YOLD + c);
+                            a.y_eval[((int64_t)ei * N + c) * a.B + idx] = v + cd(L::C_YOLD + c);
                         }
                         ++ei;
                     }
@@ -561,8 +582,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                         }
 #pragma unroll
                         for (int c = 0; c < N; ++c) {
-                            const double q0 = sm(L::S_Q + 3 * c), q1 = sm(L::S_Q + 3 * c + 1), q2 = sm(L::S_Q + 3 * c + 2);
-                            const double yo = sm(L::S_YOLD + c);
+                            const double q0 = cd(L::C_Q + 3 * c), q1 = cd(L::C_Q + 3 * c + 1), q2 = cd(L::C_Q + 3 * c + 2);
+                            const double yo = cd(L::C_YOLD + c);
                             double z[3];
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
@@ -612,8 +633,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                 } else {
                     double yJ[N];
 #pragma unroll
-                    for (int c = 0; c < N; ++c) yJ[c] = sm(L::S_YJ + c);
-                    Prob::jac(prm, sm(L::S_TJ), yJ, J);
+                    for (int c = 0; c < N; ++c) yJ[c] = cd(L::C_YJ + c);
+                    Prob::jac(prm, cd(L::C_TJ), yJ, J);
                 }
                 double hs[N];
 #pragma unroll
@@ -641,7 +662,13 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
             }
         }
         warp_converge();
-        // ================= one simplified-Newton iteration :846-940 ==========================
+        // ================= simplified-Newton iterations :846-940 ==============================
+        // The chain ends with K1_NEWTON_REPS Newton iterations back to back (a rolled loop: one copy of
+        // the code): lanes need 2-4 iterations per attempt, so a second pass is nearly always wanted by
+        // most lanes and saves a vote and a barrier; a lane that converged or failed in the first pass
+        // sits the second one out.  (Trace simulation: lane efficiency 0.75 -> 0.81, cost -12 %.)
+#pragma unroll 1
+        for (int rep = 0; rep < K1_NEWTON_REPS; ++rep) {
         if (warp_any(state == ST_NEWTON)) {
             if (state == ST_NEWTON) {
                 // the three stages as one loop body with table coefficients (unrolled by default).  Values are those of the unrolled form: the first
@@ -689,8 +716,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                         }
                         fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
                     }
-                    solve_real_sm<N>(sm, L::S_LUR, L::S_B, piv_r, fr);
-                    solve_cplx_sm<N>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
+                    solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, fr);
+                    solve_cplx_sm<N, L::SELECT>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
                     cnt[CN_NSOLVE]++;
                     double s = 0.0;
 #pragma unroll
@@ -742,8 +769,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
                         state = ST_SETUP; setup_kind = SETUP_ATTEMPT;
                     } else {                                                            // :643-647
 #pragma unroll
-                        for (int c = 0; c < N; ++c) sm(L::S_YJ + c) = y[c];
-                        sm(L::S_TJ) = t;
+                        for (int c = 0; c < N; ++c) cd(L::C_YJ + c) = y[c];
+                        cd(L::C_TJ) = t;
                         cnt[CN_NJEV]++;
                         current_jac = true; lu_valid = false;
                         state = ST_SETUP; setup_kind = SETUP_GUESS;
@@ -752,15 +779,25 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm) {
             }
         }
         warp_converge();
+        }
     }
 }
 
 #if defined(__CUDACC__)
-template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE>
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE, bool COLD_GLOBAL>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k1_kernel(const __grid_constant__ SolveArgs a) {
     extern __shared__ double k1_smem[];
+    using L = K1Layout<Prob, COLD_GLOBAL>;
     Slots<BLOCK> sm{k1_smem + threadIdx.x};
-    k1_lane_loop<Prob, Mass, CTA_WIDE>(a, sm);
+    Slots<BLOCK> cd{COLD_GLOBAL ? a.scratch + (size_t)blockIdx.x * (L::COLD * BLOCK) + threadIdx.x
+                                : k1_smem + L::HOT * BLOCK + threadIdx.x};
+    __shared__ double t_eval_sh[K1_TEVAL_SHARED];
+    const bool staged = a.T <= K1_TEVAL_SHARED;
+    if (staged) {
+        for (int i = threadIdx.x; i < a.T; i += BLOCK) t_eval_sh[i] = a.t_eval[i];
+        __syncthreads();
+    }
+    k1_lane_loop<Prob, Mass, CTA_WIDE, COLD_GLOBAL>(a, sm, cd, staged ? t_eval_sh : a.t_eval);
 }
 #endif
 

@@ -6,6 +6,7 @@
 // before GPU minutes are spent.  The product path has no CPU fallback: libbrdae.so launches
 // CUDA kernels or returns an error.
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../dae_scipy_b200/csrc/host_args.hpp"
@@ -15,9 +16,18 @@ using namespace brdae;
 
 template <class Prob, class Mass>
 static void run(const SolveArgs &a) {
-    std::vector<double> slots(K1Layout<Prob>::SLOTS, 0.0);
-    Slots<1> sm{slots.data()};
-    k1_lane_loop<Prob, Mass, false>(a, sm);
+    // both layouts of the kernel: cold state next to the factors, or in its own (global-memory) slice
+    if (!std::getenv("BRDAE_SIM_COLD_GLOBAL")) {
+        using L = K1Layout<Prob, false>;
+        std::vector<double> slots(L::SHARED_SLOTS, 0.0);
+        Slots<1> sm{slots.data()}, cd{slots.data() + L::HOT};
+        k1_lane_loop<Prob, Mass, false, false>(a, sm, cd, a.t_eval);
+    } else {
+        using L = K1Layout<Prob, true>;
+        std::vector<double> hot(L::SHARED_SLOTS, 0.0), cold(L::COLD, 0.0);
+        Slots<1> sm{hot.data()}, cd{cold.data()};
+        k1_lane_loop<Prob, Mass, false, true>(a, sm, cd, a.t_eval);
+    }
 }
 
 template <class Prob>
