@@ -84,6 +84,7 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
     a.predictive_newton = o->predictive_newton_stop; a.extrapolate = o->extrapolated_guess;
     a.all_newton = o->all_newton_iterations; a.constant_dt = o->constant_dt;
     a.has_jac_const = b->jac_const != nullptr;
+    a.newton_reps = 3;
     if (b->n <= BRDAE_NMAX_SMALL) {
         for (int c = 0; c < b->n; ++c) {
             a.atol[c] = b->atol[c];

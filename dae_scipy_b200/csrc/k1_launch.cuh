@@ -1,12 +1,19 @@
 // k1_launch.cuh -- launch helper shared by the k1_*.cu translation units.
 #pragma once
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "radau_k1.cuh"
 
 namespace brdae {
 
 template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE = false, bool COLD_GLOBAL = false>
-int k1_launch(const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
+int k1_launch(const SolveArgs &a_in, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only, int newton_reps = 3) {
+    // Newton passes per cycle: a scheduling knob tuned per problem family (results do not depend on it);
+    // BRDAE_NEWTON_REPS overrides it for experiments
+    SolveArgs a = a_in;
+    a.newton_reps = newton_reps;
+    if (const char *e = std::getenv("BRDAE_NEWTON_REPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) a.newton_reps = v; }
     using L = K1Layout<Prob, COLD_GLOBAL>;
     constexpr int smem = L::SHARED_SLOTS * BLOCK * (int)sizeof(double);
     int64_t want = (a.B + BLOCK - 1) / BLOCK;

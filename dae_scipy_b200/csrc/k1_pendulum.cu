@@ -20,8 +20,8 @@ namespace brdae {
 template <int INDEX>
 static int go(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {
     using Prob = Pendulum<INDEX>;
-    if (dense_mass) return k1_launch<Prob, MassDense<5>, K1_PEND_BLOCK, K1_PEND_MINB, K1_PEND_CTAWIDE, K1_PEND_COLD>(a, sms, s, g, geom_only);
-    return k1_launch<Prob, typename Prob::Mass, K1_PEND_BLOCK, K1_PEND_MINB, K1_PEND_CTAWIDE, K1_PEND_COLD>(a, sms, s, g, geom_only);
+    if (dense_mass) return k1_launch<Prob, MassDense<5>, K1_PEND_BLOCK, K1_PEND_MINB, K1_PEND_CTAWIDE, K1_PEND_COLD>(a, sms, s, g, geom_only, 4);
+    return k1_launch<Prob, typename Prob::Mass, K1_PEND_BLOCK, K1_PEND_MINB, K1_PEND_CTAWIDE, K1_PEND_COLD>(a, sms, s, g, geom_only, 4);
 }
 
 int k1_pendulum(int index, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only) {

@@ -10,13 +10,16 @@
 // expensive states -- FACTOR (iteration matrices + both LUs), NEWTON (one simplified-Newton
 // iteration) and ERREST (error estimate, accept/reject, controller, dense output) -- and one
 // cheap one (SETUP: step prologue, attempt set-up, starting guess).  The blocks are laid out in the
-// order a system walks through them, ERREST -> SETUP -> FACTOR -> NEWTON.  Every trip of the loop the
-// CTA votes once and enters that chain at the expensive block most lanes wait for, running it down to
-// NEWTON: a lane that converged does its error estimate, the next step's set-up, the refactorisation
-// if one is due and its first Newton iteration in a single trip, lanes waiting further down the
-// chain join on the way, and entering at NEWTON skips ERREST and FACTOR for everybody -- a block is
-// never executed for the sake of a straggler.  (A trace-driven simulation of the pendulum ensemble,
-// profiles/tools/sched_sim.py, puts the chain 10 % ahead of running only the majority block.)
+// order a system walks through them and every trip of the loop is one fixed CYCLE
+//     ERREST -> SETUP -> retire -> FACTOR -> NEWTON x newton_reps,
+// each block executed by exactly the lanes that wait for it (a warp none of whose lanes wants a block
+// skips it).  A lane that converged does its error estimate, the next step's set-up, the
+// refactorisation if one is due and its next Newton iterations in a single cycle, and because an
+// attempt needs 2-4 Newton iterations the lanes of a CTA phase-lock onto the cycle by themselves: no
+// vote, one barrier per cycle.  History (pendulum ensemble, 1M systems): every block every trip 301 ms;
+// majority vote per block 109 ms; majority entry into the chain 96 ms; + two Newton passes 83 ms;
+// fixed cycle with four passes 76 ms.  profiles/tools/sched_sim.py replays the oracle's event traces
+// under such policies and predicted each of these steps (lane efficiency 0.56 -> 0.80).
 //
 // Storage (N = 5): the real and complex LU factors (3 N^2 doubles), f(t,y), y_old, the dense
 // output coefficients Q (3N) and the point (t_J, y_J) the Jacobian was last evaluated at live in
@@ -35,9 +38,6 @@
 
 #ifndef K1_TEVAL_SHARED
 #define K1_TEVAL_SHARED 256      // output grids up to this many points are staged in shared memory
-#endif
-#ifndef K1_NEWTON_REPS
-#define K1_NEWTON_REPS 2
 #endif
 
 namespace brdae {
@@ -283,25 +283,14 @@ struct K1Layout {
 BRDAE_D bool warp_all(bool x) { return __all_sync(0xffffffffu, x); }
 BRDAE_D bool warp_any(bool x) { return __any_sync(0xffffffffu, x); }
 BRDAE_D int warp_count(bool x) { return __popc(__ballot_sync(0xffffffffu, x)); }
-// vote scope: one warp, or the whole CTA (all warps then run the same block at the same time and
-// share its instruction-cache lines)
-// one vote per trip: how many lanes are alive / wait for FACTOR / NEWTON / ERREST.  CTA-wide votes
-// cost a single barrier: every warp posts its four ballot counts (packed 4 x 16 bit) into a
-// double-buffered shared slot, and after the barrier every thread sums the slots.
-struct Votes { int alive, nF, nN, nE; };
+// Once per cycle: is any lane of the scope still alive?  CTA-wide this is the one barrier of the
+// cycle (BAR.RED.OR): it keeps the warps of the SM in step, so that they walk through the same block
+// at the same time and share its instruction-cache lines (with free-running warps the kernel was
+// instruction-fetch bound: SM I-cache hit rate 51 %, profiles/r01_k1_ncu_summary.md).
 template <bool CTA_WIDE>
-BRDAE_D Votes vote(int state, unsigned trip) {
-    const int a = warp_count(state != ST_EXIT), f = warp_count(state == ST_FACTOR);
-    const int n = warp_count(state == ST_NEWTON), e = warp_count(state == ST_ERREST);
-    if (!CTA_WIDE) return Votes{a, f, n, e};
-    __shared__ unsigned long long posted[2][32];
-    const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0)
-        posted[trip & 1][warp] = (unsigned long long)a | ((unsigned long long)f << 16) | ((unsigned long long)n << 32) | ((unsigned long long)e << 48);
-    __syncthreads();
-    unsigned long long sum = 0;
-    for (int w = 0; w < nwarps; ++w) sum += posted[trip & 1][w];
-    return Votes{(int)(sum & 0xffff), (int)((sum >> 16) & 0xffff), (int)((sum >> 32) & 0xffff), (int)(sum >> 48)};
+BRDAE_D bool cycle_sync(bool alive) {
+    if (CTA_WIDE) return __syncthreads_or(alive) != 0;
+    return __any_sync(0xffffffffu, alive);
 }
 BRDAE_D void warp_converge() { __syncwarp(); }
 BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
@@ -321,11 +310,8 @@ BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
 inline bool warp_all(bool x) { return x; }
 inline bool warp_any(bool x) { return x; }
 inline int warp_count(bool x) { return x ? 1 : 0; }
-struct Votes { int alive, nF, nN, nE; };
 template <bool CTA_WIDE>
-inline Votes vote(int state, unsigned) {
-    return Votes{state != ST_EXIT, state == ST_FACTOR, state == ST_NEWTON, state == ST_ERREST};
-}
+inline bool cycle_sync(bool alive) { return alive; }
 inline void warp_converge() {}
 inline long long fetch_system(bool want, unsigned long long *counter) { return want ? (long long)((*counter)++) : -1; }
 #endif
@@ -368,7 +354,6 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 
     const int MAXIT = a.maxit;
     const double dir = a.dir;
-    unsigned trip = 0;
 
     for (;;) {
         int finish_status = 1;  // 1 = still running
@@ -405,24 +390,14 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     }
                 }
             }
-            if (!CTA_WIDE && warp_all(state == ST_EXIT)) break;
         }
         warp_converge();
 
-        // ================= vote: where this trip enters the chain ERREST -> SETUP -> FACTOR -> NEWTON ==
-        // The blocks are laid out in the order a system walks through them, and a trip runs the chain
-        // from the block most lanes wait for down to NEWTON: a lane that converged does its error
-        // estimate, the next step's set-up, the refactorisation if one is due and its first Newton
-        // iteration in ONE trip, and lanes already waiting further down the chain join in on the way.
-        // Entering at NEWTON skips ERREST and FACTOR for everybody (they are never run for stragglers).
-        // Lanes in SETUP (a Newton failure of the previous trip) vote with FACTOR, where they are headed.
-        const Votes v = vote<CTA_WIDE>(state, trip++);
-        if (CTA_WIDE && v.alive == 0) break;
-        const int nF = v.nF, nN = v.nN, nE = v.nE;
-        const int run = (nN > 0 && nN >= nE && nN >= nF) ? ST_NEWTON : ((nE > 0 && nE >= nF) ? ST_ERREST : ST_FACTOR);
+        // ================= one barrier per cycle; leave when every lane of the scope is done ==========
+        if (!cycle_sync<CTA_WIDE>(state != ST_EXIT)) break;
 
         // ================= error estimate, accept/reject, epilogue :660-784 ===================
-        if (run == ST_ERREST) {
+        if (warp_any(state == ST_ERREST)) {
             if (state == ST_ERREST) {
                 double Z[3][N];
 #pragma unroll
@@ -621,7 +596,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
             }
         }
         // ================= (re)factorisation :594-613 =========================================
-        if (run != ST_NEWTON && warp_any(state == ST_FACTOR)) {
+        if (warp_any(state == ST_FACTOR)) {
             if (state == ST_FACTOR) {
                 if (a.scale_residuals) inv_h_lu = inv_h;
                 double J[N][N];
@@ -663,12 +638,10 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
         }
         warp_converge();
         // ================= simplified-Newton iterations :846-940 ==============================
-        // The chain ends with K1_NEWTON_REPS Newton iterations back to back (a rolled loop: one copy of
-        // the code): lanes need 2-4 iterations per attempt, so a second pass is nearly always wanted by
-        // most lanes and saves a vote and a barrier; a lane that converged or failed in the first pass
-        // sits the second one out.  (Trace simulation: lane efficiency 0.75 -> 0.81, cost -12 %.)
+        // a rolled loop (one copy of the code) of a.newton_reps passes; a lane that converged or failed
+        // sits the remaining passes out
 #pragma unroll 1
-        for (int rep = 0; rep < K1_NEWTON_REPS; ++rep) {
+        for (int rep = 0; rep < a.newton_reps; ++rep) {
         if (warp_any(state == ST_NEWTON)) {
             if (state == ST_NEWTON) {
                 // the three stages as one loop body with table coefficients (unrolled by default).  Values are those of the unrolled form: the first
