@@ -345,7 +345,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
     // Newton scope
     double W[3][N];
     int k = 0, nbad = 0, n_iter = 0;
-    double dwn_old = 0, rate = 0, safety = 0;
+    double dwn_old = 0, rate = 0;
     bool have_old = false, have_rate = false;
 #pragma unroll
     for (int c = 0; c < N; ++c) { y[c] = 0; inv_ns[c] = 0; W[0][c] = W[1][c] = W[2][c] = 0; }
@@ -406,6 +406,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     Z[1][c] = stage_z<1>(W[0][c], W[1][c], W[2][c]);
                     Z[2][c] = stage_z<2>(W[0][c], W[1][c], W[2][c]);
                 }
+                const double safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);   // :631
                 double error_norm = 0.0;
                 bool accepted = true;
                 if (!a.constant_dt) {
@@ -671,7 +672,6 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 }
                 cnt[CN_NFEV] += 3;
                 int outcome = 0;  // 0 continue, 1 converged, 2 stop (not converged)
-                bool update_old = true;
                 if (!finite) outcome = 2;
                 else {
                     double mw0[N], mw1[N], mw2[N];
@@ -702,38 +702,42 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     const double dwn = sqrt(s) * a.rsq3n;
 #pragma unroll
                     for (int c = 0; c < N; ++c) { W[0][c] += fr[c]; W[1][c] += fcr[c]; W[2][c] += fci[c]; }
-                    double dw_true = 0, dw_true_max = 0;
-                    if (have_old) {
-                        rate = dwn / dwn_old; have_rate = true;
-                        const double inv1 = 1.0 / (1.0 - rate);
-                        dw_true = rate * inv1 * dwn;
-                        double rp = rate;          // rate**(MAXIT-k): uniform trip count, per-lane select
-                        for (int e = 1; e < MAXIT; ++e) rp = (e < MAXIT - k) ? rp * rate : rp;
-                        dw_true_max = rp * inv1 * dwn;
-                    }
-                    if (dwn < a.newton_tol) outcome = 1;
-                    else if (have_rate) {
-                        bool fall = true;
-                        if (rate >= 1) {
-                            if (rate < 100 && nbad < a.nmax_bad) { nbad++; update_old = false; fall = false; }
-                            else if (!a.all_newton) { outcome = 2; fall = false; }
-                        }
-                        if (fall) {
-                            if (dw_true < a.newton_tol) outcome = 1;
-                            else if (dw_true_max > a.newton_tol && a.predictive_newton) {
-                                if (nbad < a.nmax_bad) { nbad++; update_old = false; }
-                                else if (!a.all_newton) outcome = 2;
-                            }
-                        }
-                    }
-                    if (outcome == 0 && update_old) { dwn_old = dwn; have_old = true; }
+                    // convergence logic :880-932 as straight-line predicate algebra: the nested ifs of the
+                    // reference compiled to a cascade of divergent branches at the very end of the block's
+                    // dependency chain, where nothing is left to hide their latency
+                    const bool had_old = have_old;
+                    const double r_new = dwn / (had_old ? dwn_old : 1.0);
+                    rate = had_old ? r_new : rate;
+                    have_rate = have_rate || had_old;
+                    const double inv1 = 1.0 / (1.0 - rate);
+                    const double dw_true = rate * inv1 * dwn;
+                    double rp = rate;              // rate**(MAXIT-k) by repeated multiplication: straight-line selects for
+                    const int npow = MAXIT - k;    // the usual iteration limits, a (uniform) loop beyond
+#pragma unroll
+                    for (int e = 1; e < 8; ++e) rp = (e < npow) ? rp * rate : rp;
+                    for (int e = 8; e < MAXIT; ++e) rp = (e < npow) ? rp * rate : rp;
+                    const double dw_true_max = rp * inv1 * dwn;
+                    const bool conv_now = dwn < a.newton_tol;
+                    const bool live = have_rate && !conv_now;
+                    const bool bad_ok = nbad < a.nmax_bad;
+                    const bool ge1 = live && rate >= 1;
+                    const bool retry_a = ge1 && rate < 100 && bad_ok;                 // diverging, but allowed a bad iteration
+                    const bool stop_b = ge1 && !retry_a && !a.all_newton;
+                    const bool fall = live && !retry_a && !stop_b;
+                    const bool conv_c = fall && dw_true < a.newton_tol;
+                    const bool slow_d = fall && !conv_c && dw_true_max > a.newton_tol && a.predictive_newton;
+                    const bool retry_d = slow_d && bad_ok, stop_d = slow_d && !bad_ok && !a.all_newton;
+                    outcome = (conv_now || conv_c) ? 1 : ((stop_b || stop_d) ? 2 : 0);
+                    nbad += (retry_a || retry_d) ? 1 : 0;
+                    const bool keep_old = retry_a || retry_d || conv_now || conv_c || stop_b || stop_d;   // :928 dW_norm_old
+                    dwn_old = keep_old ? dwn_old : dwn;
+                    have_old = have_old || !keep_old;
                 }
                 if (outcome == 0) {
                     ++k;
                     if (k >= MAXIT) { outcome = 2; n_iter = MAXIT; }
                 } else n_iter = k + 1;
                 if (outcome != 0) {
-                    safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);   // :631
                     if (outcome == 1) state = ST_ERREST;
                     else if (current_jac) {                                            // :650-658
                         cnt[CN_NFAIL]++;
