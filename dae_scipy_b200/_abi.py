@@ -42,6 +42,7 @@ class BrdaeOptions(C.Structure):
                 ("always_2nd_estimate", C.c_int32), ("predictive_controller", C.c_int32),
                 ("predictive_newton_stop", C.c_int32), ("extrapolated_guess", C.c_int32),
                 ("all_newton_iterations", C.c_int32), ("constant_dt", C.c_int32),
+                ("jac_finite_differences", C.c_int32), ("reserved", C.c_int32),
                 ("nmax_step", C.c_int64)]
 
 
@@ -87,7 +88,7 @@ SOLVER_OPTION_NAMES = (tuple(_FLOAT_OPTS) + tuple(_BOOL_OPTS) +
 
 
 def make_options(*, first_step=None, max_step=math.inf, newton_tol=None, max_newton_ite=6,
-                 max_bad_ite=None, nmax_step=math.inf, **kw) -> BrdaeOptions:
+                 max_bad_ite=None, nmax_step=math.inf, jac_finite_differences=False, **kw) -> BrdaeOptions:
     """Keyword surface of RadauDAE.__init__ -> brdae_options (validation as in scipy
     common.py:10-24: first_step/max_step must be positive)."""
     o = BrdaeOptions()
@@ -103,6 +104,7 @@ def make_options(*, first_step=None, max_step=math.inf, newton_tol=None, max_new
     o.max_newton_ite = int(max_newton_ite)
     o.max_bad_ite = -1 if max_bad_ite is None else int(max_bad_ite)
     o.nmax_step = 0 if nmax_step is None or math.isinf(nmax_step) else int(nmax_step)
+    o.jac_finite_differences = int(bool(jac_finite_differences))
     for key, (field, default) in _FLOAT_OPTS.items():
         setattr(o, field, float(kw.pop(key, default)))
     for key, (field, default) in _BOOL_OPTS.items():

@@ -146,13 +146,17 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
             mass = None
 
     jac_const = None
+    fd = False
     if isinstance(jac, str):
         if jac != "analytic":
             raise ValueError("`jac` must be 'analytic' or a constant [n, n] matrix.")
     elif jac is None:
-        raise NotImplementedError(
-            "finite-difference Jacobians (jac=None in the reference, radauDAE.py:468-481) are not "
-            "available in the batched solver yet; use jac='analytic' or a constant matrix.")
+        # the reference's default (radauDAE.py:468-481): scipy num_jac forward differences of the RHS
+        # functor with adaptive column factors, on the device (thread-per-system problems)
+        if prob.name == "npendulum":
+            raise NotImplementedError("finite-difference Jacobians are not available for the n-pendulum chain "
+                                      "kernels; use jac='analytic'.")
+        fd = True
     elif callable(jac):
         raise ValueError("Python Jacobian callables cannot run on the device; use jac='analytic'.")
     else:
@@ -170,7 +174,7 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
     del ignored
     extraneous = {k: options.pop(k) for k in list(options) if k not in _abi.SOLVER_OPTION_NAMES}
     warn_extraneous(extraneous)
-    opts = _abi.make_options(**options)
+    opts = _abi.make_options(jac_finite_differences=fd, **options)
     if n > 8 and prob.name != "npendulum":
         raise ValueError("thread-per-system kernels support at most 8 unknowns.")
     return HostBatch(problem=prob, n=n, B=B, t0=t0, t_bound=tf, t_eval=te, rtol=rtol, atol=at,
@@ -248,7 +252,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     mass_matrix : 'problem' (default: the problem's own matrix, per-system for the transistor),
                   an [n, n] array shared by the ensemble, or None (identity, as in the reference).
     var_index   : [n] integers 0..3 or None (all differential), as in the reference.
-    jac         : 'analytic' (default) or a constant [n, n] matrix.
+    jac         : 'analytic' (default: the problem's analytic Jacobian functor), a constant [n, n] matrix, or
+                  None = finite differences as in the reference's default (scipy num_jac).
     """
     import torch
 

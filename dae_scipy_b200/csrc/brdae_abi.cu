@@ -60,16 +60,18 @@ void brdae_default_options(brdae_options *o) {
     o->scale_residuals = 1; o->scale_newton_norm = 1; o->scale_error = 1; o->zero_algebraic_error = 0;
     o->always_2nd_estimate = 1; o->predictive_controller = 1; o->predictive_newton_stop = 1;
     o->extrapolated_guess = 1; o->all_newton_iterations = 0; o->constant_dt = 0; o->nmax_step = 0;
+    o->jac_finite_differences = 0; o->reserved = 0;
 }
 
-size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *) {
+size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *o) {
     if (!b) return 0;
     size_t bytes = kCounterBytes;
     if (b->problem == BRDAE_NPENDULUM)
         bytes += npendulum_uses_k3(b->n, b->n_systems) ? k3_scratch_bytes(b->n, b->n_systems) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
     else {      // K1: per-CTA slice of cold per-lane state (kernels that keep it in shared memory need none)
         LaunchGeom g{};
-        if (launch_geometry(b->problem, b->mass != nullptr, b->n, b->n_systems, sm_count(), &g) == BRDAE_OK) bytes += g.scratch_bytes;
+        const bool fd = o && o->jac_finite_differences && !b->jac_const;
+        if (launch_geometry(b->problem, b->mass != nullptr, fd, b->n, b->n_systems, sm_count(), &g) == BRDAE_OK) bytes += g.scratch_bytes;
     }
     return bytes;
 }
@@ -77,7 +79,7 @@ size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *) {
 int brdae_launch_info(const brdae_batch *b, int32_t *grid, int32_t *block, int32_t *smem_bytes) {
     if (!b) return BRDAE_ERR_BAD_ARGUMENT;
     LaunchGeom g;
-    int rc = launch_geometry(b->problem, b->mass != nullptr, b->n, b->n_systems, sm_count(), &g);
+    int rc = launch_geometry(b->problem, b->mass != nullptr, false, b->n, b->n_systems, sm_count(), &g);
     if (rc != BRDAE_OK) return rc;
     if (grid) *grid = g.grid;
     if (block) *block = g.block;

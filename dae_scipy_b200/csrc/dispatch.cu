@@ -34,9 +34,9 @@ static int route(int problem, bool dense_mass, const SolveArgs &a, const brdae_b
     return BRDAE_ERR_UNKNOWN_PROBLEM;
 }
 
-int launch_geometry(int problem, bool dense_mass, int n, int64_t B, int sms, LaunchGeom *g) {
+int launch_geometry(int problem, bool dense_mass, bool jac_fd, int n, int64_t B, int sms, LaunchGeom *g) {
     SolveArgs a{};
-    a.B = B; a.n = n;
+    a.B = B; a.n = n; a.jac_fd = jac_fd ? 1 : 0;
     return route(problem, dense_mass, a, nullptr, sms, nullptr, g, true);
 }
 

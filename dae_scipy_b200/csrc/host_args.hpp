@@ -46,6 +46,7 @@ inline int validate(const brdae_batch *b, const brdae_options *o) {
         if (b->var_index && (b->var_index[c] < 0 || b->var_index[c] > 3)) return BRDAE_ERR_BAD_ARGUMENT;
     }
     if (o->first_step > 0 && o->first_step > std::fabs(b->t_bound - b->t0)) return BRDAE_ERR_BAD_ARGUMENT;
+    if (o->jac_finite_differences && !b->jac_const && b->problem == BRDAE_NPENDULUM) return BRDAE_ERR_UNSUPPORTED;
     return BRDAE_OK;
 }
 
@@ -85,6 +86,7 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
     a.all_newton = o->all_newton_iterations; a.constant_dt = o->constant_dt;
     a.has_jac_const = b->jac_const != nullptr;
     a.newton_reps = 3;
+    a.jac_fd = (o->jac_finite_differences && !b->jac_const) ? 1 : 0;
     if (b->n <= BRDAE_NMAX_SMALL) {
         for (int c = 0; c < b->n; ++c) {
             a.atol[c] = b->atol[c];

@@ -10,7 +10,7 @@ namespace brdae {
 struct LaunchGeom { int grid, block, smem; size_t scratch_bytes; };   // scratch_bytes: K1 cold-state slice of the workspace
 
 // geometry that launch_solver would use (no launch)
-int launch_geometry(int problem, bool dense_mass, int n, int64_t B, int sms, LaunchGeom *g);
+int launch_geometry(int problem, bool dense_mass, bool jac_fd, int n, int64_t B, int sms, LaunchGeom *g);
 // launch the kernel matching (problem, mass kind) on `stream`
 int launch_solver(int problem, bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t stream);
 

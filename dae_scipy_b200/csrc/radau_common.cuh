@@ -88,6 +88,7 @@ struct SolveArgs {
     int32_t scale_residuals, scale_newton_norm, scale_error, zero_algebraic_error;
     int32_t always_2nd, predictive_controller, predictive_newton, extrapolate, all_newton, constant_dt;
     int32_t has_jac_const;
+    int32_t jac_fd;        // K1: finite-difference Jacobian (jac=None of the reference)
     int32_t newton_reps;   // K1: Newton passes per cycle (scheduling only, results do not depend on it)
     // small-problem (n <= BRDAE_NMAX_SMALL) uniform vectors; K2 reads its own from global memory
     double atol[BRDAE_NMAX_SMALL];

@@ -42,7 +42,7 @@
 
 namespace brdae {
 
-enum : int { ST_IDLE = 0, ST_SETUP, ST_FACTOR, ST_NEWTON, ST_ERREST, ST_EXIT };
+enum : int { ST_IDLE = 0, ST_SETUP, ST_FACTOR, ST_NEWTON, ST_ERREST, ST_JACFD, ST_EXIT };
 // what a lane entering SETUP still has to do
 enum : int { SETUP_STEP = 0, SETUP_ATTEMPT = 1, SETUP_GUESS = 2 };
 
@@ -259,7 +259,10 @@ BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, un
 // With COLD_GLOBAL they live in a per-CTA slice of the workspace (coalesced, L2-resident: 31 slots x
 // 148 x 384 lanes = 14 MB) and shared memory holds nothing but the factors: 600 B per lane instead of
 // 928 B, i.e. 12 warps per SM instead of 8.
-template <class Prob, bool COLD_GLOBAL = false>
+// With FD (finite-difference Jacobian, jac=None of the reference) the Jacobian cannot be re-materialised
+// from (t_J, y_J): it is kept, with the N adaptive column factors of scipy's num_jac, in the per-CTA
+// slice of the workspace as well (N^2 + N more global slots).
+template <class Prob, bool COLD_GLOBAL = false, bool FD = false>
 struct K1Layout {
     static constexpr int N = Prob::N;
     static constexpr bool SELECT = COLD_GLOBAL;     // no scratch slots: permute right-hand sides with selects
@@ -275,8 +278,72 @@ struct K1Layout {
     static constexpr int C_TJ = C_YJ + N;
     static constexpr int COLD = C_TJ + 1;
     static constexpr int SHARED_SLOTS = COLD_GLOBAL ? HOT : HOT + COLD;
-    static constexpr int GLOBAL_SLOTS = COLD_GLOBAL ? COLD : 0;
+    static constexpr int G_J = COLD_GLOBAL ? COLD : 0;       // global slots: [cold state] [J, N x N] [column factors, N]
+    static constexpr int G_FAC = G_J + N * N;
+    static constexpr int GLOBAL_SLOTS = (COLD_GLOBAL ? COLD : 0) + (FD ? N * N + N : 0);
 };
+
+// ---- finite-difference Jacobian: scipy.integrate._ivp.common.num_jac (scipy 1.18.1 common.py:268-452,
+// called from radauDAE.py:475-480 with threshold = atol), dense branch, one column at a time; the
+// columns are scaled by the reciprocal of h (arithmetic contract) -----------------
+constexpr double NJ_FACTOR0 = 0x1.0000000000000p-26;       // EPS ** 0.5
+constexpr double NJ_DIFF_REJECT = 0x1.6a09e667f3bcdp-46;   // EPS ** 0.875
+constexpr double NJ_DIFF_SMALL = 0x1.0000000000000p-39;    // EPS ** 0.75
+constexpr double NJ_DIFF_BIG = 0x1.0000000000000p-13;      // EPS ** 0.25
+constexpr double NJ_MIN_FACTOR = 0x1.f400000000000p-43;    // 1e3 * EPS
+// f(t, y + h e_i) into fn; largest |fn - f| and max(|f|, |fn|) of that row
+template <class Prob, int N>
+BRDAE_HD void fd_column(const typename Prob::P &prm, double t, const double (&y)[N], const double (&f)[N], int i, double h,
+                        double (&fn)[N], double &md, double &scale) {
+    double yp[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) yp[c] = y[c] + (c == i ? h : 0.0);
+    Prob::rhs(prm, t, yp, fn);
+    md = fabs(fn[0] - f[0]);
+    double fm = f[0], fnm = fn[0];
+#pragma unroll
+    for (int r = 1; r < N; ++r) {
+        const double d = fabs(fn[r] - f[r]);
+        const bool g = d > md;
+        md = g ? d : md; fm = g ? f[r] : fm; fnm = g ? fn[r] : fnm;
+    }
+    scale = fmax(fabs(fm), fabs(fnm));
+}
+// J (global slots gj(G_J ...)) and the column factors (gj(G_FAC ...)) at (t, y) with f = f(t, y)
+template <class Prob, class L, class SG>
+BRDAE_HD void num_jac_fd(const typename Prob::P &prm, const SolveArgs &a, double t, const double (&y)[Prob::N],
+                         const double (&f)[Prob::N], const SG &gj) {
+    constexpr int N = Prob::N;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+        double yi = y[0], fi = f[0];
+#pragma unroll
+        for (int c = 1; c < N; ++c) { yi = (c == i) ? y[c] : yi; fi = (c == i) ? f[c] : fi; }
+        const double ys = (fi >= 0 ? 1.0 : -1.0) * fmax(a.atol[i], fabs(yi));
+        double fac = gj(L::G_FAC + i);
+        double h = (yi + fac * ys) - yi;
+        while (h == 0) { fac *= 10; h = (yi + fac * ys) - yi; }
+        double fn[N], md, scale;
+        fd_column<Prob, N>(prm, t, y, f, i, h, fn, md, scale);
+        if (md < NJ_DIFF_REJECT * scale) {
+            const double fac_new = 10 * fac;
+            const double h_new = (yi + fac_new * ys) - yi;
+            double fn2[N], md2, scale2;
+            fd_column<Prob, N>(prm, t, y, f, i, h_new, fn2, md2, scale2);
+            if (md * scale2 < md2 * scale) {
+                fac = fac_new; h = h_new; scale = scale2; md = md2;
+#pragma unroll
+                for (int r = 0; r < N; ++r) fn[r] = fn2[r];
+            }
+        }
+        const double rh = 1.0 / h;
+#pragma unroll
+        for (int r = 0; r < N; ++r) gj(L::G_J + r * N + i) = (fn[r] - f[r]) * rh;
+        if (md < NJ_DIFF_SMALL * scale) fac *= 10;
+        if (md > NJ_DIFF_BIG * scale) fac *= 0.1;
+        gj(L::G_FAC + i) = fmax(fac, NJ_MIN_FACTOR);
+    }
+}
 
 // warp-level helpers; the host build (tests/host_sim) runs a "warp" of one lane
 #if defined(__CUDA_ARCH__)
@@ -320,10 +387,11 @@ inline long long fetch_system(bool want, unsigned long long *counter) { return w
 // `t_eval` is the output grid as the lanes should read it (the kernel stages short grids in shared
 // memory: the check "is the next output point inside this step" runs after every accepted step, and a
 // global load there put an L2 round trip on the critical path of every ERREST pass).
-template <class Prob, class Mass, bool CTA_WIDE, bool COLD_GLOBAL, class S, class SC>
-BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const double *t_eval) {
+// `gj` addresses this lane's global-memory slots of the finite-difference mode (unused otherwise).
+template <class Prob, class Mass, bool CTA_WIDE, bool COLD_GLOBAL, bool FD, class S, class SC, class SG>
+BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const SG &gj, const double *t_eval) {
     constexpr int N = Prob::N;
-    using L = K1Layout<Prob, COLD_GLOBAL>;
+    using L = K1Layout<Prob, COLD_GLOBAL, FD>;
     typename Prob::P prm;
 
     // ---- lane state ---------------------------------------------------------------------
@@ -381,6 +449,11 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     hist_state = false; current_jac = true; lu_valid = false; have_sol = false;
                     inv_h_lu = 1.0; ei = 0; nsteps = 0;
                     state = ST_SETUP; setup_kind = SETUP_STEP;
+                    if (FD && !a.has_jac_const) {                        // J0 = num_jac(t0, y0, f0) :475-481
+#pragma unroll
+                        for (int c = 0; c < N; ++c) gj(L::G_FAC + c) = NJ_FACTOR0;
+                        state = ST_JACFD;
+                    }
                     if (t == a.tb) {  // OdeSolver.step corner case (scipy base.py:193-198)
                         for (; ei < a.T; ++ei)
 #pragma unroll
@@ -501,12 +574,23 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         ++ei;
                     }
                     if (dir * (t - a.tb) >= 0) finish_status = BRDAE_STATUS_FINISHED;
-                    else { state = ST_SETUP; setup_kind = SETUP_STEP; }
+                    else { state = (FD && recompute) ? ST_JACFD : ST_SETUP; setup_kind = SETUP_STEP; }
                 }
             }
         }
         warp_converge();
 
+        // ================= finite-difference Jacobian at (t, y), f = f(t, y) :475-481 ===========
+        if (FD && warp_any(state == ST_JACFD)) {
+            if (state == ST_JACFD) {
+                double fcur[N];
+#pragma unroll
+                for (int c = 0; c < N; ++c) fcur[c] = cd(L::C_F + c);
+                num_jac_fd<Prob, L>(prm, a, t, y, fcur, gj);
+                state = ST_SETUP;
+            }
+            warp_converge();
+        }
         // ================= cheap set-up: prologue :516-562, attempt :564-588, guess :580-583 ===
         if (warp_any(state == ST_SETUP && finish_status == 1)) {
             if (state == ST_SETUP && finish_status == 1) {
@@ -606,6 +690,11 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     for (int r = 0; r < N; ++r)
 #pragma unroll
                         for (int c = 0; c < N; ++c) J[r][c] = a.jac_const[r * N + c];
+                } else if (FD) {
+#pragma unroll
+                    for (int r = 0; r < N; ++r)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) J[r][c] = gj(L::G_J + r * N + c);
                 } else {
                     double yJ[N];
 #pragma unroll
@@ -750,7 +839,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         cd(L::C_TJ) = t;
                         cnt[CN_NJEV]++;
                         current_jac = true; lu_valid = false;
-                        state = ST_SETUP; setup_kind = SETUP_GUESS;
+                        state = FD ? ST_JACFD : ST_SETUP; setup_kind = SETUP_GUESS;
                     }
                 }
             }
@@ -761,20 +850,20 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 }
 
 #if defined(__CUDACC__)
-template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE, bool COLD_GLOBAL>
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE, bool COLD_GLOBAL, bool FD>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k1_kernel(const __grid_constant__ SolveArgs a) {
     extern __shared__ double k1_smem[];
-    using L = K1Layout<Prob, COLD_GLOBAL>;
+    using L = K1Layout<Prob, COLD_GLOBAL, FD>;
     Slots<BLOCK> sm{k1_smem + threadIdx.x};
-    Slots<BLOCK> cd{COLD_GLOBAL ? a.scratch + (size_t)blockIdx.x * (L::COLD * BLOCK) + threadIdx.x
-                                : k1_smem + L::HOT * BLOCK + threadIdx.x};
+    Slots<BLOCK> gj{a.scratch + (size_t)blockIdx.x * (L::GLOBAL_SLOTS * BLOCK) + threadIdx.x};   // [slot][lane] slice of this CTA
+    Slots<BLOCK> cd{COLD_GLOBAL ? gj.base : k1_smem + L::HOT * BLOCK + threadIdx.x};
     __shared__ double t_eval_sh[K1_TEVAL_SHARED];
     const bool staged = a.T <= K1_TEVAL_SHARED;
     if (staged) {
         for (int i = threadIdx.x; i < a.T; i += BLOCK) t_eval_sh[i] = a.t_eval[i];
         __syncthreads();
     }
-    k1_lane_loop<Prob, Mass, CTA_WIDE, COLD_GLOBAL>(a, sm, cd, staged ? t_eval_sh : a.t_eval);
+    k1_lane_loop<Prob, Mass, CTA_WIDE, COLD_GLOBAL, FD>(a, sm, cd, gj, staged ? t_eval_sh : a.t_eval);
 }
 #endif
 

@@ -6,7 +6,8 @@
  * (reference README.md:19-21; class RadauDAE at scipyDAE/radauDAE.py:126; constructor keywords
  * :263-278; step loop :515-791; driver with t_eval slicing :1079-1157 and scipy ivp.py:659-732).
  * One call of `brdae_solve` stands for B such solve_ivp calls -- one per system of the ensemble --
- * with the problem's RHS and analytic Jacobian compiled in as device functors
+ * with the problem's RHS and analytic Jacobian compiled in as device functors (or, with
+ * jac_finite_differences, the reference's default finite-difference Jacobian of that RHS)
  * (reference closures: tests/pendulum.py:130-148, tests/robertson.py:80-87,
  * tests/transistor_amplifier.py:48-56, tests/recursive_pendulum.py:93-118).
  *
@@ -26,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BRDAE_ABI_VERSION 1
+#define BRDAE_ABI_VERSION 2
 #define BRDAE_NMAX_SMALL 8 /* largest state size of the thread-per-system kernels */
 
 /* problems (device functors); ids are stable */
@@ -87,6 +88,10 @@ typedef struct brdae_options {
     int32_t extrapolated_guess;       /* bUseExtrapolatedGuess = 1 */
     int32_t all_newton_iterations;    /* bPerformAllNewtonIterations = 0 */
     int32_t constant_dt;              /* 0 */
+    int32_t jac_finite_differences;   /* 0; 1 = jac=None of the reference: scipy num_jac forward differences
+                                         with adaptive column factors (radauDAE.py:468-481); ignored when
+                                         jac_const is given; thread-per-system problems only */
+    int32_t reserved;                 /* 0 */
     int64_t nmax_step;                /* <=0: unlimited */
 } brdae_options;
 

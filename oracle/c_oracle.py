@@ -33,6 +33,7 @@ class OrcOptions(C.Structure):
                 ("always_2nd_estimate", C.c_int32), ("predictive_controller", C.c_int32),
                 ("predictive_newton_stop", C.c_int32), ("extrapolated_guess", C.c_int32),
                 ("all_newton_iterations", C.c_int32), ("constant_dt", C.c_int32),
+                ("jac_finite_differences", C.c_int32), ("reserved", C.c_int32),
                 ("nmax_step", C.c_int64)]
 
 
@@ -63,8 +64,9 @@ def make_options(first_step=None, max_step=np.inf, newton_tol=None, factor_on_no
                  scale_error=True, zero_algebraic_error=False, bAlwaysApply2ndEstimate=True,
                  bUsePredictiveController=True, bUsePredictiveNewtonStoppingCriterion=True,
                  bUseExtrapolatedGuess=True, bPerformAllNewtonIterations=False, constant_dt=False,
-                 nmax_step=None):
+                 nmax_step=None, jac="analytic"):
     o = OrcOptions()
+    o.jac_finite_differences = int(jac is None)     # jac=None: finite differences, as in the reference
     o.first_step = -1.0 if first_step is None else float(first_step)
     o.max_step = float(max_step)
     o.newton_tol = -1.0 if newton_tol is None else float(newton_tol)

@@ -50,6 +50,7 @@ def run_reference_with_counters(ens, over=None):
     mm = opts.pop("mass_matrix")
     vi = opts.pop("var_index")
     nmax_step = opts.pop("nmax_step", np.inf)
+    fd = "jac" in opts and opts.pop("jac") is None     # jac=None: the reference's finite-difference Jacobian
     B, n = ens["y0"].shape
     te = np.asarray(ens["t_eval"], dtype=float)
     T = te.size
@@ -65,6 +66,8 @@ def run_reference_with_counters(ens, over=None):
         fun, jac, mass, _ = build_system(ens["problem"], p, n)
         if not isinstance(mm, str):
             mass = mm
+        if fd:
+            jac = None
         with contextlib.redirect_stdout(io.StringIO()):
             solver = RadauDAE(fun, t0, np.array(ens["y0"][i], dtype=float), tf, jac=jac, mass_matrix=mass,
                               var_index=None if vi is None else np.asarray(vi, dtype=float), **opts)
@@ -213,6 +216,11 @@ def main():
     save("kat_robertson_ode", dict(problem="robertson_ode", t_span=(0.0, 5e6), y0=prob.ROBERTSON_Y0[None, :],
                                    params=np.array([[0.04, 1e4, 3e7]]), t_eval=np.array([1.0, 1e3, 5e6]),
                                    options=dict(rob_script, mass_matrix="problem", var_index=np.array([0, 0, 0]))))
+    # --- the reference's default Jacobian mode: jac=None, scipy num_jac finite differences (radauDAE.py:468-481)
+    save("fd_pendulum3", E.pendulum_ensemble(8, t_end=1.0), dict(jac=None))
+    save("fd_pendulum2", E.pendulum_ensemble(8, t_end=1.0, index=2), dict(jac=None))
+    save("fd_robertson", E.robertson_ensemble(8, t_end=1e3), dict(jac=None))
+    save("fd_transistor", E.transistor_ensemble(4, t_end=0.05), dict(jac=None))
     # --- n-pendulum chains (dense analytic Jacobian handed to the reference)
     save("ens_npendulum_n4", E.npendulum_ensemble(3, n_nodes=4))
     save("ens_npendulum_n10", E.npendulum_ensemble(2, n_nodes=10))

@@ -221,8 +221,25 @@ class _Setup:
 
         # Jacobian modes (radauDAE.py:482-511): callable, or constant matrix
         if jac is None:
-            raise NotImplementedError("finite-difference Jacobian mode is not restated")
-        if callable(jac):
+            # finite differences, radauDAE.py:468-481: scipy's own num_jac (third-party, common.py:268-452)
+            # on the uncounted vectorised wrapper of scipy base.py:143-149, threshold = atol, the
+            # adaptive column factors carried from call to call
+            from scipy.integrate._ivp.common import num_jac
+            self.jac_factor = None
+
+            def fun_vectorized(t, y):
+                f = np.empty_like(y)
+                for i, yi in enumerate(y.T):
+                    f[:, i] = np.asarray(fun(t, yi), dtype=float)
+                return f
+
+            def fd_jac(t, y, f):
+                self.cnt.njev += 1
+                J, self.jac_factor = num_jac(fun_vectorized, t, y, f, self.atol, self.jac_factor, None)
+                return J
+            J = fd_jac(t0, y0, self.f)
+            self.jac = fd_jac
+        elif callable(jac):
             J = np.asarray(jac(t0, y0), dtype=float)
             self.cnt.njev = 1
 

@@ -60,6 +60,8 @@ typedef struct {
     int32_t scale_residuals, scale_newton_norm, scale_error, zero_algebraic_error;
     int32_t always_2nd_estimate, predictive_controller, predictive_newton_stop;
     int32_t extrapolated_guess, all_newton_iterations, constant_dt;
+    int32_t jac_finite_differences; /* jac=None: scipy num_jac forward differences (:468-481) */
+    int32_t reserved;
     int64_t nmax_step;  /* <=0: unlimited (solve_ivp_custom :1081) */
 } orc_options;
 
@@ -522,6 +524,7 @@ typedef struct {
     int n;
     double *y, *f, *yold, *Q /*[n][3]*/, *W /*[3][n]*/, *Z /*[3][n]*/, *F, *J, *M;
     double *fr, *fcr, *fci, *mw0, *mw1, *mw2, *inv_ns, *inv_es, *ze, *err, *tmp, *hs, *sq;
+    double *jfac, *yp, *fn, *fn2; /* finite-difference Jacobian: column factors, perturbed state, f there */
     int *mlo, *mhi;
     lu_pair lu;
 } work;
@@ -539,6 +542,7 @@ static void work_alloc(work *w, int n) {
     w->inv_ns = xcalloc(N, 8); w->inv_es = xcalloc(N, 8); w->ze = xcalloc(N, 8);
     w->err = xcalloc(N, 8); w->tmp = xcalloc(N, 8); w->hs = xcalloc(N, 8); w->sq = xcalloc(3 * N, 8);
     w->mlo = xcalloc(N, sizeof(int)); w->mhi = xcalloc(N, sizeof(int));
+    w->jfac = xcalloc(N, 8); w->yp = xcalloc(N, 8); w->fn = xcalloc(N, 8); w->fn2 = xcalloc(N, 8);
     w->lu.n = n;
     w->lu.lr = xcalloc(N * N, 8); w->lu.lcr = xcalloc(N * N, 8); w->lu.lci = xcalloc(N * N, 8);
     w->lu.pr = xcalloc(N, sizeof(int)); w->lu.pc = xcalloc(N, sizeof(int));
@@ -548,6 +552,7 @@ static void work_free(work *w) {
     free(w->J); free(w->M); free(w->fr); free(w->fcr); free(w->fci); free(w->mw0); free(w->mw1);
     free(w->mw2); free(w->inv_ns); free(w->inv_es); free(w->ze); free(w->err); free(w->tmp);
     free(w->hs); free(w->sq); free(w->mlo); free(w->mhi);
+    free(w->jfac); free(w->yp); free(w->fn); free(w->fn2);
     free(w->lu.lr); free(w->lu.lcr); free(w->lu.lci); free(w->lu.pr); free(w->lu.pc);
 }
 
@@ -567,6 +572,54 @@ static void stage_Z(int n, const double *W, int i, double *z) {
 static char *g_trace = NULL;
 static int g_trace_cap = 0, g_trace_len = 0;
 static void trace_ev(char c) { if (g_trace && g_trace_len < g_trace_cap) g_trace[g_trace_len++] = c; }
+
+/* Finite-difference Jacobian: scipy.integrate._ivp.common.num_jac (scipy 1.18.1 common.py:268-452,
+ * called from radauDAE.py:475-480 with threshold = atol and the column factors kept between calls),
+ * dense branch, restated column by column (the reference evaluates all columns in one vectorised
+ * call; every operation is element-wise, so the values are the same).  Spec deviation: the columns
+ * are scaled by the reciprocal of h instead of divided by h.  Function evaluations made here are
+ * not counted in nfev (scipy base.py:143-149 `fun_vectorized`). */
+#define NJ_FACTOR0 0x1.0000000000000p-26         /* EPS ** 0.5 */
+#define NJ_DIFF_REJECT 0x1.6a09e667f3bcdp-46     /* EPS ** 0.875 */
+#define NJ_DIFF_SMALL 0x1.0000000000000p-39      /* EPS ** 0.75 */
+#define NJ_DIFF_BIG 0x1.0000000000000p-13        /* EPS ** 0.25 */
+#define NJ_MIN_FACTOR 0x1.f400000000000p-43      /* 1e3 * EPS */
+static void fd_column(const prob_ctx *pc, int n, double t, const double *y, const double *f, int i, double h,
+                      double *yp, double *fn, int *mi_out, double *md_out) {
+    for (int c = 0; c < n; ++c) yp[c] = y[c] + (c == i ? h : 0.0);
+    prob_rhs(pc, t, yp, fn);
+    int mi = 0;
+    double md = fabs(fn[0] - f[0]);
+    for (int r = 1; r < n; ++r) { const double d = fabs(fn[r] - f[r]); if (d > md) { md = d; mi = r; } }
+    *mi_out = mi; *md_out = md;
+}
+static void num_jac_fd(const prob_ctx *pc, work *w, double t, const double *atol) {
+    const int n = w->n;
+    const double *y = w->y, *f = w->f;
+    for (int i = 0; i < n; ++i) {
+        const double ys = (f[i] >= 0 ? 1.0 : -1.0) * fmax(atol[i], fabs(y[i]));
+        double fac = w->jfac[i];
+        double h = (y[i] + fac * ys) - y[i];
+        while (h == 0) { fac *= 10; h = (y[i] + fac * ys) - y[i]; }
+        int mi; double md;
+        fd_column(pc, n, t, y, f, i, h, w->yp, w->fn, &mi, &md);
+        double scale = fmax(fabs(f[mi]), fabs(w->fn[mi]));
+        const double *fcol = w->fn;
+        if (md < NJ_DIFF_REJECT * scale) {
+            const double fac_new = 10 * fac;
+            const double h_new = (y[i] + fac_new * ys) - y[i];
+            int mi2; double md2;
+            fd_column(pc, n, t, y, f, i, h_new, w->yp, w->fn2, &mi2, &md2);
+            const double scale2 = fmax(fabs(f[mi2]), fabs(w->fn2[mi2]));
+            if (md * scale2 < md2 * scale) { fac = fac_new; h = h_new; fcol = w->fn2; scale = scale2; md = md2; }
+        }
+        const double rh = 1.0 / h;
+        for (int r = 0; r < n; ++r) w->J[r * n + i] = (fcol[r] - f[r]) * rh;
+        if (md < NJ_DIFF_SMALL * scale) fac *= 10;
+        if (md > NJ_DIFF_BIG * scale) fac *= 0.1;
+        w->jfac[i] = fmax(fac, NJ_MIN_FACTOR);
+    }
+}
 
 /* Integrate one system.  Layout of the batch arrays is SoA: element (row, sys) at row*B+sys. */
 static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, const double *mass_in,
@@ -616,7 +669,9 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
     double h_abs_state = (o->first_step > 0) ? o->first_step : dir * fmin(1e-6, fabs(tb - t0)); /* :307-315 */
     double h_abs_old_state = 0, err_old_state = 0;
     int hist_state = 0;
-    if (has_jac_fn) { prob_jac(pc, t, w->y, w->J); cnt[C_NJEV] = 1; } /* :483-484 */
+    const int fd = has_jac_fn && o->jac_finite_differences;
+    if (fd) { for (int c = 0; c < n; ++c) w->jfac[c] = NJ_FACTOR0; num_jac_fd(pc, w, t, atol); cnt[C_NJEV] = 1; } /* :475-481 */
+    else if (has_jac_fn) { prob_jac(pc, t, w->y, w->J); cnt[C_NJEV] = 1; } /* :483-484 */
     else memcpy(w->J, jac_const, sizeof(double) * n * n);
     int current_jac = 1, lu_valid = 0, have_sol = 0;
     double inv_h_sol = 0, t_sol_old = 0, inv_h_lu = 1.0;
@@ -778,7 +833,8 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 safety = o->safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter); /* :631 */
                 if (converged) break;
                 if (current_jac) break;                                            /* :638-641 */
-                prob_jac(pc, t, w->y, w->J); cnt[C_NJEV]++;                        /* :643 */
+                if (fd) num_jac_fd(pc, w, t, atol); else prob_jac(pc, t, w->y, w->J);
+                cnt[C_NJEV]++;                                                     /* :643 */
                 current_jac = 1; lu_valid = 0;
             }
             if (!converged) {                                                      /* :650-658 */
@@ -833,7 +889,10 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
         if (!recompute && factor < 1.2) factor = 1; else lu_valid = 0;
         for (int c = 0; c < n; ++c) { w->yold[c] = w->y[c]; w->y[c] = w->y[c] + w->Z[2 * n + c]; }
         prob_rhs(pc, t_new, w->y, w->f); cnt[C_NFEV]++;
-        if (recompute) { prob_jac(pc, t_new, w->y, w->J); cnt[C_NJEV]++; current_jac = 1; }
+        if (recompute) {
+            if (fd) num_jac_fd(pc, w, t_new, atol); else prob_jac(pc, t_new, w->y, w->J);
+            cnt[C_NJEV]++; current_jac = 1;
+        }
         else if (has_jac_fn) current_jac = 0;
         h_abs_old_state = h_abs_state; err_old_state = error_norm; hist_state = 1;
         h_abs_state = h_abs * factor;

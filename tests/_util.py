@@ -75,6 +75,7 @@ def run_numpy_oracle(ens, **over):
     opts.update(over)
     mm = opts.pop("mass_matrix")
     vi = opts.pop("var_index")
+    fd = "jac" in opts and opts.pop("jac") is None          # jac=None: finite differences, as in the reference
     B, n = ens["y0"].shape
     T = len(ens["t_eval"])
     out = dict(y=np.full((B, n, T), np.nan), status=np.zeros(B, np.int32), n_eval=np.zeros(B, np.int32),
@@ -84,6 +85,8 @@ def run_numpy_oracle(ens, **over):
         fun, jac, mass, _ = prob.build(ens["problem"], p, n)
         if not isinstance(mm, str):
             mass = mm
+        if fd:
+            jac = None
         r = orc.solve(fun, ens["t_span"], ens["y0"][i], jac=jac, mass_matrix=mass,
                       var_index=None if vi is None else np.asarray(vi, dtype=float), t_eval=ens["t_eval"], **opts)
         k = r.y.shape[1]

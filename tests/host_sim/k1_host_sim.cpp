@@ -7,6 +7,7 @@
 // CUDA kernels or returns an error.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "../../dae_scipy_b200/csrc/host_args.hpp"
@@ -16,18 +17,20 @@ using namespace brdae;
 
 template <class Prob, class Mass>
 static void run(const SolveArgs &a) {
-    // both layouts of the kernel: cold state next to the factors, or in its own (global-memory) slice
-    if (!std::getenv("BRDAE_SIM_COLD_GLOBAL")) {
-        using L = K1Layout<Prob, false>;
-        std::vector<double> slots(L::SHARED_SLOTS, 0.0);
-        Slots<1> sm{slots.data()}, cd{slots.data() + L::HOT};
-        k1_lane_loop<Prob, Mass, false, false>(a, sm, cd, a.t_eval);
-    } else {
-        using L = K1Layout<Prob, true>;
-        std::vector<double> hot(L::SHARED_SLOTS, 0.0), cold(L::COLD, 0.0);
-        Slots<1> sm{hot.data()}, cd{cold.data()};
-        k1_lane_loop<Prob, Mass, false, true>(a, sm, cd, a.t_eval);
-    }
+    // both layouts of the kernel (cold state next to the factors, or in its own global-memory slice) and
+    // the finite-difference Jacobian mode
+    const bool cold = std::getenv("BRDAE_SIM_COLD_GLOBAL") != nullptr;
+    auto go = [&](auto cold_c, auto fd_c) {
+        constexpr bool COLD = decltype(cold_c)::value, FD = decltype(fd_c)::value;
+        using L = K1Layout<Prob, COLD, FD>;
+        std::vector<double> hot(L::SHARED_SLOTS, 0.0), glob(L::GLOBAL_SLOTS + 1, 0.0);
+        Slots<1> sm{hot.data()}, gj{glob.data()}, cd{COLD ? glob.data() : hot.data() + L::HOT};
+        k1_lane_loop<Prob, Mass, false, COLD, FD>(a, sm, cd, gj, a.t_eval);
+    };
+    if (cold && a.jac_fd) go(std::true_type{}, std::true_type{});
+    else if (cold) go(std::true_type{}, std::false_type{});
+    else if (a.jac_fd) go(std::false_type{}, std::true_type{});
+    else go(std::false_type{}, std::false_type{});
 }
 
 template <class Prob>

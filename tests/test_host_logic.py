@@ -67,8 +67,11 @@ def test_option_defaults_follow_the_reference_constructor():
     hb3 = _prep(mass_matrix=None)
     assert np.array_equal(hb3.mass, np.eye(5))  # reference default: identity
     assert _prep(var_index=None).var_index.tolist() == [0] * 5
-    with pytest.raises(NotImplementedError):
-        _prep(jac=None)
+    assert o.jac_finite_differences == 0
+    assert _prep(jac=None).options.jac_finite_differences == 1      # reference default: finite differences
+    with pytest.raises(NotImplementedError):                        # not for the chain kernels
+        e = br.ensembles.npendulum_ensemble(2, n_nodes=4)
+        br.prepare(e["problem"], e["t_span"], e["y0"].shape, t_eval=e["t_eval"], **dict(e["options"], jac=None))
 
 
 def test_ensembles_are_seeded_and_prefix_stable():
