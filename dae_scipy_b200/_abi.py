@@ -54,7 +54,9 @@ class BrdaeBatch(C.Structure):
                 ("atol", C.c_void_p), ("rtol", C.c_double), ("t0", C.c_double),
                 ("t_bound", C.c_double),
                 ("y_eval", C.c_void_p), ("n_eval", C.c_void_p), ("t_final", C.c_void_p),
-                ("y_final", C.c_void_p), ("status", C.c_void_p), ("counters", C.c_void_p)]
+                ("y_final", C.c_void_p), ("status", C.c_void_p), ("counters", C.c_void_p),
+                ("dense_cap", C.c_int32), ("reserved0", C.c_int32),
+                ("dense_t", C.c_void_p), ("dense_y", C.c_void_p), ("dense_q", C.c_void_p)]
 
 
 # keyword -> (options field, default) : the RadauDAE constructor surface, radauDAE.py:263-278

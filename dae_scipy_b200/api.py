@@ -70,8 +70,10 @@ class HostBatch:
         b.jac_const = self.jac_const.ctypes.data if self.jac_const is not None else None
         b.var_index = self.var_index.ctypes.data
         b.atol = self.atol.ctypes.data
-        for k in ("y0", "params", "t_eval", "y_eval", "n_eval", "t_final", "y_final", "status", "counters"):
+        for k in ("y0", "params", "t_eval", "y_eval", "n_eval", "t_final", "y_final", "status", "counters",
+                  "dense_t", "dense_y", "dense_q"):
             setattr(b, k, ptr.get(k))
+        b.dense_cap = int(ptr.get("dense_cap") or 0)
         return b
 
 
@@ -191,6 +193,7 @@ class BatchedOdeResult:
     """
 
     def __init__(self, t, y_eval_tnb, n_eval, status, t_final, y_final_nb, counters_cb):
+        self.sol = None                     # BatchedOdeSolution when dense_output=True
         self.t = t
         self._y_eval = y_eval_tnb           # [T, n, B] as written by the kernel (coalesced SoA)
         self.n_eval = n_eval
@@ -229,6 +232,49 @@ class BatchedOdeResult:
         return out
 
 
+class BatchedOdeSolution:
+    """What `solve_ivp(dense_output=True)` returns as `sol` (scipy OdeSolution over the reference's
+    RadauDenseOutput cubics, radauDAE.py:951-982), for every system of the ensemble.
+
+    The kernels record, per system, the end time, end state and interpolation coefficients Q of each of the
+    first `max_dense_steps` accepted steps; `ts`/`ys` are also what the reference returns as `OdeResult.t`/`.y`
+    when `t_eval` is None.  Arrays are host copies in the row-per-system layout:
+      n_steps [B]; ts [B, K+1] (ts[:, 0] = t0, NaN beyond n_steps); ys [B, n, K+1]; Q [B, K, n, 3];
+      truncated [B] (the system took more than K steps: `sol` is only valid up to ts[i, K]).
+    `sol(t)` -> [B, n, len(t)] evaluates all systems at the times `t` (OdeSolution semantics: segment by
+    searchsorted, times outside the recorded range are extrapolated from the first/last step); `sol.system(i)`
+    returns the callable of one system."""
+
+    def __init__(self, t0, y0, dense_t, dense_y, dense_q, n_steps, truncated, ascending):
+        B, K = dense_t.shape
+        self.n_steps, self.truncated, self.ascending = n_steps, truncated, ascending
+        self.ts = np.concatenate([np.full((B, 1), t0), dense_t], axis=1)
+        self.ys = np.concatenate([y0[:, :, None], dense_y], axis=2)
+        self.Q = dense_q
+        beyond = np.arange(K + 1)[None, :] > n_steps[:, None]
+        self.ts[beyond] = np.nan
+        self.ys[np.broadcast_to(beyond[:, None, :], self.ys.shape)] = np.nan
+
+    def __call__(self, t):
+        t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        B, K1 = self.ts.shape
+        valid = np.arange(K1)[None, :] <= self.n_steps[:, None]
+        sgn = 1.0 if self.ascending else -1.0
+        # searchsorted(ts, t, side='left') per system on the recorded boundaries (ascending after the sign flip)
+        below = (sgn * self.ts[:, :, None] < sgn * t[None, None, :]) & valid[:, :, None]
+        seg = np.clip(below.sum(axis=1) - 1, 0, np.maximum(self.n_steps, 1)[:, None] - 1)        # [B, m]
+        rows = np.arange(B)[:, None]
+        t_old, t_new = self.ts[rows, seg], self.ts[rows, seg + 1]
+        x = (t[None, :] - t_old) / (t_new - t_old)
+        Q = self.Q[rows, seg]                                                                   # [B, m, n, 3]
+        y = Q[..., 0] * x[..., None] + Q[..., 1] * (x * x)[..., None] + Q[..., 2] * (x * x * x)[..., None]
+        y = y + np.moveaxis(self.ys, 2, 1)[rows, seg]
+        return np.moveaxis(y, 1, 2)                                                             # [B, n, m]
+
+    def system(self, i):
+        return lambda t: self(np.atleast_1d(t))[i] if np.ndim(t) else self([t])[i, :, 0]
+
+
 def _as_device_f64(x, device, torch):
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=torch.float64)
@@ -236,7 +282,7 @@ def _as_device_f64(x, device, torch):
 
 
 def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_eval=None,
-                      dense_output=False, events=None, device=None, stream=None, **options):
+                      dense_output=False, max_dense_steps=None, events=None, device=None, stream=None, **options):
     """Integrate B independent systems  M y' = f(t, y)  from t_span[0] to t_span[1] on one GPU.
 
     Parameters follow `scipy.integrate.solve_ivp(..., method=RadauDAE, **options)` of the
@@ -254,6 +300,9 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     var_index   : [n] integers 0..3 or None (all differential), as in the reference.
     jac         : 'analytic' (default: the problem's analytic Jacobian functor), a constant [n, n] matrix, or
                   None = finite differences as in the reference's default (scipy num_jac).
+    dense_output, max_dense_steps : record every accepted step (up to `max_dense_steps` per system, required
+                  with dense_output=True: the record takes 8 (4 n + 1) bytes per step and system) and return
+                  `result.sol`, a BatchedOdeSolution.  Times known in advance are cheaper through `t_eval`.
     """
     import torch
 
@@ -261,9 +310,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
         raise ValueError("`method` must be RadauDAE.")
     if events:
         raise NotImplementedError("events are not supported by the batched solver")
-    if dense_output:
-        raise NotImplementedError("dense_output=True (a ragged OdeSolution per system) is not available; "
-                                  "pass the times you need through `t_eval`.")
+    if dense_output and (max_dense_steps is None or int(max_dense_steps) < 1):
+        raise ValueError("dense_output=True needs `max_dense_steps` (steps recorded per system).")
     if not torch.cuda.is_available():
         raise RuntimeError("solve_ivp_batched needs a CUDA device; there is no CPU fallback.")
     lib = _abi.load()
@@ -296,6 +344,12 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
                "t_eval": te_d.data_ptr() if T else None, "y_eval": y_eval.data_ptr() if T else None,
                "n_eval": n_eval.data_ptr(), "t_final": t_final.data_ptr(), "y_final": y_final.data_ptr(),
                "status": status.data_ptr(), "counters": counters.data_ptr()}
+        if dense_output:
+            K = int(max_dense_steps)
+            dense_t = torch.empty((K, B), dtype=torch.float64, device=dev)
+            dense_y = torch.empty((K, n, B), dtype=torch.float64, device=dev)
+            dense_q = torch.empty((K, n, 3, B), dtype=torch.float64, device=dev)
+            ptr.update(dense_cap=K, dense_t=dense_t.data_ptr(), dense_y=dense_y.data_ptr(), dense_q=dense_q.data_ptr())
         batch = hb.struct(ptr)
         ws_bytes = int(lib.brdae_workspace_bytes(C.byref(batch), C.byref(hb.options)))
         ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
@@ -305,7 +359,21 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
         ws.record_stream(cu_stream)
     res = BatchedOdeResult(hb.t_eval, y_eval[:T], n_eval, status, t_final, y_final, counters)
     res._keepalive = (y0_soa, par_soa, te_d, ws)
+    if dense_output:
+        cu_stream.synchronize()
+        res.sol = make_ode_solution(hb, y0_d.cpu().numpy(), dense_t.cpu().numpy(), dense_y.cpu().numpy(),
+                                    dense_q.cpu().numpy(), status.cpu().numpy(), counters.cpu().numpy())
     return res
+
+
+def make_ode_solution(hb, y0, dense_t_kb, dense_y_knb, dense_q_kn3b, status, counters_cb):
+    """Kernel-layout step record ([K][B], [K][n][B], [K][n][3][B]) -> BatchedOdeSolution."""
+    K = dense_t_kb.shape[0]
+    nstep = counters_cb[_abi.COUNTER_NAMES.index("nstep")]
+    accepted = nstep - (status == _abi.STATUS_TOO_SMALL_STEP) - (status == _abi.STATUS_LU_FAILED)   # the failing step() call was counted
+    return BatchedOdeSolution(hb.t0, y0, np.ascontiguousarray(dense_t_kb.T), np.ascontiguousarray(dense_y_knb.transpose(2, 1, 0)),
+                              np.ascontiguousarray(dense_q_kn3b.transpose(3, 0, 1, 2)), np.minimum(accepted, K).astype(np.int64),
+                              accepted > K, hb.t_bound >= hb.t0)
 
 
 class PinnedArray:

@@ -26,7 +26,10 @@ static int route(int problem, bool dense_mass, const SolveArgs &a, const brdae_b
     case BRDAE_ROBERTSON: return k1_robertson(dense_mass, a, sms, s, g, geom_only);
     case BRDAE_TRANSISTOR: return k1_transistor(dense_mass, a, sms, s, g, geom_only);
     case BRDAE_NPENDULUM:
-        if (npendulum_uses_k3(a.n, a.B)) return k3_npendulum(dense_mass, a, b, sms, s, g, geom_only);
+        if (npendulum_uses_k3(a.n, a.B)) {
+            if (a.dense_cap > 0) return BRDAE_ERR_UNSUPPORTED;      // the experimental lane-per-rope kernel keeps no step record
+            return k3_npendulum(dense_mass, a, b, sms, s, g, geom_only);
+        }
         return k2_npendulum(dense_mass, a, b, sms, s, g, geom_only);
     case BRDAE_ROBERTSON_ODE: case BRDAE_JAY: case BRDAE_POLYDAE2: case BRDAE_LINEAR7:
         return k1_extra(problem, dense_mass, a, sms, s, g, geom_only);

@@ -40,6 +40,7 @@ inline int validate(const brdae_batch *b, const brdae_options *o) {
         if (b->n_t_eval > 0 && (!b->t_eval || !b->y_eval)) return BRDAE_ERR_BAD_ARGUMENT;
     }
     if (!b->atol) return BRDAE_ERR_BAD_ARGUMENT;
+    if (b->dense_cap < 0 || (b->dense_cap > 0 && !(b->dense_t && b->dense_y && b->dense_q))) return BRDAE_ERR_BAD_ARGUMENT;
     if (!(b->rtol > 0) || !(o->max_step > 0) || o->max_newton_ite < 1) return BRDAE_ERR_BAD_ARGUMENT;
     for (int c = 0; c < b->n; ++c) {
         if (!(b->atol[c] >= 0)) return BRDAE_ERR_BAD_ARGUMENT;
@@ -57,6 +58,8 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
     a.y0 = b->y0; a.params = b->params; a.t_eval = b->t_eval;
     a.y_eval = b->y_eval; a.n_eval = b->n_eval; a.t_final = b->t_final; a.y_final = b->y_final;
     a.status = b->status; a.counters = b->counters;
+    a.dense_t = b->dense_t; a.dense_y = b->dense_y; a.dense_q = b->dense_q;
+    a.dense_cap = (b->dense_t && b->dense_y && b->dense_q) ? b->dense_cap : 0;
     a.work_counter = static_cast<unsigned long long *>(workspace);
     a.scratch = reinterpret_cast<double *>(static_cast<char *>(workspace) + kCounterBytes);
     a.t0 = b->t0; a.tb = b->t_bound;

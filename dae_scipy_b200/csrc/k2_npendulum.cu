@@ -580,6 +580,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__
             h_abs_state = h_abs * factor;
             t_sol_old = t; inv_h_sol = inv_h; have_sol = true;
             t = t_new;
+            if (a.dense_cap > 0 && nsteps <= a.dense_cap) {      // OdeSolution record of this step (brdae.h)
+                const int64_t ks = nsteps - 1;         // one accepted step per step() call
+                if (tid == 0) a.dense_t[ks * a.B + idx] = t;
+                for (int c = tid; c < N; c += nthr) {
+                    a.dense_y[(ks * N + c) * a.B + idx] = s.y[c];
+                    for (int j = 0; j < 3; ++j) a.dense_q[((ks * N + c) * 3 + j) * a.B + idx] = s.Q[3 * c + j];
+                }
+            }
             if (dir * (t - a.tb) >= 0) status = BRDAE_STATUS_FINISHED;
             while (ei < a.T) {
                 const double te = a.t_eval[ei];

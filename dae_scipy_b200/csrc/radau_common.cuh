@@ -78,6 +78,8 @@ struct SolveArgs {
     int32_t *n_eval;
     double *t_final, *y_final;
     int32_t *status, *counters;
+    double *dense_t, *dense_y, *dense_q;   // optional per-step record (brdae.h), dense_cap steps per system
+    int32_t dense_cap;
     unsigned long long *work_counter;
     double *scratch;  // per-CTA global scratch (K2)
     double t0, tb, dir, rtol;

@@ -558,6 +558,16 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     }
                     t_sol_old = t; inv_h_sol = inv_h; have_sol = true;
                     t = t_new;
+                    if (a.dense_cap > 0 && nsteps <= a.dense_cap) {      // OdeSolution record of this step
+                        const int64_t ks = nsteps - 1;         // one accepted step per step() call
+                        a.dense_t[ks * a.B + idx] = t;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            a.dense_y[(ks * N + c) * a.B + idx] = y[c];
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) a.dense_q[((ks * N + c) * 3 + j) * a.B + idx] = Q[c][j];
+                        }
+                    }
                     // driver: t_eval points inside (t_old, t]  (searchsorted side='right', ivp.py:711-729)
                     while (ei < a.T) {
                         const double te = t_eval[ei];

@@ -117,6 +117,16 @@ typedef struct brdae_batch {
     double *y_final;          /* [dev]  [n][B] */
     int32_t *status;          /* [dev]  [B] BRDAE_STATUS_* */
     int32_t *counters;        /* [dev]  [BRDAE_NCOUNTERS][B] */
+    /* Optional record of every accepted step: what solve_ivp(dense_output=True) keeps as OdeSolution
+     * (radauDAE.py:951-982, 1097-1134) and, with t_eval=None, as OdeResult.t / .y.  Step k of a system
+     * ends at dense_t[k] with state dense_y[k]; inside it y(t) = y_old + Q (x, x^2, x^3)^T with
+     * x = (t - t_old)/(dense_t[k] - t_old), (t_old, y_old) the end of step k-1 (or t0, y0).  A system
+     * records its first min(naccpt, dense_cap) steps.  All NULL / 0 = off.  brdae_solve only. */
+    int32_t dense_cap;        /* K */
+    int32_t reserved0;
+    double *dense_t;          /* [dev]  [K][B] */
+    double *dense_y;          /* [dev]  [K][n][B] */
+    double *dense_q;          /* [dev]  [K][n][3][B]: Q[c][j] of step k at ((k*n + c)*3 + j)*B + sys */
 } brdae_batch;
 
 int brdae_abi_version(void);

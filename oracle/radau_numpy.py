@@ -148,6 +148,19 @@ class OracleResult:
     t_final: float
     y_final: np.ndarray
     steps_t: list = field(default_factory=list)     # accepted step end times
+    interpolants: list = field(default_factory=list)   # dense_output=True: the per-step RadauDenseOutput objects
+
+    def sol(self, t):
+        """OdeSolution of solve_ivp(dense_output=True) (scipy base.py OdeSolution, ascending or descending
+        ts): segment by searchsorted, clipped to the first/last step."""
+        ts = np.array([self.interpolants[0].t_old] + [c.t_old + c.h for c in self.interpolants])
+        t = np.atleast_1d(np.asarray(t, dtype=float))
+        if ts[-1] >= ts[0]:
+            ind = np.searchsorted(ts, t, side="left")
+        else:
+            ind = np.searchsorted(-ts, -t, side="right")
+        seg = np.clip(ind - 1, 0, len(self.interpolants) - 1)
+        return np.stack([self.interpolants[k](x) for k, x in zip(seg, t)], axis=1)
     log: list = field(default_factory=list)         # per-attempt records when trace=True
 
     @property
@@ -523,7 +536,7 @@ def _advance_one_step(s: _Setup):
     return True, FAIL_NONE, None
 
 
-def solve(fun, t_span, y0, *, t_eval=None, nmax_step=np.inf, trace=False, **options):
+def solve(fun, t_span, y0, *, t_eval=None, nmax_step=np.inf, trace=False, dense_output=False, **options):
     """Driver loop with t_eval slicing (scipy ivp.py:659-732; radauDAE.py:1079-1157).
 
     Returns an OracleResult; `y` is laid out [n, T_reached] like OdeResult.y.
@@ -552,6 +565,7 @@ def solve(fun, t_span, y0, *, t_eval=None, nmax_step=np.inf, trace=False, **opti
     else:
         ts, ys = [], []
     steps_t = []
+    interpolants = []
     status = None
     fail_code = FAIL_NONE
     message = None
@@ -579,6 +593,8 @@ def solve(fun, t_span, y0, *, t_eval=None, nmax_step=np.inf, trace=False, **opti
             status = STATUS_FINISHED
         t = s.t
         steps_t.append(t)
+        if dense_output and not const_out:
+            interpolants.append(s.sol)
         if t_eval is None:
             ts.append(t)
             ys.append(s.y)
@@ -612,4 +628,4 @@ def solve(fun, t_span, y0, *, t_eval=None, nmax_step=np.inf, trace=False, **opti
         y_out = np.empty((s.n, 0))
     return OracleResult(t=t_out, y=y_out, status=status, fail_code=fail_code, message=message,
                         counters=s.cnt, t_final=float(s.t), y_final=np.array(s.y),
-                        steps_t=steps_t, log=s.trace or [])
+                        steps_t=steps_t, interpolants=interpolants, log=s.trace or [])

@@ -103,8 +103,9 @@ def run_numpy_oracle(ens, **over):
 _sim = None
 
 
-def run_kernel_source_on_cpu(ens, **over):
-    """tests/host_sim: the K1 kernel SOURCE compiled for the host, one lane."""
+def run_kernel_source_on_cpu(ens, dense_cap=0, **over):
+    """tests/host_sim: the K1 kernel SOURCE compiled for the host, one lane.  With dense_cap > 0 the per-step
+    record is requested too and returned as out["sol"] (a BatchedOdeSolution)."""
     global _sim
     import dae_scipy_b200 as br
     from dae_scipy_b200 import _abi
@@ -125,10 +126,18 @@ def run_kernel_source_on_cpu(ens, **over):
     ptr = {k: v.ctypes.data for k, v in out.items()}
     ptr.update(y0=y0s.ctypes.data, params=ps.ctypes.data if ps is not None else None,
                t_eval=hb.t_eval.ctypes.data if T else None)
+    if dense_cap:
+        dense = {"dense_t": np.full((dense_cap, B), np.nan), "dense_y": np.full((dense_cap, n, B), np.nan),
+                 "dense_q": np.full((dense_cap, n, 3, B), np.nan)}
+        ptr.update({k: v.ctypes.data for k, v in dense.items()}, dense_cap=dense_cap)
     b = hb.struct(ptr)
     rc = _sim.sim_solve(C.byref(b), C.byref(hb.options))
     assert rc == 0, f"sim_solve returned {rc}"
-    return dict(y=np.ascontiguousarray(out["y_eval"][:T].transpose(2, 1, 0)), status=out["status"],
+    extra = {}
+    if dense_cap:
+        from dae_scipy_b200.api import make_ode_solution
+        extra["sol"] = make_ode_solution(hb, y0, dense["dense_t"], dense["dense_y"], dense["dense_q"], out["status"], out["counters"])
+    return dict(extra, y=np.ascontiguousarray(out["y_eval"][:T].transpose(2, 1, 0)), status=out["status"],
                 n_eval=out["n_eval"], counters=np.ascontiguousarray(out["counters"].T),
                 y_final=np.ascontiguousarray(out["y_final"].T), t_final=out["t_final"])
 

@@ -47,6 +47,10 @@ def _need_gpu():
     ("pendulum3_max_step", lambda: E.pendulum_ensemble(256), dict(max_step=0.02)),
     ("pendulum3_constant_dt", lambda: E.pendulum_ensemble(64, t_end=0.5), dict(constant_dt=True, max_step=0.01, first_step=0.01, newton_tol=1e-8)),
     ("robertson_vector_atol", lambda: E.robertson_ensemble(256), dict(atol=np.array([1e-8, 1e-12, 1e-8]))),
+    ("fd_jacobian_pendulum3", lambda: E.pendulum_ensemble(512), dict(jac=None)),
+    ("fd_jacobian_pendulum1", lambda: E.pendulum_ensemble(128, index=1), dict(jac=None)),
+    ("fd_jacobian_robertson", lambda: E.robertson_ensemble(512, t_end=1e3), dict(jac=None)),
+    ("fd_jacobian_dense_mass", lambda: E.pendulum_ensemble(64), dict(jac=None, mass_matrix=np.diag([1., 1, 1, 1, 0]) * 1.5)),
     ("ragged_sizes_1", lambda: E.pendulum_ensemble(1), {}),
     ("ragged_sizes_33", lambda: E.pendulum_ensemble(33), {}),
     ("ragged_sizes_129", lambda: E.robertson_ensemble(129), {}),
@@ -163,6 +167,35 @@ def test_invalid_y0_raises_like_scipy():
     y0[2, 1] = np.nan
     with pytest.raises(ValueError, match="must be finite"):
         br.solve_ivp_batched(ens["problem"], ens["t_span"], y0, ens["params"], t_eval=ens["t_eval"], **ens["options"])
+
+
+def test_gpu_dense_output_record_equals_kernel_source_and_t_eval():
+    """dense_output=True: the per-step record of the CUDA kernels (K1 and K2) -- bit-identical to the record of
+    the kernel source run on the CPU (K1), consistent with the t_eval output of the same call, capped runs."""
+    from _util import run_kernel_source_on_cpu
+    ens = E.pendulum_ensemble(96, t_end=1.0)
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"],
+                               dense_output=True, max_dense_steps=300, **ens["options"])
+    cpu = run_kernel_source_on_cpu(ens, dense_cap=300)
+    sol = res.sol
+    assert np.array_equal(sol.n_steps, cpu["sol"].n_steps) and not sol.truncated.any()
+    assert np.array_equal(sol.ts, cpu["sol"].ts, equal_nan=True) and np.array_equal(sol.ys, cpu["sol"].ys, equal_nan=True)
+    for i in range(96):
+        k = sol.n_steps[i]
+        assert np.array_equal(sol.Q[i, :k], cpu["sol"].Q[i, :k])
+    np.testing.assert_allclose(sol(ens["t_eval"]), res.numpy()["y"], rtol=1e-9, atol=1e-11)
+    cut = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], dense_output=True,
+                               max_dense_steps=5, **ens["options"]).sol
+    assert cut.truncated.all() and np.array_equal(cut.ts[:, :6], sol.ts[:, :6])
+    # chain kernel (CTA per rope)
+    ens = E.npendulum_ensemble(5, n_nodes=6)
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"],
+                               dense_output=True, max_dense_steps=2000, **ens["options"])
+    out = res.numpy()
+    assert (res.sol.n_steps == out["naccpt"]).all() and not res.sol.truncated.any()
+    np.testing.assert_allclose(res.sol(ens["t_eval"]), out["y"], rtol=1e-8, atol=1e-10)
+    last = res.sol.ys[np.arange(5), :, res.sol.n_steps]
+    assert np.array_equal(last, out["y_final"])
 
 
 # ---------------------------------------------------------------- (2) against the reference fixtures
