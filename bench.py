@@ -319,6 +319,26 @@ def main():
                                   f"(oracle/radau_numpy.py, bit-identical to RadauDAE where the reference runs), "
                                   f"Pool({cores}), {dt:.1f} s"}
 
+    # second, stronger CPU comparator: the scalar C restatement of the same arithmetic
+    # contract (oracle/radau_ref.c, the parity checker of the tests), OpenMP over all host cores
+    cpu_native = None
+    if rank == 0 and not args.no_cpu_baseline and gen_key != "npendulum":
+        try:
+            from oracle import c_oracle
+            cores = os.cpu_count() or 1
+            ns = int(min(B, 2048 * cores))
+            o2 = dict(ens["options"]); mm = o2.pop("mass_matrix")
+            par = ens["params"][:ns] if ens["params"] is not None else np.zeros((ns, 0))
+            c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"][:cores], par[:cores], t_eval=ens["t_eval"], **o2)  # warm
+            t0 = time.perf_counter()
+            c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"][:ns], par, t_eval=ens["t_eval"], **o2)
+            dt = time.perf_counter() - t0
+            cpu_native = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                          "sample": f"first {ns} systems of the same ensemble, scalar C restatement of the arithmetic contract "
+                                    f"(oracle/radau_ref.c), OpenMP over {cores} threads, {dt:.1f} s"}
+        except Exception as exc:      # the checker library is test infrastructure; never fail the bench on it
+            cpu_native = {"unavailable": repr(exc)}
+
     if rank == 0:
         geom = dict(zip(("grid", "block", "smem"), _launch_info(br, ens, B)))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -331,7 +351,7 @@ def main():
                            "l2_policy": "inputs+outputs per step (%.0f MB) larger than the 126 MB L2" % (abytes / 1e6),
                            "parallelism": f"ensemble sharded over {world} GPU(s), no data-path collective",
                            "launch": geom},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_native": cpu_native, "e2e": e2e,
                 "gpu_launches": args.steps, "clocks": clk.summary(),
                 "status_histogram": dict(zip(("finished", "too_small_step", "lu_failed", "nmax_step"), statuses)),
                 "mean_accepted_steps": float(out_counts[4]) / B}

@@ -1,12 +1,14 @@
 // k1_pendulum.cu -- K1 instantiations for the single pendulum, index 3 / 2 / 1.
 #include "k1_launch.cuh"
 
-// launch geometry (overridable for tuning experiments)
+// launch geometry (overridable for tuning experiments): two 128-thread CTAs per SM.  With the fixed cycle a
+// CTA synchronises once per cycle, and two half-size CTAs wait less at that barrier than one 256-thread CTA
+// (1M systems: 71.9 ms against 73.9 ms; four 64-thread CTAs lose the shared instruction stream: 96.6 ms).
 #ifndef K1_PEND_BLOCK
-#define K1_PEND_BLOCK 256
+#define K1_PEND_BLOCK 128
 #endif
 #ifndef K1_PEND_MINB
-#define K1_PEND_MINB 1
+#define K1_PEND_MINB 2
 #endif
 #ifndef K1_PEND_CTAWIDE
 #define K1_PEND_CTAWIDE true
