@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--workload", default="pendulum3_1M_tend2", choices=sorted(WORKLOADS))
     ap.add_argument("--systems", type=int, default=0, help="override the ensemble size per GPU")
     ap.add_argument("--ref-sample", type=int, default=4096, help="systems per step of the CPU arm")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="systems of the in-run cpu_baseline (0 = 48 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="systems of the in-run cpu_baseline (0 = 384 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -312,7 +312,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns = args.cpu_sample or min(B, 48 * cores)
+        ns = args.cpu_sample or min(B, 384 * cores)     # about 15-20 s of CPU work on the pendulum workload
         rate, dt, nn = cpu_reference_rate(ens, ns, cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"first {nn} systems of the same ensemble, numpy restatement of the reference "
@@ -326,7 +326,7 @@ def main():
         try:
             from oracle import c_oracle
             cores = os.cpu_count() or 1
-            ns = int(min(B, 2048 * cores))
+            ns = int(min(B, 65536 * cores))      # about 10 s
             o2 = dict(ens["options"]); mm = o2.pop("mass_matrix")
             par = ens["params"][:ns] if ens["params"] is not None else np.zeros((ns, 0))
             c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"][:cores], par[:cores], t_eval=ens["t_eval"], **o2)  # warm

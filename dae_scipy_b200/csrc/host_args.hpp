@@ -58,6 +58,10 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
     a.y0 = b->y0; a.params = b->params; a.t_eval = b->t_eval;
     a.y_eval = b->y_eval; a.n_eval = b->n_eval; a.t_final = b->t_final; a.y_final = b->y_final;
     a.status = b->status; a.counters = b->counters;
+    a.y0_sc = a.par_sc = a.yf_sc = a.cn_sq = a.ye_sc = b->n_systems;      // structure-of-arrays
+    a.y0_sb = a.par_sb = a.yf_sb = a.cn_sb = a.ye_sb = 1;
+    a.ye_st = (int64_t)b->n * b->n_systems;
+    a.chunk_done = nullptr; a.chunk_flags = nullptr; a.chunk_size = 0; a.input_ready = nullptr;
     a.dense_t = b->dense_t; a.dense_y = b->dense_y; a.dense_q = b->dense_q;
     a.dense_cap = (b->dense_t && b->dense_y && b->dense_q) ? b->dense_cap : 0;
     a.work_counter = static_cast<unsigned long long *>(workspace);

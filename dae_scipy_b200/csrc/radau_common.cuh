@@ -78,6 +78,19 @@ struct SolveArgs {
     int32_t *n_eval;
     double *t_final, *y_final;
     int32_t *status, *counters;
+    // element strides of the batch arrays (K1): entry (row c, system s) of y0 lives at c*y0_sc + s*y0_sb, and so
+    // on; y_eval entry (point e, row c, system s) at e*ye_st + c*ye_sc + s*ye_sb.  Structure-of-arrays
+    // (brdae_solve) is sc = B, sb = 1; the row-per-system entry runs the kernel directly on [B][n] / [B][n][T].
+    int64_t y0_sc, y0_sb, par_sc, par_sb, ye_st, ye_sc, ye_sb, yf_sc, yf_sb, cn_sq, cn_sb;
+    // optional completion signalling for pipelined copy-out (row-per-system entry): systems are handed out in
+    // index order, chunk k = systems [k*chunk_size, (k+1)*chunk_size); the lane that retires the last system
+    // of a chunk raises chunk_flags[k] (host-mapped memory) after a system-wide fence
+    int32_t *chunk_done;
+    volatile int32_t *chunk_flags;
+    int64_t chunk_size;
+    // optional pipelined copy-in: input_ready[k] != 0 once y0/params of chunk k have arrived (written by a
+    // host-to-device copy queued behind the chunk's data); a lane waits for its system's chunk before loading it
+    const volatile int32_t *input_ready;
     double *dense_t, *dense_y, *dense_q;   // optional per-step record (brdae.h), dense_cap steps per system
     int32_t dense_cap;
     unsigned long long *work_counter;

@@ -373,6 +373,18 @@ BRDAE_D long long fetch_system(bool want, unsigned long long *counter) {
     }
     return idx;
 }
+// Completion signal of the pipelined copy-out: count this system into its chunk; whoever completes the chunk
+// raises its flag in host-mapped memory (the "last block" pattern: every lane fences its results before the
+// count, the last one fences system-wide before the flag).
+BRDAE_D void signal_chunk(const SolveArgs &a, long long idx) {
+    __threadfence();
+    const long long k = idx / a.chunk_size, first = k * a.chunk_size;
+    const int expect = (int)((a.B - first < a.chunk_size) ? a.B - first : a.chunk_size);
+    if (atomicAdd(&a.chunk_done[k], 1) + 1 == expect) {
+        __threadfence_system();
+        a.chunk_flags[k] = 1;
+    }
+}
 #else
 inline bool warp_all(bool x) { return x; }
 inline bool warp_any(bool x) { return x; }
@@ -432,10 +444,17 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 if (got >= a.B) state = ST_EXIT;
                 else {
                     idx = got;
-                    Prob::load(prm, a.params, a.B, idx);
+#if defined(__CUDA_ARCH__)
+                    if (a.input_ready) {           // pipelined copy-in: this system's chunk may still be on its way
+                        const volatile int32_t *ready = a.input_ready + idx / a.chunk_size;
+                        while (*ready == 0) __nanosleep(256);
+                        __threadfence();
+                    }
+#endif
+                    Prob::load(prm, a.params, a.par_sc, idx * a.par_sb);
                     t = a.t0;
 #pragma unroll
-                    for (int c = 0; c < N; ++c) y[c] = a.y0[(int64_t)c * a.B + idx];
+                    for (int c = 0; c < N; ++c) y[c] = a.y0[c * a.y0_sc + idx * a.y0_sb];
                     double f0[N];
                     Prob::rhs(prm, t, y, f0);                            // :304
 #pragma unroll
@@ -457,7 +476,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     if (t == a.tb) {  // OdeSolver.step corner case (scipy base.py:193-198)
                         for (; ei < a.T; ++ei)
 #pragma unroll
-                            for (int c = 0; c < N; ++c) a.y_eval[((int64_t)ei * N + c) * a.B + idx] = y[c];
+                            for (int c = 0; c < N; ++c) a.y_eval[ei * a.ye_st + c * a.ye_sc + idx * a.ye_sb] = y[c];
                         finish_status = BRDAE_STATUS_FINISHED;
                         state = ST_IDLE;
                     }
@@ -579,7 +598,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                             double v = Q[c][0] * x;
                             v = fma(Q[c][1], x2, v);
                             v = fma(Q[c][2], x3, v);
-                            a.y_eval[((int64_t)ei * N + c) * a.B + idx] = v + cd(L::C_YOLD + c);
+                            a.y_eval[ei * a.ye_st + c * a.ye_sc + idx * a.ye_sb] = v + cd(L::C_YOLD + c);
                         }
                         ++ei;
                     }
@@ -679,14 +698,17 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 const double qnan = NAN;
                 for (int e = ei; e < a.T; ++e)
 #pragma unroll
-                    for (int c = 0; c < N; ++c) a.y_eval[((int64_t)e * N + c) * a.B + idx] = qnan;
+                    for (int c = 0; c < N; ++c) a.y_eval[e * a.ye_st + c * a.ye_sc + idx * a.ye_sb] = qnan;
                 a.n_eval[idx] = ei;
                 a.t_final[idx] = t;
 #pragma unroll
-                for (int c = 0; c < N; ++c) a.y_final[(int64_t)c * a.B + idx] = y[c];
+                for (int c = 0; c < N; ++c) a.y_final[c * a.yf_sc + idx * a.yf_sb] = y[c];
                 a.status[idx] = finish_status;
 #pragma unroll
-                for (int q = 0; q < CN_COUNT; ++q) a.counters[(int64_t)q * a.B + idx] = cnt[q];
+                for (int q = 0; q < CN_COUNT; ++q) a.counters[q * a.cn_sq + idx * a.cn_sb] = cnt[q];
+#if defined(__CUDA_ARCH__)
+                if (a.chunk_done) signal_chunk(a, idx);
+#endif
                 state = ST_IDLE;
             }
         }

@@ -151,7 +151,8 @@ int brdae_solve(const brdae_batch *batch, const brdae_options *opts, void *works
 int brdae_solve_host(const brdae_batch *host_batch, const brdae_options *opts);
 
 /* Host-buffer call in the row-per-system layout a per-system solve_ivp user already holds:
- * y0 [B][n], params [B][n_params] in; y_eval [B][n][T] (OdeResult.y per system), y_final [B][n],
+ * y0 [B][n], params [B][n_params] in; y_eval [B][T][n] (the transpose of OdeResult.y per system: the n
+ * unknowns of one output point are contiguous, which is how a lane writes them), y_final [B][n],
  * counters [B][BRDAE_NCOUNTERS] out; n_eval, t_final, status [B].  The permutations to and from
  * the kernels' structure-of-arrays layout are done on the device. */
 int brdae_solve_host_rows(const brdae_batch *host_batch_rows, const brdae_options *opts);
