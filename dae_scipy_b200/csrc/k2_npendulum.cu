@@ -46,146 +46,267 @@ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
 #define AB(ab, r, c) (ab)[(r) * WB + ((c) - (r) + KL)]
 
-// ---- banded LU, one warp, real ---------------------------------------------------------------
-__device__ void lu_band_real(double *ab, int *piv, int N) {
+// ---- banded LU and triangular solves, one warp each, on REGISTER WINDOWS -----------------------
+// The first version walked the band in memory: per column a pivot search, a row exchange, the
+// multipliers and the rank-1 update, each a dependent round trip through shared memory or L2 with a
+// __syncwarp between them -- ~550 warp instructions and several memory latencies per column, N columns
+// in sequence (ncu: profiles/r01_k2_ncu_summary.md).  Here the active part of the elimination lives in
+// registers.  LU: lane (c & 31) owns column c and holds its rows k..k+KL (the pivot candidates); the
+// window is KU+KL+1 = 17 columns wide, a column keeps its lane for as long as it is in the window, so
+// nothing moves between lanes when the window slides.  The pivot column's lane finds the pivot among its
+// ten registers (no shuffle tree), the multipliers are broadcast with shuffles, every lane exchanges
+// rows and updates its own column in registers, the finished U row and L column are stored once, and the
+// row entering the window is the only load of the step.  Every matrix entry is read once and written
+// once; no memory latency is left on the column-to-column critical path.  Substitutions: the right-hand
+// side slides through a 32-lane register window (shuffle down by one per column), the factor entries of
+// the next column are prefetched.  Arithmetic (operands, order, fma) is unchanged: bit-identical results.
+constexpr int UW = KU + KL;                       // width of U above the diagonal after pivoting (16)
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+__device__ __noinline__ void lu_band_real(double *ab, int *piv, int N) {
     const int lane = threadIdx.x & 31;
-    for (int k = 0; k < N; ++k) {
-        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + KU + KL);
-        double v = -1.0;
-        int idx = k + lane;
-        if (idx <= rmax) v = fabs(AB(ab, idx, k));
+    double w[KL + 1];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const double v2 = __shfl_down_sync(0xffffffffu, v, off);
-            const int i2 = __shfl_down_sync(0xffffffffu, idx, off);
-            if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+    for (int i = 0; i <= KL; ++i) w[i] = (lane <= UW && lane < N && i < N) ? AB(ab, i, lane) : 0.0;   // rows 0..9, column `lane`
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const int j = (lane - k) & 31, c = k + j;          // this lane's column and its offset in the window
+        const int rmo = imin(N - 1, k + KL) - k;           // rows k .. k+rmo exist
+        const int Lp = k & 31;                             // lane of the pivot column
+        // the row that enters the window after this step (one entry per lane), issued early
+        const int rn = k + KL + 1, jn = (lane - (k + 1)) & 31, cn = k + 1 + jn;
+        const double wnew = (rn < N && jn <= UW && cn < N) ? AB(ab, rn, cn) : 0.0;
+        int po = 0;
+        double best = fabs(w[0]);
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) {
+            const double v = fabs(w[i]);
+            const bool g = (i <= rmo) && v > best;
+            best = g ? v : best; po = g ? i : po;
         }
-        const int p = __shfl_sync(0xffffffffu, idx, 0);
-        if (lane == 0) piv[k] = p;
-        if (p != k) {
-            const int c = k + lane;
-            if (c <= cmax) { const double u = AB(ab, k, c); AB(ab, k, c) = AB(ab, p, c); AB(ab, p, c) = u; }
+        po = __shfl_sync(FULL, po, Lp);
+        if (po != 0) {   // warp-uniform: exchange rows k and k+po of this lane's column
+            const double t0 = w[0];
+            double tp = t0;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) { const bool sw = (i == po); tp = sw ? w[i] : tp; w[i] = sw ? t0 : w[i]; }
+            w[0] = tp;
         }
-        __syncwarp();
-        const double rcp = 1.0 / AB(ab, k, k);
-        __syncwarp();
-        if (lane == 0) AB(ab, k, k) = rcp;
-        if (lane < rmax - k) { const int r = k + 1 + lane; AB(ab, r, k) = AB(ab, r, k) * rcp; }
-        __syncwarp();
-        const int nr = rmax - k, nc = cmax - k;
-        for (int e = lane; e < nr * nc; e += 32) {
-            const int r = k + 1 + e / nc, c = k + 1 + e % nc;
-            AB(ab, r, c) = fma(-AB(ab, r, k), AB(ab, k, c), AB(ab, r, c));
+        const double rcp = 1.0 / shfl_d(w[0], Lp);         // uniform: no lane takes a division slow path of its own
+        double l[KL + 1];
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) l[i] = shfl_d(w[i] * rcp, Lp);
+        if (j == 0) {
+            piv[k] = k + po;
+            AB(ab, k, k) = rcp;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) if (i <= rmo) AB(ab, k + i, k) = l[i];
+        } else if (j <= UW && c < N) {
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) if (i <= rmo) w[i] = fma(-l[i], w[0], w[i]);
+            AB(ab, k, c) = w[0];                           // finished row of U
         }
-        __syncwarp();
+        // slide: row k leaves, row k+KL+1 enters; the pivot lane starts over as an empty column
+#pragma unroll
+        for (int i = 0; i < KL; ++i) w[i] = (j == 0) ? 0.0 : w[i + 1];
+        w[KL] = wnew;
     }
+    __syncwarp();
 }
 // complex, pivot on |re| + |im|
-__device__ void lu_band_cplx(double *ar, double *ai, int *piv, int N) {
+__device__ __noinline__ void lu_band_cplx(double *ar, double *ai, int *piv, int N) {
     const int lane = threadIdx.x & 31;
-    for (int k = 0; k < N; ++k) {
-        const int rmax = imin(N - 1, k + KL), cmax = imin(N - 1, k + KU + KL);
-        double v = -1.0;
-        int idx = k + lane;
-        if (idx <= rmax) v = fabs(AB(ar, idx, k)) + fabs(AB(ai, idx, k));
+    double wr[KL + 1], wi[KL + 1];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const double v2 = __shfl_down_sync(0xffffffffu, v, off);
-            const int i2 = __shfl_down_sync(0xffffffffu, idx, off);
-            if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+    for (int i = 0; i <= KL; ++i) {
+        const bool in = (lane <= UW && lane < N && i < N);
+        wr[i] = in ? AB(ar, i, lane) : 0.0;
+        wi[i] = in ? AB(ai, i, lane) : 0.0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const int j = (lane - k) & 31, c = k + j;
+        const int rmo = imin(N - 1, k + KL) - k;
+        const int Lp = k & 31;
+        const int rn = k + KL + 1, jn = (lane - (k + 1)) & 31, cn = k + 1 + jn;
+        const bool inn = (rn < N && jn <= UW && cn < N);
+        const double wrn = inn ? AB(ar, rn, cn) : 0.0, win = inn ? AB(ai, rn, cn) : 0.0;
+        int po = 0;
+        double best = fabs(wr[0]) + fabs(wi[0]);
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) {
+            const double v = fabs(wr[i]) + fabs(wi[i]);
+            const bool g = (i <= rmo) && v > best;
+            best = g ? v : best; po = g ? i : po;
         }
-        const int p = __shfl_sync(0xffffffffu, idx, 0);
-        if (lane == 0) piv[k] = p;
-        if (p != k) {
-            const int c = k + lane;
-            if (c <= cmax) {
-                double u = AB(ar, k, c); AB(ar, k, c) = AB(ar, p, c); AB(ar, p, c) = u;
-                u = AB(ai, k, c); AB(ai, k, c) = AB(ai, p, c); AB(ai, p, c) = u;
+        po = __shfl_sync(FULL, po, Lp);
+        if (po != 0) {
+            const double t0r = wr[0], t0i = wi[0];
+            double tpr = t0r, tpi = t0i;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) {
+                const bool sw = (i == po);
+                tpr = sw ? wr[i] : tpr; tpi = sw ? wi[i] : tpi;
+                wr[i] = sw ? t0r : wr[i]; wi[i] = sw ? t0i : wi[i];
             }
+            wr[0] = tpr; wi[0] = tpi;
         }
-        __syncwarp();
-        const double pr = AB(ar, k, k), pi = AB(ai, k, k);
+        const double pr = shfl_d(wr[0], Lp), pi = shfl_d(wi[0], Lp);      // uniform pivot
         const double invd = 1.0 / fma(pr, pr, pi * pi);
         const double qr = pr * invd, qi = -(pi * invd);
-        __syncwarp();
-        if (lane == 0) { AB(ar, k, k) = qr; AB(ai, k, k) = qi; }
-        if (lane < rmax - k) {
-            const int r = k + 1 + lane;
-            const double xr = AB(ar, r, k), xi = AB(ai, r, k);
-            AB(ar, r, k) = fma(xr, qr, -(xi * qi));
-            AB(ai, r, k) = fma(xr, qi, xi * qr);
+        double lr[KL + 1], li[KL + 1];
+#pragma unroll
+        for (int i = 1; i <= KL; ++i) {
+            lr[i] = shfl_d(fma(wr[i], qr, -(wi[i] * qi)), Lp);
+            li[i] = shfl_d(fma(wr[i], qi, wi[i] * qr), Lp);
         }
-        __syncwarp();
-        const int nr = rmax - k, nc = cmax - k;
-        for (int e = lane; e < nr * nc; e += 32) {
-            const int r = k + 1 + e / nc, c = k + 1 + e % nc;
-            const double lr = AB(ar, r, k), li = AB(ai, r, k), ur = AB(ar, k, c), ui = AB(ai, k, c);
-            double xr = AB(ar, r, c), xi = AB(ai, r, c);
-            xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
-            xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
-            AB(ar, r, c) = xr; AB(ai, r, c) = xi;
+        if (j == 0) {
+            piv[k] = k + po;
+            AB(ar, k, k) = qr; AB(ai, k, k) = qi;
+#pragma unroll
+            for (int i = 1; i <= KL; ++i) if (i <= rmo) { AB(ar, k + i, k) = lr[i]; AB(ai, k + i, k) = li[i]; }
+        } else if (j <= UW && c < N) {
+            const double ur = wr[0], ui = wi[0];
+#pragma unroll
+            for (int i = 1; i <= KL; ++i)
+                if (i <= rmo) {
+                    double xr = wr[i], xi = wi[i];
+                    xr = fma(-lr[i], ur, xr); xr = fma(li[i], ui, xr);
+                    xi = fma(-lr[i], ui, xi); xi = fma(-li[i], ur, xi);
+                    wr[i] = xr; wi[i] = xi;
+                }
+            AB(ar, k, c) = ur; AB(ai, k, c) = ui;
         }
-        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < KL; ++i) { wr[i] = (j == 0) ? 0.0 : wr[i + 1]; wi[i] = (j == 0) ? 0.0 : wi[i + 1]; }
+        wr[KL] = wrn; wi[KL] = win;
     }
+    __syncwarp();
 }
 // ---- banded triangular solves, one warp each ---------------------------------------------------
-__device__ void solve_band_real(const double *ab, const int *piv, double *b, int N) {
+// forward: lane i holds b[k+i]; backward: lane i holds b[k-i]; the window slides by one lane per column and
+// the factor entries, pivot index and entering right-hand-side entry of the next column are loaded one
+// column ahead.  The loops are deliberately NOT unrolled and the routines not inlined: the CTAs of an SM run
+// different phases of the step at the same time, and code size decides whether they fit the instruction cache.
+__device__ __noinline__ void solve_band_real(const double *ab, const int *piv, double *b, int N) {
     const int lane = threadIdx.x & 31;
-    for (int k = 0; k < N; ++k) {
-        const int p = piv[k], rmax = imin(N - 1, k + KL);
-        if (p != k && lane == 0) { const double u = b[k]; b[k] = b[p]; b[p] = u; }
-        __syncwarp();
-        const double bk = b[k];
-        if (lane < rmax - k) { const int r = k + 1 + lane; b[r] = fma(-AB(ab, r, k), bk, b[r]); }
-        __syncwarp();
+    {
+        const int klim = (lane >= 1 && lane <= KL) ? N - lane : 0;      // row k+lane exists  <=>  k < klim
+        const double *lp = ab + lane * (WB - 1) + KL;                  // &AB(ab, k+lane, k) = lp + k*WB
+        double bw = (lane < N) ? b[lane] : 0.0;
+        double lc = (0 < klim) ? lp[0] : 0.0;
+        int pc = piv[0];
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            const int k1 = k + 1;
+            const double ln = (k1 < klim) ? lp[k1 * WB] : 0.0;
+            const int pn = (k1 < N) ? piv[k1] : 0;
+            const double bin = (lane == 31 && k + 32 < N) ? b[k + 32] : 0.0;
+            const int po = pc - k;
+            if (po != 0) {                                              // warp-uniform: exchange entries k and k+po
+                const double v0 = shfl_d(bw, 0), vp = shfl_d(bw, po);
+                bw = (lane == po) ? v0 : (lane == 0 ? vp : bw);
+            }
+            const double bk = shfl_d(bw, 0);
+            if (lane == 0) b[k] = bk;
+            if (k < klim) bw = fma(-lc, bk, bw);
+            bw = __shfl_down_sync(FULL, bw, 1);
+            if (lane == 31) bw = bin;
+            lc = ln; pc = pn;
+        }
     }
-    for (int k = N - 1; k >= 0; --k) {
-        const int rmin = imax(0, k - (KU + KL));
-        const double xk = b[k] * AB(ab, k, k);
-        __syncwarp();
-        if (lane == 0) b[k] = xk;
-        if (lane < k - rmin) { const int r = rmin + lane; b[r] = fma(-AB(ab, r, k), xk, b[r]); }
-        __syncwarp();
+    __syncwarp();
+    {
+        // back substitution, column oriented: x_k = b_k * (1/u_kk), then b_r -= u_rk x_k for the UW rows above
+        const int kmin = (lane >= 1 && lane <= UW) ? lane : N;          // row k-lane exists  <=>  k >= kmin
+        const double *up = ab + KL - lane * (WB - 1);                   // &AB(ab, k-lane, k) = up + k*WB
+        const double *dp = ab + KL;                                     // &AB(ab, k, k) = dp + k*WB
+        double bw = (N - 1 - lane >= 0) ? b[N - 1 - lane] : 0.0;
+        double uc = (N - 1 >= kmin) ? up[(N - 1) * WB] : 0.0, dc = dp[(N - 1) * WB];
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; --k) {
+            const int k1 = k - 1;
+            const double un = (k1 >= kmin) ? up[k1 * WB] : 0.0;
+            const double dn = (k1 >= 0) ? dp[k1 * WB] : 0.0;
+            const double bin = (lane == 31 && k - 32 >= 0) ? b[k - 32] : 0.0;
+            const double xk = shfl_d(bw, 0) * dc;
+            if (lane == 0) b[k] = xk;
+            if (k >= kmin) bw = fma(-uc, xk, bw);
+            bw = __shfl_down_sync(FULL, bw, 1);
+            if (lane == 31) bw = bin;
+            uc = un; dc = dn;
+        }
     }
+    __syncwarp();
 }
-__device__ void solve_band_cplx(const double *ar, const double *ai, const int *piv, double *br, double *bi, int N) {
+__device__ __noinline__ void solve_band_cplx(const double *ar, const double *ai, const int *piv, double *br, double *bi, int N) {
     const int lane = threadIdx.x & 31;
-    for (int k = 0; k < N; ++k) {
-        const int p = piv[k], rmax = imin(N - 1, k + KL);
-        if (p != k && lane == 0) {
-            double u = br[k]; br[k] = br[p]; br[p] = u;
-            u = bi[k]; bi[k] = bi[p]; bi[p] = u;
+    {
+        const int klim = (lane >= 1 && lane <= KL) ? N - lane : 0;
+        const int lo = lane * (WB - 1) + KL;
+        double wr = (lane < N) ? br[lane] : 0.0, wi = (lane < N) ? bi[lane] : 0.0;
+        double lcr = (0 < klim) ? ar[lo] : 0.0, lci = (0 < klim) ? ai[lo] : 0.0;
+        int pc = piv[0];
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            const int k1 = k + 1;
+            const double lnr = (k1 < klim) ? ar[lo + k1 * WB] : 0.0, lni = (k1 < klim) ? ai[lo + k1 * WB] : 0.0;
+            const int pn = (k1 < N) ? piv[k1] : 0;
+            const bool in = (lane == 31 && k + 32 < N);
+            const double inr = in ? br[k + 32] : 0.0, ini = in ? bi[k + 32] : 0.0;
+            const int po = pc - k;
+            if (po != 0) {
+                const double v0r = shfl_d(wr, 0), v0i = shfl_d(wi, 0), vpr = shfl_d(wr, po), vpi = shfl_d(wi, po);
+                wr = (lane == po) ? v0r : (lane == 0 ? vpr : wr);
+                wi = (lane == po) ? v0i : (lane == 0 ? vpi : wi);
+            }
+            const double xr = shfl_d(wr, 0), xi = shfl_d(wi, 0);
+            if (lane == 0) { br[k] = xr; bi[k] = xi; }
+            if (k < klim) {
+                double yr = wr, yi = wi;
+                yr = fma(-lcr, xr, yr); yr = fma(lci, xi, yr);
+                yi = fma(-lcr, xi, yi); yi = fma(-lci, xr, yi);
+                wr = yr; wi = yi;
+            }
+            wr = __shfl_down_sync(FULL, wr, 1); wi = __shfl_down_sync(FULL, wi, 1);
+            if (lane == 31) { wr = inr; wi = ini; }
+            lcr = lnr; lci = lni; pc = pn;
         }
-        __syncwarp();
-        const double xr = br[k], xi = bi[k];
-        if (lane < rmax - k) {
-            const int r = k + 1 + lane;
-            const double lr = AB(ar, r, k), li = AB(ai, r, k);
-            double yr = br[r], yi = bi[r];
-            yr = fma(-lr, xr, yr); yr = fma(li, xi, yr);
-            yi = fma(-lr, xi, yi); yi = fma(-li, xr, yi);
-            br[r] = yr; bi[r] = yi;
-        }
-        __syncwarp();
     }
-    for (int k = N - 1; k >= 0; --k) {
-        const int rmin = imax(0, k - (KU + KL));
-        const double qr = AB(ar, k, k), qi = AB(ai, k, k);
-        const double sr = br[k], si = bi[k];
-        const double xr = fma(sr, qr, -(si * qi));
-        const double xi = fma(sr, qi, si * qr);
-        __syncwarp();
-        if (lane == 0) { br[k] = xr; bi[k] = xi; }
-        if (lane < k - rmin) {
-            const int r = rmin + lane;
-            const double ur = AB(ar, r, k), ui = AB(ai, r, k);
-            double yr = br[r], yi = bi[r];
-            yr = fma(-ur, xr, yr); yr = fma(ui, xi, yr);
-            yi = fma(-ur, xi, yi); yi = fma(-ui, xr, yi);
-            br[r] = yr; bi[r] = yi;
+    __syncwarp();
+    {
+        const int kmin = (lane >= 1 && lane <= UW) ? lane : N;
+        const int uo = KL - lane * (WB - 1);
+        const bool in0 = (N - 1 - lane >= 0);
+        double wr = in0 ? br[N - 1 - lane] : 0.0, wi = in0 ? bi[N - 1 - lane] : 0.0;
+        const int kl0 = (N - 1) * WB;
+        double ucr = (N - 1 >= kmin) ? ar[uo + kl0] : 0.0, uci = (N - 1 >= kmin) ? ai[uo + kl0] : 0.0;
+        double qr = ar[KL + kl0], qi = ai[KL + kl0];
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; --k) {
+            const int k1 = k - 1;
+            const double unr = (k1 >= kmin) ? ar[uo + k1 * WB] : 0.0, uni = (k1 >= kmin) ? ai[uo + k1 * WB] : 0.0;
+            const double qnr = (k1 >= 0) ? ar[KL + k1 * WB] : 0.0, qni = (k1 >= 0) ? ai[KL + k1 * WB] : 0.0;
+            const bool in = (lane == 31 && k - 32 >= 0);
+            const double inr = in ? br[k - 32] : 0.0, ini = in ? bi[k - 32] : 0.0;
+            const double sr = shfl_d(wr, 0), si = shfl_d(wi, 0);
+            const double xr = fma(sr, qr, -(si * qi));
+            const double xi = fma(sr, qi, si * qr);
+            if (lane == 0) { br[k] = xr; bi[k] = xi; }
+            if (k >= kmin) {
+                double yr = wr, yi = wi;
+                yr = fma(-ucr, xr, yr); yr = fma(uci, xi, yr);
+                yi = fma(-ucr, xi, yi); yi = fma(-uci, xr, yi);
+                wr = yr; wi = yi;
+            }
+            wr = __shfl_down_sync(FULL, wr, 1); wi = __shfl_down_sync(FULL, wi, 1);
+            if (lane == 31) { wr = inr; wi = ini; }
+            ucr = unr; uci = uni; qr = qnr; qi = qni;
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // sum of squares of v[e] * s[e mod N], e < m, by warp 0: 32 interleaved chains + shuffle tree.
