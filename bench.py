@@ -222,8 +222,10 @@ def main():
         torch.cuda.synchronize(dev)
 
     res = None
-    for _ in range(args.warmup):
+    for _ in range(args.warmup):       # warm-up steps are whole steps: the statistics all_reduce (NCCL set-up) included
         res = one_pass()
+        csum = res.counters.sum(dim=1, dtype=torch.int64)
+        reduce_statistics(csum, status_histogram(res.status), dist if world > 1 else None, dev)
     barrier()
     # measured FP64 roofline denominator (burst DFMA probe on this device)
     fp64_peak = br.fp64_peak_tflops(60.0)
