@@ -43,7 +43,7 @@ WORKLOADS = {
 
 
 # measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum) / systems of the profiled launch
-NCU_DRAM_BYTES_PER_SYSTEM = {"pendulum3_1M_tend2": (161.36e6 + 332.84e6) / 262144}
+NCU_DRAM_BYTES_PER_SYSTEM = {"pendulum3_1M_tend2": (157.39e6 + 328.64e6) / 262144}     # profiles/r01_k1_ncu_summary.md, v7
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -268,7 +268,7 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback"
     hbm_gbs = abytes / (kms * 1e-3) / 1e9
     # DRAM traffic of one launch: per-system dram__bytes_read + dram__bytes_write of the ncu --set full capture
-    # committed under profiles/ (r01_k1_ncu_summary.md: 494 MB for 262,144 pendulum systems), scaled to this launch
+    # committed under profiles/ (r01_k1_ncu_summary.md: 486 MB for 262,144 pendulum systems), scaled to this launch
     traffic = NCU_DRAM_BYTES_PER_SYSTEM.get(args.workload)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
