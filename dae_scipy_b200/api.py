@@ -194,6 +194,8 @@ class BatchedOdeResult:
 
     def __init__(self, t, y_eval_tnb, n_eval, status, t_final, y_final_nb, counters_cb):
         self.sol = None                     # BatchedOdeSolution when dense_output=True
+        self.t_events = self.y_events = None    # per system, per event (lists of arrays) when events were given
+        self._event_cut = None                  # (terminated [B], t_stop [B], y_stop [B, n], ascending)
         self.t = t
         self._y_eval = y_eval_tnb           # [T, n, B] as written by the kernel (coalesced SoA)
         self.n_eval = n_eval
@@ -274,6 +276,59 @@ class BatchedOdeSolution:
     def system(self, i):
         return lambda t: self(np.atleast_1d(t))[i] if np.ndim(t) else self([t])[i, :, 0]
 
+    def step(self, i, k):
+        """The cubic of step k of system i as a callable t -> y[n] (RadauDenseOutput, radauDAE.py:959-982)."""
+        t_old, h = self.ts[i, k], self.ts[i, k + 1] - self.ts[i, k]
+        Q, y_old = self.Q[i, k], self.ys[i, :, k]
+
+        def cubic(t):
+            x = (np.asarray(t, dtype=np.float64) - t_old) / h
+            p = np.stack([x, x * x, x * x * x])
+            return (Q @ p) + (y_old if p.ndim == 1 else y_old[:, None])
+        return cubic
+
+
+def find_events(sol, events, t0, y0):
+    """Event location on the recorded solution, with the semantics of `scipy.integrate.solve_ivp(events=...)`
+    (scipy ivp.py: `prepare_events`, `find_active_events`, `handle_events` -- scipy's own helpers are used; the
+    reference's `solve_ivp_custom` wraps the same ones, radauDAE.py:1059-1129).  `events` are Python callables
+    `event(t, y)` with the optional attributes `terminal` and `direction`; they are evaluated on the host, step by
+    step, on each system's record, and roots are bracketed inside a step and refined on its cubic interpolant.
+    Returns (t_events, y_events, terminated, t_stop, y_stop): `t_events[i][e]` is the array of times at which
+    event e fired for system i; a terminal event cuts that system's record at `t_stop[i]`.  The integration on
+    the device is not interrupted: it is the reported result that ends at the event."""
+    from scipy.integrate._ivp.ivp import find_active_events, handle_events, prepare_events
+    events, max_events, direction = prepare_events(events)
+    B, n = sol.ys.shape[0], sol.ys.shape[1]
+    t_events = [[[] for _ in events] for _ in range(B)]
+    y_events = [[[] for _ in events] for _ in range(B)]
+    terminated = np.zeros(B, dtype=bool)
+    t_stop = np.full(B, np.nan)
+    y_stop = np.full((B, n), np.nan)
+    for i in range(B):
+        g = [ev(t0, y0[i]) for ev in events]
+        count = np.zeros(len(events))
+        for k in range(int(sol.n_steps[i])):
+            t_old, t = sol.ts[i, k], sol.ts[i, k + 1]
+            g_new = [ev(t, sol.ys[i, :, k + 1]) for ev in events]
+            active = find_active_events(g, g_new, direction)
+            if active.size > 0:
+                cubic = sol.step(i, k)
+                count[active] += 1
+                idx, roots, terminate = handle_events(cubic, events, active, count, max_events, t_old, t)
+                for e, te in zip(idx, roots):
+                    t_events[i][e].append(te)
+                    y_events[i][e].append(cubic(te))
+                if terminate:
+                    terminated[i] = True
+                    t_stop[i] = roots[-1]
+                    y_stop[i] = cubic(roots[-1])
+                    break
+            g = g_new
+    t_events = [[np.asarray(te) for te in sys_t] for sys_t in t_events]
+    y_events = [[np.asarray(ye).reshape(-1, n) for ye in sys_y] for sys_y in y_events]
+    return t_events, y_events, terminated, t_stop, y_stop
+
 
 def _as_device_f64(x, device, torch):
     if isinstance(x, torch.Tensor):
@@ -300,6 +355,10 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     var_index   : [n] integers 0..3 or None (all differential), as in the reference.
     jac         : 'analytic' (default: the problem's analytic Jacobian functor), a constant [n, n] matrix, or
                   None = finite differences as in the reference's default (scipy num_jac).
+    events      : callable or list of callables `event(t, y)` with optional `terminal` / `direction` attributes, as in
+                  scipy's solve_ivp; located on the host on the per-step record (implies dense_output=True, so
+                  `max_dense_steps` is required); `result.t_events[i][e]`, `result.y_events[i][e]`, and a terminal
+                  event cuts that system's reported result (status 1), see `find_events`.
     dense_output, max_dense_steps : record every accepted step (up to `max_dense_steps` per system, required
                   with dense_output=True: the record takes 8 (4 n + 1) bytes per step and system) and return
                   `result.sol`, a BatchedOdeSolution.  Times known in advance are cheaper through `t_eval`.
@@ -308,10 +367,12 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
 
     if not (method is RadauDAE or method == "RadauDAE"):
         raise ValueError("`method` must be RadauDAE.")
-    if events:
-        raise NotImplementedError("events are not supported by the batched solver")
+    if events and not dense_output:
+        dense_output = True                    # events are located on the per-step record
+    if callable(events):
+        events = (events,)
     if dense_output and (max_dense_steps is None or int(max_dense_steps) < 1):
-        raise ValueError("dense_output=True needs `max_dense_steps` (steps recorded per system).")
+        raise ValueError("dense_output=True (and events) need `max_dense_steps` (steps recorded per system).")
     if not torch.cuda.is_available():
         raise RuntimeError("solve_ivp_batched needs a CUDA device; there is no CPU fallback.")
     lib = _abi.load()
@@ -361,8 +422,14 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     res._keepalive = (y0_soa, par_soa, te_d, ws)
     if dense_output:
         cu_stream.synchronize()
-        res.sol = make_ode_solution(hb, y0_d.cpu().numpy(), dense_t.cpu().numpy(), dense_y.cpu().numpy(),
+        y0_h = y0_d.cpu().numpy()
+        res.sol = make_ode_solution(hb, y0_h, dense_t.cpu().numpy(), dense_y.cpu().numpy(),
                                     dense_q.cpu().numpy(), status.cpu().numpy(), counters.cpu().numpy())
+        if events:
+            if res.sol.truncated.any():
+                raise RuntimeError("`max_dense_steps` is too small for event location: a system took more steps than recorded.")
+            res.t_events, res.y_events, term, t_stop, y_stop = find_events(res.sol, events, hb.t0, y0_h)
+            res._event_cut = (term, t_stop, y_stop, hb.t_bound >= hb.t0)
     return res
 
 

@@ -129,6 +129,50 @@ def save(name, ens, over=None):
           f"mean acc/rej/fail {c[:, 4].mean():.1f}/{c[:, 5].mean():.1f}/{c[:, 6].mean():.1f}")
 
 
+def pendulum_events():
+    """Event functions of the events fixture / tests: x crosses zero (both directions, not terminal) and the
+    vertical velocity crosses zero upwards, terminal at its second occurrence."""
+    def x_zero(t, y):
+        return y[0]
+
+    def vy_up(t, y):
+        return y[3]
+    vy_up.direction = 1.0
+    vy_up.terminal = 2
+    return [x_zero, vy_up]
+
+
+def save_events(name, ens):
+    """scipy.integrate.solve_ivp(method=RadauDAE, events=...) of the reference, system by system."""
+    from scipy.integrate import solve_ivp
+    opts = dict(ens["options"])
+    mm, vi = opts.pop("mass_matrix"), opts.pop("var_index")
+    B, n = ens["y0"].shape
+    events = pendulum_events()
+    tev = np.full((B, len(events), 16), np.nan)
+    status = np.zeros(B, dtype=np.int32)
+    t_final = np.zeros(B)
+    y_final = np.zeros((B, n))
+    n_eval = np.zeros(B, dtype=np.int32)
+    for i in range(B):
+        fun, jac, mass, _ = build_system(ens["problem"], ens["params"][i], n)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = solve_ivp(fun, ens["t_span"], ens["y0"][i], method=RadauDAE, t_eval=ens["t_eval"], events=events, jac=jac,
+                          mass_matrix=mass, var_index=np.asarray(vi, dtype=float), dense_output=True, **opts)
+        for e, te in enumerate(r.t_events):
+            tev[i, e, :len(te)] = te
+        status[i] = r.status
+        n_eval[i] = r.t.size
+        t_final[i] = r.sol.ts[-1] if r.status != 1 else r.t_events[1][-1]
+        y_final[i] = r.sol(t_final[i])
+    meta = dict(problem=ens["problem"], t_span=list(ens["t_span"]),
+                options={k: v for k, v in opts.items()}, mass_matrix="problem")
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), y0=ens["y0"], params=ens["params"], t_eval=ens["t_eval"],
+                        var_index=np.asarray(vi, dtype=np.int32), t_events=tev, status=status, t_final=t_final, y_final=y_final,
+                        n_eval=n_eval, meta=np.array(json.dumps(meta)))
+    print(f"{name}: status {status.tolist()} events/system {np.isfinite(tev).sum(axis=2).tolist()}")
+
+
 def single(problem, y0, params, t_span, t_eval, options):
     return dict(problem=problem, t_span=tuple(t_span), y0=np.atleast_2d(np.asarray(y0, dtype=float)),
                 params=None if params is None else np.atleast_2d(np.asarray(params, dtype=float)),
@@ -221,6 +265,8 @@ def main():
     save("fd_pendulum2", E.pendulum_ensemble(8, t_end=1.0, index=2), dict(jac=None))
     save("fd_robertson", E.robertson_ensemble(8, t_end=1e3), dict(jac=None))
     save("fd_transistor", E.transistor_ensemble(4, t_end=0.05), dict(jac=None))
+    # --- events (scipy's solve_ivp driving the reference solver)
+    save_events("events_pendulum3", E.pendulum_ensemble(6, t_end=3.0, n_t_eval=31))
     # --- n-pendulum chains (dense analytic Jacobian handed to the reference)
     save("ens_npendulum_n4", E.npendulum_ensemble(3, n_nodes=4))
     save("ens_npendulum_n10", E.npendulum_ensemble(2, n_nodes=10))

@@ -22,7 +22,9 @@ PARITY_FACTOR = 10.0
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Trajectory fixtures (the events fixture has its own layout and its own test)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith("events_"))
 
 
 def load_golden(name):

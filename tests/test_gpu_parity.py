@@ -198,6 +198,22 @@ def test_gpu_dense_output_record_equals_kernel_source_and_t_eval():
     assert np.array_equal(last, out["y_final"])
 
 
+def test_gpu_events_terminal_cut_matches_scipy_with_the_reference_solver():
+    """events=...: located on the step record of the CUDA run; a terminal event cuts the reported result like scipy."""
+    from test_events import _fixture, pendulum_events
+    ens, ref = _fixture()
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"],
+                               events=pendulum_events(), max_dense_steps=800, **ens["options"])
+    out = res.numpy()
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["n_eval"], ref["n_eval"])
+    np.testing.assert_allclose(out["t_final"], ref["t_final"], atol=2e-6)
+    for i in range(ens["y0"].shape[0]):
+        for e in range(2):
+            want = ref["t_events"][i, e]
+            np.testing.assert_allclose(out["t_events"][i][e], want[np.isfinite(want)], rtol=0, atol=2e-6)
+        assert np.isnan(out["y"][i][:, out["n_eval"][i]:]).all() and np.isfinite(out["y"][i][:, :out["n_eval"][i]]).all()
+
+
 # ---------------------------------------------------------------- (2) against the reference fixtures
 @pytest.mark.parametrize("name", golden_names())
 def test_gpu_against_reference_fixture(name):
