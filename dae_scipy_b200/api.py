@@ -230,6 +230,18 @@ class BatchedOdeResult:
                "y_final": self.y_final.cpu().numpy(), "counters": self.counters.t().cpu().numpy()}
         for i, name in enumerate(_abi.COUNTER_NAMES):
             out[name] = out["counters"][:, i]
+        if self._event_cut is not None:         # a terminal event ends the reported result (scipy: status 1)
+            term, t_stop, y_stop, asc = self._event_cut
+            t = out["t"]
+            for i in np.nonzero(term)[0]:
+                keep = (t <= t_stop[i]) if asc else (t >= t_stop[i])
+                keep &= np.arange(t.size) < out["n_eval"][i]
+                out["y"][i][:, ~keep] = np.nan
+                out["n_eval"][i] = int(keep.sum())
+                out["status"][i] = 1
+                out["t_final"][i] = t_stop[i]
+                out["y_final"][i] = y_stop[i]
+            out["t_events"], out["y_events"] = self.t_events, self.y_events
         out["success"] = out["status"] >= 0
         return out
 
