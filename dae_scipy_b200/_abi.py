@@ -117,13 +117,16 @@ def make_options(*, first_step=None, max_step=math.inf, newton_tol=None, max_new
 
 
 _lib = None
+_plugin_libs = {}      # path -> CDLL of a plugin build (dae_scipy_b200/plugin.py)
 
 
 def load(path: str | None = None):
-    """Load libbrdae.so and declare its prototypes.  Raises if it is not built."""
+    """Load libbrdae.so (or the plugin build at `path`) and declare its prototypes.  Raises if it is not built."""
     global _lib
     if _lib is not None and path is None:
         return _lib
+    if path is not None and path in _plugin_libs:
+        return _plugin_libs[path]
     p = path or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(
@@ -158,6 +161,8 @@ def load(path: str | None = None):
     lib.brdae_fp64_peak_probe.argtypes = [C.c_double, C.POINTER(C.c_double), C.c_void_p]
     if path is None:
         _lib = lib
+    else:
+        _plugin_libs[path] = lib
     return lib
 
 

@@ -152,6 +152,8 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
     if isinstance(jac, str):
         if jac != "analytic":
             raise ValueError("`jac` must be 'analytic' or a constant [n, n] matrix.")
+        if not prob.has_jac:
+            fd = True          # a user problem compiled without a Jacobian body: the reference's default, num_jac
     elif jac is None:
         # the reference's default (radauDAE.py:468-481): scipy num_jac forward differences of the RHS
         # functor with adaptive column factors, on the device (thread-per-system problems)
@@ -387,7 +389,7 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
         raise ValueError("dense_output=True (and events) need `max_dense_steps` (steps recorded per system).")
     if not torch.cuda.is_available():
         raise RuntimeError("solve_ivp_batched needs a CUDA device; there is no CPU fallback.")
-    lib = _abi.load()
+    lib = _abi.load(get_problem(problem).lib_path)      # the stock library, or the plugin build of a user problem
     dev = torch.device(device) if device is not None else (
         y0.device if isinstance(y0, torch.Tensor) and y0.is_cuda else torch.device("cuda", torch.cuda.current_device()))
 
@@ -503,7 +505,7 @@ def solve_ivp_batched_host(problem, t_span, y0, params=None, *, t_eval=None, buf
     library.  This is the entry a numpy/scipy user of the reference binds to and what bench.py
     times as the end-to-end path.  `buffers` (from `host_buffers`) lets repeated calls reuse
     page-locked result arrays; the returned arrays are then views of those buffers."""
-    lib = _abi.load()
+    lib = _abi.load(get_problem(problem).lib_path)
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     hb = prepare(problem, t_span, y0.shape, t_eval=t_eval, params=params, **options)
     prob, n, B, T = hb.problem, hb.n, hb.B, hb.t_eval.size

@@ -18,7 +18,8 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbrdae.so")
 
 SOURCES = ["brdae_abi.cu", "dispatch.cu", "k1_pendulum.cu", "k1_robertson.cu", "k1_transistor.cu", "k1_extra.cu",
-           "k2_npendulum.cu", "k3_npendulum_lanes.cu", "fp64_peak.cu", "layout.cu"]
+           "k2_npendulum.cu", "k3_npendulum_lanes.cu", "fp64_peak.cu", "layout.cu", "k1_user.cu"]
+USER_TU = "k1_user.cu"       # stub in the stock library, the user's functor in a plugin build
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -72,6 +73,24 @@ def build_variant(tag: str, defines: dict) -> str:
         objs = list(ex.map(one, SOURCES))
     subprocess.run([_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"],
                    check=True)
+    return lib
+
+
+def build_plugin(header: str, lib: str) -> str:
+    """Plugin build: compile k1_user.cu WITH the user's problem header and link it, in place of the stub,
+    with the stock objects into `lib` -- a complete libbrdae whose problem BRDAE_USER is that functor."""
+    build()                                                  # the stock objects (no-op when up to date)
+    obj = os.path.splitext(lib)[0] + ".k1_user.o"
+    cmd = [_nvcc(), *NVCC_FLAGS, f'-DBRDAE_USER_HEADER="{os.path.abspath(header)}"', "-c",
+           os.path.join(CSRC, USER_TU), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for the user problem {header}:\n{r.stdout}\n{r.stderr}")
+    objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES if s != USER_TU] + [obj]
+    r = subprocess.run([_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return lib
 
 

@@ -51,6 +51,13 @@ int brdae_problem_lookup(const char *name, int32_t *problem, int32_t *n, int32_t
             if (n_params) *n_params = p.n_params;
             return BRDAE_OK;
         }
+    if (const ProblemInfo *u = user_problem_info())        // plugin build: "user" or the functor's own name
+        if (std::strcmp(name, "user") == 0 || std::strcmp(name, u->name) == 0) {
+            if (problem) *problem = u->id;
+            if (n) *n = u->n;
+            if (n_params) *n_params = u->n_params;
+            return BRDAE_OK;
+        }
     return BRDAE_ERR_UNKNOWN_PROBLEM;
 }
 

@@ -21,8 +21,12 @@ static const ProblemInfo kProblems[] = {
     {"polydae2", BRDAE_POLYDAE2, 2, 5}, {"linear7", BRDAE_LINEAR7, 7, 7},
 };
 
+// the problem of a plugin build (k1_user.cu), nullptr in the stock library
+const ProblemInfo *user_problem_info();
+
 inline const ProblemInfo *find_problem(int32_t id) {
     for (const auto &p : kProblems) if (p.id == id) return &p;
+    if (id == BRDAE_USER) return user_problem_info();
     return nullptr;
 }
 

@@ -19,6 +19,8 @@ int k1_pendulum(int index, bool dense_mass, const SolveArgs &a, int sms, cudaStr
 int k1_robertson(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 int k1_transistor(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 int k1_extra(int problem, bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+// the user-supplied functor of a plugin build (k1_user.cu); BRDAE_ERR_UNKNOWN_PROBLEM in the stock library
+int k1_user(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 // CTA-per-system banded kernel for the n-pendulum chain (k2_npendulum.cu)
 int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 size_t k2_scratch_bytes(int n, int sms, int64_t B);

@@ -71,5 +71,43 @@ def npendulum_ensemble(B, n_nodes=20, n_t_eval=21, seed=3, t_end=None):
                              mass_matrix="problem", var_index=prob.var_index_array(n)))
 
 
+# ---------------------------------------------------------------- a USER problem (dae_scipy_b200/plugin.py)
+# The batch-reactor DAE of the reference's tests/reactor.py:74-133 is not compiled into the stock library: it is
+# the worked example of the plugin path -- three lines of CUDA C++ instead of the script's Python closure.
+REACTOR_RHS = """f[0] = -p[0] * y[0] * y[1];
+                 f[1] = y[1] - (p[2] - (p[1] - y[0]));
+                 f[2] = y[2] - (p[1] - y[0]);"""
+REACTOR_JAC = """J[0][0] = -p[0] * y[1]; J[0][1] = -p[0] * y[0];
+                 J[1][0] = -1.0; J[1][1] = 1.0;
+                 J[2][0] = 1.0; J[2][2] = 1.0;"""
+
+
+def reactor_problem(analytic_jacobian=True):
+    """Compile (once, cached) and register the reactor functor; returns its `Problem`.  Without the Jacobian body
+    the plugin has finite differences only, like the reference script (jac=None)."""
+    from .plugin import compile_problem
+    return compile_problem("reactor" if analytic_jacobian else "reactor_fd", 3, REACTOR_RHS,
+                           REACTOR_JAC if analytic_jacobian else None, param_names=("k", "Ca0", "Cb0"),
+                           param_defaults=(1.47, 0.0209, 0.0209 / 3), mass_diag=(1, 0, 0), var_index=(0, 1, 1),
+                           t_span=(0.0, 20.0))
+
+
+def reactor_ensemble(B, t_end=20.0, n_t_eval=21, seed=4):
+    """k = 1.47 * 10**U(-0.5, 0.5), Ca0 = 0.0209 * 10**U(-0.3, 0.3), Cb0 = Ca0 / 3 * 10**U(-0.2, 0.2); script
+    options of reactor.py:108-133.  `problem` is the NAME "reactor": call `reactor_problem()` first on the paths
+    that need the device functor."""
+    rng = np.random.default_rng(seed)
+    u = rng.random((B, 3))
+    k = 1.47 * 10.0 ** (u[:, 0] - 0.5)
+    Ca0 = 0.0209 * 10.0 ** (0.6 * u[:, 1] - 0.3)
+    Cb0 = Ca0 / 3 * 10.0 ** (0.4 * u[:, 2] - 0.2)
+    y0 = np.stack([Ca0, Cb0, np.zeros(B)], axis=1)
+    return dict(problem="reactor", t_span=(0.0, float(t_end)), y0=y0, params=np.stack([k, Ca0, Cb0], axis=1),
+                t_eval=np.linspace(0.0, t_end, n_t_eval),
+                options=dict(rtol=1e-6, atol=1e-7, first_step=1e-8, max_newton_ite=20, max_bad_ite=3, min_factor=0.2,
+                             max_factor=10, scale_residuals=False, scale_newton_norm=False, scale_error=False,
+                             mass_matrix="problem", var_index=np.array([0, 1, 1], dtype=np.int32)))
+
+
 ENSEMBLES = {"pendulum": pendulum_ensemble, "robertson": robertson_ensemble,
              "transistor": transistor_ensemble, "npendulum": npendulum_ensemble}

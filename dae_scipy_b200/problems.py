@@ -29,6 +29,12 @@ class Problem:
     t_span: tuple                # the reference script's t_span
     per_system_mass: bool = False  # mass matrix built from each system's parameters
     doc: str = ""
+    # user problems (dae_scipy_b200/plugin.py): own diag(0/1) mass matrix, whether an analytic Jacobian functor
+    # exists, and the plugin library / generated functor header that hold them
+    mass_diag: tuple | None = None
+    has_jac: bool = True
+    lib_path: str | None = None
+    header_path: str | None = None
 
     @property
     def n_params(self):
@@ -39,6 +45,8 @@ class Problem:
 
     def mass(self, params=None, n=None):
         """The reference's mass matrix for this problem (one system)."""
+        if self.mass_diag is not None:
+            return np.diag(np.asarray(self.mass_diag, dtype=np.float64))
         if self.name.startswith("pendulum"):
             M = np.eye(5)
             M[-1, -1] = 0

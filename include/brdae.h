@@ -42,7 +42,13 @@ enum {
     BRDAE_ROBERTSON_ODE = 6, /* tests/robertson.py:69-77 (ODE form), params (k1,k2,k3)   n=3 */
     BRDAE_JAY = 7,       /* tests/jay_dae.py:22-68, params (nonlinear flag)             n=5 */
     BRDAE_POLYDAE2 = 8,  /* tests/validation_dense_output.py:23-59 (p=2), params a4..a0 n=2 */
-    BRDAE_LINEAR7 = 9    /* tests/linear_ODE_with_mass_matrix.py:32-39, params c[7]     n=7 */
+    BRDAE_LINEAR7 = 9,   /* tests/linear_ODE_with_mass_matrix.py:32-39, params c[7]     n=7 */
+    /* The one problem of a PLUGIN build of this library: the `fun` / `jac` closures a user of the reference
+     * hands to solve_ivp (radauDAE.py:263-266, 464-513), written as a device functor (n <= BRDAE_NMAX_SMALL)
+     * and compiled into a copy of the library (csrc/k1_user.cu; dae_scipy_b200/plugin.py shows the recipe).
+     * Its name, n and n_params are reported by brdae_problem_lookup(); the stock library answers
+     * BRDAE_ERR_UNKNOWN_PROBLEM for it. */
+    BRDAE_USER = 100
 };
 
 /* per-system status, same meaning as OdeResult.status (radauDAE.py:986-989, 1087-1091) */

@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure) — generate tests/golden/*.npz by running THE REFERENCE ITSELF.
 
 Run in the build container, where /root/reference is mounted:
-    python oracle/gen_golden.py
+    python oracle/gen_golden.py [name-prefix ...]
 It imports `scipyDAE.radauDAE.RadauDAE` from /root/reference and drives it with
 `scipy.integrate.solve_ivp(method=RadauDAE)` exactly like the reference scripts do
 (tests/pendulum.py:266-280, tests/robertson.py:105-116, tests/transistor_amplifier.py:78-88,
@@ -107,7 +107,12 @@ def run_reference_with_counters(ens, over=None):
     return dict(y=y, status=status, n_eval=n_eval, counters=counters, y_final=y_final, t_final=t_final)
 
 
+ONLY = tuple(sys.argv[1:])       # optional name prefixes: regenerate just those fixtures
+
+
 def save(name, ens, over=None):
+    if ONLY and not name.startswith(ONLY):
+        return
     out = run_reference_with_counters(ens, over)
     opts = dict(ens["options"])
     opts.update(over or {})
@@ -144,6 +149,8 @@ def pendulum_events():
 
 def save_events(name, ens):
     """scipy.integrate.solve_ivp(method=RadauDAE, events=...) of the reference, system by system."""
+    if ONLY and not name.startswith(ONLY):
+        return
     from scipy.integrate import solve_ivp
     opts = dict(ens["options"])
     mm, vi = opts.pop("mass_matrix"), opts.pop("var_index")
@@ -265,6 +272,10 @@ def main():
     save("fd_pendulum2", E.pendulum_ensemble(8, t_end=1.0, index=2), dict(jac=None))
     save("fd_robertson", E.robertson_ensemble(8, t_end=1e3), dict(jac=None))
     save("fd_transistor", E.transistor_ensemble(4, t_end=0.05), dict(jac=None))
+    # --- a user problem (plugin path): the batch reactor of the reference's tests/reactor.py with the script's
+    #     options, analytic Jacobian and the script's own jac=None
+    save("user_reactor", E.reactor_ensemble(8))
+    save("user_reactor_fd", E.reactor_ensemble(8), dict(jac=None))
     # --- events (scipy's solve_ivp driving the reference solver)
     save_events("events_pendulum3", E.pendulum_ensemble(6, t_end=3.0, n_t_eval=31))
     # --- n-pendulum chains (dense analytic Jacobian handed to the reference)

@@ -124,6 +124,25 @@ def robertson_ode(k1=0.04, k2=1e4, k3=3e7):
 ROBERTSON_Y0 = np.array([1., 0., 0.])
 
 
+# ------------------------------------------------------------------------- batch reactor
+def reactor(k=1.47, Ca0=0.0209, Cb0=0.0209 / 3):
+    """Index-1 batch-reactor DAE of the reference's issue reproduction, tests/reactor.py:74-106 (Cc0 = 0):
+    Ca' = -k Ca Cb, 0 = Cb - (Cb0 - (Ca0 - Ca)), 0 = Cc - (Ca0 - Ca).  The script has no Jacobian (jac=None);
+    the analytic one here is for the like-for-like runs."""
+    mass = np.diag([1., 0., 0.])
+
+    def fun(t, y):
+        return np.array([-k * y[0] * y[1],
+                         y[1] - (Cb0 - (Ca0 - y[0])),
+                         y[2] - (Ca0 - y[0])])
+
+    def jac(t, y):
+        return np.array([[-k * y[1], -k * y[0], 0.],
+                         [-1., 1., 0.],
+                         [1., 0., 1.]])
+    return fun, jac, mass, np.array([0, 1, 1])
+
+
 # ------------------------------------------------------------------------- Jay 1995
 def jay(nonlinear=1.0):
     """Index-3 DAE of Jay 1995, jay_dae.py:22-68 (y1, y2, z1, z2, lambda).  The reference has no
@@ -371,4 +390,6 @@ def build(problem, params=(), n=None):
         return polydae2(*params)
     if problem == "linear7":
         return linear7(*params)
+    if problem == "reactor":
+        return reactor(*params)
     raise ValueError(problem)

@@ -22,9 +22,9 @@ PARITY_FACTOR = 10.0
 
 
 def golden_names():
-    """Trajectory fixtures (the events fixture has its own layout and its own test)."""
+    """Trajectory fixtures of the stock problems (the events and user-problem fixtures have their own tests)."""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("events_"))
+                  if not os.path.basename(p).startswith(("events_", "user_")))       # user_*: tests/test_user_problem.py
 
 
 def load_golden(name):
@@ -102,19 +102,35 @@ def run_numpy_oracle(ens, **over):
 
 
 # ------------------------------------------------------------------ kernel source on the CPU
-_sim = None
+_sims = {}
+
+
+def _host_sim(problem):
+    """The harness library: the stock one, or -- for a user problem of dae_scipy_b200/plugin.py -- the same harness
+    compiled (g++, next to the plugin library) with that problem's generated functor header."""
+    import subprocess
+    from dae_scipy_b200 import _abi
+    src_dir = os.path.join(ROOT, "tests", "host_sim")
+    path = os.path.join(src_dir, "libk1_host_sim.so")
+    if problem.header_path:
+        path = os.path.join(os.path.dirname(problem.header_path), "libk1_host_sim_user.so")
+        if not os.path.exists(path):
+            subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                            "-mfma", "-x", "c++", f'-DBRDAE_USER_HEADER="{problem.header_path}"',
+                            os.path.join(src_dir, "k1_host_sim.cpp"), "-o", path], check=True)
+    if path not in _sims:
+        sim = C.CDLL(path)
+        sim.sim_solve.restype = C.c_int
+        sim.sim_solve.argtypes = [C.POINTER(_abi.BrdaeBatch), C.POINTER(_abi.BrdaeOptions)]
+        _sims[path] = sim
+    return _sims[path]
 
 
 def run_kernel_source_on_cpu(ens, dense_cap=0, **over):
     """tests/host_sim: the K1 kernel SOURCE compiled for the host, one lane.  With dense_cap > 0 the per-step
     record is requested too and returned as out["sol"] (a BatchedOdeSolution)."""
-    global _sim
     import dae_scipy_b200 as br
-    from dae_scipy_b200 import _abi
-    if _sim is None:
-        _sim = C.CDLL(os.path.join(ROOT, "tests", "host_sim", "libk1_host_sim.so"))
-        _sim.sim_solve.restype = C.c_int
-        _sim.sim_solve.argtypes = [C.POINTER(_abi.BrdaeBatch), C.POINTER(_abi.BrdaeOptions)]
+    _sim = _host_sim(br.get_problem(ens["problem"]))
     opts = dict(ens["options"])
     opts.update(over)
     y0 = np.ascontiguousarray(ens["y0"], dtype=np.float64)

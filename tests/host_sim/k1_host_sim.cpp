@@ -12,6 +12,17 @@
 
 #include "../../dae_scipy_b200/csrc/host_args.hpp"
 #include "../../dae_scipy_b200/csrc/radau_k1.cuh"
+#ifdef BRDAE_USER_HEADER        // a user problem (dae_scipy_b200/plugin.py): the same generated functor header as the plugin build
+#include BRDAE_USER_HEADER
+namespace brdae {
+const ProblemInfo *user_problem_info() {
+    static const ProblemInfo pi{UserProblem::name(), BRDAE_USER, UserProblem::N, UserProblem::NP};
+    return &pi;
+}
+}
+#else
+namespace brdae { const ProblemInfo *user_problem_info() { return nullptr; } }
+#endif
 
 using namespace brdae;
 
@@ -57,6 +68,9 @@ extern "C" int sim_solve(const brdae_batch *b, const brdae_options *o) {
     case BRDAE_JAY: run_mass<Jay>(dense, a); break;
     case BRDAE_POLYDAE2: run_mass<PolyDAE2>(dense, a); break;
     case BRDAE_LINEAR7: run_mass<Linear7>(dense, a); break;
+#ifdef BRDAE_USER_HEADER
+    case BRDAE_USER: run_mass<UserProblem>(dense, a); break;
+#endif
     default: return BRDAE_ERR_UNSUPPORTED;
     }
     return BRDAE_OK;

@@ -300,3 +300,49 @@ def test_full_size_robertson_ensemble_properties():
     k = 1024
     ref = run_c_oracle(dict(ens, y0=ens["y0"][:k], params=ens["params"][:k]))
     assert np.array_equal(y[:k].cpu().numpy(), ref["y"])
+
+
+# ---------------------------------------------------------------- (4) user problems: the plugin build of the library
+def test_gpu_user_problem_plugin_against_kernel_source_and_reference_fixture():
+    """dae_scipy_b200/plugin.py: the reference's batch-reactor script (tests/reactor.py) as a user functor.  The
+    plugin library on the GPU is bit-identical to the same kernel source run on the CPU and reproduces the
+    reference's own run (fixtures from oracle/gen_golden.py): tolerance and identical step counts."""
+    from _util import run_kernel_source_on_cpu
+    prob = E.reactor_problem()
+    for name in ("user_reactor", "user_reactor_fd"):
+        ens, ref = load_golden(name)
+        out = run_gpu(ens)
+        assert_bit_identical(out, run_kernel_source_on_cpu(ens), name + ": GPU plugin vs kernel source on the CPU")
+        o = ens["options"]
+        assert scaled_error(out["y"], ref["y"], o["rtol"], o["atol"]) <= PARITY_FACTOR
+        assert count_agreement(out["counters"], ref["counters"]) == 1.0 and np.array_equal(out["status"], ref["status"])
+    # a real ensemble: refills, ragged last warp, the host-buffer entry and a dense mass matrix through the same plugin
+    ens = E.reactor_ensemble(50001)
+    out = run_gpu(ens)
+    assert (out["status"] == 0).all()
+    first = dict(ens, y0=ens["y0"][:256], params=ens["params"][:256])
+    sim = run_kernel_source_on_cpu(first)
+    assert np.array_equal(out["y"][:256], sim["y"]) and np.array_equal(out["counters"][:256], sim["counters"])
+    assert_bit_identical(run_gpu(ens, host_api=True), out, "plugin: brdae_solve_host_rows vs brdae_solve")
+    Ca, Cb, Cc = out["y"][:, 0], out["y"][:, 1], out["y"][:, 2]           # the two algebraic constraints of the DAE
+    Ca0, Cb0 = ens["params"][:, 1:2], ens["params"][:, 2:3]
+    assert np.abs(Cb - (Cb0 - (Ca0 - Ca))).max() < 1e-9 and np.abs(Cc - (Ca0 - Ca)).max() < 1e-9
+    dense = run_gpu(first, mass_matrix=1.0 * prob.mass() + 0.0)           # same matrix, dense-mass instantiation
+    assert scaled_error(dense["y"], sim["y"], 1e-6, 1e-7) <= PARITY_FACTOR
+
+
+def test_gpu_user_problem_stiff_forced_oscillator_against_numpy_oracle():
+    """A user functor with a time-dependent right-hand side and a libm call (device sin differs from glibc by <= 2 ulp:
+    tolerance, not bits) against the reference-equivalent numpy oracle driven by the closure form of the problem."""
+    from test_user_problem import vdp_ensemble, vdp_numpy_oracle, vdp_problem
+    vdp_problem()
+    ens = vdp_ensemble(8)
+    out, ref = run_gpu(ens), vdp_numpy_oracle(ens)
+    assert (out["status"] == 0).all()
+    assert scaled_error(out["y"], ref["y"], 1e-6, 1e-8) <= PARITY_FACTOR
+    assert count_agreement(out["counters"], ref["counters"]) >= 0.75
+    tot, tot_ref = out["counters"].sum(axis=0), ref["counters"].sum(axis=0)
+    assert np.all(np.abs(tot - tot_ref) <= 0.02 * np.maximum(tot_ref, 50))
+    fd = run_gpu(ens, jac=None)                                            # the reference's default Jacobian mode
+    ref_fd = vdp_numpy_oracle(ens, jac=False)
+    assert scaled_error(fd["y"], ref_fd["y"], 1e-6, 1e-8) <= PARITY_FACTOR
