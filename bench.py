@@ -109,7 +109,14 @@ def _cpu_worker(args):
     opts.pop("mass_matrix", None)
     var_index = opts.pop("var_index", None)
     done = 0
-    with contextlib.redirect_stdout(io.StringIO()):
+    # one BLAS thread per process: the pool already uses every core, and the LAPACK calls of the chain problems
+    # (N = 100..500) would otherwise start a full OpenBLAS thread team in each forked worker (measured: 50x slower)
+    try:
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=1)
+    except Exception:
+        limit = contextlib.nullcontext()
+    with limit, contextlib.redirect_stdout(io.StringIO()):
         for i in range(y0s.shape[0]):
             fun, jac, mass, vi = prob.build(problem, params[i], y0s.shape[1])
             r = orc.solve(fun, t_span, y0s[i], jac=jac, mass_matrix=mass,

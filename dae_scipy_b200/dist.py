@@ -72,3 +72,36 @@ def status_histogram(status):
     import torch
     s = status if isinstance(status, torch.Tensor) else torch.as_tensor(np.asarray(status))
     return torch.stack([(s == 0).sum(), (s == -1).sum(), (s == -2).sum(), (s == 2).sum()]).to(torch.int64)
+
+
+def solve_ivp_sharded(problem, t_span, y0, params=None, *, dist=None, gather_dst=None, device=None, **kwargs):
+    """The whole ensemble (`y0` [B, n], `params` [B, p]: host arrays every rank holds, or can slice) integrated by all
+    ranks of the default process group, one GPU per process: this rank solves the contiguous shard
+    `shard_bounds(B, world, rank)` with `solve_ivp_batched` (no data-path collective), the summed counters and the
+    status histogram are all-reduced, and with `gather_dst=r` the per-system results are gathered onto rank r in
+    ensemble order (NCCL over NVLink with the nccl backend).
+
+    Returns a dict: `local` (this rank's BatchedOdeResult), `shard` (lo, hi), `counters_sum` [9] and
+    `status_histogram` [4] over the WHOLE ensemble (on every rank), and on `gather_dst` also `y` [B, n, T],
+    `status`, `n_eval`, `t_final`, `y_final` [B, n], `counters` [B, 9] as device tensors (None elsewhere)."""
+    import torch
+    from .api import solve_ivp_batched
+    if dist is None:
+        import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    world, rank = (dist.get_world_size(), dist.get_rank()) if multi else (1, 0)
+    B = int(y0.shape[0])
+    lo, hi = shard_bounds(B, world, rank)
+    res = solve_ivp_batched(problem, t_span, y0[lo:hi], None if params is None else params[lo:hi], device=device, **kwargs)
+    dev = res.status.device
+    csum, hist = reduce_statistics(res.counters.sum(dim=1, dtype=torch.int64), status_histogram(res.status),
+                                   dist if multi else None, dev)
+    out = {"local": res, "shard": (lo, hi), "counters_sum": csum, "status_histogram": hist}
+    if gather_dst is not None:
+        local = {"y_eval": res._y_eval, "status": res.status, "n_eval": res.n_eval, "t_final": res.t_final,
+                 "y_final": res.y_final.t().contiguous(), "counters": res.counters}
+        g = gather_results(local, B, dist, dst=gather_dst) if multi else local
+        if g is not None:
+            out.update(y=g["y_eval"].permute(2, 1, 0), status=g["status"], n_eval=g["n_eval"], t_final=g["t_final"],
+                       y_final=g["y_final"].t(), counters=g["counters"].t())
+    return out

@@ -346,3 +346,20 @@ def test_gpu_user_problem_stiff_forced_oscillator_against_numpy_oracle():
     fd = run_gpu(ens, jac=None)                                            # the reference's default Jacobian mode
     ref_fd = vdp_numpy_oracle(ens, jac=False)
     assert scaled_error(fd["y"], ref_fd["y"], 1e-6, 1e-8) <= PARITY_FACTOR
+
+
+# ---------------------------------------------------------------- (5) the ensemble sharded over the GPUs of the box
+def test_gpu_two_rank_nccl_sharded_solve():
+    """dist.solve_ivp_sharded under torchrun with two ranks (nccl): needs two GPUs, skipped on a one-GPU box (the
+    host-side logic of the same path runs in tests/test_host_logic.py with gloo)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "_nccl_worker.py")],
+                       capture_output=True, text=True, timeout=600, cwd=os.path.dirname(here))
+    assert r.returncode == 0 and "rank0 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
