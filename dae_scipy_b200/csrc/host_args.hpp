@@ -45,6 +45,13 @@ inline int validate(const brdae_batch *b, const brdae_options *o) {
     }
     if (!b->atol) return BRDAE_ERR_BAD_ARGUMENT;
     if (b->dense_cap < 0 || (b->dense_cap > 0 && !(b->dense_t && b->dense_y && b->dense_q))) return BRDAE_ERR_BAD_ARGUMENT;
+    if (b->n_events < 0 || b->n_events > BRDAE_MAX_EVENTS) return BRDAE_ERR_BAD_ARGUMENT;
+    if (b->n_events > 0) {
+        if (b->problem == BRDAE_NPENDULUM) return BRDAE_ERR_UNSUPPORTED;      // thread-per-system kernels only
+        if (b->event_cap < 1 || !b->event_coef || !b->event_level || !b->event_direction || !b->event_terminal) return BRDAE_ERR_BAD_ARGUMENT;
+        if (b->n_systems > 0 && (!b->event_count || !b->event_t)) return BRDAE_ERR_BAD_ARGUMENT;
+        for (int e = 0; e < b->n_events; ++e) if (b->event_terminal[e] < 0) return BRDAE_ERR_BAD_ARGUMENT;
+    }
     if (!(b->rtol > 0) || !(o->max_step > 0) || o->max_newton_ite < 1) return BRDAE_ERR_BAD_ARGUMENT;
     for (int c = 0; c < b->n; ++c) {
         if (!(b->atol[c] >= 0)) return BRDAE_ERR_BAD_ARGUMENT;
@@ -68,6 +75,12 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
     a.chunk_done = nullptr; a.chunk_flags = nullptr; a.chunk_size = 0; a.input_ready = nullptr;
     a.dense_t = b->dense_t; a.dense_y = b->dense_y; a.dense_q = b->dense_q;
     a.dense_cap = (b->dense_t && b->dense_y && b->dense_q) ? b->dense_cap : 0;
+    a.n_events = b->n_events; a.ev_cap = b->event_cap;
+    a.ev_count = b->event_count; a.ev_t = b->event_t; a.ev_y = b->event_y;
+    for (int e = 0; e < b->n_events; ++e) {
+        a.ev_dir[e] = b->event_direction[e]; a.ev_term[e] = b->event_terminal[e]; a.ev_level[e] = b->event_level[e];
+        for (int c = 0; c < b->n && c < BRDAE_NMAX_SMALL; ++c) a.ev_coef[e][c] = b->event_coef[e * b->n + c];
+    }
     a.work_counter = static_cast<unsigned long long *>(workspace);
     a.scratch = reinterpret_cast<double *>(static_cast<char *>(workspace) + kCounterBytes);
     a.t0 = b->t0; a.tb = b->t_bound;

@@ -7,7 +7,7 @@
 
 namespace brdae {
 
-template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE, bool COLD_GLOBAL, bool FD>
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE, bool COLD_GLOBAL, bool FD, bool EVENTS>
 int k1_launch_mode(const SolveArgs &a_in, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only, int newton_reps) {
     // Newton passes per cycle: a scheduling knob tuned per problem family (results do not depend on it);
     // BRDAE_NEWTON_REPS overrides it for experiments
@@ -22,7 +22,7 @@ int k1_launch_mode(const SolveArgs &a_in, int sms, cudaStream_t s, LaunchGeom *g
     if (grid < 1) grid = 1;
     if (g) { g->grid = grid; g->block = BLOCK; g->smem = smem; g->scratch_bytes = (size_t)grid * BLOCK * L::GLOBAL_SLOTS * sizeof(double); }
     if (geom_only) return BRDAE_OK;
-    auto kern = k1_kernel<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, FD>;
+    auto kern = k1_kernel<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, FD, EVENTS>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BRDAE_ERR_CUDA;
     kern<<<grid, BLOCK, smem, s>>>(a);
     return cudaPeekAtLastError() == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;
@@ -31,8 +31,13 @@ int k1_launch_mode(const SolveArgs &a_in, int sms, cudaStream_t s, LaunchGeom *g
 // analytic / constant Jacobian, or the finite-difference instantiation when the batch asks for it
 template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE = false, bool COLD_GLOBAL = false>
 int k1_launch(const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only, int newton_reps = 3) {
-    if (a.jac_fd) return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, true>(a, sms, s, g, geom_only, newton_reps);
-    return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, false>(a, sms, s, g, geom_only, newton_reps);
+    // device-side events (brdae_batch.n_events > 0) are their own instantiations: the event code costs the plain kernels nothing
+    if (a.n_events > 0) {
+        if (a.jac_fd) return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, true, true>(a, sms, s, g, geom_only, newton_reps);
+        return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, false, true>(a, sms, s, g, geom_only, newton_reps);
+    }
+    if (a.jac_fd) return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, true, false>(a, sms, s, g, geom_only, newton_reps);
+    return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, false, false>(a, sms, s, g, geom_only, newton_reps);
 }
 
 }  // namespace brdae

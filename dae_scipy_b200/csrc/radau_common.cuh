@@ -93,6 +93,12 @@ struct SolveArgs {
     const volatile int32_t *input_ready;
     double *dense_t, *dense_y, *dense_q;   // optional per-step record (brdae.h), dense_cap steps per system
     int32_t dense_cap;
+    // optional device-side events (brdae.h): g_e(y) = ev_coef[e] . y - ev_level[e]
+    int32_t n_events, ev_cap;
+    int32_t ev_dir[BRDAE_MAX_EVENTS], ev_term[BRDAE_MAX_EVENTS];
+    double ev_level[BRDAE_MAX_EVENTS], ev_coef[BRDAE_MAX_EVENTS][BRDAE_NMAX_SMALL];
+    int32_t *ev_count;
+    double *ev_t, *ev_y;
     unsigned long long *work_counter;
     double *scratch;  // per-CTA global scratch (K2)
     double t0, tb, dir, rtol;

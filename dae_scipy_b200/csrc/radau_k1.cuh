@@ -45,6 +45,7 @@ namespace brdae {
 enum : int { ST_IDLE = 0, ST_SETUP, ST_FACTOR, ST_NEWTON, ST_ERREST, ST_JACFD, ST_EXIT };
 // what a lane entering SETUP still has to do
 enum : int { SETUP_STEP = 0, SETUP_ATTEMPT = 1, SETUP_GUESS = 2 };
+constexpr int RUNNING = 0x7fff;     // finish_status of a lane whose system goes on (not a BRDAE_STATUS_* value)
 
 // lane-strided shared-memory slots of one lane
 template <int STRIDE>
@@ -400,7 +401,7 @@ inline long long fetch_system(bool want, unsigned long long *counter) { return w
 // memory: the check "is the next output point inside this step" runs after every accepted step, and a
 // global load there put an L2 round trip on the critical path of every ERREST pass).
 // `gj` addresses this lane's global-memory slots of the finite-difference mode (unused otherwise).
-template <class Prob, class Mass, bool CTA_WIDE, bool COLD_GLOBAL, bool FD, class S, class SC, class SG>
+template <class Prob, class Mass, bool CTA_WIDE, bool COLD_GLOBAL, bool FD, bool EVENTS, class S, class SC, class SG>
 BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const SG &gj, const double *t_eval) {
     constexpr int N = Prob::N;
     using L = K1Layout<Prob, COLD_GLOBAL, FD>;
@@ -436,7 +437,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
     const double dir = a.dir;
 
     for (;;) {
-        int finish_status = 1;  // 1 = still running
+        int finish_status = RUNNING;
         // ================= refill idle lanes =================================================
         if (warp_any(state == ST_IDLE)) {
             const long long got = fetch_system(state == ST_IDLE, a.work_counter);
@@ -468,6 +469,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     hist_state = false; current_jac = true; lu_valid = false; have_sol = false;
                     inv_h_lu = 1.0; ei = 0; nsteps = 0;
                     state = ST_SETUP; setup_kind = SETUP_STEP;
+                    if (EVENTS)
+                        for (int e = 0; e < a.n_events; ++e) a.ev_count[e * a.B + idx] = 0;
                     if (FD && !a.has_jac_const) {                        // J0 = num_jac(t0, y0, f0) :475-481
 #pragma unroll
                         for (int c = 0; c < N; ++c) gj(L::G_FAC + c) = NJ_FACTOR0;
@@ -577,6 +580,68 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     }
                     t_sol_old = t; inv_h_sol = inv_h; have_sol = true;
                     t = t_new;
+                    bool ev_stop = false;
+                    double x_cut = 1.0;
+                    if (EVENTS) {
+                        // scipy solve_ivp(events=...) on this step (ivp.py find_active_events / handle_events, which
+                        // radauDAE.py:1110-1129 wraps): an event function that changed sign in its direction is located on
+                        // the step's cubic -- for g linear in y the scalar cubic g_old + a1 x + a2 x^2 + a3 x^3 -- by
+                        // bisection to the last bit; occurrences are counted and recorded per event, and the earliest root
+                        // whose event reached its terminal count ends the system there (later roots of the step are dropped)
+                        double xr[BRDAE_MAX_EVENTS];
+                        bool act[BRDAE_MAX_EVENTS];
+                        int stop_e = -1;
+                        double x_stop = 2.0;
+#pragma unroll 1
+                        for (int e = 0; e < a.n_events; ++e) {
+                            double g0 = -a.ev_level[e], g1 = -a.ev_level[e], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                            for (int c = 0; c < N; ++c) {
+                                const double ce = a.ev_coef[e][c];
+                                g0 = fma(ce, cd(L::C_YOLD + c), g0); g1 = fma(ce, y[c], g1);
+                                a1 = fma(ce, Q[c][0], a1); a2 = fma(ce, Q[c][1], a2); a3 = fma(ce, Q[c][2], a3);
+                            }
+                            const bool up = g0 <= 0 && g1 >= 0, down = g0 >= 0 && g1 <= 0;
+                            act[e] = a.ev_dir[e] > 0 ? up : (a.ev_dir[e] < 0 ? down : (up || down));
+                            xr[e] = 2.0;
+                            if (act[e]) {
+                                double lo = 0.0, hi = 1.0, x = 0.0;
+                                if (g0 == 0) x = 0.0;
+                                else if (g1 == 0) x = 1.0;
+                                else {
+                                    const bool pos0 = g0 > 0;
+                                    for (int it = 0; it < 64 && lo < hi; ++it) {
+                                        const double mid = 0.5 * (lo + hi);
+                                        if (!(mid > lo && mid < hi)) break;
+                                        const double pm = fma(mid, fma(mid, fma(mid, a3, a2), a1), g0);
+                                        if ((pm > 0) == pos0 && pm != 0) lo = mid; else hi = mid;
+                                    }
+                                    x = hi;
+                                }
+                                xr[e] = x;
+                                const int cnt = a.ev_count[e * a.B + idx] + 1;
+                                if (a.ev_term[e] > 0 && cnt >= a.ev_term[e] && x < x_stop) { x_stop = x; stop_e = e; }
+                            }
+                        }
+#pragma unroll 1
+                        for (int e = 0; e < a.n_events; ++e) {
+                            if (!act[e]) continue;
+                            if (stop_e >= 0 && !(xr[e] < x_stop || (xr[e] == x_stop && e <= stop_e))) continue;
+                            const int k_ev = a.ev_count[e * a.B + idx];
+                            a.ev_count[e * a.B + idx] = k_ev + 1;
+                            if (k_ev < a.ev_cap) {
+                                const double x = xr[e], x2 = x * x, x3 = x2 * x;
+                                a.ev_t[((int64_t)e * a.ev_cap + k_ev) * a.B + idx] = fma(x, h, t_sol_old);
+                                if (a.ev_y)
+#pragma unroll
+                                    for (int c = 0; c < N; ++c)
+                                        a.ev_y[(((int64_t)e * a.ev_cap + k_ev) * N + c) * a.B + idx] =
+                                            fma(Q[c][2], x3, fma(Q[c][1], x2, Q[c][0] * x)) + cd(L::C_YOLD + c);
+                            }
+                        }
+                        ev_stop = stop_e >= 0;
+                        x_cut = x_stop;
+                    }
                     if (a.dense_cap > 0 && nsteps <= a.dense_cap) {      // OdeSolution record of this step
                         const int64_t ks = nsteps - 1;         // one accepted step per step() call
                         a.dense_t[ks * a.B + idx] = t;
@@ -586,6 +651,12 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 #pragma unroll
                             for (int j = 0; j < 3; ++j) a.dense_q[((ks * N + c) * 3 + j) * a.B + idx] = Q[c][j];
                         }
+                    }
+                    if (EVENTS && ev_stop) {     // status 1: the result ends at the event (ivp.py: t = roots[-1]; y = sol(t));
+                        const double x = x_cut, x2 = x * x, x3 = x2 * x;     // the step record above keeps the whole step
+                        t = fma(x, h, t_sol_old);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) y[c] = fma(Q[c][2], x3, fma(Q[c][1], x2, Q[c][0] * x)) + cd(L::C_YOLD + c);
                     }
                     // driver: t_eval points inside (t_old, t]  (searchsorted side='right', ivp.py:711-729)
                     while (ei < a.T) {
@@ -602,7 +673,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         }
                         ++ei;
                     }
-                    if (dir * (t - a.tb) >= 0) finish_status = BRDAE_STATUS_FINISHED;
+                    if (EVENTS && ev_stop) finish_status = BRDAE_STATUS_EVENT;
+                    else if (dir * (t - a.tb) >= 0) finish_status = BRDAE_STATUS_FINISHED;
                     else { state = (FD && recompute) ? ST_JACFD : ST_SETUP; setup_kind = SETUP_STEP; }
                 }
             }
@@ -621,8 +693,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
             warp_converge();
         }
         // ================= cheap set-up: prologue :516-562, attempt :564-588, guess :580-583 ===
-        if (warp_any(state == ST_SETUP && finish_status == 1)) {
-            if (state == ST_SETUP && finish_status == 1) {
+        if (warp_any(state == ST_SETUP && finish_status == RUNNING)) {
+            if (state == ST_SETUP && finish_status == RUNNING) {
                 if (setup_kind == SETUP_STEP) {
                     ++nsteps;
                     if (a.nmax_step > 0 && nsteps > a.nmax_step) finish_status = BRDAE_STATUS_NMAX_STEP;
@@ -637,7 +709,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         rejected = false;
                     }
                 }
-                if (finish_status == 1 && setup_kind <= SETUP_ATTEMPT) {
+                if (finish_status == RUNNING && setup_kind <= SETUP_ATTEMPT) {
                     if (h_abs < min_step) finish_status = BRDAE_STATUS_TOO_SMALL_STEP;
                     else {
                         h = h_abs * dir;
@@ -655,7 +727,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         mr = MU_REAL * inv_h; mcr = MU_CR * inv_h; mci = MU_CI * inv_h;
                     }
                 }
-                if (finish_status == 1) {
+                if (finish_status == RUNNING) {
                     // W = TI Z0, Z0 from the previous step's cubic evaluated beyond its interval
                     if (!have_sol || !a.extrapolate) {
 #pragma unroll
@@ -693,8 +765,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
             }
         }
         // ================= retire a finished / failed system ==================================
-        if (warp_any(finish_status != 1)) {
-            if (finish_status != 1) {
+        if (warp_any(finish_status != RUNNING)) {
+            if (finish_status != RUNNING) {
                 const double qnan = NAN;
                 for (int e = ei; e < a.T; ++e)
 #pragma unroll
@@ -882,7 +954,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 }
 
 #if defined(__CUDACC__)
-template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE, bool COLD_GLOBAL, bool FD>
+template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE, bool COLD_GLOBAL, bool FD, bool EVENTS = false>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k1_kernel(const __grid_constant__ SolveArgs a) {
     extern __shared__ double k1_smem[];
     using L = K1Layout<Prob, COLD_GLOBAL, FD>;
@@ -895,7 +967,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k1_kernel(const __grid_cons
         for (int i = threadIdx.x; i < a.T; i += BLOCK) t_eval_sh[i] = a.t_eval[i];
         __syncthreads();
     }
-    k1_lane_loop<Prob, Mass, CTA_WIDE, COLD_GLOBAL, FD>(a, sm, cd, gj, staged ? t_eval_sh : a.t_eval);
+    k1_lane_loop<Prob, Mass, CTA_WIDE, COLD_GLOBAL, FD, EVENTS>(a, sm, cd, gj, staged ? t_eval_sh : a.t_eval);
 }
 #endif
 

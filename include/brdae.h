@@ -27,8 +27,9 @@
 extern "C" {
 #endif
 
-#define BRDAE_ABI_VERSION 2
+#define BRDAE_ABI_VERSION 3
 #define BRDAE_NMAX_SMALL 8 /* largest state size of the thread-per-system kernels */
+#define BRDAE_MAX_EVENTS 4 /* event functions located on the device per call */
 
 /* problems (device functors); ids are stable */
 enum {
@@ -54,6 +55,7 @@ enum {
 /* per-system status, same meaning as OdeResult.status (radauDAE.py:986-989, 1087-1091) */
 enum {
     BRDAE_STATUS_FINISHED = 0,
+    BRDAE_STATUS_EVENT = 1,           /* "A termination event occurred." (scipy ivp.py:15-16; radauDAE.py:1110-1129) */
     BRDAE_STATUS_TOO_SMALL_STEP = -1, /* OdeSolver.TOO_SMALL_STEP, radauDAE.py:565-568 */
     BRDAE_STATUS_LU_FAILED = -2,      /* radauDAE.py:611-613 (never produced: see DESIGN.md) */
     BRDAE_STATUS_NMAX_STEP = 2        /* solve_ivp_custom nmax_step, radauDAE.py:1081-1084 */
@@ -133,6 +135,24 @@ typedef struct brdae_batch {
     double *dense_t;          /* [dev]  [K][B] */
     double *dense_y;          /* [dev]  [K][n][B] */
     double *dense_q;          /* [dev]  [K][n][3][B]: Q[c][j] of step k at ((k*n + c)*3 + j)*B + sys */
+    /* Optional EVENTS located on the device, with the semantics of solve_ivp(events=...) (scipy ivp.py
+     * prepare_events / find_active_events / handle_events, which radauDAE.py:1059-1129 wraps), for event
+     * functions that are linear in the state:  g_e(t, y) = sum_j event_coef[e][j] * y_j - event_level[e].
+     * After every accepted step an event whose g changed sign in the allowed direction (event_direction[e]:
+     * < 0 only + to -, > 0 only - to +, 0 both) is located on the step's cubic interpolant; its time and state are
+     * recorded (the first event_cap occurrences per event and system; event_count counts all of them) and, if
+     * event_terminal[e] = k > 0, the k-th occurrence ends that system there: status BRDAE_STATUS_EVENT,
+     * t_final / y_final = the event point, t_eval points beyond it are not produced.  n_events = 0 = off.
+     * Thread-per-system problems, brdae_solve only. */
+    int32_t n_events;         /* E <= BRDAE_MAX_EVENTS */
+    int32_t event_cap;        /* C */
+    const double *event_coef;        /* [host] [E][n] */
+    const double *event_level;       /* [host] [E] */
+    const int32_t *event_direction;  /* [host] [E] */
+    const int32_t *event_terminal;   /* [host] [E] */
+    int32_t *event_count;     /* [dev]  [E][B] */
+    double *event_t;          /* [dev]  [E][C][B]; entries at or beyond the count are not written */
+    double *event_y;          /* [dev]  [E][C][n][B], may be NULL */
 } brdae_batch;
 
 int brdae_abi_version(void);
