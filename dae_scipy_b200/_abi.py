@@ -17,7 +17,10 @@ COUNTER_NAMES = ("nfev", "njev", "nlu", "nstep", "naccpt", "nrejct", "nfailed", 
                  "nlusolve_errorest")
 NCOUNTERS = len(COUNTER_NAMES)
 
+ABI_VERSION = 3
+MAX_EVENTS = 4
 STATUS_FINISHED = 0
+STATUS_EVENT = 1
 STATUS_TOO_SMALL_STEP = -1
 STATUS_LU_FAILED = -2
 STATUS_NMAX_STEP = 2
@@ -25,6 +28,7 @@ STATUS_NMAX_STEP = 2
 # OdeResult.message texts (scipy ivp.py:13-14, base.py:130; radauDAE.py:986-989)
 MESSAGES = {
     STATUS_FINISHED: "The solver successfully reached the end of the integration interval.",
+    STATUS_EVENT: "A termination event occurred.",
     STATUS_TOO_SMALL_STEP: "Required step size is less than spacing between numbers.",
     STATUS_LU_FAILED: "LU decomposition failed",
     STATUS_NMAX_STEP: "Too many time steps have been performed",
@@ -56,7 +60,11 @@ class BrdaeBatch(C.Structure):
                 ("y_eval", C.c_void_p), ("n_eval", C.c_void_p), ("t_final", C.c_void_p),
                 ("y_final", C.c_void_p), ("status", C.c_void_p), ("counters", C.c_void_p),
                 ("dense_cap", C.c_int32), ("reserved0", C.c_int32),
-                ("dense_t", C.c_void_p), ("dense_y", C.c_void_p), ("dense_q", C.c_void_p)]
+                ("dense_t", C.c_void_p), ("dense_y", C.c_void_p), ("dense_q", C.c_void_p),
+                ("n_events", C.c_int32), ("event_cap", C.c_int32),
+                ("event_coef", C.c_void_p), ("event_level", C.c_void_p), ("event_direction", C.c_void_p),
+                ("event_terminal", C.c_void_p), ("event_count", C.c_void_p), ("event_t", C.c_void_p),
+                ("event_y", C.c_void_p)]
 
 
 # keyword -> (options field, default) : the RadauDAE constructor surface, radauDAE.py:263-278

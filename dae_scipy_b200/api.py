@@ -32,6 +32,45 @@ class RadauDAE:
     name = "RadauDAE"
 
 
+class LinearEvent:
+    """An event function that is linear in the state, g(t, y) = coef . y - level, with scipy's `terminal` / `direction`
+    attributes (solve_ivp(events=...), scipy ivp.py:25-60): such events are located ON THE DEVICE, inside the step that
+    crosses them, and a terminal one stops the integration of that system there.  `coef` is an [n] vector or the index
+    of one unknown; `terminal` may be True or the occurrence count that terminates (scipy >= 1.13).  It is also an
+    ordinary callable, so it works wherever a Python event function does."""
+
+    def __init__(self, coef, level=0.0, direction=0.0, terminal=False, n=None):
+        if np.ndim(coef) == 0:
+            if n is None:
+                raise ValueError("LinearEvent(index, ...) needs n, the number of unknowns.")
+            c = np.zeros(int(n))
+            c[int(coef)] = 1.0
+            coef = c
+        self.coef = np.ascontiguousarray(coef, dtype=np.float64)
+        self.level = float(level)
+        self.direction = float(direction)
+        self.terminal = terminal
+
+    def __call__(self, t, y):
+        return float(np.dot(self.coef, np.asarray(y)[:self.coef.size]) - self.level)
+
+
+def pack_linear_events(events, n):
+    """[LinearEvent] -> the arrays of brdae_batch (coef [E, n], level [E], direction [E], terminal count [E])."""
+    if len(events) > _abi.MAX_EVENTS:
+        raise ValueError(f"at most {_abi.MAX_EVENTS} events can be located on the device.")
+    for ev in events:
+        if ev.coef.shape != (n,):
+            raise ValueError(f"LinearEvent coefficients must have shape {(n,)}.")
+    coef = np.ascontiguousarray(np.stack([ev.coef for ev in events]))
+    level = np.array([ev.level for ev in events], dtype=np.float64)
+    direction = np.array([int(np.sign(ev.direction)) for ev in events], dtype=np.int32)
+    terminal = np.array([int(ev.terminal) if ev.terminal is not None else 0 for ev in events], dtype=np.int32)   # True -> 1
+    if np.any(terminal < 0):
+        raise ValueError("`terminal` must be a bool or a positive occurrence count.")
+    return coef, level, direction, terminal
+
+
 def warn_extraneous(extraneous):
     """scipy common.py:27-43 — same warning text."""
     if extraneous:
@@ -54,6 +93,7 @@ class HostBatch:
     mass: np.ndarray | None     # float64 [n, n] shared matrix, None = the problem's own (device functor)
     jac_const: np.ndarray | None
     options: _abi.BrdaeOptions
+    events: tuple | None = None    # device-side events: (coef [E, n], level [E], direction [E] int32, terminal [E] int32)
 
     def struct(self, ptr) -> _abi.BrdaeBatch:
         """Fill a brdae_batch; `ptr` maps field name -> address of the batch-sized buffers."""
@@ -74,6 +114,13 @@ class HostBatch:
                   "dense_t", "dense_y", "dense_q"):
             setattr(b, k, ptr.get(k))
         b.dense_cap = int(ptr.get("dense_cap") or 0)
+        if self.events is not None and ptr.get("event_cap"):
+            coef, level, direction, terminal = self.events
+            b.n_events, b.event_cap = coef.shape[0], int(ptr["event_cap"])
+            b.event_coef, b.event_level = coef.ctypes.data, level.ctypes.data
+            b.event_direction, b.event_terminal = direction.ctypes.data, terminal.ctypes.data
+            for k in ("event_count", "event_t", "event_y"):
+                setattr(b, k, ptr.get(k))
         return b
 
 
@@ -198,6 +245,7 @@ class BatchedOdeResult:
         self.sol = None                     # BatchedOdeSolution when dense_output=True
         self.t_events = self.y_events = None    # per system, per event (lists of arrays) when events were given
         self._event_cut = None                  # (terminated [B], t_stop [B], y_stop [B, n], ascending)
+        self.event_count = self.event_t = self.event_y = None   # device-side events: [E, B], [E, cap, B], [E, cap, n, B]
         self.t = t
         self._y_eval = y_eval_tnb           # [T, n, B] as written by the kernel (coalesced SoA)
         self.n_eval = n_eval
@@ -232,6 +280,13 @@ class BatchedOdeResult:
                "y_final": self.y_final.cpu().numpy(), "counters": self.counters.t().cpu().numpy()}
         for i, name in enumerate(_abi.COUNTER_NAMES):
             out[name] = out["counters"][:, i]
+        if self.event_count is not None:        # events located on the device: arrays, and scipy's per-system lists
+            cnt, et, ey = self.event_count.cpu().numpy(), self.event_t.cpu().numpy(), self.event_y.cpu().numpy()
+            out["event_count"], out["event_t"], out["event_y"] = cnt.T, et.transpose(2, 0, 1), ey.transpose(3, 0, 1, 2)
+            cap = et.shape[1]
+            k = np.minimum(cnt, cap)
+            out["t_events"] = [[out["event_t"][i, e, :k[e, i]] for e in range(cnt.shape[0])] for i in range(cnt.shape[1])]
+            out["y_events"] = [[out["event_y"][i, e, :k[e, i]] for e in range(cnt.shape[0])] for i in range(cnt.shape[1])]
         if self._event_cut is not None:         # a terminal event ends the reported result (scipy: status 1)
             term, t_stop, y_stop, asc = self._event_cut
             t = out["t"]
@@ -351,7 +406,8 @@ def _as_device_f64(x, device, torch):
 
 
 def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_eval=None,
-                      dense_output=False, max_dense_steps=None, events=None, device=None, stream=None, **options):
+                      dense_output=False, max_dense_steps=None, events=None, max_events=8, device=None, stream=None,
+                      **options):
     """Integrate B independent systems  M y' = f(t, y)  from t_span[0] to t_span[1] on one GPU.
 
     Parameters follow `scipy.integrate.solve_ivp(..., method=RadauDAE, **options)` of the
@@ -369,7 +425,12 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     var_index   : [n] integers 0..3 or None (all differential), as in the reference.
     jac         : 'analytic' (default: the problem's analytic Jacobian functor), a constant [n, n] matrix, or
                   None = finite differences as in the reference's default (scipy num_jac).
-    events      : callable or list of callables `event(t, y)` with optional `terminal` / `direction` attributes, as in
+    events      : `LinearEvent`s (g = coef . y - level) are located ON THE DEVICE inside the step that crosses them: no step
+                  record is needed, `result.event_count` [E, B], `result.event_t` [E, max_events, B] and `result.event_y`
+                  [E, max_events, n, B] stay on the device (`.numpy()` also builds scipy's `t_events` / `y_events` lists),
+                  and a terminal event STOPS the integration of that system (status 1, `t_final` / `y_final` = the event
+                  point).  Thread-per-system problems; the n-pendulum chain and arbitrary Python callables use the host path:
+                  callable or list of callables `event(t, y)` with optional `terminal` / `direction` attributes, as in
                   scipy's solve_ivp; located on the host on the per-step record (implies dense_output=True, so
                   `max_dense_steps` is required); `result.t_events[i][e]`, `result.y_events[i][e]`, and a terminal
                   event cuts that system's reported result (status 1), see `find_events`.
@@ -381,10 +442,15 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
 
     if not (method is RadauDAE or method == "RadauDAE"):
         raise ValueError("`method` must be RadauDAE.")
-    if events and not dense_output:
-        dense_output = True                    # events are located on the per-step record
     if callable(events):
         events = (events,)
+    device_events = None
+    if events and all(isinstance(ev, LinearEvent) for ev in events) and get_problem(problem).name != "npendulum":
+        device_events, events = tuple(events), None       # located by the kernel; nothing to do on the host
+        if int(max_events) < 1:
+            raise ValueError("`max_events` (occurrences recorded per event and system) must be at least 1.")
+    if events and not dense_output:
+        dense_output = True                    # Python event functions are located on the per-step record
     if dense_output and (max_dense_steps is None or int(max_dense_steps) < 1):
         raise ValueError("dense_output=True (and events) need `max_dense_steps` (steps recorded per system).")
     if not torch.cuda.is_available():
@@ -395,6 +461,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
 
     hb = prepare(problem, t_span, tuple(y0.shape), t_eval=t_eval, params=params, **options)
     prob, n, B, T = hb.problem, hb.n, hb.B, hb.t_eval.size
+    if device_events:
+        hb.events = pack_linear_events(device_events, n)
     y0_d = _as_device_f64(y0, dev, torch)
     if not torch.isfinite(y0_d).all():
         raise ValueError("All components of the initial state `y0` must be finite.")
@@ -425,6 +493,12 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
             dense_y = torch.empty((K, n, B), dtype=torch.float64, device=dev)
             dense_q = torch.empty((K, n, 3, B), dtype=torch.float64, device=dev)
             ptr.update(dense_cap=K, dense_t=dense_t.data_ptr(), dense_y=dense_y.data_ptr(), dense_q=dense_q.data_ptr())
+        if device_events:
+            E_, cap = len(device_events), int(max_events)
+            event_count = torch.zeros((E_, B), dtype=torch.int32, device=dev)
+            event_t = torch.full((E_, cap, B), float("nan"), dtype=torch.float64, device=dev)
+            event_y = torch.full((E_, cap, n, B), float("nan"), dtype=torch.float64, device=dev)
+            ptr.update(event_cap=cap, event_count=event_count.data_ptr(), event_t=event_t.data_ptr(), event_y=event_y.data_ptr())
         batch = hb.struct(ptr)
         ws_bytes = int(lib.brdae_workspace_bytes(C.byref(batch), C.byref(hb.options)))
         ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
@@ -434,6 +508,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
         ws.record_stream(cu_stream)
     res = BatchedOdeResult(hb.t_eval, y_eval[:T], n_eval, status, t_final, y_final, counters)
     res._keepalive = (y0_soa, par_soa, te_d, ws)
+    if device_events:
+        res.event_count, res.event_t, res.event_y = event_count, event_t, event_y
     if dense_output:
         cu_stream.synchronize()
         y0_h = y0_d.cpu().numpy()

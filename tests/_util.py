@@ -126,9 +126,10 @@ def _host_sim(problem):
     return _sims[path]
 
 
-def run_kernel_source_on_cpu(ens, dense_cap=0, **over):
+def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, **over):
     """tests/host_sim: the K1 kernel SOURCE compiled for the host, one lane.  With dense_cap > 0 the per-step
-    record is requested too and returned as out["sol"] (a BatchedOdeSolution)."""
+    record is requested too and returned as out["sol"] (a BatchedOdeSolution); with `events` (LinearEvents) the
+    device-side event location runs and out["event_count" | "event_t" | "event_y"] are returned ([B, E, ...])."""
     import dae_scipy_b200 as br
     _sim = _host_sim(br.get_problem(ens["problem"]))
     opts = dict(ens["options"])
@@ -148,10 +149,20 @@ def run_kernel_source_on_cpu(ens, dense_cap=0, **over):
         dense = {"dense_t": np.full((dense_cap, B), np.nan), "dense_y": np.full((dense_cap, n, B), np.nan),
                  "dense_q": np.full((dense_cap, n, 3, B), np.nan)}
         ptr.update({k: v.ctypes.data for k, v in dense.items()}, dense_cap=dense_cap)
+    if events:
+        from dae_scipy_b200.api import pack_linear_events
+        hb.events = pack_linear_events(events, n)
+        E_ = len(events)
+        evb = {"event_count": np.zeros((E_, B), np.int32), "event_t": np.full((E_, max_events, B), np.nan),
+               "event_y": np.full((E_, max_events, n, B), np.nan)}
+        ptr.update({k: v.ctypes.data for k, v in evb.items()}, event_cap=max_events)
     b = hb.struct(ptr)
     rc = _sim.sim_solve(C.byref(b), C.byref(hb.options))
     assert rc == 0, f"sim_solve returned {rc}"
     extra = {}
+    if events:
+        extra.update(event_count=evb["event_count"].T.copy(), event_t=evb["event_t"].transpose(2, 0, 1).copy(),
+                     event_y=evb["event_y"].transpose(3, 0, 1, 2).copy())
     if dense_cap:
         from dae_scipy_b200.api import make_ode_solution
         extra["sol"] = make_ode_solution(hb, y0, dense["dense_t"], dense["dense_y"], dense["dense_q"], out["status"], out["counters"])

@@ -363,3 +363,55 @@ def test_gpu_two_rank_nccl_sharded_solve():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "_nccl_worker.py")],
                        capture_output=True, text=True, timeout=600, cwd=os.path.dirname(here))
     assert r.returncode == 0 and "rank0 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ---------------------------------------------------------------- (6) events located by the kernel (LinearEvent)
+def test_gpu_device_side_events_against_kernel_source_and_scipy_fixture():
+    """solve_ivp_batched(events=[LinearEvent...]): the systems stop at their terminal event on the device.  Bit-identical
+    to the kernel source on the CPU; occurrences, status and end points as scipy's solve_ivp with the reference solver."""
+    from _util import run_kernel_source_on_cpu
+    from test_events import _fixture, linear_pendulum_events
+    import torch
+    ens, ref = _fixture()
+    evs = linear_pendulum_events()
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], events=evs,
+                               max_events=4, **ens["options"])
+    torch.cuda.synchronize()
+    out = res.numpy()
+    sim = run_kernel_source_on_cpu(ens, events=evs, max_events=4)
+    for k in ("status", "n_eval", "counters", "event_count"):
+        assert np.array_equal(out[k], sim[k]), k
+    for k in ("y", "y_final", "t_final", "event_t", "event_y"):
+        assert np.array_equal(out[k], sim[k], equal_nan=True), k
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["n_eval"], ref["n_eval"])
+    np.testing.assert_allclose(out["t_final"], ref["t_final"], rtol=0, atol=2e-6)
+    for i in range(ens["y0"].shape[0]):
+        for e in range(2):
+            want = ref["t_events"][i, e]
+            want = want[np.isfinite(want)]
+            assert out["t_events"][i][e].shape == want.shape
+            np.testing.assert_allclose(out["t_events"][i][e], want, rtol=0, atol=2e-6)
+    # an ensemble: every pendulum stops at its first upward zero of vy; the work after the event is not done
+    big = E.pendulum_ensemble(100003, t_end=10.0)
+    stop = [br.LinearEvent(3, n=5, direction=1.0, terminal=True)]
+    r1 = br.solve_ivp_batched(big["problem"], big["t_span"], big["y0"], big["params"], t_eval=big["t_eval"], events=stop,
+                              max_events=1, **big["options"])
+    r0 = br.solve_ivp_batched(big["problem"], big["t_span"], big["y0"], big["params"], t_eval=big["t_eval"], **big["options"])
+    torch.cuda.synchronize()
+    st = r1.status.cpu().numpy()
+    assert (st == 1).all() and (r0.status == 0).all()
+    assert float(r1.y_final[:, 3].abs().max()) < 1e-9                       # vy = 0 at the event
+    assert bool((r1.event_count == 1).all()) and bool(torch.equal(r1.event_t[0, 0], r1.t_final))
+    assert int(r1.nstep.sum()) < 0.5 * int(r0.nstep.sum())
+    # the plugin build has the same event code: the reactor stops when Ca has dropped to half its initial value
+    prob = E.reactor_problem()
+    rens = E.reactor_ensemble(64)
+    half = [br.LinearEvent(0, n=3, level=0.0104, direction=-1.0, terminal=True)]
+    rr = br.solve_ivp_batched(prob, rens["t_span"], rens["y0"], rens["params"], t_eval=rens["t_eval"], events=half,
+                              **rens["options"])
+    torch.cuda.synchronize()
+    rsim = run_kernel_source_on_cpu(rens, events=half)
+    ro = rr.numpy()
+    assert np.array_equal(ro["status"], rsim["status"]) and np.array_equal(ro["t_final"], rsim["t_final"])
+    hit = ro["status"] == 1
+    assert hit.any() and np.abs(ro["y_final"][hit, 0] - 0.0104).max() < 1e-12
