@@ -403,10 +403,10 @@ def test_gpu_device_side_events_against_kernel_source_and_scipy_fixture():
     assert float(r1.y_final[:, 3].abs().max()) < 1e-9                       # vy = 0 at the event
     assert bool((r1.event_count == 1).all()) and bool(torch.equal(r1.event_t[0, 0], r1.t_final))
     assert int(r1.nstep.sum()) < 0.5 * int(r0.nstep.sum())
-    # the plugin build has the same event code: the reactor stops when Ca has dropped to half its initial value
+    # the plugin build has the same event code: the reactor stops when the product concentration Cc reaches 0.004
     prob = E.reactor_problem()
     rens = E.reactor_ensemble(64)
-    half = [br.LinearEvent(0, n=3, level=0.0104, direction=-1.0, terminal=True)]
+    half = [br.LinearEvent(2, n=3, level=0.004, direction=1.0, terminal=True)]
     rr = br.solve_ivp_batched(prob, rens["t_span"], rens["y0"], rens["params"], t_eval=rens["t_eval"], events=half,
                               **rens["options"])
     torch.cuda.synchronize()
@@ -414,4 +414,4 @@ def test_gpu_device_side_events_against_kernel_source_and_scipy_fixture():
     ro = rr.numpy()
     assert np.array_equal(ro["status"], rsim["status"]) and np.array_equal(ro["t_final"], rsim["t_final"])
     hit = ro["status"] == 1
-    assert hit.any() and np.abs(ro["y_final"][hit, 0] - 0.0104).max() < 1e-12
+    assert hit.any() and not hit.all() and np.abs(ro["y_final"][hit, 2] - 0.004).max() < 1e-12
