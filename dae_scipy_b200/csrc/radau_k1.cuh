@@ -36,6 +36,9 @@
 #pragma once
 #include "problems.cuh"
 
+#ifndef BRDAE_K1_IDENT_FASTPATH
+#define BRDAE_K1_IDENT_FASTPATH 1    // substitutions on compile-time addresses when no lane of the warp pivoted (0: always the general code)
+#endif
 #ifndef K1_TEVAL_SHARED
 #define K1_TEVAL_SHARED 256      // output grids up to this many points are staged in shared memory
 #endif
@@ -196,12 +199,15 @@ BRDAE_HD void permute_rhs(const S &sm, int scratch, unsigned perm, double (&b)[N
 }
 // ---- triangular solves streaming the factors from lane-strided shared memory ----------------
 // b is put into pivoted order by a round trip through N scratch slots (dynamic load address).
-template <int N, bool SELECT, class S>
+// IDENT: the caller knows that no row was exchanged in this factorisation (perm is the identity for every lane of
+// the warp, which is the rule for the pendulum and Robertson families): the right-hand side needs no permutation and
+// every factor address is a compile-time offset.  Same loads, same arithmetic, same bits.
+template <int N, bool SELECT, bool IDENT = false, class S>
 BRDAE_HD void solve_real_sm(const S &sm, int base, int scratch, unsigned perm, double (&b)[N]) {
-    permute_rhs<N, SELECT>(sm, scratch, perm, b);
+    if (!IDENT) permute_rhs<N, SELECT>(sm, scratch, perm, b);
     int ro[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) ro[i] = base + row_of<N>(perm, i);
+    for (int i = 0; i < N; ++i) ro[i] = base + (IDENT ? i * N : row_of<N>(perm, i));
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double bk = b[k];
@@ -217,13 +223,15 @@ BRDAE_HD void solve_real_sm(const S &sm, int base, int scratch, unsigned perm, d
         for (int r = 0; r < k; ++r) b[r] = fma(-sm(ro[r] + k), xk, b[r]);
     }
 }
-template <int N, bool SELECT, class S>
+template <int N, bool SELECT, bool IDENT = false, class S>
 BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, unsigned perm, double (&br)[N], double (&bi)[N]) {
-    permute_rhs<N, SELECT>(sm, scratch, perm, br);
-    permute_rhs<N, SELECT>(sm, scratch, perm, bi);
+    if (!IDENT) {
+        permute_rhs<N, SELECT>(sm, scratch, perm, br);
+        permute_rhs<N, SELECT>(sm, scratch, perm, bi);
+    }
     int ro[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) ro[i] = row_of<N>(perm, i);
+    for (int i = 0; i < N; ++i) ro[i] = IDENT ? i * N : row_of<N>(perm, i);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double xr = br[k], xi = bi[k];
@@ -493,6 +501,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 
         // ================= error estimate, accept/reject, epilogue :660-784 ===================
         if (warp_any(state == ST_ERREST)) {
+            const bool ident_r = BRDAE_K1_IDENT_FASTPATH && warp_all(state != ST_ERREST || piv_r == perm_identity(N));
             if (state == ST_ERREST) {
                 double Z[3][N];
 #pragma unroll
@@ -521,7 +530,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 #pragma unroll
                     for (int c = 0; c < N; ++c) err[c] = cd(L::C_F + c) + mze[c];
                     for (int pass = 0;; ++pass) {
-                        solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, err);   // rhs NOT scaled by hscale
+                        if (ident_r) solve_real_sm<N, L::SELECT, true>(sm, L::S_LUR, L::S_B, piv_r, err);   // rhs NOT scaled by hscale
+                        else solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, err);
                         cnt[CN_NSOLVE_ERR]++;
                         double s = 0.0;
 #pragma unroll
@@ -837,6 +847,10 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 #pragma unroll 1
         for (int rep = 0; rep < a.newton_reps; ++rep) {
         if (warp_any(state == ST_NEWTON)) {
+            // no lane of the warp exchanged a row in its current factorisations (always, for the pendulum and Robertson
+            // ensembles): the substitutions below run on compile-time addresses, without the permutation round trip
+            const unsigned perm_id = perm_identity(N);
+            const bool ident = BRDAE_K1_IDENT_FASTPATH && warp_all(state != ST_NEWTON || (piv_r == perm_id && piv_c == perm_id));
             if (state == ST_NEWTON) {
                 // the three stages as one loop body with table coefficients (unrolled by default).  Values are those of the unrolled form: the first
                 // accumulation fma(a, F, 0) equals a*F, and (T W)_2 = fma(0, W2, fma(1, W1, 1*W0)) = W0 + W1.
@@ -882,8 +896,13 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         }
                         fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
                     }
-                    solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, fr);
-                    solve_cplx_sm<N, L::SELECT>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
+                    if (ident) {
+                        solve_real_sm<N, L::SELECT, true>(sm, L::S_LUR, L::S_B, piv_r, fr);
+                        solve_cplx_sm<N, L::SELECT, true>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
+                    } else {
+                        solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, fr);
+                        solve_cplx_sm<N, L::SELECT>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
+                    }
                     cnt[CN_NSOLVE]++;
                     double s = 0.0;
 #pragma unroll
