@@ -63,6 +63,7 @@ BRDAE_CX bool mass_row_empty(int r) {
 // ---------------------------------------------------------------- pendulum (index 3, 2, 1)
 template <int INDEX>
 struct Pendulum {
+    static constexpr bool kStaticLU = true, kFirstIterSkip = true;     // measured: profiles/r01_k1_fastpaths.md
     static constexpr int N = 5, NP = 3;
     // im = 1/m and r0s = r0*r0 are formed once per system (the contract multiplies by 1/m where the
     // reference divides by m; identical for the reference's m = 1)
@@ -103,6 +104,7 @@ struct Pendulum {
 
 // ---------------------------------------------------------------- Robertson DAE
 struct Robertson {
+    static constexpr bool kStaticLU = true, kFirstIterSkip = true;
     static constexpr int N = 3, NP = 3;
     struct P { double k1, k2, k3; };
     using Mass = MassDiag01<3, 0x3u>;  // robertson.py:78
@@ -173,6 +175,7 @@ struct Transistor {
 // ---------------------------------------------------------------- Robertson, ODE formulation
 // robertson.py:69-77; used by the reference's DAE-vs-ODE cross-check (:249-251)
 struct RobertsonODE {
+    static constexpr bool kStaticLU = true, kFirstIterSkip = true;
     static constexpr int N = 3, NP = 3;
     struct P { double k1, k2, k3; };
     using Mass = MassDiag01<3, 0x7u>;

@@ -39,6 +39,12 @@
 #ifndef BRDAE_K1_IDENT_FASTPATH
 #define BRDAE_K1_IDENT_FASTPATH 1    // substitutions on compile-time addresses when no lane of the warp pivoted (0: always the general code)
 #endif
+#ifndef BRDAE_K1_FIRST_ITER_FASTPATH
+#define BRDAE_K1_FIRST_ITER_FASTPATH 1    // skip the rate arithmetic of the Newton convergence test when no lane of the warp has a previous norm
+#endif
+#ifndef BRDAE_K1_STATIC_LU
+#define BRDAE_K1_STATIC_LU 1    // optimistic factorisation on compile-time row addresses for systems that have never pivoted
+#endif
 #ifndef K1_TEVAL_SHARED
 #define K1_TEVAL_SHARED 256      // output grids up to this many points are staged in shared memory
 #endif
@@ -116,6 +122,73 @@ BRDAE_HD unsigned lu_real_left(const S &sm, int base, ColFn &&column) {
         sm(base + row_of<N>(perm, k) + k) = rcp;
     }
     return perm;
+}
+// The same factorisation for a matrix that needs no row exchange -- every pivot candidate search ends on the diagonal,
+// which is the rule for the pendulum and Robertson iteration matrices: rows are addressed by compile-time offsets and a
+// column never takes the round trip through its parking slots.  Returns false (factors unusable) as soon as a pivot is
+// found off the diagonal; the caller then runs the general routine.  When it returns true it has executed exactly the
+// arithmetic of the general routine with the identity permutation.
+template <int N, class S, class ColFn>
+BRDAE_HD bool lu_real_static(const S &sm, int base, ColFn &&column) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double cur[N];
+        column(k, cur);
+#pragma unroll
+        for (int j = 0; j < k; ++j) {
+            const double cj = cur[j];
+#pragma unroll
+            for (int r = j + 1; r < N; ++r) cur[r] = fma(-sm(base + r * N + j), cj, cur[r]);
+        }
+        const double best = fabs(cur[k]);
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) ok = ok && !(fabs(cur[r]) > best);
+        const double rcp = 1.0 / cur[k];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (i != k) sm(base + i * N + k) = (i < k) ? cur[i] : cur[i] * rcp;
+        sm(base + k * N + k) = rcp;
+    }
+    return ok;
+}
+template <int N, class S, class ColFn>
+BRDAE_HD bool lu_cplx_static(const S &sm, int base_r, int base_i, ColFn &&column) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double cr[N], ci[N];
+        column(k, cr, ci);
+#pragma unroll
+        for (int j = 0; j < k; ++j) {
+            const double ur = cr[j], ui = ci[j];
+#pragma unroll
+            for (int r = j + 1; r < N; ++r) {
+                const double lr = sm(base_r + r * N + j), li = sm(base_i + r * N + j);
+                double xr = cr[r], xi = ci[r];
+                xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
+                xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
+                cr[r] = xr; ci[r] = xi;
+            }
+        }
+        const double best = fabs(cr[k]) + fabs(ci[k]);
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) ok = ok && !(fabs(cr[r]) + fabs(ci[r]) > best);
+        const double pr = cr[k], pi = ci[k];
+        const double invd = 1.0 / fma(pr, pr, pi * pi);
+        const double qr = pr * invd, qi = -(pi * invd);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int dst = i * N + k;
+            if (i < k) { sm(base_r + dst) = cr[i]; sm(base_i + dst) = ci[i]; }
+            else if (i > k) {
+                sm(base_r + dst) = fma(cr[i], qr, -(ci[i] * qi));
+                sm(base_i + dst) = fma(cr[i], qi, ci[i] * qr);
+            }
+        }
+        sm(base_r + k * N + k) = qr; sm(base_i + k * N + k) = qi;
+    }
+    return ok;
 }
 // complex: pivot on |re|+|im| (BLAS izamax), reciprocal pivot conj(p)/|p|^2
 template <int N, class S, class ColFn>
@@ -354,6 +427,17 @@ BRDAE_HD void num_jac_fd(const typename Prob::P &prm, const SolveArgs &a, double
     }
 }
 
+// Per-problem scheduling traits (results do not depend on them; measured in profiles/r01_k1_fastpaths.md):
+//   kStaticLU       -- the iteration matrices of this problem practically never need a row exchange: factorise
+//                      optimistically on compile-time row addresses (falls back per system on the first off-diagonal pivot);
+//   kFirstIterSkip  -- the lanes phase-lock onto the cycle, so whole warps sit at the first Newton iteration together:
+//                      skip the rate arithmetic of the convergence test there.
+// A problem functor opts in with `static constexpr bool kStaticLU = true;` etc.; the default is off.
+template <class P, class = void> struct trait_static_lu { static constexpr bool value = false; };
+template <class P> struct trait_static_lu<P, decltype((void)P::kStaticLU)> { static constexpr bool value = P::kStaticLU; };
+template <class P, class = void> struct trait_first_iter_skip { static constexpr bool value = false; };
+template <class P> struct trait_first_iter_skip<P, decltype((void)P::kFirstIterSkip)> { static constexpr bool value = P::kFirstIterSkip; };
+
 // warp-level helpers; the host build (tests/host_sim) runs a "warp" of one lane
 #if defined(__CUDA_ARCH__)
 BRDAE_D bool warp_all(bool x) { return __all_sync(0xffffffffu, x); }
@@ -420,7 +504,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
     long long idx = -1;
     double t = 0, y[N];
     double h_abs_state = 0, h_abs_old_state = 0, err_old_state = 0;
-    bool hist_state = false, current_jac = true, lu_valid = false, have_sol = false;
+    bool hist_state = false, current_jac = true, lu_valid = false, have_sol = false, lu_static_ok = true;
     double inv_h_sol = 1, t_sol_old = 0, inv_h_lu = 1.0;
     unsigned piv_r = 0, piv_c = 0;
     int cnt[CN_COUNT];
@@ -474,7 +558,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     cnt[CN_NFEV] = 1;
                     cnt[CN_NJEV] = a.has_jac_const ? 0 : 1;
                     h_abs_state = a.h0;
-                    hist_state = false; current_jac = true; lu_valid = false; have_sol = false;
+                    hist_state = false; current_jac = true; lu_valid = false; have_sol = false; lu_static_ok = true;
                     inv_h_lu = 1.0; ei = 0; nsteps = 0;
                     state = ST_SETUP; setup_kind = SETUP_STEP;
                     if (EVENTS)
@@ -796,6 +880,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
         }
         // ================= (re)factorisation :594-613 =========================================
         if (warp_any(state == ST_FACTOR)) {
+            const bool static_lu = BRDAE_K1_STATIC_LU && trait_static_lu<Prob>::value && warp_all(state != ST_FACTOR || lu_static_ok);
             if (state == ST_FACTOR) {
                 if (a.scale_residuals) inv_h_lu = inv_h;
                 double J[N][N];
@@ -818,14 +903,14 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 double hs[N];
 #pragma unroll
                 for (int r = 0; r < N; ++r) hs[r] = (a.scale_residuals && a.var_index[r] >= 1) ? inv_h_lu : 1.0;
-                piv_r = lu_real_left<N>(sm, L::S_LUR, [&](int kc, double (&col)[N]) {
+                auto col_real = [&](int kc, double (&col)[N]) {
 #pragma unroll
                     for (int r = 0; r < N; ++r) {
                         const double v = Mass::nz(r, kc) ? fma(mr, Mass::get(prm, a, r, kc), -J[r][kc]) : -J[r][kc];
                         col[r] = hs[r] * v;
                     }
-                });
-                piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, [&](int kc, double (&cr)[N], double (&ci)[N]) {
+                };
+                auto col_cplx = [&](int kc, double (&cr)[N], double (&ci)[N]) {
 #pragma unroll
                     for (int r = 0; r < N; ++r) {
                         const bool nz = Mass::nz(r, kc);
@@ -834,7 +919,20 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         cr[r] = hs[r] * v;
                         ci[r] = nz ? hs[r] * (mci * m) : 0.0;
                     }
-                });
+                };
+                // Optimistic factorisation without row exchanges while this system has never needed one (and no lane of
+                // the warp would have to run the general code next to it); a pivot off the diagonal repeats the
+                // factorisation with the general routine and switches the system over for good.
+                bool need_general = !static_lu;
+                if (static_lu) {
+                    const bool ok = lu_real_static<N>(sm, L::S_LUR, col_real) && lu_cplx_static<N>(sm, L::S_LCR, L::S_LCI, col_cplx);
+                    piv_r = piv_c = perm_identity(N);
+                    if (!ok) { need_general = true; lu_static_ok = false; }
+                }
+                if (need_general) {
+                    piv_r = lu_real_left<N>(sm, L::S_LUR, col_real);
+                    piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, col_cplx);
+                }
                 cnt[CN_NLU]++;
                 lu_valid = true;
                 state = ST_NEWTON;
@@ -851,6 +949,10 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
             // ensembles): the substitutions below run on compile-time addresses, without the permutation round trip
             const unsigned perm_id = perm_identity(N);
             const bool ident = BRDAE_K1_IDENT_FASTPATH && warp_all(state != ST_NEWTON || (piv_r == perm_id && piv_c == perm_id));
+            // every Newton lane of the warp is at the first iteration of its attempt (the lanes phase-lock onto the cycle, so
+            // this is the common case in the first pass): there is no previous increment norm, hence no rate, and the
+            // division / power / reciprocal chain of the convergence test would only produce values nobody reads
+            const bool any_old = !(BRDAE_K1_FIRST_ITER_FASTPATH && trait_first_iter_skip<Prob>::value) || warp_any(state == ST_NEWTON && have_old);
             if (state == ST_NEWTON) {
                 // the three stages as one loop body with table coefficients (unrolled by default).  Values are those of the unrolled form: the first
                 // accumulation fma(a, F, 0) equals a*F, and (T W)_2 = fma(0, W2, fma(1, W1, 1*W0)) = W0 + W1.
@@ -917,6 +1019,12 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     // convergence logic :880-932 as straight-line predicate algebra: the nested ifs of the
                     // reference compiled to a cascade of divergent branches at the very end of the block's
                     // dependency chain, where nothing is left to hide their latency
+                    if (!any_old) {       // first iteration everywhere: rate, have_rate and nbad keep their values (:880-932 with
+                        const bool conv_now = dwn < a.newton_tol;      // dW_norm_old is None)
+                        outcome = conv_now ? 1 : 0;
+                        dwn_old = conv_now ? dwn_old : dwn;
+                        have_old = !conv_now;
+                    } else {
                     const bool had_old = have_old;
                     const double r_new = dwn / (had_old ? dwn_old : 1.0);
                     rate = had_old ? r_new : rate;
@@ -944,6 +1052,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     const bool keep_old = retry_a || retry_d || conv_now || conv_c || stop_b || stop_d;   // :928 dW_norm_old
                     dwn_old = keep_old ? dwn_old : dwn;
                     have_old = have_old || !keep_old;
+                    }
                 }
                 if (outcome == 0) {
                     ++k;

@@ -60,6 +60,9 @@ extern "C" int sim_solve(const brdae_batch *b, const brdae_options *o) {
     fill_common(a, b, o, ws);
     const bool dense = b->mass != nullptr;
     switch (b->problem) {
+#ifdef BRDAE_USER_HEADER            // the harness of a user problem holds that problem only (compiles in seconds)
+    case BRDAE_USER: run_mass<UserProblem>(dense, a); break;
+#else
     case BRDAE_PENDULUM3: run_mass<Pendulum<3>>(dense, a); break;
     case BRDAE_PENDULUM2: run_mass<Pendulum<2>>(dense, a); break;
     case BRDAE_PENDULUM1: run_mass<Pendulum<1>>(dense, a); break;
@@ -69,8 +72,6 @@ extern "C" int sim_solve(const brdae_batch *b, const brdae_options *o) {
     case BRDAE_JAY: run_mass<Jay>(dense, a); break;
     case BRDAE_POLYDAE2: run_mass<PolyDAE2>(dense, a); break;
     case BRDAE_LINEAR7: run_mass<Linear7>(dense, a); break;
-#ifdef BRDAE_USER_HEADER
-    case BRDAE_USER: run_mass<UserProblem>(dense, a); break;
 #endif
     default: return BRDAE_ERR_UNSUPPORTED;
     }
