@@ -43,7 +43,7 @@ WORKLOADS = {
 
 
 # measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum) / systems of the profiled launch
-NCU_DRAM_BYTES_PER_SYSTEM = {"pendulum3_1M_tend2": (157.39e6 + 328.64e6) / 262144}     # profiles/r01_k1_ncu_summary.md, v7
+NCU_DRAM_BYTES_PER_SYSTEM = {"pendulum3_1M_tend2": (158.95e6 + 334.40e6) / 262144}     # profiles/r01_k1_fastpaths.md, v8
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -275,12 +275,12 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback"
     hbm_gbs = abytes / (kms * 1e-3) / 1e9
     # DRAM traffic of one launch: per-system dram__bytes_read + dram__bytes_write of the ncu --set full capture
-    # committed under profiles/ (r01_k1_ncu_summary.md: 486 MB for 262,144 pendulum systems), scaled to this launch
+    # committed under profiles/ (r01_k1_fastpaths.md: 493 MB for 262,144 pendulum systems), scaled to this launch
     traffic = NCU_DRAM_BYTES_PER_SYSTEM.get(args.workload)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
                 "traffic": None if traffic is None else traffic * B,
-                "traffic_source": None if traffic is None else "ncu --set full, profiles/r01_k1_ncu_summary.md (per system x systems of this launch)",
+                "traffic_source": None if traffic is None else "ncu --set full, profiles/r01_k1_fastpaths.md (per system x systems of this launch)",
                 "peak_source": "measured in this run: dependent-chain DFMA probe (brdae_fp64_peak_probe)",
                 "kernel": {"pendulum": "k1_kernel<Pendulum<3>,MassDiag01>", "npendulum": "k2_kernel"}.get(gen_key, f"k1_kernel<{gen_key}>"),
                 "kernel_ms": kms, "flops_per_launch": fl, "flops_per_trajectory": fl / B,
