@@ -275,7 +275,10 @@ static int host_rows_single_launch(const brdae_batch *hb, const brdae_options *o
     // The kernel is launched FIRST and its lanes wait for the chunk of the system they are handed; the copy-in
     // then streams chunk by chunk on its own stream, each chunk followed by its ready flag (from pageable host
     // memory cudaMemcpyAsync stages synchronously, so this thread is busy copying while the kernel already runs).
-    serial_in = std::getenv("BRDAE_ROWS_SERIAL_IN") != nullptr;      // A/B switch for tuning
+    // Under an injected CUDA tool (ncu, compute-sanitizer: CUDA_INJECTION64_PATH) a launch may not return before the
+    // kernel has ended, and the copies it waits for would never be queued: copy in first, on the kernel's stream.
+    serial_in = std::getenv("BRDAE_ROWS_SERIAL_IN") != nullptr       // A/B switch for tuning
+                || std::getenv("CUDA_INJECTION64_PATH") != nullptr || std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr;
     if (serial_in) {
         CK(cudaMemcpyAsync(dy0, hb->y0, sizeof(double) * n * B, cudaMemcpyHostToDevice, s));
         if (np > 0) CK(cudaMemcpyAsync(dpar, hb->params, sizeof(double) * np * B, cudaMemcpyHostToDevice, s));
