@@ -45,6 +45,9 @@
 #ifndef BRDAE_K1_STATIC_LU
 #define BRDAE_K1_STATIC_LU 1    // optimistic factorisation on compile-time row addresses for systems that have never pivoted
 #endif
+#ifndef BRDAE_SIM_COUNT
+#define BRDAE_SIM_COUNT(i)      // tests/host_sim counts how often the fast paths and their fall-backs run; nothing on the device
+#endif
 #ifndef K1_TEVAL_SHARED
 #define K1_TEVAL_SHARED 256      // output grids up to this many points are staged in shared memory
 #endif
@@ -927,9 +930,11 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 if (static_lu) {
                     const bool ok = lu_real_static<N>(sm, L::S_LUR, col_real) && lu_cplx_static<N>(sm, L::S_LCR, L::S_LCI, col_cplx);
                     piv_r = piv_c = perm_identity(N);
-                    if (!ok) { need_general = true; lu_static_ok = false; }
+                    BRDAE_SIM_COUNT(0);
+                    if (!ok) { need_general = true; lu_static_ok = false; BRDAE_SIM_COUNT(1); }
                 }
                 if (need_general) {
+                    BRDAE_SIM_COUNT(2);
                     piv_r = lu_real_left<N>(sm, L::S_LUR, col_real);
                     piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, col_cplx);
                 }
@@ -999,9 +1004,11 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         fr[c] = ar * hs; fcr[c] = br * hs; fci[c] = bi * hs;
                     }
                     if (ident) {
+                        BRDAE_SIM_COUNT(3);
                         solve_real_sm<N, L::SELECT, true>(sm, L::S_LUR, L::S_B, piv_r, fr);
                         solve_cplx_sm<N, L::SELECT, true>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
                     } else {
+                        BRDAE_SIM_COUNT(4);
                         solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, fr);
                         solve_cplx_sm<N, L::SELECT>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
                     }
@@ -1021,6 +1028,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     // dependency chain, where nothing is left to hide their latency
                     if (!any_old) {       // first iteration everywhere: rate, have_rate and nbad keep their values (:880-932 with
                         const bool conv_now = dwn < a.newton_tol;      // dW_norm_old is None)
+                        BRDAE_SIM_COUNT(5);
                         outcome = conv_now ? 1 : 0;
                         dwn_old = conv_now ? dwn_old : dwn;
                         have_old = !conv_now;

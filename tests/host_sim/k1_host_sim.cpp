@@ -10,6 +10,12 @@
 #include <type_traits>
 #include <vector>
 
+// how often the kernel's fast paths and their fall-backs ran (tests assert that both sides are exercised):
+// 0 optimistic LU attempts, 1 of them abandoned, 2 general LUs, 3 Newton passes on static addresses, 4 on pivoted ones,
+// 5 first-iteration convergence tests
+static long g_sim_counts[8];
+extern "C" long *sim_counts() { return g_sim_counts; }
+#define BRDAE_SIM_COUNT(i) (++g_sim_counts[i])
 #include "../../dae_scipy_b200/csrc/host_args.hpp"
 #include "../../dae_scipy_b200/csrc/radau_k1.cuh"
 #ifdef BRDAE_USER_HEADER        // a user problem (dae_scipy_b200/plugin.py): the same generated functor header as the plugin build

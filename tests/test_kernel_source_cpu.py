@@ -70,3 +70,39 @@ def test_t0_equals_t_bound_returns_initial_state():
 def test_kernel_source_on_reference_fixture_inputs(name):
     ens, _ = load_golden(name)
     assert_bit_identical(run_kernel_source_on_cpu(ens), run_c_oracle(ens), name)
+
+
+def _sim_counts(ens, **over):
+    """Run the kernel source and return how often its fast paths and their fall-backs ran (tests/host_sim counters):
+    [optimistic LU attempts, abandoned ones, general LUs, Newton passes on static addresses, on pivoted ones,
+    first-iteration convergence tests]."""
+    import ctypes as C
+    from _util import _host_sim
+    sim = _host_sim(br.get_problem(ens["problem"]))
+    sim.sim_counts.restype = C.POINTER(C.c_long)
+    c = sim.sim_counts()
+    for i in range(8):
+        c[i] = 0
+    out = run_kernel_source_on_cpu(ens, **over)
+    return out, [c[i] for i in range(6)]
+
+
+def test_fast_paths_and_their_fallbacks_are_exercised_and_bit_identical():
+    """K1 fast paths (profiles/r01_k1_fastpaths.md) never change a bit: the index-3 pendulum and Robertson never pivot
+    (optimistic LU and static substitutions throughout), the index-1 / index-2 pendulums and a mass matrix that shifts
+    the pivots abandon the optimistic LU and run the general code, the transistor (traits off) never tries it."""
+    out, c = _sim_counts(E.pendulum_ensemble(48))
+    assert c[0] > 0 and c[1] == 0 and c[2] == 0 and c[3] > 0 and c[4] == 0 and c[5] > 0
+    out, c = _sim_counts(E.robertson_ensemble(48))
+    assert c[0] > 0 and c[1] == 0 and c[2] == 0 and c[4] == 0 and c[5] > 0
+    ens = E.pendulum_ensemble(32, index=2)
+    out, c = _sim_counts(ens)
+    assert c[1] > 0 and c[2] > 0 and c[3] > 0 and c[4] > 0           # both kinds of factorisation and of substitution
+    assert_bit_identical(out, run_c_oracle(ens), "pendulum2: mixed static / general")
+    ens = E.pendulum_ensemble(48)
+    M = np.diag([0.05, 0.05, 1.0, 1.0, 0.0])                          # pivots move off the diagonal, systems still finish
+    out, c = _sim_counts(ens, mass_matrix=M)
+    assert c[1] == 48 and c[0] == 48 and c[2] > 0 and c[4] > 0 and (out["status"] == 0).all()
+    assert_bit_identical(out, run_c_oracle(ens, mass_matrix=M), "pendulum3 with shifted pivots")
+    out, c = _sim_counts(E.transistor_ensemble(4, t_end=0.02))
+    assert c[0] == 0 and c[5] == 0 and c[2] > 0 and c[4] > 0
