@@ -110,3 +110,20 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "from oracle" not in text and "import oracle" not in text and "oracle/" not in text.replace("oracle/ ", ""), f
+
+
+def test_integration_md_stub_matches_the_abi():
+    """The ctypes stub INTEGRATION.md tells a maintainer of the reference to add is executed here (definitions only):
+    its structs must have the layout of include/brdae.h, i.e. of the package's own mirror."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = text.split("```python", 1)[1].split("```", 1)[0]
+    code = code.replace('C.CDLL("libbrdae.so")', f'C.CDLL({_abi.LIB_PATH!r})')
+    _lib()
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    Options, Batch = ns["Options"], ns["Batch"]
+    assert C.sizeof(Options) == C.sizeof(_abi.BrdaeOptions) and C.sizeof(Batch) == C.sizeof(_abi.BrdaeBatch)
+    assert [f[0] for f in Options._fields_] == [f[0] for f in _abi.BrdaeOptions._fields_]
+    assert [(f[0], getattr(Batch, f[0]).offset) for f in Batch._fields_] == \
+           [(f[0], getattr(_abi.BrdaeBatch, f[0]).offset) for f in _abi.BrdaeBatch._fields_]
+    assert callable(ns["solve_ivp_ensemble"]) and ns["_lib"].brdae_abi_version() == _abi.ABI_VERSION
