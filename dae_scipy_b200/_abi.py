@@ -64,7 +64,7 @@ class BrdaeBatch(C.Structure):
                 ("n_events", C.c_int32), ("event_cap", C.c_int32),
                 ("event_coef", C.c_void_p), ("event_level", C.c_void_p), ("event_direction", C.c_void_p),
                 ("event_terminal", C.c_void_p), ("event_count", C.c_void_p), ("event_t", C.c_void_p),
-                ("event_y", C.c_void_p)]
+                ("event_y", C.c_void_p), ("event_functor", C.c_void_p)]
 
 
 # keyword -> (options field, default) : the RadauDAE constructor surface, radauDAE.py:263-278

@@ -55,20 +55,42 @@ class LinearEvent:
         return float(np.dot(self.coef, np.asarray(y)[:self.coef.size]) - self.level)
 
 
-def pack_linear_events(events, n):
-    """[LinearEvent] -> the arrays of brdae_batch (coef [E, n], level [E], direction [E], terminal count [E])."""
+class FunctorEvent:
+    """The k-th event function compiled into a user problem (`compile_problem(..., events=[...])`): any, also nonlinear,
+    g_k(t, y), located on the device like a LinearEvent, with the same `direction` / `terminal` semantics.  `fun` is an
+    optional Python restatement `fun(t, y)`; with it the object is an ordinary event callable too (host-side location)."""
+
+    def __init__(self, k, direction=0.0, terminal=False, fun=None):
+        self.k = int(k)
+        self.direction = float(direction)
+        self.terminal = terminal
+        self.fun = fun
+
+    def __call__(self, t, y):
+        if self.fun is None:
+            raise TypeError("this FunctorEvent exists on the device only (no Python restatement `fun` was given).")
+        return self.fun(t, y)
+
+
+def pack_linear_events(events, n, n_event_functions=0):
+    """[LinearEvent | FunctorEvent] -> the arrays of brdae_batch (coef [E, n], level [E], direction [E], terminal count [E],
+    functor index [E] with -1 for the linear form)."""
     if len(events) > _abi.MAX_EVENTS:
         raise ValueError(f"at most {_abi.MAX_EVENTS} events can be located on the device.")
     for ev in events:
-        if ev.coef.shape != (n,):
+        if isinstance(ev, FunctorEvent):
+            if not 0 <= ev.k < n_event_functions:
+                raise ValueError(f"FunctorEvent({ev.k}): the problem was compiled with {n_event_functions} event function(s).")
+        elif ev.coef.shape != (n,):
             raise ValueError(f"LinearEvent coefficients must have shape {(n,)}.")
-    coef = np.ascontiguousarray(np.stack([ev.coef for ev in events]))
-    level = np.array([ev.level for ev in events], dtype=np.float64)
+    coef = np.ascontiguousarray(np.stack([np.zeros(n) if isinstance(ev, FunctorEvent) else ev.coef for ev in events]))
+    level = np.array([0.0 if isinstance(ev, FunctorEvent) else ev.level for ev in events], dtype=np.float64)
+    functor = np.array([ev.k if isinstance(ev, FunctorEvent) else -1 for ev in events], dtype=np.int32)
     direction = np.array([int(np.sign(ev.direction)) for ev in events], dtype=np.int32)
     terminal = np.array([int(ev.terminal) if ev.terminal is not None else 0 for ev in events], dtype=np.int32)   # True -> 1
     if np.any(terminal < 0):
         raise ValueError("`terminal` must be a bool or a positive occurrence count.")
-    return coef, level, direction, terminal
+    return coef, level, direction, terminal, functor
 
 
 def warn_extraneous(extraneous):
@@ -93,7 +115,7 @@ class HostBatch:
     mass: np.ndarray | None     # float64 [n, n] shared matrix, None = the problem's own (device functor)
     jac_const: np.ndarray | None
     options: _abi.BrdaeOptions
-    events: tuple | None = None    # device-side events: (coef [E, n], level [E], direction [E] int32, terminal [E] int32)
+    events: tuple | None = None    # device-side events: (coef [E, n], level [E], direction, terminal, functor index [E] int32)
 
     def struct(self, ptr) -> _abi.BrdaeBatch:
         """Fill a brdae_batch; `ptr` maps field name -> address of the batch-sized buffers."""
@@ -115,10 +137,11 @@ class HostBatch:
             setattr(b, k, ptr.get(k))
         b.dense_cap = int(ptr.get("dense_cap") or 0)
         if self.events is not None and ptr.get("event_cap"):
-            coef, level, direction, terminal = self.events
+            coef, level, direction, terminal, functor = self.events
             b.n_events, b.event_cap = coef.shape[0], int(ptr["event_cap"])
             b.event_coef, b.event_level = coef.ctypes.data, level.ctypes.data
             b.event_direction, b.event_terminal = direction.ctypes.data, terminal.ctypes.data
+            b.event_functor = functor.ctypes.data
             for k in ("event_count", "event_t", "event_y"):
                 setattr(b, k, ptr.get(k))
         return b
@@ -425,7 +448,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     var_index   : [n] integers 0..3 or None (all differential), as in the reference.
     jac         : 'analytic' (default: the problem's analytic Jacobian functor), a constant [n, n] matrix, or
                   None = finite differences as in the reference's default (scipy num_jac).
-    events      : `LinearEvent`s (g = coef . y - level) are located ON THE DEVICE inside the step that crosses them: no step
+    events      : `LinearEvent`s (g = coef . y - level) and, for user problems compiled with event functions, `FunctorEvent`s
+                  (any g_k(t, y)) are located ON THE DEVICE inside the step that crosses them: no step
                   record is needed, `result.event_count` [E, B], `result.event_t` [E, max_events, B] and `result.event_y`
                   [E, max_events, n, B] stay on the device (`.numpy()` also builds scipy's `t_events` / `y_events` lists),
                   and a terminal event STOPS the integration of that system (status 1, `t_final` / `y_final` = the event
@@ -445,7 +469,7 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     if callable(events):
         events = (events,)
     device_events = None
-    if events and all(isinstance(ev, LinearEvent) for ev in events) and get_problem(problem).name != "npendulum":
+    if events and all(isinstance(ev, (LinearEvent, FunctorEvent)) for ev in events) and get_problem(problem).name != "npendulum":
         device_events, events = tuple(events), None       # located by the kernel; nothing to do on the host
         if int(max_events) < 1:
             raise ValueError("`max_events` (occurrences recorded per event and system) must be at least 1.")
@@ -462,7 +486,7 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     hb = prepare(problem, t_span, tuple(y0.shape), t_eval=t_eval, params=params, **options)
     prob, n, B, T = hb.problem, hb.n, hb.B, hb.t_eval.size
     if device_events:
-        hb.events = pack_linear_events(device_events, n)
+        hb.events = pack_linear_events(device_events, n, prob.n_event_functions)
     y0_d = _as_device_f64(y0, dev, torch)
     if not torch.isfinite(y0_d).all():
         raise ValueError("All components of the initial state `y0` must be finite.")

@@ -50,7 +50,10 @@ inline int validate(const brdae_batch *b, const brdae_options *o) {
         if (b->problem == BRDAE_NPENDULUM) return BRDAE_ERR_UNSUPPORTED;      // thread-per-system kernels only
         if (b->event_cap < 1 || !b->event_coef || !b->event_level || !b->event_direction || !b->event_terminal) return BRDAE_ERR_BAD_ARGUMENT;
         if (b->n_systems > 0 && (!b->event_count || !b->event_t)) return BRDAE_ERR_BAD_ARGUMENT;
-        for (int e = 0; e < b->n_events; ++e) if (b->event_terminal[e] < 0) return BRDAE_ERR_BAD_ARGUMENT;
+        for (int e = 0; e < b->n_events; ++e) {
+            if (b->event_terminal[e] < 0) return BRDAE_ERR_BAD_ARGUMENT;
+            if (b->event_functor && b->event_functor[e] >= 0 && b->problem != BRDAE_USER) return BRDAE_ERR_UNSUPPORTED;   // the stock functors define none
+        }
     }
     if (!(b->rtol > 0) || !(o->max_step > 0) || o->max_newton_ite < 1) return BRDAE_ERR_BAD_ARGUMENT;
     for (int c = 0; c < b->n; ++c) {
@@ -79,6 +82,7 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
     a.ev_count = b->event_count; a.ev_t = b->event_t; a.ev_y = b->event_y;
     for (int e = 0; e < b->n_events; ++e) {
         a.ev_dir[e] = b->event_direction[e]; a.ev_term[e] = b->event_terminal[e]; a.ev_level[e] = b->event_level[e];
+        a.ev_functor[e] = b->event_functor ? b->event_functor[e] : -1;
         for (int c = 0; c < b->n && c < BRDAE_NMAX_SMALL; ++c) a.ev_coef[e][c] = b->event_coef[e * b->n + c];
     }
     a.work_counter = static_cast<unsigned long long *>(workspace);

@@ -95,7 +95,7 @@ struct SolveArgs {
     int32_t dense_cap;
     // optional device-side events (brdae.h): g_e(y) = ev_coef[e] . y - ev_level[e]
     int32_t n_events, ev_cap;
-    int32_t ev_dir[BRDAE_MAX_EVENTS], ev_term[BRDAE_MAX_EVENTS];
+    int32_t ev_dir[BRDAE_MAX_EVENTS], ev_term[BRDAE_MAX_EVENTS], ev_functor[BRDAE_MAX_EVENTS];   // ev_functor: -1 = linear form
     double ev_level[BRDAE_MAX_EVENTS], ev_coef[BRDAE_MAX_EVENTS][BRDAE_NMAX_SMALL];
     int32_t *ev_count;
     double *ev_t, *ev_y;

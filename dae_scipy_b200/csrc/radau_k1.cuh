@@ -441,6 +441,16 @@ template <class P> struct trait_static_lu<P, decltype((void)P::kStaticLU)> { sta
 template <class P, class = void> struct trait_first_iter_skip { static constexpr bool value = false; };
 template <class P> struct trait_first_iter_skip<P, decltype((void)P::kFirstIterSkip)> { static constexpr bool value = P::kFirstIterSkip; };
 
+// Event functions of the problem functor itself (plugin builds): `static constexpr int NEVENTS` and
+// `static double event(const P &, int k, double t, const double (&y)[N])`; problems without them have none.
+template <class P, class = void> struct trait_n_events { static constexpr int value = 0; };
+template <class P> struct trait_n_events<P, decltype((void)P::NEVENTS)> { static constexpr int value = P::NEVENTS; };
+template <class Prob>
+BRDAE_HD double functor_event(const typename Prob::P &prm, int k, double t, const double (&y)[Prob::N]) {
+    if constexpr (trait_n_events<Prob>::value > 0) return (k < trait_n_events<Prob>::value) ? Prob::event(prm, k, t, y) : 0.0;
+    else return 0.0;
+}
+
 // warp-level helpers; the host build (tests/host_sim) runs a "warp" of one lane
 #if defined(__CUDA_ARCH__)
 BRDAE_D bool warp_all(bool x) { return __all_sync(0xffffffffu, x); }
@@ -692,11 +702,20 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 #pragma unroll 1
                         for (int e = 0; e < a.n_events; ++e) {
                             double g0 = -a.ev_level[e], g1 = -a.ev_level[e], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                            const int fk = a.ev_functor[e];      // >= 0: a (nonlinear) event function of the problem functor
+                            double yo[N];
 #pragma unroll
-                            for (int c = 0; c < N; ++c) {
-                                const double ce = a.ev_coef[e][c];
-                                g0 = fma(ce, cd(L::C_YOLD + c), g0); g1 = fma(ce, y[c], g1);
-                                a1 = fma(ce, Q[c][0], a1); a2 = fma(ce, Q[c][1], a2); a3 = fma(ce, Q[c][2], a3);
+                            for (int c = 0; c < N; ++c) yo[c] = cd(L::C_YOLD + c);
+                            if (fk >= 0) {
+                                g0 = functor_event<Prob>(prm, fk, t_sol_old, yo);
+                                g1 = functor_event<Prob>(prm, fk, t, y);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < N; ++c) {
+                                    const double ce = a.ev_coef[e][c];
+                                    g0 = fma(ce, yo[c], g0); g1 = fma(ce, y[c], g1);
+                                    a1 = fma(ce, Q[c][0], a1); a2 = fma(ce, Q[c][1], a2); a3 = fma(ce, Q[c][2], a3);
+                                }
                             }
                             const bool up = g0 <= 0 && g1 >= 0, down = g0 >= 0 && g1 <= 0;
                             act[e] = a.ev_dir[e] > 0 ? up : (a.ev_dir[e] < 0 ? down : (up || down));
@@ -710,7 +729,14 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                                     for (int it = 0; it < 64 && lo < hi; ++it) {
                                         const double mid = 0.5 * (lo + hi);
                                         if (!(mid > lo && mid < hi)) break;
-                                        const double pm = fma(mid, fma(mid, fma(mid, a3, a2), a1), g0);
+                                        double pm;
+                                        if (fk >= 0) {           // g(t, sol(t)) on the step's interpolant, as scipy's root finder sees it
+                                            double ym[N];
+                                            const double m2 = mid * mid, m3 = m2 * mid;
+#pragma unroll
+                                            for (int c = 0; c < N; ++c) ym[c] = fma(Q[c][2], m3, fma(Q[c][1], m2, Q[c][0] * mid)) + yo[c];
+                                            pm = functor_event<Prob>(prm, fk, fma(mid, h, t_sol_old), ym);
+                                        } else pm = fma(mid, fma(mid, fma(mid, a3, a2), a1), g0);
                                         if ((pm > 0) == pos0 && pm != 0) lo = mid; else hi = mid;
                                     }
                                     x = hi;

@@ -35,6 +35,7 @@ class Problem:
     has_jac: bool = True
     lib_path: str | None = None
     header_path: str | None = None
+    n_event_functions: int = 0      # (nonlinear) event functions compiled into the functor: FunctorEvent(k), k < this
 
     @property
     def n_params(self):

@@ -153,6 +153,9 @@ typedef struct brdae_batch {
     int32_t *event_count;     /* [dev]  [E][B] */
     double *event_t;          /* [dev]  [E][C][B]; entries at or beyond the count are not written */
     double *event_y;          /* [dev]  [E][C][n][B], may be NULL */
+    const int32_t *event_functor;    /* [host] [E] or NULL: k >= 0 = event e is the k-th event function g_k(t, y) of the problem
+                                        functor itself (plugin builds: UserProblem::event, any nonlinear function; coef and
+                                        level of that event are ignored), -1 = the linear form above */
 } brdae_batch;
 
 int brdae_abi_version(void);

@@ -151,7 +151,7 @@ def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, **over
         ptr.update({k: v.ctypes.data for k, v in dense.items()}, dense_cap=dense_cap)
     if events:
         from dae_scipy_b200.api import pack_linear_events
-        hb.events = pack_linear_events(events, n)
+        hb.events = pack_linear_events(events, n, hb.problem.n_event_functions)
         E_ = len(events)
         evb = {"event_count": np.zeros((E_, B), np.int32), "event_t": np.full((E_, max_events, B), np.nan),
                "event_y": np.full((E_, max_events, n, B), np.nan)}

@@ -133,9 +133,9 @@ def test_device_side_events_direction_level_cap_and_no_events():
 
 def test_linear_event_packing_and_validation():
     from dae_scipy_b200.api import pack_linear_events
-    coef, level, direction, terminal = pack_linear_events(linear_pendulum_events(), 5)
+    coef, level, direction, terminal, functor = pack_linear_events(linear_pendulum_events(), 5)
     assert coef.shape == (2, 5) and coef[0, 0] == 1 and coef[1, 3] == 1 and level.tolist() == [0.0, 0.0]
-    assert direction.tolist() == [0, 1] and terminal.tolist() == [0, 2]
+    assert direction.tolist() == [0, 1] and terminal.tolist() == [0, 2] and functor.tolist() == [-1, -1]
     assert pack_linear_events([LinearEvent(1, n=3, terminal=True)], 3)[3].tolist() == [1]
     with pytest.raises(ValueError):
         pack_linear_events([LinearEvent(0, n=5)] * 5, 5)            # at most BRDAE_MAX_EVENTS

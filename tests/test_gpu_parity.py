@@ -415,3 +415,24 @@ def test_gpu_device_side_events_against_kernel_source_and_scipy_fixture():
     assert np.array_equal(ro["status"], rsim["status"]) and np.array_equal(ro["t_final"], rsim["t_final"])
     hit = ro["status"] == 1
     assert hit.any() and not hit.all() and np.abs(ro["y_final"][hit, 2] - 0.004).max() < 1e-12
+
+
+def test_gpu_user_event_functions_bit_identical_to_kernel_source():
+    """FunctorEvent: nonlinear event functions compiled into a plugin build, located and applied by the kernel on the GPU
+    exactly as by the kernel source on the CPU (whose roots tests/test_user_problem.py checks against scipy's helpers)."""
+    from _util import run_kernel_source_on_cpu
+    from test_user_problem import reactor_with_events
+    import torch
+    prob = reactor_with_events()
+    ens = dict(E.reactor_ensemble(96), problem=prob)
+    evs = [br.FunctorEvent(0, direction=-1.0, terminal=True), br.FunctorEvent(1), br.LinearEvent(2, n=3, level=0.002, direction=1.0)]
+    res = br.solve_ivp_batched(prob, ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], events=evs, max_events=4,
+                               **ens["options"])
+    torch.cuda.synchronize()
+    out = res.numpy()
+    sim = run_kernel_source_on_cpu(ens, events=evs, max_events=4)
+    for k in ("status", "n_eval", "counters", "event_count"):
+        assert np.array_equal(out[k], sim[k]), k
+    for k in ("y", "y_final", "t_final", "event_t", "event_y"):
+        assert np.array_equal(out[k], sim[k], equal_nan=True), k
+    assert (out["status"] == 1).any() and (out["status"] == 0).any() and out["event_count"].sum(axis=0).min() > 0

@@ -141,3 +141,54 @@ def test_user_vdp_kernel_source_on_cpu_against_numpy_oracle():
     tot, tot_ref = out["counters"].sum(axis=0), ref["counters"].sum(axis=0)
     assert np.all(np.abs(tot - tot_ref) <= 0.02 * np.maximum(tot_ref, 50))
     assert out["counters"][:, 5].sum() > 0 and out["counters"][:, 1].min() > 1    # the hard paths were exercised
+
+
+def reactor_with_events():
+    """The reactor functor with two nonlinear event functions compiled in: the reaction rate k Ca Cb, and the squared
+    distance of (Ca, Cb) from the origin."""
+    return br.compile_problem("reactor_ev", 3, E.REACTOR_RHS, E.REACTOR_JAC, param_names=("k", "Ca0", "Cb0"),
+                              param_defaults=(1.47, 0.0209, 0.0209 / 3), mass_diag=(1, 0, 0), var_index=(0, 1, 1),
+                              t_span=(0.0, 20.0), events=["p[0] * y[0] * y[1] - 2.0e-4", "y[0] * y[0] + y[1] * y[1] - 4.0e-4"],
+                              static_lu=True, first_iter_skip=True)
+
+
+def test_user_event_functions_are_located_by_the_kernel():
+    """FunctorEvent: nonlinear g_k(t, y) compiled into the plugin, located inside the step by the kernel source (run on the
+    CPU) with scipy's semantics -- checked against scipy's own event helpers applied, on the host, to the step record of the
+    uninterrupted run with the Python restatements of the same functions."""
+    from dae_scipy_b200.api import FunctorEvent, find_events
+    prob = reactor_with_events()
+    assert prob.n_event_functions == 2
+    ens = dict(E.reactor_ensemble(24), problem=prob)
+    k = ens["params"][:, 0]
+
+    def make(i):        # per-system closures for the host-side checker (the rate event depends on the system's k)
+        rate = lambda t, y: k[i] * y[0] * y[1] - 2.0e-4              # noqa: E731
+        rate.direction, rate.terminal = -1.0, True
+        dist = lambda t, y: y[0] * y[0] + y[1] * y[1] - 4.0e-4       # noqa: E731
+        return [rate, dist]
+    evs = [FunctorEvent(0, direction=-1.0, terminal=True), FunctorEvent(1)]
+    out = U.run_kernel_source_on_cpu(ens, events=evs, max_events=4)
+    full = U.run_kernel_source_on_cpu(ens, dense_cap=200)
+    n_term = 0
+    for i in range(ens["y0"].shape[0]):
+        one = full["sol"]
+        sub = type(one).__new__(type(one))                # the record of system i alone
+        sub.n_steps, sub.truncated, sub.ascending = one.n_steps[i:i + 1], one.truncated[i:i + 1], one.ascending
+        sub.ts, sub.ys, sub.Q = one.ts[i:i + 1], one.ys[i:i + 1], one.Q[i:i + 1]
+        t_host, y_host, term, t_stop, y_stop = find_events(sub, make(i), ens["t_span"][0], ens["y0"][i:i + 1])
+        assert bool(term[0]) == (out["status"][i] == 1)
+        for e in range(2):
+            kk = out["event_count"][i, e]
+            assert kk == t_host[0][e].size
+            np.testing.assert_allclose(out["event_t"][i, e, :kk], t_host[0][e], rtol=0, atol=1e-9)
+        if term[0]:
+            n_term += 1
+            np.testing.assert_allclose(out["t_final"][i], t_stop[0], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(out["y_final"][i], y_stop[0], rtol=0, atol=1e-12)
+            assert abs(k[i] * out["y_final"][i, 0] * out["y_final"][i, 1] - 2.0e-4) < 1e-15
+            assert out["counters"][i, 3] <= full["counters"][i, 3]
+    assert 0 < n_term < ens["y0"].shape[0]                # some systems stop at the rate event, some never reach it
+    assert out["event_count"][:, 1].sum() > 0             # the observer fired too
+    with pytest.raises(ValueError):
+        U.run_kernel_source_on_cpu(ens, events=[FunctorEvent(2)])          # only two event functions were compiled
