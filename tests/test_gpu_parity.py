@@ -51,6 +51,7 @@ def _need_gpu():
     ("fd_jacobian_pendulum1", lambda: E.pendulum_ensemble(128, index=1), dict(jac=None)),
     ("fd_jacobian_robertson", lambda: E.robertson_ensemble(512, t_end=1e3), dict(jac=None)),
     ("fd_jacobian_dense_mass", lambda: E.pendulum_ensemble(64), dict(jac=None, mass_matrix=np.diag([1., 1, 1, 1, 0]) * 1.5)),
+    ("pendulum3_long_t_eval", lambda: E.pendulum_ensemble(128, n_t_eval=401), {}),     # > K1_TEVAL_SHARED points: grid read from global memory
     ("ragged_sizes_1", lambda: E.pendulum_ensemble(1), {}),
     ("ragged_sizes_33", lambda: E.pendulum_ensemble(33), {}),
     ("ragged_sizes_129", lambda: E.robertson_ensemble(129), {}),

@@ -15,6 +15,7 @@ CASES = {
     "pendulum3_t10": (lambda: E.pendulum_ensemble(16, t_end=10.0), {}),
     "pendulum2": (lambda: E.pendulum_ensemble(32, index=2), {}),
     "pendulum1": (lambda: E.pendulum_ensemble(32, index=1), {}),
+    "pendulum3_long_t_eval": (lambda: E.pendulum_ensemble(8, n_t_eval=401), {}),      # more points than the kernel stages on chip
     "pendulum3_default_first_step": (lambda: E.pendulum_ensemble(16, t_end=0.5), dict(first_step=None)),
     "pendulum3_dense_mass": (lambda: E.pendulum_ensemble(16), dict(mass_matrix=np.diag([1., 1, 1, 1, 0]) * 1.5)),
     "pendulum3_identity_mass": (lambda: E.pendulum_ensemble(8, t_end=0.2), dict(mass_matrix=None, var_index=None)),
