@@ -437,3 +437,30 @@ def test_gpu_user_event_functions_bit_identical_to_kernel_source():
     for k in ("y", "y_final", "t_final", "event_t", "event_y"):
         assert np.array_equal(out[k], sim[k], equal_nan=True), k
     assert (out["status"] == 1).any() and (out["status"] == 0).any() and out["event_count"].sum(axis=0).min() > 0
+
+
+# ---------------------------------------------------------------- (7) the binding INTEGRATION.md gives a reference maintainer
+def test_gpu_integration_md_stub_runs_and_matches():
+    """The ctypes stub of INTEGRATION.md, executed as written (brdae_solve_host: structure-of-arrays host buffers), returns
+    what the package's own entry returns."""
+    import os
+    from _util import ROOT
+    from dae_scipy_b200 import _abi
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = text.split("```python", 1)[1].split("```", 1)[0].replace('C.CDLL("libbrdae.so")', f'C.CDLL({_abi.LIB_PATH!r})')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    ens = E.pendulum_ensemble(1000)
+    o = ens["options"]
+    sol = ns["solve_ivp_ensemble"]("pendulum3", ens["t_span"], ens["y0"], ens["params"], ens["t_eval"], rtol=o["rtol"],
+                                   atol=o["atol"], first_step=o["first_step"], var_index=o["var_index"])
+    ref = run_gpu(ens)
+    assert np.array_equal(sol["y"], ref["y"]) and np.array_equal(sol["status"], ref["status"])
+    assert np.array_equal(sol["naccpt"], ref["counters"][:, 4]) and np.array_equal(sol["y_final"], ref["y_final"])
+    rob = E.robertson_ensemble(500)                                   # radau keywords pass through by name
+    ro = rob["options"]
+    sol = ns["solve_ivp_ensemble"]("robertson", rob["t_span"], rob["y0"], rob["params"], rob["t_eval"], rtol=ro["rtol"],
+                                   atol=ro["atol"], first_step=ro["first_step"], var_index=ro["var_index"],
+                                   max_bad_ite=ro["max_bad_ite"], scale_newton_norm=ro["scale_newton_norm"])
+    ref = run_gpu(rob)
+    assert np.array_equal(sol["y"], ref["y"]) and np.array_equal(sol["nfev"], ref["counters"][:, 0])
