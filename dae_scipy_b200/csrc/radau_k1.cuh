@@ -702,7 +702,9 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 #pragma unroll 1
                         for (int e = 0; e < a.n_events; ++e) {
                             double g0 = -a.ev_level[e], g1 = -a.ev_level[e], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                            const int fk = a.ev_functor[e];      // >= 0: a (nonlinear) event function of the problem functor
+                            // >= 0: a (nonlinear) event function of the problem functor; problems that define none compile to the
+                            // linear form alone
+                            const int fk = (trait_n_events<Prob>::value > 0) ? a.ev_functor[e] : -1;
                             double yo[N];
 #pragma unroll
                             for (int c = 0; c < N; ++c) yo[c] = cd(L::C_YOLD + c);
