@@ -101,7 +101,7 @@ def drain_order(n, alive, last):       # E whenever anyone converged would starv
     return majority(n, alive, last)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "cycle"):
     nsys = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     trs = traces(nsys)
     ev = "".join(trs)
@@ -112,3 +112,87 @@ if __name__ == "__main__":
                           ("sticky.5", sticky(0.5)), ("drain", drain_order)):
             row.append(f"{name} {simulate(trs, G, pol):.3f}")
         print("  ".join(row))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The shipped policy (fixed cycle E -> F -> N x reps, one CTA of W warps) and an upper bound for migrating systems
+# between the warps of a CTA (same lane index, so the lane-strided shared-memory columns stay conflict-free):
+#     python profiles/tools/sched_sim.py cycle [nsys]
+def simulate_cycle(trs, W=4, reps=4, migrate=None, migrate_cost=0.0):
+    """Lane efficiency of the fixed cycle for one CTA of W warps.  `migrate`: None, or a key function ranking the W systems
+    that share a lane index (they are re-dealt to the warps in that order before every cycle); `migrate_cost` is charged per
+    warp and cycle.  A block is executed by a warp when any of its lanes waits for it."""
+    queue = list(range(len(trs)))[::-1]
+    sysid = [[None] * 32 for _ in range(W)]
+    pos = [[0] * 32 for _ in range(W)]
+
+    def refill(w, l):
+        if queue:
+            sysid[w][l] = queue.pop(); pos[w][l] = 0
+        else:
+            sysid[w][l] = None
+    for w in range(W):
+        for l in range(32):
+            refill(w, l)
+    useful = executed = 0.0
+
+    def nxt(w, l):
+        s = sysid[w][l]
+        return None if s is None else trs[s][pos[w][l]]
+
+    def advance(w, l):
+        pos[w][l] += 1
+        if pos[w][l] >= len(trs[sysid[w][l]]):
+            refill(w, l)
+
+    def block(kind):
+        nonlocal useful, executed
+        for w in range(W):
+            lanes = [l for l in range(32) if nxt(w, l) == kind]
+            if lanes:
+                executed += COST[kind] * 32
+                useful += COST[kind] * len(lanes)
+                for l in lanes:
+                    advance(w, l)
+    while any(sysid[w][l] is not None for w in range(W) for l in range(32)):
+        if migrate is not None:
+            for l in range(32):
+                col = sorted(((sysid[w][l], pos[w][l]) for w in range(W)), key=lambda sp: migrate(trs, sp[0], sp[1], reps))
+                for w in range(W):
+                    sysid[w][l], pos[w][l] = col[w]
+            executed += migrate_cost * 32 * W
+        block("E"); block("F")
+        for _ in range(reps):
+            block("N")
+    return useful / executed
+
+
+def key_newton_passes(trs, s, p, reps):
+    """How many of the cycle's Newton passes the system will use (what a lane knows only approximately: an upper bound)."""
+    if s is None:
+        return -1
+    t = trs[s]
+    while p < len(t) and t[p] in "EF":
+        p += 1
+    n = 0
+    while p < len(t) and t[p] == "N" and n < reps:
+        p += 1; n += 1
+    return -n
+
+
+def key_state_only(trs, s, p, reps):
+    """What a lane does know at the top of a cycle: whether it is in the middle of a Newton sequence or at its start."""
+    if s is None:
+        return 2
+    return 0 if trs[s][p] == "N" else 1
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cycle":
+    nsys = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+    trs = traces(nsys)
+    for reps in (3, 4, 5):
+        print(f"reps={reps}: fixed cycle {simulate_cycle(trs, 4, reps):.3f}   "
+              f"migration by Newton passes to come (oracle, free) {simulate_cycle(trs, 4, reps, key_newton_passes):.3f}   "
+              f"(cost of one Newton pass per cycle) {simulate_cycle(trs, 4, reps, key_newton_passes, COST['N']):.3f}   "
+              f"migration by state only {simulate_cycle(trs, 4, reps, key_state_only):.3f}")
+    sys.exit(0)
