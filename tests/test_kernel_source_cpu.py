@@ -107,3 +107,46 @@ def test_fast_paths_and_their_fallbacks_are_exercised_and_bit_identical():
     assert_bit_identical(out, run_c_oracle(ens, mass_matrix=M), "pendulum3 with shifted pivots")
     out, c = _sim_counts(E.transistor_ensemble(4, t_end=0.02))
     assert c[0] == 0 and c[5] == 0 and c[2] > 0 and c[4] > 0
+
+
+def test_kernel_source_random_option_combinations():
+    """Seeded differential run over the option surface (RadauDAE keywords of radauDAE.py:263-278 in random combinations,
+    on all three problem families, analytic and finite-difference Jacobians, perturbed mass matrices): the kernel source and the
+    C oracle must stay bit-identical whatever is switched on.  Step counts are capped so that pathological combinations
+    (a method configured against itself takes millions of failed attempts) end quickly -- with the same status."""
+    rng = np.random.default_rng(20261020)
+    flags = ["scale_residuals", "scale_newton_norm", "scale_error", "zero_algebraic_error", "bAlwaysApply2ndEstimate",
+             "bUsePredictiveController", "bUsePredictiveNewtonStoppingCriterion", "bUseExtrapolatedGuess", "bPerformAllNewtonIterations"]
+    ranges = {"rtol": (-8, -3), "atol": (-10, -4), "max_step": (-3, 0), "newton_tol": (-8, -2), "jacobianRecomputeFactor": (-5, 0)}
+    for case in range(24):
+        kind = rng.choice(["pendulum3", "pendulum2", "pendulum1", "robertson", "transistor"])
+        seed = int(rng.integers(1 << 30))
+        if kind.startswith("pendulum"):
+            ens = E.pendulum_ensemble(4, index=int(kind[-1]), t_end=float(rng.choice([0.3, 1.0, 2.0])), seed=seed)
+        elif kind == "robertson":
+            ens = E.robertson_ensemble(4, t_end=float(rng.choice([1e1, 1e3, 1e5])), seed=seed)
+        else:
+            ens = E.transistor_ensemble(2, t_end=0.01, seed=seed)
+        over = {"nmax_step": int(rng.integers(100, 400))}
+        for f in flags:
+            if rng.random() < 0.3:
+                over[f] = bool(rng.integers(2))
+        for k, (lo, hi) in ranges.items():
+            if rng.random() < 0.25:
+                over[k] = float(10 ** rng.uniform(lo, hi))
+        if rng.random() < 0.2: over["max_newton_ite"] = int(rng.integers(2, 12))
+        if rng.random() < 0.2: over["max_bad_ite"] = int(rng.integers(0, 4))
+        if rng.random() < 0.2: over["min_factor"] = float(rng.uniform(0.05, 0.5))
+        if rng.random() < 0.2: over["max_factor"] = float(rng.uniform(2, 20))
+        if rng.random() < 0.2: over["safety_factor"] = float(rng.uniform(0.5, 0.99))
+        if rng.random() < 0.15: over["factor_on_non_convergence"] = float(rng.uniform(0.1, 0.8))
+        if rng.random() < 0.15: over["jac"] = None
+        if rng.random() < 0.15 and kind != "transistor":
+            n = ens["y0"].shape[1]
+            M = br.get_problem(ens["problem"]).mass().copy()
+            M[:n - 1, :n - 1] += 0.1 * rng.standard_normal((n - 1, n - 1))
+            over["mass_matrix"] = M
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert_bit_identical(run_kernel_source_on_cpu(ens, **over), run_c_oracle(ens, **over), f"case {case}: {kind} {over}")
