@@ -325,6 +325,29 @@ class BatchedOdeResult:
         out["success"] = out["status"] >= 0
         return out
 
+    def system(self, i):
+        """System i as the `OdeResult` the reference's `solve_ivp(fun_i, ..., method=RadauDAE)` returns (scipy ivp.py
+        `OdeResult`; radauDAE.py:1183-1194): `t` (the `t_eval` points reached; with `t_eval=None` and a step record, the
+        steps taken), `y` [n, len(t)], `sol`, `t_events`, `y_events`, `nfev`, `njev`, `nlu`, `status`, `message`, `success`
+        -- plus the reference solver's own counters.  Host copies of the whole result are made once and cached."""
+        from scipy.integrate._ivp.ivp import OdeResult
+        if getattr(self, "_host", None) is None:
+            self._host = self.numpy()
+        h, i = self._host, int(i)
+        k = int(h["n_eval"][i])
+        t, y = h["t"][:k], h["y"][i][:, :k]
+        if h["t"].size == 0 and self.sol is not None:            # t_eval=None: the steps themselves (ivp.py:699-701)
+            ns = int(self.sol.n_steps[i])
+            t, y = self.sol.ts[i, :ns + 1], self.sol.ys[i, :, :ns + 1]
+        status = int(h["status"][i])
+        extra = {name: int(h[name][i]) for name in _abi.COUNTER_NAMES if name not in ("nfev", "njev", "nlu")}
+        return OdeResult(t=t, y=y, sol=None if self.sol is None else self.sol.system(i),
+                         t_events=None if h.get("t_events") is None else h["t_events"][i],
+                         y_events=None if h.get("y_events") is None else h["y_events"][i],
+                         nfev=int(h["nfev"][i]), njev=int(h["njev"][i]), nlu=int(h["nlu"][i]), status=status,
+                         message=_abi.MESSAGES.get(status, "unknown status"), success=status >= 0,
+                         t_final=float(h["t_final"][i]), y_final=h["y_final"][i], **extra)
+
 
 class BatchedOdeSolution:
     """What `solve_ivp(dense_output=True)` returns as `sol` (scipy OdeSolution over the reference's

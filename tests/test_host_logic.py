@@ -120,3 +120,34 @@ def test_two_rank_gloo_gather_and_reduce():
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "rank0 ok" in outs[0]
+
+
+def test_per_system_ode_result_view():
+    """BatchedOdeResult.system(i): the OdeResult a user of the reference gets from solve_ivp, rebuilt from the batch arrays.
+    The arrays come from the kernel source run on the CPU (kernel layout, CPU tensors), the expected values from the
+    reference's own run of the same system (tests/golden/g1_pendulum3_single.npz)."""
+    import torch
+    from dae_scipy_b200.api import BatchedOdeResult
+    from _util import load_golden, run_kernel_source_on_cpu
+    ens, ref = load_golden("g1_pendulum3_single")
+    out = run_kernel_source_on_cpu(ens, dense_cap=400)
+    res = BatchedOdeResult(np.asarray(ens["t_eval"], dtype=float), torch.as_tensor(out["y"]).permute(2, 1, 0).contiguous(),
+                           torch.as_tensor(out["n_eval"]), torch.as_tensor(out["status"]), torch.as_tensor(out["t_final"]),
+                           torch.as_tensor(out["y_final"]).t().contiguous(), torch.as_tensor(out["counters"]).t().contiguous())
+    res.sol = out["sol"]
+    r = res.system(0)
+    assert r.success and r.status == 0 and r.message.startswith("The solver successfully reached the end")
+    assert r.t.shape == (21,) and r.y.shape == (5, 21)
+    assert np.abs(r.y - ref["y"][0]).max() <= 10 * (1e-6 + 1e-6 * np.abs(ref["y"][0]).max())
+    assert (r.nfev, r.njev, r.nlu) == tuple(int(v) for v in ref["counters"][0, :3])
+    assert (r.naccpt, r.nrejct, r.nfailed) == tuple(int(v) for v in ref["counters"][0, 4:7])
+    np.testing.assert_allclose(r.sol(r.t[5]), r.y[:, 5], rtol=0, atol=1e-13)         # the dense output goes through the t_eval values
+    assert r.t_events is None and float(r.t_final) == 2.0
+    # t_eval=None: the steps themselves, as the reference returns them
+    res2 = BatchedOdeResult(np.empty(0), torch.empty((0, 5, 1), dtype=torch.float64), torch.zeros(1, dtype=torch.int32),
+                            torch.as_tensor(out["status"]), torch.as_tensor(out["t_final"]),
+                            torch.as_tensor(out["y_final"]).t().contiguous(), torch.as_tensor(out["counters"]).t().contiguous())
+    res2.sol = out["sol"]
+    r2 = res2.system(0)
+    assert r2.t.shape == (r.naccpt + 1,) and r2.t[0] == 0.0 and r2.t[-1] == 2.0 and r2.y.shape == (5, r.naccpt + 1)
+    np.testing.assert_array_equal(r2.y[:, -1], out["y_final"][0])
