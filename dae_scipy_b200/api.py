@@ -192,6 +192,10 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
 
     if var_index is None:
         vi = np.zeros(n, dtype=np.int32)                   # radauDAE.py:389-390: all differential
+    elif isinstance(var_index, str):
+        if var_index != "problem":
+            raise ValueError("`var_index` must be None, an [n] array or the string 'problem'.")
+        vi = np.ascontiguousarray(prob.var_index_array(n), dtype=np.int32)      # the reference script's own choice
     else:
         v = np.asarray(var_index)
         if v.ndim != 1 or v.size != n:
@@ -468,7 +472,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     y0      : [B, n] array or tensor.       params : [B, p] array/tensor, None = defaults.
     mass_matrix : 'problem' (default: the problem's own matrix, per-system for the transistor),
                   an [n, n] array shared by the ensemble, or None (identity, as in the reference).
-    var_index   : [n] integers 0..3 or None (all differential), as in the reference.
+    var_index   : [n] integers 0..3 or None (all differential), as in the reference; 'problem' = the one the reference's
+                  script for this problem passes.
     jac         : 'analytic' (default: the problem's analytic Jacobian functor), a constant [n, n] matrix, or
                   None = finite differences as in the reference's default (scipy num_jac).
     events      : `LinearEvent`s (g = coef . y - level) and, for user problems compiled with event functions, `FunctorEvent`s

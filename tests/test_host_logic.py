@@ -151,3 +151,12 @@ def test_per_system_ode_result_view():
     r2 = res2.system(0)
     assert r2.t.shape == (r.naccpt + 1,) and r2.t[0] == 0.0 and r2.t[-1] == 2.0 and r2.y.shape == (5, r.naccpt + 1)
     np.testing.assert_array_equal(r2.y[:, -1], out["y_final"][0])
+
+
+def test_var_index_of_the_problem():
+    hb = br.prepare("pendulum3", (0.0, 1.0), (3, 5), var_index="problem")
+    assert hb.var_index.tolist() == [0, 0, 0, 0, 3]
+    assert br.prepare("npendulum", (0.0, 1.0), (2, 10), var_index="problem").var_index.tolist() == [0, 0, 2, 2, 3] * 2
+    assert br.prepare("pendulum3", (0.0, 1.0), (3, 5)).var_index.tolist() == [0] * 5        # None: all differential, as in the reference
+    with pytest.raises(ValueError):
+        br.prepare("pendulum3", (0.0, 1.0), (3, 5), var_index="auto")
