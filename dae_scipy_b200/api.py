@@ -16,7 +16,6 @@ without a CUDA device the call raises — there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
-import math
 import warnings
 from dataclasses import dataclass
 

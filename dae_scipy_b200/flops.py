@@ -14,7 +14,6 @@ For the banded CTA-per-system kernel 2/3 n^3 becomes 2 N kl (kl + ku) and 2 n^2 
 """
 from __future__ import annotations
 
-import numpy as np
 
 # per right-hand-side / Jacobian evaluation; n-pendulum figures are per node
 F_RHS = {"pendulum3": 12, "pendulum2": 12, "pendulum1": 20, "robertson": 15, "transistor": 22, "npendulum": 17}

@@ -13,7 +13,7 @@ Only numpy is used here; nothing in this module integrates anything.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

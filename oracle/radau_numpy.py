@@ -30,7 +30,6 @@ Only the dense (non-sparse) branch and the callable/constant Jacobian modes are 
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass, field
 
 import numpy as np

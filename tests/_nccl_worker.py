@@ -4,7 +4,6 @@ rank 0 over NCCL and compared with the same ensemble integrated by rank 0 alone.
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -7,7 +7,6 @@ import re
 import subprocess
 import tempfile
 
-import numpy as np
 import pytest
 
 import dae_scipy_b200 as br

@@ -7,7 +7,6 @@ import os
 import numpy as np
 import pytest
 
-import dae_scipy_b200 as br
 from dae_scipy_b200.api import LinearEvent, find_events
 from _util import GOLDEN_DIR, run_kernel_source_on_cpu
 
