@@ -144,3 +144,44 @@ def test_linear_event_packing_and_validation():
         LinearEvent(2)                                              # an index needs n
     ev = LinearEvent([1.0, -1.0], level=0.25)
     assert ev(0.0, np.array([2.0, 0.5])) == 1.25                     # an ordinary event callable as well
+
+
+def test_device_side_events_random_combinations_against_scipy_helpers():
+    """Seeded differential run: random linear events (single components and dense functionals, random levels, directions,
+    terminal after the 1st / 2nd / 3rd occurrence or never, forward and backward integration, several events at once) located
+    by the kernel source, against scipy's find_active_events / handle_events / brentq applied on the host to the step record
+    of the uninterrupted run: same occurrences, same terminations, times to 1e-9."""
+    import dae_scipy_b200 as br
+    E = br.ensembles
+    rng = np.random.default_rng(20261021)
+    scale = np.array([1, 1, 3, 3, 10.0])
+    n_fired = n_term = 0
+    for case in range(14):
+        ens = E.pendulum_ensemble(3, t_end=float(rng.choice([1.0, 3.0])), seed=int(rng.integers(1 << 30)), n_t_eval=int(rng.integers(2, 40)))
+        if rng.random() < 0.3:
+            ens["t_span"] = (ens["t_span"][1], ens["t_span"][0])
+            ens["t_eval"] = ens["t_eval"][::-1].copy()
+        evs = []
+        for _ in range(int(rng.integers(1, 5))):
+            coef = np.zeros(5)
+            if rng.random() < 0.5:
+                coef[int(rng.integers(5))] = 1.0
+            else:
+                coef = rng.standard_normal(5) / scale
+            level = float(coef @ ens["y0"].mean(axis=0) + rng.standard_normal() * 0.3 * np.abs(coef * scale).sum())
+            evs.append(LinearEvent(coef, level=level, direction=float(rng.choice([-1, 0, 1])),
+                                   terminal=[False, False, True, 2, 3][int(rng.integers(5))]))
+        out = run_kernel_source_on_cpu(ens, events=evs, max_events=64)
+        full = run_kernel_source_on_cpu(ens, dense_cap=3000)
+        t_host, _, term, t_stop, _ = find_events(full["sol"], evs, ens["t_span"][0], ens["y0"])
+        assert term.tolist() == (out["status"] == 1).tolist(), case
+        for i in range(3):
+            for e in range(len(evs)):
+                k = out["event_count"][i, e]
+                assert k == t_host[i][e].size, (case, i, e)
+                np.testing.assert_allclose(out["event_t"][i, e, :k], t_host[i][e], rtol=0, atol=3e-9)
+                n_fired += int(k)
+            if term[i]:
+                n_term += 1
+                np.testing.assert_allclose(out["t_final"][i], t_stop[i], rtol=0, atol=3e-9)
+    assert n_fired > 50 and n_term > 5            # the run did exercise occurrences and terminations
