@@ -18,7 +18,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbrdae.so")
 
 SOURCES = ["brdae_abi.cu", "dispatch.cu", "k1_pendulum.cu", "k1_robertson.cu", "k1_transistor.cu", "k1_extra.cu",
-           "k2_npendulum.cu", "k3_npendulum_lanes.cu", "fp64_peak.cu", "layout.cu", "k1_user.cu"]
+           "k2_npendulum.cu", "k4_chain.cu", "fp64_peak.cu", "layout.cu", "k1_user.cu"]
 USER_TU = "k1_user.cu"       # stub in the stock library, the user's functor in a plugin build
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",

@@ -76,7 +76,7 @@ size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *o) {
     if (!b) return 0;
     size_t bytes = kCounterBytes;
     if (b->problem == BRDAE_NPENDULUM)
-        bytes += npendulum_uses_k3(b->n, b->n_systems) ? k3_scratch_bytes(b->n, b->n_systems) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
+        bytes += npendulum_uses_k4(b->n, b->n_systems) ? k4_scratch_bytes(b->n, b->n_systems) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
     else {      // K1: per-CTA slice of cold per-lane state (kernels that keep it in shared memory need none)
         LaunchGeom g{};
         const bool fd = o && o->jac_finite_differences && !b->jac_const;

@@ -6,15 +6,14 @@
 
 namespace brdae {
 
-// Chains: CTA-per-rope (K2, state in shared memory) for small batches, lane-per-rope (K3, state in
-// global memory) once there are enough ropes to fill the machine with lanes.
-bool npendulum_uses_k3(int n, int64_t B) {
-    (void)n;
+// Chains: the lane-per-rope block-elimination kernel K4 (chain_k4.cuh) is the chain solver.  The CTA-per-system band
+// kernel K2 implements the general banded contract (pivoted band LU) on the same problem; it is selected with
+// BRDAE_NPENDULUM_KERNEL=k2 (tests of the band path) and is what a user-supplied mass matrix would need.
+bool npendulum_uses_k4(int n, int64_t B) {
+    (void)n; (void)B;
     const char *force = std::getenv("BRDAE_NPENDULUM_KERNEL");
     if (force && std::strcmp(force, "k2") == 0) return false;
-    if (force && std::strcmp(force, "k3") == 0) return true;
-    (void)B;
-    return false;   // K3 is correct but not yet competitive; opt-in only
+    return true;
 }
 
 static int route(int problem, bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s,
@@ -26,10 +25,7 @@ static int route(int problem, bool dense_mass, const SolveArgs &a, const brdae_b
     case BRDAE_ROBERTSON: return k1_robertson(dense_mass, a, sms, s, g, geom_only);
     case BRDAE_TRANSISTOR: return k1_transistor(dense_mass, a, sms, s, g, geom_only);
     case BRDAE_NPENDULUM:
-        if (npendulum_uses_k3(a.n, a.B)) {
-            if (a.dense_cap > 0) return BRDAE_ERR_UNSUPPORTED;      // the experimental lane-per-rope kernel keeps no step record
-            return k3_npendulum(dense_mass, a, b, sms, s, g, geom_only);
-        }
+        if (npendulum_uses_k4(a.n, a.B)) return k4_chain(dense_mass, a, b, sms, s, g, geom_only);
         return k2_npendulum(dense_mass, a, b, sms, s, g, geom_only);
     case BRDAE_ROBERTSON_ODE: case BRDAE_JAY: case BRDAE_POLYDAE2: case BRDAE_LINEAR7:
         return k1_extra(problem, dense_mass, a, sms, s, g, geom_only);

@@ -336,8 +336,9 @@ __device__ void rope_rhs(const Rope &s, const double *Y, double *F) {
         const double dx = (i == 0) ? q[0] : q[0] - q[-5];
         const double dy = (i == 0) ? q[1] : q[1] - q[-4];
         const double rs = dx * dx + dy * dy;
-        s.aa[i] = q[4] * dx / rs;
-        s.bb[i] = q[4] * dy / rs;
+        const double ir = 1.0 / rs;              // one reciprocal per rod (oracle npe_rhs)
+        s.aa[i] = (q[4] * dx) * ir;
+        s.bb[i] = (q[4] * dy) * ir;
         F[5 * i + 4] = rs - s.r0s[i];
     }
     __syncthreads();

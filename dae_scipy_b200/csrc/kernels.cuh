@@ -24,11 +24,11 @@ int k1_user(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, Launch
 // CTA-per-system banded kernel for the n-pendulum chain (k2_npendulum.cu)
 int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 size_t k2_scratch_bytes(int n, int sms, int64_t B);
-// lane-per-rope kernel for large ensembles of chains (k3_npendulum_lanes.cu)
-int k3_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
-size_t k3_scratch_bytes(int n, int64_t B);
-// which chain kernel a batch of B ropes with n unknowns uses (BRDAE_NPENDULUM_KERNEL=k2|k3 overrides)
-bool npendulum_uses_k3(int n, int64_t B);
+// lane-per-rope block-elimination kernel for the chain (k4_chain.cu, chain_k4.cuh)
+int k4_chain(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
+size_t k4_scratch_bytes(int n, int64_t B);
+// which chain kernel a batch of B ropes with n unknowns uses (BRDAE_NPENDULUM_KERNEL=k2 selects the band kernel)
+bool npendulum_uses_k4(int n, int64_t B);
 
 // layout.cu: dst[z*dst_zs + c*dst_rs + r] = src[z*src_zs + r*src_rs + c] for r < R, c < C, z < Z
 // (rows <-> structure-of-arrays permutations of the host-buffer entry points)

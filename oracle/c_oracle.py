@@ -64,8 +64,11 @@ def make_options(first_step=None, max_step=np.inf, newton_tol=None, factor_on_no
                  scale_error=True, zero_algebraic_error=False, bAlwaysApply2ndEstimate=True,
                  bUsePredictiveController=True, bUsePredictiveNewtonStoppingCriterion=True,
                  bUseExtrapolatedGuess=True, bPerformAllNewtonIterations=False, constant_dt=False,
-                 nmax_step=None, jac="analytic"):
+                 nmax_step=None, jac="analytic", chain_linear_algebra="block"):
+    """`chain_linear_algebra`: "block" = the chain spec of the n-pendulum (block elimination, what the lane-per-rope kernel
+    implements), "band" = the banded LU of the general contract (the CTA-per-system band kernel)."""
     o = OrcOptions()
+    o.reserved = {"block": 0, "band": 1}[chain_linear_algebra]
     o.jac_finite_differences = int(jac is None)     # jac=None: finite differences, as in the reference
     o.first_step = -1.0 if first_step is None else float(first_step)
     o.max_step = float(max_step)

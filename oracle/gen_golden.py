@@ -282,6 +282,10 @@ def main():
     save("ens_npendulum_n4", E.npendulum_ensemble(3, n_nodes=4))
     save("ens_npendulum_n10", E.npendulum_ensemble(2, n_nodes=10))
     save("ens_npendulum_n20", E.npendulum_ensemble(2, n_nodes=20))
+    # the chain sizes of the bench configurations (BASELINE configs[4]: n = 20..100), first ropes of the bench ensembles,
+    # full t_end (the reference factorises dense 250 x 250 / 500 x 500 matrices here: minutes per rope)
+    save("ens_npendulum_n50", E.npendulum_ensemble(4, n_nodes=50))
+    save("ens_npendulum_n100", E.npendulum_ensemble(4, n_nodes=100))
 
 
 if __name__ == "__main__":

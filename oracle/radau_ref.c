@@ -234,7 +234,8 @@ static void npe_rhs(const prob_ctx *c, double t, const double *X, double *f) {
         double dx = (i == 0) ? q[0] : q[0] - q[-5];
         double dy = (i == 0) ? q[1] : q[1] - q[-4];
         double rs = dx * dx + dy * dy;
-        double a = q[4] * dx / rs, b = q[4] * dy / rs;
+        double ir = 1.0 / rs;                 /* one reciprocal per rod (chain spec) */
+        double a = (q[4] * dx) * ir, b = (q[4] * dy) * ir;
         double *o = f + 5 * i;
         o[0] = q[2];
         o[1] = q[3];
@@ -475,6 +476,265 @@ static void solve_cplx(const lu_pair *L, double *br, double *bi) {
     }
 }
 
+/* ---- chain block elimination: the linear algebra of the n-pendulum ("chain spec") ----
+ * The iteration matrix mu M - J of the chain (recursive_pendulum.py:93-127; M = diag(1,1,1,1,0) per node) is
+ * block tridiagonal in the nodes.  Rows x_i, y_i read  mu p - v = r, so the velocity increments are eliminated
+ * exactly (v = mu p - r) and what is left per node is a 3 x 3 block in u_i = (dx_i, dy_i, dlambda_i):
+ *     D_i u_i + L_i u_{i-1} + U_i u_{i+1} = g_i,   g = (r_vx + mu r_x, r_vy + mu r_y, r_lambda),
+ * L_i with a zero third column and U_i with a zero third row.  It is factorised node by node,
+ *     E_0 = D_0,  E_i = D_i - L_i E_{i-1}^-1 U_{i-1},
+ * each E_i inverted explicitly by Gauss-Jordan elimination with partial pivoting inside the block (first
+ * maximum of |a|, |re|+|im| for the complex system, reciprocal pivots), and solved by
+ *     z_i = E_i^-1 (g_i - L_i z_{i-1}),   u_i = z_i - E_i^-1 U_i u_{i+1}.
+ * The matrix is NOT row-scaled by hscale (radauDAE.py:600-606): in the Newton iteration the scaling cancels, and
+ * the one place where the reference applies the scaled factors to an unscaled right-hand side -- the error
+ * estimate, SURVEY Q9 -- multiplies those rows of the right-hand side by the h of the factorisation instead.
+ * Every product/sum below is written in the order the CUDA kernel (csrc/k4_chain.cu) evaluates it. */
+typedef struct { double adx, ady, bdy, al, bl, dx2, dy2; } cnode;
+
+static void chain_jac(const prob_ctx *c, const double *X, cnode *nd) {
+    for (int i = 0; i < c->nn; ++i) {
+        const double *q = X + 5 * i;
+        double dx = (i == 0) ? q[0] : q[0] - q[-5];
+        double dy = (i == 0) ? q[1] : q[1] - q[-4];
+        double rs = dx * dx + dy * dy, l = q[4];
+        double rs2 = rs * rs;
+        nd[i].adx = l * (rs - 2 * dx * dx) / rs2;
+        nd[i].ady = l * (-2 * dx * dy) / rs2;
+        nd[i].bdy = l * (rs - 2 * dy * dy) / rs2;
+        nd[i].al = dx / rs;
+        nd[i].bl = dy / rs;
+        nd[i].dx2 = 2 * dx;
+        nd[i].dy2 = 2 * dy;
+    }
+}
+/* V = E^-1, Gauss-Jordan with partial pivoting; E is destroyed */
+static void inv3_real(double E[3][3], double V[3][3]) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) V[r][c] = (r == c) ? 1.0 : 0.0;
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+        double best = fabs(E[k][k]);
+        for (int r = k + 1; r < 3; ++r) { double v = fabs(E[r][k]); if (v > best) { best = v; p = r; } }
+        if (p != k)
+            for (int c = 0; c < 3; ++c) {
+                double t = E[k][c]; E[k][c] = E[p][c]; E[p][c] = t;
+                t = V[k][c]; V[k][c] = V[p][c]; V[p][c] = t;
+            }
+        double rcp = 1.0 / E[k][k];
+        for (int c = k + 1; c < 3; ++c) E[k][c] = E[k][c] * rcp;
+        for (int c = 0; c < 3; ++c) V[k][c] = V[k][c] * rcp;
+        for (int r = 0; r < 3; ++r) {
+            if (r == k) continue;
+            double f = E[r][k];
+            for (int c = k + 1; c < 3; ++c) E[r][c] = fma(-f, E[k][c], E[r][c]);
+            for (int c = 0; c < 3; ++c) V[r][c] = fma(-f, V[k][c], V[r][c]);
+        }
+    }
+}
+static void inv3_cplx(double Er[3][3], double Ei[3][3], double Vr[3][3], double Vi[3][3]) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { Vr[r][c] = (r == c) ? 1.0 : 0.0; Vi[r][c] = 0.0; }
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+        double best = fabs(Er[k][k]) + fabs(Ei[k][k]);
+        for (int r = k + 1; r < 3; ++r) { double v = fabs(Er[r][k]) + fabs(Ei[r][k]); if (v > best) { best = v; p = r; } }
+        if (p != k)
+            for (int c = 0; c < 3; ++c) {
+                double t = Er[k][c]; Er[k][c] = Er[p][c]; Er[p][c] = t;
+                t = Ei[k][c]; Ei[k][c] = Ei[p][c]; Ei[p][c] = t;
+                t = Vr[k][c]; Vr[k][c] = Vr[p][c]; Vr[p][c] = t;
+                t = Vi[k][c]; Vi[k][c] = Vi[p][c]; Vi[p][c] = t;
+            }
+        double pr = Er[k][k], pi = Ei[k][k];
+        double invd = 1.0 / fma(pr, pr, pi * pi);
+        double qr = pr * invd, qi = -(pi * invd);
+        for (int c = k + 1; c < 3; ++c) {
+            double xr = Er[k][c], xi = Ei[k][c];
+            Er[k][c] = fma(xr, qr, -(xi * qi)); Ei[k][c] = fma(xr, qi, xi * qr);
+        }
+        for (int c = 0; c < 3; ++c) {
+            double xr = Vr[k][c], xi = Vi[k][c];
+            Vr[k][c] = fma(xr, qr, -(xi * qi)); Vi[k][c] = fma(xr, qi, xi * qr);
+        }
+        for (int r = 0; r < 3; ++r) {
+            if (r == k) continue;
+            double fr = Er[r][k], fi = Ei[r][k];
+            for (int c = k + 1; c < 3; ++c) {
+                double ur = Er[k][c], ui = Ei[k][c], xr = Er[r][c], xi = Ei[r][c];
+                xr = fma(-fr, ur, xr); xr = fma(fi, ui, xr);
+                xi = fma(-fr, ui, xi); xi = fma(-fi, ur, xi);
+                Er[r][c] = xr; Ei[r][c] = xi;
+            }
+            for (int c = 0; c < 3; ++c) {
+                double ur = Vr[k][c], ui = Vi[k][c], xr = Vr[r][c], xi = Vi[r][c];
+                xr = fma(-fr, ur, xr); xr = fma(fi, ui, xr);
+                xi = fma(-fr, ui, xi); xi = fma(-fi, ur, xi);
+                Vr[r][c] = xr; Vi[r][c] = xi;
+            }
+        }
+    }
+}
+typedef struct {
+    int nn;
+    cnode *nd;                 /* rod quantities of the Jacobian, [nn] */
+    double *vr;                /* E_i^-1 of the real system, [nn][9] */
+    double *vcr, *vci;         /* E_i^-1 of the complex system */
+    double *zr, *zcr, *zci;    /* forward-substituted blocks, [nn][3] */
+} chain_lu;
+
+/* coupling blocks of node i: L_i[:, 0:2] (3 x 2, to node i-1) and U_{i-1}[0:2, :] (2 x 3, node i-1 to node i) */
+static void chain_L(const prob_ctx *c, const cnode *nd, int i, double L[3][2]) {
+    double im = c->inv_m[i];
+    L[0][0] = im * nd[i].adx; L[0][1] = im * nd[i].ady;
+    L[1][0] = im * nd[i].ady; L[1][1] = im * nd[i].bdy;
+    L[2][0] = nd[i].dx2;      L[2][1] = nd[i].dy2;
+}
+static void chain_U(const prob_ctx *c, const cnode *nd, int i /* block U_i couples node i to node i+1 */, double U[2][3]) {
+    double im = c->inv_m[i];
+    U[0][0] = im * nd[i + 1].adx; U[0][1] = im * nd[i + 1].ady; U[0][2] = im * nd[i + 1].al;
+    U[1][0] = im * nd[i + 1].ady; U[1][1] = im * nd[i + 1].bdy; U[1][2] = im * nd[i + 1].bl;
+}
+/* both factorisations; mr, (mcr, mci) = mu / h */
+static void chain_factor(const prob_ctx *c, chain_lu *C, double mr, double mcr, double mci) {
+    const int nn = C->nn;
+    const cnode *nd = C->nd;
+    const double m2 = mr * mr;
+    const double m2r = fma(mcr, mcr, -(mci * mci)), m2i = 2 * (mcr * mci);
+    for (int i = 0; i < nn; ++i) {
+        double im = c->inv_m[i];
+        double sxx = im * nd[i].adx, sxy = im * nd[i].ady, syy = im * nd[i].bdy;
+        if (i < nn - 1) { sxx = sxx + im * nd[i + 1].adx; sxy = sxy + im * nd[i + 1].ady; syy = syy + im * nd[i + 1].bdy; }
+        double e02 = -(im * nd[i].al), e12 = -(im * nd[i].bl);
+        double Er[3][3] = {{m2 - sxx, -sxy, e02}, {-sxy, m2 - syy, e12}, {-nd[i].dx2, -nd[i].dy2, 0.0}};
+        double Cr[3][3] = {{m2r - sxx, -sxy, e02}, {-sxy, m2r - syy, e12}, {-nd[i].dx2, -nd[i].dy2, 0.0}};
+        double Ci[3][3] = {{m2i, 0.0, 0.0}, {0.0, m2i, 0.0}, {0.0, 0.0, 0.0}};
+        if (i > 0) {
+            double L[3][2], U[2][3];
+            chain_L(c, nd, i, L);
+            chain_U(c, nd, i - 1, U);
+            const double *G = C->vr + 9 * (i - 1), *Gr = C->vcr + 9 * (i - 1), *Gi = C->vci + 9 * (i - 1);
+            double X[2][3], Xr[2][3], Xi[2][3];
+            for (int r = 0; r < 2; ++r)
+                for (int k = 0; k < 3; ++k) {
+                    X[r][k] = fma(G[3 * r + 1], U[1][k], G[3 * r] * U[0][k]);
+                    Xr[r][k] = fma(Gr[3 * r + 1], U[1][k], Gr[3 * r] * U[0][k]);
+                    Xi[r][k] = fma(Gi[3 * r + 1], U[1][k], Gi[3 * r] * U[0][k]);
+                }
+            for (int r = 0; r < 3; ++r)
+                for (int k = 0; k < 3; ++k) {
+                    Er[r][k] = Er[r][k] - fma(L[r][1], X[1][k], L[r][0] * X[0][k]);
+                    Cr[r][k] = Cr[r][k] - fma(L[r][1], Xr[1][k], L[r][0] * Xr[0][k]);
+                    Ci[r][k] = Ci[r][k] - fma(L[r][1], Xi[1][k], L[r][0] * Xi[0][k]);
+                }
+        }
+        double V[3][3], Vr[3][3], Vi[3][3];
+        inv3_real(Er, V);
+        inv3_cplx(Cr, Ci, Vr, Vi);
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k) {
+                C->vr[9 * i + 3 * r + k] = V[r][k]; C->vcr[9 * i + 3 * r + k] = Vr[r][k]; C->vci[9 * i + 3 * r + k] = Vi[r][k];
+            }
+    }
+}
+/* b (5 per node: x, y, vx, vy, lambda) <- (mu M - J)^-1 b, real system */
+static void chain_solve_real(const prob_ctx *c, chain_lu *C, double mr, double *b) {
+    const int nn = C->nn;
+    const cnode *nd = C->nd;
+    double *z = C->zr;
+    for (int i = 0; i < nn; ++i) {
+        const double *r = b + 5 * i, *V = C->vr + 9 * i;
+        double g[3] = {fma(mr, r[0], r[2]), fma(mr, r[1], r[3]), r[4]};
+        if (i > 0) {
+            double L[3][2];
+            chain_L(c, nd, i, L);
+            for (int q = 0; q < 3; ++q) g[q] = fma(-L[q][1], z[3 * (i - 1) + 1], fma(-L[q][0], z[3 * (i - 1)], g[q]));
+        }
+        for (int q = 0; q < 3; ++q) z[3 * i + q] = fma(V[3 * q + 2], g[2], fma(V[3 * q + 1], g[1], V[3 * q] * g[0]));
+    }
+    double u[3] = {0, 0, 0};
+    for (int i = nn - 1; i >= 0; --i) {
+        const double *V = C->vr + 9 * i;
+        double un[3];
+        if (i == nn - 1) { for (int q = 0; q < 3; ++q) un[q] = z[3 * i + q]; }
+        else {
+            double U[2][3];
+            chain_U(c, nd, i, U);
+            double w0 = fma(U[0][2], u[2], fma(U[0][1], u[1], U[0][0] * u[0]));
+            double w1 = fma(U[1][2], u[2], fma(U[1][1], u[1], U[1][0] * u[0]));
+            for (int q = 0; q < 3; ++q) un[q] = fma(-V[3 * q + 1], w1, fma(-V[3 * q], w0, z[3 * i + q]));
+        }
+        double *r = b + 5 * i;
+        double v1 = fma(mr, un[0], -r[0]), v2 = fma(mr, un[1], -r[1]);
+        r[0] = un[0]; r[1] = un[1]; r[2] = v1; r[3] = v2; r[4] = un[2];
+        u[0] = un[0]; u[1] = un[1]; u[2] = un[2];
+    }
+}
+static void chain_solve_cplx(const prob_ctx *c, chain_lu *C, double mcr, double mci, double *br, double *bi) {
+    const int nn = C->nn;
+    const cnode *nd = C->nd;
+    double *zr = C->zcr, *zi = C->zci;
+    for (int i = 0; i < nn; ++i) {
+        const double *rr = br + 5 * i, *ri = bi + 5 * i, *Vr = C->vcr + 9 * i, *Vi = C->vci + 9 * i;
+        /* g = r_v + mu r_p (complex product) */
+        double gr[3] = {fma(-mci, ri[0], fma(mcr, rr[0], rr[2])), fma(-mci, ri[1], fma(mcr, rr[1], rr[3])), rr[4]};
+        double gi[3] = {fma(mci, rr[0], fma(mcr, ri[0], ri[2])), fma(mci, rr[1], fma(mcr, ri[1], ri[3])), ri[4]};
+        if (i > 0) {
+            double L[3][2];
+            chain_L(c, nd, i, L);
+            for (int q = 0; q < 3; ++q) {
+                gr[q] = fma(-L[q][1], zr[3 * (i - 1) + 1], fma(-L[q][0], zr[3 * (i - 1)], gr[q]));
+                gi[q] = fma(-L[q][1], zi[3 * (i - 1) + 1], fma(-L[q][0], zi[3 * (i - 1)], gi[q]));
+            }
+        }
+        for (int q = 0; q < 3; ++q) {
+            double sr = fma(Vr[3 * q], gr[0], -(Vi[3 * q] * gi[0]));
+            double si = fma(Vr[3 * q], gi[0], Vi[3 * q] * gr[0]);
+            for (int k = 1; k < 3; ++k) {
+                sr = fma(Vr[3 * q + k], gr[k], sr); sr = fma(-Vi[3 * q + k], gi[k], sr);
+                si = fma(Vr[3 * q + k], gi[k], si); si = fma(Vi[3 * q + k], gr[k], si);
+            }
+            zr[3 * i + q] = sr; zi[3 * i + q] = si;
+        }
+    }
+    double ur[3] = {0, 0, 0}, ui[3] = {0, 0, 0};
+    for (int i = nn - 1; i >= 0; --i) {
+        const double *Vr = C->vcr + 9 * i, *Vi = C->vci + 9 * i;
+        double nr[3], ni[3];
+        if (i == nn - 1) { for (int q = 0; q < 3; ++q) { nr[q] = zr[3 * i + q]; ni[q] = zi[3 * i + q]; } }
+        else {
+            double U[2][3];
+            chain_U(c, nd, i, U);
+            double w0r = fma(U[0][2], ur[2], fma(U[0][1], ur[1], U[0][0] * ur[0]));
+            double w0i = fma(U[0][2], ui[2], fma(U[0][1], ui[1], U[0][0] * ui[0]));
+            double w1r = fma(U[1][2], ur[2], fma(U[1][1], ur[1], U[1][0] * ur[0]));
+            double w1i = fma(U[1][2], ui[2], fma(U[1][1], ui[1], U[1][0] * ui[0]));
+            for (int q = 0; q < 3; ++q) {
+                double xr = zr[3 * i + q], xi = zi[3 * i + q];
+                xr = fma(-Vr[3 * q], w0r, xr); xr = fma(Vi[3 * q], w0i, xr);
+                xi = fma(-Vr[3 * q], w0i, xi); xi = fma(-Vi[3 * q], w0r, xi);
+                xr = fma(-Vr[3 * q + 1], w1r, xr); xr = fma(Vi[3 * q + 1], w1i, xr);
+                xi = fma(-Vr[3 * q + 1], w1i, xi); xi = fma(-Vi[3 * q + 1], w1r, xi);
+                nr[q] = xr; ni[q] = xi;
+            }
+        }
+        double *rr = br + 5 * i, *ri = bi + 5 * i;
+        /* v = mu p - r */
+        double v1r = fma(-mci, ni[0], fma(mcr, nr[0], -rr[0])), v1i = fma(mci, nr[0], fma(mcr, ni[0], -ri[0]));
+        double v2r = fma(-mci, ni[1], fma(mcr, nr[1], -rr[1])), v2i = fma(mci, nr[1], fma(mcr, ni[1], -ri[1]));
+        rr[0] = nr[0]; rr[1] = nr[1]; rr[2] = v1r; rr[3] = v2r; rr[4] = nr[2];
+        ri[0] = ni[0]; ri[1] = ni[1]; ri[2] = v1i; ri[3] = v2i; ri[4] = ni[2];
+        for (int q = 0; q < 3; ++q) { ur[q] = nr[q]; ui[q] = ni[q]; }
+    }
+}
+/* chain norms: five fma chains, one per unknown of a node, walked from the last node to the first and over the
+ * stacked vectors (m of them) in order; folded as ((s0+s1)+(s2+s3))+s4 */
+static double chain_sum_squares(const double *v, int nn, int m) {
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int i = nn - 1; i >= 0; --i)
+        for (int c = 0; c < 5; ++c)
+            for (int q = 0; q < m; ++q) { double x = v[(size_t)q * 5 * nn + 5 * i + c]; s[c] = fma(x, x, s[c]); }
+    return ((s[0] + s[1]) + (s[2] + s[3])) + s[4];
+}
+
 /* M.v with M dense row-major; the fma chain runs over the columns in increasing order and
  * skips structural zeros of M (adding an exact zero changes nothing) */
 static void mass_mv(int n, const double *M, const int *mlo, const int *mhi, const double *v, double *o) {
@@ -527,6 +787,7 @@ typedef struct {
     double *jfac, *yp, *fn, *fn2; /* finite-difference Jacobian: column factors, perturbed state, f there */
     int *mlo, *mhi;
     lu_pair lu;
+    chain_lu ch;     /* n-pendulum: block elimination (allocated when n % 5 == 0) */
 } work;
 
 static void *xcalloc(size_t n, size_t s) { void *p = calloc(n ? n : 1, s); if (!p) abort(); return p; }
@@ -546,6 +807,11 @@ static void work_alloc(work *w, int n) {
     w->lu.n = n;
     w->lu.lr = xcalloc(N * N, 8); w->lu.lcr = xcalloc(N * N, 8); w->lu.lci = xcalloc(N * N, 8);
     w->lu.pr = xcalloc(N, sizeof(int)); w->lu.pc = xcalloc(N, sizeof(int));
+    int nn = n / 5;
+    w->ch.nn = nn;
+    w->ch.nd = xcalloc((size_t)nn, sizeof(cnode));
+    w->ch.vr = xcalloc(9 * (size_t)nn, 8); w->ch.vcr = xcalloc(9 * (size_t)nn, 8); w->ch.vci = xcalloc(9 * (size_t)nn, 8);
+    w->ch.zr = xcalloc(3 * (size_t)nn, 8); w->ch.zcr = xcalloc(3 * (size_t)nn, 8); w->ch.zci = xcalloc(3 * (size_t)nn, 8);
 }
 static void work_free(work *w) {
     free(w->y); free(w->f); free(w->yold); free(w->Q); free(w->W); free(w->Z); free(w->F);
@@ -554,6 +820,7 @@ static void work_free(work *w) {
     free(w->hs); free(w->sq); free(w->mlo); free(w->mhi);
     free(w->jfac); free(w->yp); free(w->fn); free(w->fn2);
     free(w->lu.lr); free(w->lu.lcr); free(w->lu.lci); free(w->lu.pr); free(w->lu.pc);
+    free(w->ch.nd); free(w->ch.vr); free(w->ch.vcr); free(w->ch.vci); free(w->ch.zr); free(w->ch.zcr); free(w->ch.zci);
 }
 
 /* Z_i = (T W)_i, fma chain over the stages in order 0,1,2; T[2] = (1,1,0) */
@@ -643,6 +910,12 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
     const double rsq3n = 1.0 / sqrt(3.0 * n), rsqn = 1.0 / sqrt((double)n);
     const double rsqdiff = 1.0 / sqrt((double)(n - n_alg));
     const int has_jac_fn = (jac_const == NULL);
+    /* the chain with its own mass matrix and analytic Jacobian: block elimination (the "chain spec"); reserved = 1
+     * keeps the banded LU of the general contract (what the band kernel K2 implements) */
+    const int chain = (pc->problem == PB_NPENDULUM && mass_in == NULL && jac_const == NULL
+                       && !o->jac_finite_differences && o->reserved == 0);
+    double h_lu = 1.0;   /* chain: the h of the current factorisation (rows scaled by hscale in the reference) */
+    double mr_f = 0, mcr_f = 0, mci_f = 0;   /* chain: mu / h of the current factorisation (the velocity elimination uses it) */
 
     /* mass matrix: given (shared) or the problem's own */
     if (mass_in) memcpy(w->M, mass_in, sizeof(double) * n * n);
@@ -671,6 +944,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
     int hist_state = 0;
     const int fd = has_jac_fn && o->jac_finite_differences;
     if (fd) { for (int c = 0; c < n; ++c) w->jfac[c] = NJ_FACTOR0; num_jac_fd(pc, w, t, atol); cnt[C_NJEV] = 1; } /* :475-481 */
+    else if (chain) { chain_jac(pc, w->y, w->ch.nd); cnt[C_NJEV] = 1; }
     else if (has_jac_fn) { prob_jac(pc, t, w->y, w->J); cnt[C_NJEV] = 1; } /* :483-484 */
     else memcpy(w->J, jac_const, sizeof(double) * n * n);
     int current_jac = 1, lu_valid = 0, have_sol = 0;
@@ -745,6 +1019,11 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     for (int c = 0; c < n; ++c)
                         w->hs[c] = (o->scale_residuals && var_index[c] >= 1) ? inv_h_lu : 1.0;
                     double mr = MU_REAL * inv_h, mcr = MU_CR * inv_h, mci = MU_CI * inv_h;
+                    if (chain) {
+                        if (o->scale_residuals) h_lu = h;
+                        mr_f = mr; mcr_f = mcr; mci_f = mci;
+                        chain_factor(pc, &w->ch, mr, mcr, mci);
+                    } else {
                     for (int r = 0; r < n; ++r)
                         for (int c = 0; c < n; ++c) {
                             double m = w->M[r * n + c], j = w->J[r * n + c], s = w->hs[r];
@@ -754,6 +1033,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                         }
                     lu_real(&w->lu);
                     lu_cplx(&w->lu);
+                    }
                     cnt[C_NLU]++;
                     trace_ev('F');
                     lu_valid = 1;
@@ -792,17 +1072,23 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                         double a = fma(-mr, w->mw0[c], w->fr[c]);
                         double br = fma(-mcr, w->mw1[c], w->fcr[c]); br = fma(mci, w->mw2[c], br);
                         double bi = fma(-mcr, w->mw2[c], w->fci[c]); bi = fma(-mci, w->mw1[c], bi);
-                        w->fr[c] = a * w->hs[c]; w->fcr[c] = br * w->hs[c]; w->fci[c] = bi * w->hs[c];
+                        if (chain) { w->fr[c] = a; w->fcr[c] = br; w->fci[c] = bi; }      /* no row scaling */
+                        else { w->fr[c] = a * w->hs[c]; w->fcr[c] = br * w->hs[c]; w->fci[c] = bi * w->hs[c]; }
                     }
-                    solve_real(&w->lu, w->fr);
-                    solve_cplx(&w->lu, w->fcr, w->fci);
+                    if (chain) {
+                        chain_solve_real(pc, &w->ch, mr_f, w->fr);
+                        chain_solve_cplx(pc, &w->ch, mcr_f, mci_f, w->fcr, w->fci);
+                    } else {
+                        solve_real(&w->lu, w->fr);
+                        solve_cplx(&w->lu, w->fcr, w->fci);
+                    }
                     cnt[C_NSOLVE]++;
                     for (int c = 0; c < n; ++c) {
                         w->sq[c] = w->fr[c] * w->inv_ns[c];
                         w->sq[n + c] = w->fcr[c] * w->inv_ns[c];
                         w->sq[2 * n + c] = w->fci[c] * w->inv_ns[c];
                     }
-                    double dwn = sqrt(sum_squares(w->sq, 3 * n, n > 8)) * rsq3n;
+                    double dwn = sqrt(chain ? chain_sum_squares(w->sq, n / 5, 3) : sum_squares(w->sq, 3 * n, n > 8)) * rsq3n;
                     for (int c = 0; c < n; ++c) {
                         w->W[c] += w->fr[c]; w->W[n + c] += w->fcr[c]; w->W[2 * n + c] += w->fci[c];
                     }
@@ -833,7 +1119,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 safety = o->safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter); /* :631 */
                 if (converged) break;
                 if (current_jac) break;                                            /* :638-641 */
-                if (fd) num_jac_fd(pc, w, t, atol); else prob_jac(pc, t, w->y, w->J);
+                if (fd) num_jac_fd(pc, w, t, atol); else if (chain) chain_jac(pc, w->y, w->ch.nd); else prob_jac(pc, t, w->y, w->J);
                 cnt[C_NJEV]++;                                                     /* :643 */
                 current_jac = 1; lu_valid = 0;
             }
@@ -865,13 +1151,17 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     prob_rhs(pc, t, w->tmp, w->F); cnt[C_NFEV]++;
                     for (int c = 0; c < n; ++c) w->err[c] = w->F[c] + w->mw0[c];
                 }
-                solve_real(&w->lu, w->err);    /* rhs deliberately NOT scaled by hscale */
+                if (chain) {   /* the reference applies factors of the hscale-d matrix to the unscaled vector */
+                    for (int c = 0; c < n; ++c) if (o->scale_residuals && var_index[c] >= 1) w->err[c] = w->err[c] * h_lu;
+                    chain_solve_real(pc, &w->ch, mr_f, w->err);
+                }
+                else solve_real(&w->lu, w->err);    /* rhs deliberately NOT scaled by hscale */
                 cnt[C_NSOLVE_ERR]++;
                 for (int c = 0; c < n; ++c) {
                     if (o->zero_algebraic_error && var_index[c] != 0) { w->err[c] = 0.0; w->sq[c] = 0.0; continue; }
                     w->sq[c] = w->err[c] * w->inv_es[c];
                 }
-                error_norm = sqrt(sum_squares(w->sq, n, n > 8)) * (o->zero_algebraic_error ? rsqdiff : rsqn);
+                error_norm = sqrt(chain ? chain_sum_squares(w->sq, n / 5, 1) : sum_squares(w->sq, n, n > 8)) * (o->zero_algebraic_error ? rsqdiff : rsqn);
                 if (!(error_norm > 1 && (o->always_2nd_estimate || rejected))) break;
             }
             if (error_norm > 1) {                                                   /* :713-733 */
@@ -890,7 +1180,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
         for (int c = 0; c < n; ++c) { w->yold[c] = w->y[c]; w->y[c] = w->y[c] + w->Z[2 * n + c]; }
         prob_rhs(pc, t_new, w->y, w->f); cnt[C_NFEV]++;
         if (recompute) {
-            if (fd) num_jac_fd(pc, w, t_new, atol); else prob_jac(pc, t_new, w->y, w->J);
+            if (fd) num_jac_fd(pc, w, t_new, atol); else if (chain) chain_jac(pc, w->y, w->ch.nd); else prob_jac(pc, t_new, w->y, w->J);
             cnt[C_NJEV]++; current_jac = 1;
         }
         else if (has_jac_fn) current_jac = 0;

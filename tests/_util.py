@@ -171,6 +171,44 @@ def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, **over
                 y_final=np.ascontiguousarray(out["y_final"].T), t_final=out["t_final"])
 
 
+def run_chain_kernel_source_on_cpu(ens, dense_cap=0, **over):
+    """tests/host_sim/k4_host_sim.cpp: the lane-per-rope chain kernel SOURCE (csrc/chain_k4.cuh) compiled for the host, one
+    lane with slot stride 1, pulling the ropes of the batch one after the other from the work counter."""
+    import dae_scipy_b200 as br
+    from dae_scipy_b200 import _abi
+    path = os.path.join(ROOT, "tests", "host_sim", "libk4_host_sim.so")
+    if path not in _sims:
+        sim = C.CDLL(path)
+        sim.sim_solve_chain.restype = C.c_int
+        sim.sim_solve_chain.argtypes = [C.POINTER(_abi.BrdaeBatch), C.POINTER(_abi.BrdaeOptions)]
+        _sims[path] = sim
+    opts = dict(ens["options"])
+    opts.update(over)
+    y0 = np.ascontiguousarray(ens["y0"], dtype=np.float64)
+    B, n = y0.shape
+    hb = br.prepare(ens["problem"], ens["t_span"], y0.shape, t_eval=ens["t_eval"], **opts)
+    T = hb.t_eval.size
+    y0s = np.ascontiguousarray(y0.T)
+    out = {"y_eval": np.empty((max(T, 1), n, B)), "n_eval": np.empty(B, np.int32), "t_final": np.empty(B),
+           "y_final": np.empty((n, B)), "status": np.empty(B, np.int32), "counters": np.empty((9, B), np.int32)}
+    ptr = {k: v.ctypes.data for k, v in out.items()}
+    ptr.update(y0=y0s.ctypes.data, params=None, t_eval=hb.t_eval.ctypes.data if T else None)
+    if dense_cap:
+        dense = {"dense_t": np.full((dense_cap, B), np.nan), "dense_y": np.full((dense_cap, n, B), np.nan),
+                 "dense_q": np.full((dense_cap, n, 3, B), np.nan)}
+        ptr.update({k: v.ctypes.data for k, v in dense.items()}, dense_cap=dense_cap)
+    b = hb.struct(ptr)
+    rc = _sims[path].sim_solve_chain(C.byref(b), C.byref(hb.options))
+    assert rc == 0, f"sim_solve_chain returned {rc}"
+    extra = {}
+    if dense_cap:
+        from dae_scipy_b200.api import make_ode_solution
+        extra["sol"] = make_ode_solution(hb, y0, dense["dense_t"], dense["dense_y"], dense["dense_q"], out["status"], out["counters"])
+    return dict(extra, y=np.ascontiguousarray(out["y_eval"][:T].transpose(2, 1, 0)), status=out["status"],
+                n_eval=out["n_eval"], counters=np.ascontiguousarray(out["counters"].T),
+                y_final=np.ascontiguousarray(out["y_final"].T), t_final=out["t_final"])
+
+
 # ------------------------------------------------------------------ the product (GPU)
 def run_gpu(ens, host_api=False, **over):
     import dae_scipy_b200 as br
@@ -202,7 +240,8 @@ def well_conditioned(name):
     return name in ("g1_pendulum3_single", "g2_robertson_single", "ens_pendulum3_tend2", "ens_pendulum2_tend2",
                     "ens_pendulum1_tend2", "opt_pendulum3_max_step", "opt_pendulum3_nmax_step",
                     "opt_pendulum3_dense_mass", "opt_pendulum3_backward", "opt_pendulum3_controller_off",
-                    "ens_npendulum_n4", "ens_npendulum_n10", "ens_npendulum_n20", "script_robertson",
+                    "ens_npendulum_n4", "ens_npendulum_n10", "ens_npendulum_n20", "ens_npendulum_n50", "ens_npendulum_n100",
+                    "script_robertson",
                     "kat_jay", "kat_polydae2", "kat_linear7_with_mass", "kat_linear7_without_mass", "kat_robertson_ode")
 
 

@@ -16,10 +16,6 @@ from _util import (PARITY_FACTOR, assert_bit_identical, count_agreement, golden_
 
 pytestmark = pytest.mark.gpu
 E = br.ensembles
-# Tests written after the round's GPU minutes were spent: their kernel logic is checked through the CPU harness, the first
-# run on hardware is the driver's at round end.  Non-strict, so a pass shows as XPASS and a failure does not hide the others;
-# the mark goes away once they have been seen green on a B200.
-first_hw_run = pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent; first hardware run at round end")
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -55,7 +51,7 @@ def _need_gpu():
     ("fd_jacobian_pendulum1", lambda: E.pendulum_ensemble(128, index=1), dict(jac=None)),
     ("fd_jacobian_robertson", lambda: E.robertson_ensemble(512, t_end=1e3), dict(jac=None)),
     ("fd_jacobian_dense_mass", lambda: E.pendulum_ensemble(64), dict(jac=None, mass_matrix=np.diag([1., 1, 1, 1, 0]) * 1.5)),
-    pytest.param("pendulum3_long_t_eval", lambda: E.pendulum_ensemble(128, n_t_eval=401), {}, marks=first_hw_run),   # > K1_TEVAL_SHARED points
+    ("pendulum3_long_t_eval", lambda: E.pendulum_ensemble(128, n_t_eval=401), {}),   # > K1_TEVAL_SHARED points
     ("ragged_sizes_1", lambda: E.pendulum_ensemble(1), {}),
     ("ragged_sizes_33", lambda: E.pendulum_ensemble(33), {}),
     ("ragged_sizes_129", lambda: E.robertson_ensemble(129), {}),
@@ -66,50 +62,62 @@ def test_gpu_bit_identical_to_c_oracle(case, make, over):
 
 
 @pytest.mark.parametrize("nodes,B,over", [
-    (2, 5, {}), (4, 7, {}), (10, 6, {}), (20, 4, {}),
+    (2, 5, {}), (4, 7, {}), (10, 6, {}), (20, 4, {}), (50, 3, {}),
     (4, 3, dict(nmax_step=30)), (6, 3, dict(rtol=1e-3, atol=1e-3, max_step=np.inf)),
     (3, 4, dict(zero_algebraic_error=True, bAlwaysApply2ndEstimate=False, bUsePredictiveController=False)),
     (5, 3, dict(scale_residuals=False, scale_newton_norm=False, scale_error=False, bUseExtrapolatedGuess=False)),
+    (7, 3, dict(first_step=0.05, max_newton_ite=4, max_bad_ite=0)),
 ])
-@pytest.mark.parametrize("kernel", ["k2", "k3"])
+@pytest.mark.parametrize("kernel", ["k4", "k2"])
 def test_gpu_npendulum_bit_identical_to_c_oracle(nodes, B, over, kernel, monkeypatch):
-    """K2 (CTA-per-rope, banded LU in shared memory) and K3 (lane-per-rope, state in global memory)
-    against the dense scalar oracle."""
+    """K4 (lane-per-rope, block elimination: the chain solver) against the chain spec of the scalar oracle, and K2
+    (CTA-per-system, pivoted band LU in shared memory: the general banded contract) against the oracle's band mode."""
     monkeypatch.setenv("BRDAE_NPENDULUM_KERNEL", kernel)
     ens = E.npendulum_ensemble(B, n_nodes=nodes)
-    assert_bit_identical(run_gpu(ens, **over), run_c_oracle(ens, **over), f"npendulum n={nodes} {kernel}")
+    ref = run_c_oracle(ens, chain_linear_algebra="block" if kernel == "k4" else "band", **over)
+    assert_bit_identical(run_gpu(ens, **over), ref, f"npendulum n={nodes} {kernel}")
 
 
-def test_gpu_npendulum_k3_many_ropes_with_refill_and_ragged_warps(monkeypatch):
-    monkeypatch.setenv("BRDAE_NPENDULUM_KERNEL", "k3")
+def test_gpu_npendulum_many_ropes_with_refill_and_ragged_warps():
     ens = E.npendulum_ensemble(1000, n_nodes=4, t_end=0.4)
-    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k3 1000 ropes")
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k4 1000 ropes")
     ens = E.npendulum_ensemble(3, n_nodes=40, t_end=0.3)
-    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k3 n=40")
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k4 n=40")
+    ens = E.npendulum_ensemble(2, n_nodes=100, t_end=0.5)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k4 n=100")
+
+
+def test_gpu_npendulum_bench_configurations_first_ropes_bit_identical():
+    """BASELINE configs[4] (16,384 ropes, n = 20 / 50 / 100): the first 64 ropes of each bench ensemble, full t_end,
+    bit-identical to the scalar oracle (which reproduces the reference's step counts on ens_npendulum_n*.npz)."""
+    for nodes in (20, 50, 100):
+        ens = E.npendulum_ensemble(64, n_nodes=nodes)
+        out, ref = run_gpu(ens), run_c_oracle(ens)
+        assert (out["status"] == 0).all()
+        assert_bit_identical(out, ref, f"bench ensemble n={nodes}")
 
 
 @pytest.mark.parametrize("state", ["smem", "global"])
 def test_gpu_npendulum_k2_state_placement(state, monkeypatch):
     """K2 with the rope state in shared memory, and with it in the L2-resident global scratch."""
+    monkeypatch.setenv("BRDAE_NPENDULUM_KERNEL", "k2")
     monkeypatch.setenv("BRDAE_K2_STATE", state)
     ens = E.npendulum_ensemble(40, n_nodes=6, t_end=1.0)
-    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), f"k2 state in {state}")
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens, chain_linear_algebra="band"), f"k2 state in {state}")
 
 
-def test_gpu_npendulum_default_kernel_choice_large_batch():
-    ens = E.npendulum_ensemble(1300, n_nodes=2, t_end=0.3)      # enough ropes for the global-state flavour
-    out, ref = run_gpu(ens), run_c_oracle(ens)
-    assert_bit_identical(out, ref, "default choice, 1300 ropes")
-
-
-def test_gpu_npendulum_large_chain_complex_factor_in_global_scratch():
+def test_gpu_npendulum_k2_large_chain_complex_factor_in_global_scratch(monkeypatch):
+    monkeypatch.setenv("BRDAE_NPENDULUM_KERNEL", "k2")
     ens = E.npendulum_ensemble(2, n_nodes=100, t_end=0.5)
-    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "npendulum n=100")
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens, chain_linear_algebra="band"), "npendulum n=100")
 
 
-def test_gpu_npendulum_more_ropes_than_ctas():
+def test_gpu_npendulum_more_ropes_than_lane_slots(monkeypatch):
     ens = E.npendulum_ensemble(700, n_nodes=4, t_end=0.4)
-    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "npendulum 700 ropes")
+    ref = run_c_oracle(ens)
+    assert_bit_identical(run_gpu(ens), ref, "npendulum 700 ropes")
+    monkeypatch.setenv("BRDAE_K4_MAX_SLOTS", "64")        # 700 ropes through 64 lanes: every lane is refilled ten times
+    assert_bit_identical(run_gpu(ens), ref, "npendulum 700 ropes, 64 lane slots")
 
 
 def test_gpu_constant_jacobian_mode():
@@ -422,7 +430,6 @@ def test_gpu_device_side_events_against_kernel_source_and_scipy_fixture():
     assert hit.any() and not hit.all() and np.abs(ro["y_final"][hit, 2] - 0.004).max() < 1e-12
 
 
-@first_hw_run
 def test_gpu_user_event_functions_bit_identical_to_kernel_source():
     """FunctorEvent: nonlinear event functions compiled into a plugin build, located and applied by the kernel on the GPU
     exactly as by the kernel source on the CPU (whose roots tests/test_user_problem.py checks against scipy's helpers)."""
@@ -445,7 +452,6 @@ def test_gpu_user_event_functions_bit_identical_to_kernel_source():
 
 
 # ---------------------------------------------------------------- (7) the binding INTEGRATION.md gives a reference maintainer
-@first_hw_run
 def test_gpu_integration_md_stub_runs_and_matches():
     """The ctypes stub of INTEGRATION.md, executed as written (brdae_solve_host: structure-of-arrays host buffers), returns
     what the package's own entry returns."""

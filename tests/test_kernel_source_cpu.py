@@ -1,12 +1,13 @@
-"""The K1 kernel SOURCE (dae_scipy_b200/csrc/radau_k1.cuh), compiled for the host by
-tests/host_sim and run as a warp of one lane, against the C oracle: the two are independent
-implementations of the same arithmetic contract and must agree bit for bit.  This is the
+"""The kernel SOURCES (thread-per-system K1, dae_scipy_b200/csrc/radau_k1.cuh; lane-per-rope chain kernel K4,
+csrc/chain_k4.cuh), compiled for the host by tests/host_sim and run as a warp of one lane, against the C oracle: the
+two are independent implementations of the same arithmetic contract and must agree bit for bit.  This is the
 no-GPU stand-in for tests/test_gpu_parity.py (which runs the real kernels)."""
 import numpy as np
 import pytest
 
 import dae_scipy_b200 as br
-from _util import assert_bit_identical, golden_names, load_golden, run_c_oracle, run_kernel_source_on_cpu
+from _util import (PARITY_FACTOR, assert_bit_identical, count_agreement, golden_names, load_golden, run_c_oracle,
+                   run_chain_kernel_source_on_cpu, run_kernel_source_on_cpu, scaled_error)
 
 E = br.ensembles
 
@@ -150,3 +151,57 @@ def test_kernel_source_random_option_combinations():
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             assert_bit_identical(run_kernel_source_on_cpu(ens, **over), run_c_oracle(ens, **over), f"case {case}: {kind} {over}")
+
+
+# ---------------------------------------------------------------- the chain kernel (K4, block elimination)
+CHAIN_CASES = [
+    (2, 5, {}), (4, 7, {}), (10, 6, {}), (20, 4, {}), (50, 2, {}), (100, 2, {}),
+    (4, 3, dict(nmax_step=30)), (6, 3, dict(rtol=1e-3, atol=1e-3, max_step=np.inf)),
+    (3, 4, dict(zero_algebraic_error=True, bAlwaysApply2ndEstimate=False, bUsePredictiveController=False)),
+    (5, 3, dict(scale_residuals=False, scale_newton_norm=False, scale_error=False, bUseExtrapolatedGuess=False)),
+    (7, 3, dict(first_step=0.05, max_newton_ite=4, max_bad_ite=0)),                  # failed Newton attempts, stale-Jacobian retries
+    (8, 2, dict(constant_dt=True, max_step=0.002, first_step=0.002, newton_tol=1e-8, nmax_step=150)),
+    (5, 2, dict(rtol=1e-8, atol=1e-8, bPerformAllNewtonIterations=True, nmax_step=200)),
+    (6, 2, dict(atol=np.tile([1e-5, 1e-6, 1e-4, 1e-5, 1e-3], 6), var_index=np.tile([0, 0, 1, 2, 3], 6))),   # per-unknown atol / indices
+]
+
+
+@pytest.mark.parametrize("nodes,B,over", CHAIN_CASES)
+def test_chain_kernel_source_bit_identical_to_c_oracle(nodes, B, over):
+    ens = E.npendulum_ensemble(B, n_nodes=nodes)
+    assert_bit_identical(run_chain_kernel_source_on_cpu(ens, **over), run_c_oracle(ens, **over), f"chain n={nodes} {sorted(over)}")
+
+
+def test_chain_kernel_source_backward_and_degenerate_spans():
+    ens = E.npendulum_ensemble(3, n_nodes=5, t_end=1.0)
+    ens["t_span"], ens["t_eval"] = (1.0, 0.0), np.linspace(1.0, 0.0, 7)
+    assert_bit_identical(run_chain_kernel_source_on_cpu(ens), run_c_oracle(ens), "chain backward")
+    ens = E.npendulum_ensemble(2, n_nodes=3)
+    ens["t_span"], ens["t_eval"] = (0.5, 0.5), np.array([0.5])
+    ens["options"] = dict(ens["options"], first_step=None)
+    out = run_chain_kernel_source_on_cpu(ens)
+    assert (out["status"] == 0).all() and np.array_equal(out["y"][:, :, 0], ens["y0"])
+    assert_bit_identical(out, run_c_oracle(ens), "chain t0 == t_bound")
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "npendulum" in n])
+def test_chain_kernel_source_against_reference_fixture(name):
+    """The chain kernel's source reproduces the reference's own runs (fixtures generated by oracle/gen_golden.py from
+    scipyDAE.radauDAE.RadauDAE, n = 4 ... 100 nodes): every value within tolerance and identical step counts."""
+    ens, ref = load_golden(name)
+    out = run_chain_kernel_source_on_cpu(ens)
+    o = ens["options"]
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["n_eval"], ref["n_eval"])
+    assert scaled_error(out["y"], ref["y"], o["rtol"], o["atol"]) <= PARITY_FACTOR
+    assert count_agreement(out["counters"], ref["counters"]) == 1.0
+    assert_bit_identical(out, run_c_oracle(ens), name)
+
+
+def test_chain_dense_output_record_of_the_kernel_source():
+    ens = E.npendulum_ensemble(3, n_nodes=6)
+    out = run_chain_kernel_source_on_cpu(ens, dense_cap=600)
+    sol = out["sol"]
+    assert (sol.n_steps == out["counters"][:, 4]).all() and not sol.truncated.any()
+    np.testing.assert_allclose(sol(ens["t_eval"]), out["y"], rtol=1e-8, atol=1e-10)
+    last = sol.ys[np.arange(3), :, sol.n_steps]
+    assert np.array_equal(last, out["y_final"])
