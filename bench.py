@@ -2,15 +2,18 @@
 """bench.py — DAE trajectories/s to t_end (FP64) for the batched RadauDAE hot path.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (numpy restatement
-                                                              # of the reference, all host cores)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the UNMODIFIED reference (scipyDAE RadauDAE
+                                                              # from oracle/_ref) on all host cores; its numpy port if
+                                                              # the reference did not travel with the snapshot
 
 A "step" is one pass of the hot path over one batch: the whole ensemble integrated from t0 to
 t_end.  Default workload = BASELINE.json configs[1]: index-3 pendulum, 1,048,576 varied initial
 conditions, thread-per-system, one B200 (rtol = atol = 1e-6, first_step = 1e-2, t_end = 2,
 21 t_eval points; SURVEY 8d "C2 primary").  With N > 1 every rank integrates its own 1M-system
-ensemble (weak scaling, different seeds); the only collective in the timed region is the
-all_reduce of the summed counters.  One JSON line is printed by rank 0.
+ensemble (weak scaling, different seeds); `--scaling strong` splits ONE ensemble of the workload's size over the ranks
+(BASELINE configs[2]: `--workload robertson_4M --scaling strong`).  The collective inside the timed region is the
+all_reduce of the summed counters; a second timed region adds the NCCL gather of every result onto rank 0
+(`value_with_gather`).  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -42,8 +45,15 @@ WORKLOADS = {
 }
 
 
-# measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum) / systems of the profiled launch
-NCU_DRAM_BYTES_PER_SYSTEM = {"pendulum3_1M_tend2": (158.95e6 + 334.40e6) / 262144}     # profiles/r01_k1_fastpaths.md, v8
+# DRAM traffic of one launch, per system: dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set full` capture of the
+# workload's kernel divided by the systems of the profiled launch; each entry names the committed summary it comes from.
+NCU_DRAM_BYTES_PER_SYSTEM = {
+    "pendulum3_1M_tend2": ((158.95e6 + 334.40e6) / 262144, "profiles/r01_k1_fastpaths.md (v8, 262,144 systems)"),
+    "pendulum3_1M_tend10": ((158.95e6 + 334.40e6) / 262144, "profiles/r01_k1_fastpaths.md (same kernel and output grid as t_end = 2)"),
+    "robertson_4M": ((18.2e6 + 71.0e6) / 262144, "profiles/r01_k1_ncu_summary.md (Robertson, 262,144 systems: part of that launch's output was still in L2 at kernel end)"),
+    "transistor_256k": ((10.8e6 + 12.9e6) / 65536, "profiles/r01_k1_ncu_summary.md (transistor, 65,536 systems: that launch's output was still in L2 at kernel end)"),
+    "npendulum_n20_16k": ((96.3e6 + 13.80e9) / 4096, "profiles/r02_k4_ncu_summary.md (K4, n = 20, 4,096 ropes)"),
+}
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -97,18 +107,23 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arms
+def _reference_kind():
+    """"reference": the unmodified scipyDAE.radauDAE.RadauDAE is importable (oracle/_ref travels with the snapshot, /root/reference
+    in the build container); "port": only its numpy restatement (oracle/radau_numpy.py, bit-identical where both run) is."""
+    try:
+        from oracle import reference_runner
+        return "reference" if reference_runner.reference_location() is not None else "port"
+    except Exception:
+        return "port"
+
+
 def _cpu_worker(args):
-    """Integrate a slice of the ensemble with the numpy restatement of the reference (one core)."""
+    """Integrate a slice of the ensemble on one core: with the reference itself (kind "reference") or its numpy port."""
     import contextlib
     import io
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle import radau_numpy as orc, problems_numpy as prob
-    problem, y0s, params, t_span, t_eval, options = args
-    opts = dict(options)
-    opts.pop("mass_matrix", None)
-    var_index = opts.pop("var_index", None)
-    done = 0
+    import warnings
+    warnings.filterwarnings("ignore")
+    kind, ens = args
     # one BLAS thread per process: the pool already uses every core, and the LAPACK calls of the chain problems
     # (N = 100..500) would otherwise start a full OpenBLAS thread team in each forked worker (measured: 50x slower)
     try:
@@ -117,26 +132,34 @@ def _cpu_worker(args):
     except Exception:
         limit = contextlib.nullcontext()
     with limit, contextlib.redirect_stdout(io.StringIO()):
-        for i in range(y0s.shape[0]):
-            fun, jac, mass, vi = prob.build(problem, params[i], y0s.shape[1])
-            r = orc.solve(fun, t_span, y0s[i], jac=jac, mass_matrix=mass,
+        if kind == "reference":
+            from oracle import reference_runner
+            out = reference_runner.run_reference(ens)
+            return ens["y0"].shape[0], int((out["status"] == 0).sum())
+        from oracle import radau_numpy as orc, problems_numpy as prob
+        opts = dict(ens["options"])
+        opts.pop("mass_matrix", None)
+        var_index = opts.pop("var_index", None)
+        done = 0
+        for i in range(ens["y0"].shape[0]):
+            p = ens["params"][i] if ens["params"] is not None else ()
+            fun, jac, mass, vi = prob.build(ens["problem"], p, ens["y0"].shape[1])
+            r = orc.solve(fun, ens["t_span"], ens["y0"][i], jac=jac, mass_matrix=mass,
                           var_index=None if var_index is None else np.asarray(var_index, dtype=float),
-                          t_eval=t_eval, **opts)
+                          t_eval=ens["t_eval"], **opts)
             done += int(r.status == 0)
-    return y0s.shape[0], done
+    return ens["y0"].shape[0], done
 
 
-def cpu_reference_rate(ens, n_systems, cores):
-    """traj/s of the reference algorithm (numpy restatement, oracle/radau_numpy.py) over all host
-    cores, on the first `n_systems` systems of the ensemble."""
+def cpu_reference_rate(ens, n_systems, cores, kind):
+    """traj/s of the reference path (`kind`) over `cores` processes, on the first `n_systems` systems of the ensemble."""
     import multiprocessing as mp
-    y0 = ens["y0"][:n_systems]
-    params = ens["params"][:n_systems] if ens["params"] is not None else np.zeros((n_systems, 0))
     chunks = [c for c in np.array_split(np.arange(n_systems), cores) if c.size]
-    jobs = [(ens["problem"], y0[c], params[c], ens["t_span"], ens["t_eval"], ens["options"]) for c in chunks]
+    sub = lambda c: dict(ens, y0=ens["y0"][c], params=None if ens["params"] is None else ens["params"][c])
+    jobs = [(kind, sub(c)) for c in chunks]
     ctx = mp.get_context("fork")
     with ctx.Pool(len(jobs)) as pool:
-        pool.map(_cpu_worker, [(ens["problem"], y0[:1], params[:1], ens["t_span"], ens["t_eval"], ens["options"])] * len(jobs))  # warm import
+        pool.map(_cpu_worker, [(kind, sub(np.arange(1)))] * len(jobs))      # warm import
         t0 = time.perf_counter()
         res = pool.map(_cpu_worker, jobs)
         dt = time.perf_counter() - t0
@@ -144,25 +167,31 @@ def cpu_reference_rate(ens, n_systems, cores):
     return n / dt, dt, n
 
 
+def _kind_text(kind):
+    return ("the unmodified reference (scipyDAE.radauDAE.RadauDAE installed under oracle/_ref), stepped like scipy's solve_ivp"
+            if kind == "reference" else "numpy restatement of the reference (oracle/radau_numpy.py; the reference itself is not importable here)")
+
+
 def run_reference_arm(args, ens, wl_name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    kind = _reference_kind()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_step = max(cores, min(args.ref_sample, 64 * cores))
     for _ in range(args.warmup):
-        cpu_reference_rate(ens, min(per_step, 2 * cores), cores)
-    rates, total_n, total_t = [], 0, 0.0
+        cpu_reference_rate(ens, min(per_step, 2 * cores), cores, kind)
+    total_n, total_t = 0, 0.0
     for _ in range(args.steps):
-        rate, dt, n = cpu_reference_rate(ens, per_step, cores)
-        rates.append(rate); total_n += n; total_t += dt
+        rate, dt, n = cpu_reference_rate(ens, per_step, cores, kind)
+        total_n += n; total_t += dt
     value = total_n / total_t
-    sample = f"first {per_step} systems of the {wl_name} ensemble per step, Pool({cores}), 1 BLAS thread per process"
+    sample = f"first {per_step} systems of the {wl_name} ensemble per step, {_kind_text(kind)}, Pool({cores}), 1 BLAS thread per process"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": wl_name, "systems_per_step": per_step, "parallelism": f"cpu{cores}"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -176,17 +205,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="brdae", choices=["brdae", "reference"])
     ap.add_argument("--workload", default="pendulum3_1M_tend2", choices=sorted(WORKLOADS))
-    ap.add_argument("--systems", type=int, default=0, help="override the ensemble size per GPU")
+    ap.add_argument("--systems", type=int, default=0, help="override the ensemble size (per GPU with weak scaling, in total with strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns an ensemble of the workload's size; strong: ONE such ensemble split over the ranks")
     ap.add_argument("--ref-sample", type=int, default=4096, help="systems per step of the CPU arm")
     ap.add_argument("--cpu-sample", type=int, default=0, help="systems of the in-run cpu_baseline (0 = 384 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip the second timed region (solve + NCCL gather onto rank 0)")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to the NUMA node of its GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "brdae" else args.warmup
 
     gen_key, gen_kw, B_default = WORKLOADS[args.workload]
-    B = args.systems or B_default
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,18 +231,31 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dae_scipy_b200 import _abi, flops
-    from dae_scipy_b200.dist import reduce_statistics, status_histogram
+    from dae_scipy_b200 import _abi, flops, numa
+    from dae_scipy_b200.dist import gather_results, reduce_statistics, shard_bounds, status_histogram
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    # keep this rank's threads and its page-locked result buffers on the NUMA node of its GPU (multi-GPU end-to-end rate)
+    placement = None if args.no_numa else numa.bind_to_device_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # weak scaling: every rank owns its own B-system ensemble (seed offset by rank)
-    seed = {"pendulum": 0, "robertson": 1, "transistor": 2, "npendulum": 3}[gen_key] + 1000 * rank
-    ens = br.ensembles.ENSEMBLES[gen_key](B, seed=seed, **gen_kw)
+    B_total = args.systems or B_default
+    seed0 = {"pendulum": 0, "robertson": 1, "transistor": 2, "npendulum": 3}[gen_key]
+    if args.scaling == "strong":
+        # one ensemble, contiguous balanced shards (dist.shard_bounds); the first systems do not depend on the size drawn
+        lo, hi = shard_bounds(B_total, world, rank)
+        full = br.ensembles.ENSEMBLES[gen_key](B_total, seed=seed0, **gen_kw)
+        ens = dict(full, y0=full["y0"][lo:hi], params=None if full["params"] is None else full["params"][lo:hi])
+        B = hi - lo
+        systems_all = B_total
+    else:
+        # weak scaling: every rank owns its own B-system ensemble (seed offset by rank)
+        B = B_total
+        ens = br.ensembles.ENSEMBLES[gen_key](B, seed=seed0 + 1000 * rank, **gen_kw)
+        systems_all = B * world
     prob = br.get_problem(ens["problem"])
     n, T, npar = ens["y0"].shape[1], len(ens["t_eval"]), prob.n_params
 
@@ -228,6 +273,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     res = None
     for _ in range(args.warmup):       # warm-up steps are whole steps: the statistics all_reduce (NCCL set-up) included
         res = one_pass()
@@ -242,29 +293,55 @@ def main():
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local_rank)
     clk.__enter__()
-    if True:
-        barrier()
-        e_start.record(stream)
-        for k in range(args.steps):
-            ev[k][0].record(stream)
-            res = one_pass()
-            ev[k][1].record(stream)
-            csum = res.counters.sum(dim=1, dtype=torch.int64)
-            csum, hist = reduce_statistics(csum, status_histogram(res.status), dist if world > 1 else None, dev)
-        e_stop.record(stream)
-        barrier()
-    total_ms = e_start.elapsed_time(e_stop)
+    barrier()
+    e_start.record(stream)
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        res = one_pass()
+        ev[k][1].record(stream)
+        csum = res.counters.sum(dim=1, dtype=torch.int64)
+        csum, hist = reduce_statistics(csum, status_histogram(res.status), dist if world > 1 else None, dev)
+    e_stop.record(stream)
+    barrier()
+    total_ms = max_over_ranks(e_start.elapsed_time(e_stop))
     kern_ms = [a.elapsed_time(b) for a, b in ev]
-    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(t_ms.item())
-    value = B * world * args.steps / (total_ms * 1e-3)
+    value = systems_all * args.steps / (total_ms * 1e-3)
+
+    # second timed region: the same steps plus the gather of every per-system result (y_eval, y_final, t_final, status,
+    # n_eval, counters) onto rank 0 over NCCL (dist.gather_results: NVLink / NVSwitch), which is what north_star uses NCCL for
+    with_gather = None
+    if not args.no_gather:
+        def gathered_pass():
+            r = one_pass()
+            cs, _ = reduce_statistics(r.counters.sum(dim=1, dtype=torch.int64), status_histogram(r.status), dist if world > 1 else None, dev)
+            if world > 1:
+                local = {"y_eval": r._y_eval, "status": r.status, "n_eval": r.n_eval, "t_final": r.t_final,
+                         "y_final": r.y_final.t().contiguous(), "counters": r.counters}
+                if args.scaling == "strong":
+                    return gather_results(local, systems_all, dist, dst=0)
+                return gather_results(local, systems_all, dist, dst=0)       # equal shards under weak scaling: same call
+            return r
+        g = gathered_pass()                                                   # warm-up (gather buffers, NCCL channels)
+        del g
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            g = gathered_pass()
+            del g
+        g1.record(stream)
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1))
+        gather_bytes = (world - 1) * (8 * B * n * T + 8 * B * n + 8 * B + 4 * B * 2 + 4 * B * 9) if world > 1 else 0
+        with_gather = {"value": systems_all * args.steps / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms / args.steps,
+                       "gathered_bytes_per_step_into_rank0": gather_bytes,
+                       "what": "solve + all_reduce of the statistics + dist.gather of y_eval, y_final, t_final, status, n_eval, counters onto rank 0 (NCCL)"}
 
     # roofline of the dominant (only) kernel: algorithmic FLOPs of one launch / its duration
     out_counts = res.counters.sum(dim=1, dtype=torch.int64).cpu().numpy()
     n_out = int(res.n_eval.sum().item())
-    fl = flops.algorithmic_flops(ens["problem"], n, out_counts, n_out)
+    chain = gen_key == "npendulum" and os.environ.get("BRDAE_NPENDULUM_KERNEL", "") != "k2"
+    fl = flops.algorithmic_flops(ens["problem"], n, out_counts, n_out, chain_block=chain)
     kms = float(np.mean(kern_ms))
     achieved = fl / (kms * 1e-3) / 1e12
     abytes = flops.algorithmic_bytes(n, npar, T, B)
@@ -274,18 +351,24 @@ def main():
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
     hbm_gbs = abytes / (kms * 1e-3) / 1e9
-    # DRAM traffic of one launch: per-system dram__bytes_read + dram__bytes_write of the ncu --set full capture
-    # committed under profiles/ (r01_k1_fastpaths.md: 493 MB for 262,144 pendulum systems), scaled to this launch
-    traffic = NCU_DRAM_BYTES_PER_SYSTEM.get(args.workload)
+    traffic, traffic_src = NCU_DRAM_BYTES_PER_SYSTEM.get(args.workload, (None, None))
+    kernel_name = {"pendulum": "k1_kernel<Pendulum<3>,MassDiag01>", "npendulum": "k4_kernel (lane-per-rope block elimination)" if chain else "k2_kernel"}.get(gen_key, f"k1_kernel<{gen_key}>")
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
-                "traffic": None if traffic is None else traffic * B,
-                "traffic_source": None if traffic is None else "ncu --set full, profiles/r01_k1_fastpaths.md (per system x systems of this launch)",
+                "traffic": None if traffic is None else traffic * B, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: dependent-chain DFMA probe (brdae_fp64_peak_probe)",
-                "kernel": {"pendulum": "k1_kernel<Pendulum<3>,MassDiag01>", "npendulum": "k2_kernel"}.get(gen_key, f"k1_kernel<{gen_key}>"),
-                "kernel_ms": kms, "flops_per_launch": fl, "flops_per_trajectory": fl / B,
+                "kernel": kernel_name, "kernel_ms": kms, "flops_per_launch": fl, "flops_per_trajectory": fl / B,
                 "hbm": {"algorithmic_bytes": abytes, "achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak,
                         "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src}}
+    if chain:
+        # the chain kernel streams its per-rope state (99 doubles per node) through L2/HBM once per sweep: the bytes that
+        # algorithm has to move, from the counters (flops.chain_state_bytes_per_node_sweep), against the measured HBM peak
+        per = flops.chain_state_bytes_per_node_sweep()
+        nodes = n // 5
+        state_bytes = nodes * (float(out_counts[7]) * per["newton"] + float(out_counts[2]) * per["factor"] + float(out_counts[8]) * per["error_estimate"])
+        roofline["state_stream"] = {"bytes_per_launch": state_bytes, "achieved_gbs": state_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                    "frac": state_bytes / (kms * 1e-3) / 1e9 / hbm_peak,
+                                    "note": "state traffic of the block-elimination sweeps (served by L2 while the resident ropes fit it); the kernel is bound by the latency of this stream, see profiles/r02_k4_ncu_summary.md"}
 
     statuses = hist.cpu().numpy().tolist()
 
@@ -302,14 +385,12 @@ def main():
         for _ in range(args.steps):
             out = br.solve_ivp_batched_host(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"],
                                             buffers=bufs, **ens["options"])
-        dt = time.perf_counter() - t0
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = max_over_ranks(time.perf_counter() - t0)
         h2d = 8 * B * (n + npar) + 8 * T
         d2h = 8 * B * n * T + 8 * B + 8 * B * n + 4 * B * 2 + 4 * B * 9
-        e2e = {"value": B * world * args.steps / float(t_e.item()), "unit": UNIT,
+        e2e = {"value": systems_all * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "host_write_gbs_all_ranks": d2h * world * args.steps / dt / 1e9,
                "path": "solve_ivp_batched_host -> brdae_solve_host_rows (C ABI, host buffers, row per system): argument "
                        "validation, stream-ordered device alloc, H2D of y0/params, device permutation to SoA, kernel, device "
                        "permutation of the results, D2H of y[B,n,T], y_final, t_final, status, n_eval, counters into reused "
@@ -318,35 +399,35 @@ def main():
 
     clk.__exit__(None, None, None)
 
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        ns = args.cpu_sample or min(B, 384 * cores)     # about 15-20 s of CPU work on the pendulum workload
-        rate, dt, nn = cpu_reference_rate(ens, ns, cores)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"first {nn} systems of the same ensemble, numpy restatement of the reference "
-                                  f"(oracle/radau_numpy.py, bit-identical to RadauDAE where the reference runs), "
-                                  f"Pool({cores}), {dt:.1f} s"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind = _reference_kind()
+        per_core = 384 if gen_key != "npendulum" else max(1, 64 // gen_kw["n_nodes"])       # about 15-20 s of CPU work
+        ns = args.cpu_sample or min(B, per_core * cores)
+        rate, dt, nn = cpu_reference_rate(ens, ns, cores, kind)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"first {nn} systems of the same ensemble, {_kind_text(kind)}, Pool({cores}), {dt:.1f} s"}
 
-    # second, stronger CPU comparator: the scalar C restatement of the same arithmetic
-    # contract (oracle/radau_ref.c, the parity checker of the tests), OpenMP over all host cores
+    # second, stronger CPU comparator: the scalar C restatement of the same arithmetic contract (oracle/radau_ref.c,
+    # the parity checker of the tests), OpenMP with an explicit thread count.  N = 1 only: under torchrun OMP_NUM_THREADS is 1
+    # and the cores are shared with the other ranks.
     cpu_native = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import c_oracle
-            cores = os.cpu_count() or 1
             ns = int(min(B, 65536 * cores))      # about 10 s
-            if gen_key == "npendulum":           # chains: a few ropes per core (the restatement stores the band in dense arrays)
-                ns = int(min(B, cores * max(1, 400 // gen_kw["n_nodes"])))
+            if gen_key == "npendulum":
+                ns = int(min(B, cores * max(4, 4000 // gen_kw["n_nodes"])))
             o2 = dict(ens["options"]); mm = o2.pop("mass_matrix")
             par = ens["params"][:ns] if ens["params"] is not None else np.zeros((ns, 0))
-            c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"][:cores], par[:cores], t_eval=ens["t_eval"], **o2)  # warm
+            c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"][:cores], par[:cores], t_eval=ens["t_eval"], nthreads=cores, **o2)  # warm
             t0 = time.perf_counter()
-            c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"][:ns], par, t_eval=ens["t_eval"], **o2)
+            c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"][:ns], par, t_eval=ens["t_eval"], nthreads=cores, **o2)
             dt = time.perf_counter() - t0
             cpu_native = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
                           "sample": f"first {ns} systems of the same ensemble, scalar C restatement of the arithmetic contract "
-                                    f"(oracle/radau_ref.c), OpenMP over {cores} threads, {dt:.1f} s"}
+                                    f"(oracle/radau_ref.c), omp_set_num_threads({cores}), {dt:.1f} s"}
         except Exception as exc:      # the checker library is test infrastructure; never fail the bench on it
             cpu_native = {"unavailable": repr(exc)}
 
@@ -354,17 +435,18 @@ def main():
         geom = dict(zip(("grid", "block", "smem"), _launch_info(br, ens, B)))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "problem": ens["problem"], "systems_per_gpu": B,
-                           "systems_total": B * world, "t_span": list(ens["t_span"]), "n_t_eval": T,
+                           "systems_total": systems_all, "t_span": list(ens["t_span"]), "n_t_eval": T,
                            "rtol": ens["options"]["rtol"], "atol": ens["options"]["atol"],
                            "first_step": ens["options"].get("first_step"),
                            "l2_policy": "inputs+outputs per step (%.0f MB) larger than the 126 MB L2" % (abytes / 1e6),
                            "parallelism": f"ensemble sharded over {world} GPU(s), no data-path collective",
-                           "launch": geom},
+                           "launch": geom, "host_placement": placement},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_native": cpu_native, "e2e": e2e,
+                "value_with_gather": with_gather,
                 "gpu_launches": args.steps, "clocks": clk.summary(),
-                "status_histogram": dict(zip(("finished", "too_small_step", "lu_failed", "nmax_step"), statuses)),
+                "status_histogram": dict(zip(("finished", "too_small_step", "lu_failed", "nmax_step", "terminal_event"), statuses)),
                 "mean_accepted_steps": float(out_counts[4]) / B}
         print(json.dumps(line))
     if world > 1:

@@ -142,6 +142,10 @@ def load(path: str | None = None):
             "__graft_entry__.build()).  The batched solver has no CPU fallback.")
     lib = C.CDLL(p)
     lib.brdae_abi_version.restype = C.c_int
+    have = int(lib.brdae_abi_version())
+    if have != ABI_VERSION:        # a stale build would misread the larger brdae_batch of this version: refuse it
+        raise RuntimeError(f"{p} implements ABI version {have}, this package needs {ABI_VERSION}: rebuild it "
+                           "(python -m dae_scipy_b200.build --force; plugin libraries: delete dae_scipy_b200/user_libs).")
     lib.brdae_strerror.restype = C.c_char_p
     lib.brdae_strerror.argtypes = [C.c_int]
     lib.brdae_problem_lookup.restype = C.c_int

@@ -209,6 +209,12 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
             raise ValueError("`mass_matrix` must be None, an [n, n] array or the string 'problem'.")
     elif mass_matrix is None:
         mass = np.eye(n)                                   # radauDAE.py:448-449
+        if options.get("first_step") is None:
+            # Without a mass matrix the reference takes its first step from scipy's select_initial_step (radauDAE.py:307-311),
+            # which is not restated on the device (and does not run under scipy 1.18: SURVEY 4.3).  Starting silently from
+            # the with-mass default 1e-6 would change the step sequence, so the combination is refused.
+            raise ValueError("`first_step` is required when `mass_matrix` is None (the reference would call "
+                             "scipy's select_initial_step here); pass first_step=... or the mass matrix.")
     elif callable(mass_matrix):
         raise ValueError("`mass_matrix` should be a constant matrix, but is callable")
     else:
@@ -553,7 +559,19 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
         batch = hb.struct(ptr)
         ws_bytes = int(lib.brdae_workspace_bytes(C.byref(batch), C.byref(hb.options)))
         ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
-        cu_stream = stream if stream is not None else torch.cuda.current_stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        cu_stream = stream if stream is not None else cur
+        if cu_stream != cur:
+            # the inputs above were produced on torch's current stream: order the solve after them, and keep the
+            # allocator from reusing any buffer the kernel touches before the user's stream is done with it
+            cu_stream.wait_stream(cur)
+            for ten in (y0_soa, par_soa, te_d, y_eval, n_eval, t_final, y_final, status, counters, ws):
+                if ten is not None:
+                    ten.record_stream(cu_stream)
+            for name in ("dense_t", "dense_y", "dense_q", "event_count", "event_t", "event_y"):
+                ten = locals().get(name)
+                if ten is not None:
+                    ten.record_stream(cu_stream)
         _abi.check(lib.brdae_solve(C.byref(batch), C.byref(hb.options), ws.data_ptr(), ws_bytes,
                                    C.c_void_p(cu_stream.cuda_stream)), "brdae_solve")
         ws.record_stream(cu_stream)

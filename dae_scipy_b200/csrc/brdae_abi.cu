@@ -76,7 +76,7 @@ size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *o) {
     if (!b) return 0;
     size_t bytes = kCounterBytes;
     if (b->problem == BRDAE_NPENDULUM)
-        bytes += npendulum_uses_k4(b->n, b->n_systems) ? k4_scratch_bytes(b->n, b->n_systems) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
+        bytes += npendulum_uses_k4(b->n, b->n_systems) ? k4_scratch_bytes(b->n, b->n_systems, sm_count()) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
     else {      // K1: per-CTA slice of cold per-lane state (kernels that keep it in shared memory need none)
         LaunchGeom g{};
         const bool fd = o && o->jac_finite_differences && !b->jac_const;
@@ -98,7 +98,7 @@ int brdae_launch_info(const brdae_batch *b, int32_t *grid, int32_t *block, int32
 
 // Row-per-system run of the K1 kernels: the batch arrays of `b` are [B][n] / [B][p] / [B][T][n] / [B][9] device
 // buffers, and the kernel signals the completion of every `chunk_size` systems (see SolveArgs).
-struct RowsRun { int32_t *chunk_done; volatile int32_t *chunk_flags; int64_t chunk_size; const int32_t *input_ready; };
+struct RowsRun { int32_t *chunk_done; volatile int32_t *chunk_flags; int64_t chunk_size; const int32_t *input_ready; const volatile int32_t *abort_flag; };
 
 static int solve_impl(const brdae_batch *b, const brdae_options *o, void *workspace, size_t workspace_bytes,
                       cudaStream_t stream, const RowsRun *rows) {
@@ -115,7 +115,7 @@ static int solve_impl(const brdae_batch *b, const brdae_options *o, void *worksp
         a.ye_st = n; a.ye_sc = 1; a.ye_sb = n * T;      // the n unknowns of an output point are one 8n-byte run
         a.yf_sc = 1; a.yf_sb = n; a.cn_sq = 1; a.cn_sb = BRDAE_NCOUNTERS;
         a.chunk_done = rows->chunk_done; a.chunk_flags = rows->chunk_flags; a.chunk_size = rows->chunk_size;
-        a.input_ready = rows->input_ready;
+        a.input_ready = rows->input_ready; a.abort_flag = rows->abort_flag;
     }
     if (cudaMemsetAsync(workspace, 0, kCounterBytes, stream) != cudaSuccess) return BRDAE_ERR_CUDA;
     rc = launch_solver(b->problem, b->mass != nullptr, a, b, sm_count(), stream);
@@ -277,8 +277,15 @@ static int host_rows_single_launch(const brdae_batch *hb, const brdae_options *o
     // memory cudaMemcpyAsync stages synchronously, so this thread is busy copying while the kernel already runs).
     // Under an injected CUDA tool (ncu, compute-sanitizer: CUDA_INJECTION64_PATH) a launch may not return before the
     // kernel has ended, and the copies it waits for would never be queued: copy in first, on the kernel's stream.
-    serial_in = std::getenv("BRDAE_ROWS_SERIAL_IN") != nullptr       // A/B switch for tuning
-                || std::getenv("CUDA_INJECTION64_PATH") != nullptr || std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr;
+    // The same holds for CUDA_LAUNCH_BLOCKING=1 and for debuggers.  Should a launch block in a mode not recognised here, the
+    // lanes' wait is bounded and the call returns BRDAE_ERR_CUDA instead of hanging (radau_k1.cuh, `input_lost`).
+    {
+        const char *lb = std::getenv("CUDA_LAUNCH_BLOCKING");
+        serial_in = std::getenv("BRDAE_ROWS_SERIAL_IN") != nullptr       // A/B switch for tuning
+                    || std::getenv("CUDA_INJECTION64_PATH") != nullptr || std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr
+                    || std::getenv("CUDBG_USE_LEGACY_DEBUGGER") != nullptr || std::getenv("CUDA_DEBUGGER_SOFTWARE_PREEMPTION") != nullptr
+                    || (lb && lb[0] != '\0' && lb[0] != '0');
+    }
     if (serial_in) {
         CK(cudaMemcpyAsync(dy0, hb->y0, sizeof(double) * n * B, cudaMemcpyHostToDevice, s));
         if (np > 0) CK(cudaMemcpyAsync(dpar, hb->params, sizeof(double) * np * B, cudaMemcpyHostToDevice, s));
@@ -287,7 +294,7 @@ static int host_rows_single_launch(const brdae_batch *hb, const brdae_options *o
         brdae_batch d = *hb;
         d.y0 = dy0; d.params = dpar; d.t_eval = dte; d.y_eval = dye; d.t_final = dtf; d.y_final = dyf;
         d.n_eval = dne; d.status = dst; d.counters = dcn;
-        RowsRun rr{dchunk, flags, Bc, serial_in ? nullptr : dchunk + 32};
+        RowsRun rr{dchunk, flags, Bc, serial_in ? nullptr : dchunk + 32, flags + 33};
         if (timing) CK(cudaEventRecord(ev[1], s));
         rc = solve_impl(&d, o, ws, wsb, s, &rr);
         if (rc != BRDAE_OK) goto done;
@@ -320,6 +327,12 @@ static int host_rows_single_launch(const brdae_batch *hb, const brdae_options *o
         CK(cudaMemcpyAsync(hb->status + b0, dst + b0, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, s_copy));
     }
     if (cudaGetLastError() != cudaSuccess) rc = BRDAE_ERR_CUDA;
+    if (!serial_in) {      // did any lane give up waiting for its input? (word 1 of the workspace header)
+        unsigned long long lost = 0;
+        CK(cudaMemcpyAsync(&lost, static_cast<char *>(ws) + 8, sizeof(lost), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (lost != 0) rc = BRDAE_ERR_CUDA;
+    }
     if (timing) {
         CK(cudaEventRecord(ev[3], s_copy));
         CK(cudaStreamSynchronize(s)); t_kernel_done = hms();
@@ -333,6 +346,8 @@ static int host_rows_single_launch(const brdae_batch *hb, const brdae_options *o
         std::fprintf(stderr, "\n");
     }
 done:
+    // an error between the launch and the last input copy leaves lanes waiting for chunks that will never arrive: tell them
+    if (rc != BRDAE_OK && flags) flags[33] = 1;
     for (auto &e : ev) if (e) cudaEventDestroy(e);
     if (s_in && cudaStreamSynchronize(s_in) != cudaSuccess && rc == BRDAE_OK) rc = BRDAE_ERR_CUDA;
     if (s_copy && cudaStreamSynchronize(s_copy) != cudaSuccess && rc == BRDAE_OK) rc = BRDAE_ERR_CUDA;

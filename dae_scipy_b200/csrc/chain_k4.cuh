@@ -7,7 +7,7 @@
 // This kernel uses what the chain IS: mu M - J is block tridiagonal in the nodes, the rows x_i, y_i read
 // mu p - v = r, so the velocities are eliminated exactly and a 3 x 3 block in (dx, dy, dlambda) per node is left.
 // The blocks are eliminated node by node (block Thomas), each pivot block E_i inverted explicitly with partial
-// pivoting inside the block ("chain spec"; oracle/radau_ref.c chain_factor / chain_solve_*):
+// pivoting inside the block ("chain spec"; the scalar restatement used by the tests states the same operations in the same order):
 // 14 x fewer flops than the band LU, n sequential block steps instead of 5 n column steps, and no step needs more
 // than one lane.  So ONE LANE integrates one rope (K1's control structure), with the rope's state -- 99 doubles per
 // node: y, f, y_old, Q, W, the rod quantities of the Jacobian, the Newton scales, the three inverse pivot blocks, the

@@ -14,42 +14,79 @@ constexpr int K4_BLOCK = 32;             // one warp per CTA: the warps of an SM
 constexpr size_t kHeaderBytes = 256;
 size_t align8(size_t x) { return (x + 7) / 8 * 8; }
 
-__global__ void __launch_bounds__(K4_BLOCK) k4_kernel(const __grid_constant__ SolveArgs a, double *state) {
-    // [warp][node][slot][lane]: the state of the 32 ropes of a warp is one contiguous region
+// RPW ropes per warp (lanes RPW..31 idle), at least MINB warps resident per SM.  The kernel is bound by the latency of
+// its global-memory accesses (one warp per SM measured 63 % long-scoreboard stalls and 3 % of the issue slots used,
+// profiles/r02_k4_ncu_summary.md): the ropes are the only source of parallelism, so with fewer ropes than the machine has
+// lanes they are spread over MORE WARPS rather than more lanes -- the idle lanes cost nothing while the schedulers have
+// no other warp to issue from, and a warp with fewer ropes loses fewer lanes to divergence between its ropes.
+template <int RPW, int MINB>
+__global__ void __launch_bounds__(K4_BLOCK, MINB) k4_kernel(const __grid_constant__ SolveArgs a, double *state) {
+    // [warp][node][slot][rope of the warp]: the state of the ropes of a warp is one contiguous region
     const size_t warp = blockIdx.x;
-    k4::Rope<32> R{state + warp * ((size_t)(a.n / 5) * k4::SPN * 32) + threadIdx.x};
-    k4::k4_lane_loop<32>(a, R, true);
+    const bool have = threadIdx.x < RPW;
+    k4::Rope<RPW> R{state + warp * ((size_t)(a.n / 5) * k4::SPN * RPW) + (have ? threadIdx.x : 0)};
+    k4::k4_lane_loop<RPW>(a, R, have);
+}
+
+struct K4Geom { int rpw, minb; long long warps; };
+
+int env_int(const char *name, int lo, int hi, int dflt) {
+    if (const char *e = std::getenv(name)) { const int v = std::atoi(e); if (v >= lo && v <= hi) return v; }
+    return dflt;
+}
+
+// ropes per warp and warps for a batch of B ropes on `sms` SMs: as many warps as stay resident (MINB per SM), ropes per
+// warp the smallest power of two that fits the batch into them; lanes are refilled from the work counter beyond that
+K4Geom k4_geometry(int n, int64_t B, int sms) {
+    const int nsm = sms > 0 ? sms : 148;
+    K4Geom g;
+    const int mb = env_int("BRDAE_K4_MINB", 1, 32, 16);
+    g.minb = mb >= 24 ? 32 : (mb >= 12 ? 16 : 8);
+    const long long resident = (long long)nsm * g.minb;
+    int rpw = 1;
+    while (rpw < 32 && (long long)rpw * resident < B) rpw *= 2;
+    rpw = env_int("BRDAE_K4_RPW", 1, 32, rpw);
+    int p2 = 1;
+    while (p2 < rpw) p2 *= 2;
+    g.rpw = p2;
+    long long warps = (B + g.rpw - 1) / g.rpw;
+    if (warps > resident) warps = resident;
+    // memory cap (about 48 GB of state) and the test hook that forces refills
+    const long long per_slot = (long long)(n / 5) * k4::SPN * 8;
+    long long cap = (48LL << 30) / per_slot;
+    cap = (long long)env_int("BRDAE_K4_MAX_SLOTS", 1, 1 << 30, (int)(cap > (1 << 30) ? (1 << 30) : cap));
+    if (warps * g.rpw > cap) warps = cap / g.rpw;
+    if (warps < 1) warps = 1;
+    g.warps = warps;
+    return g;
+}
+
+template <int MINB>
+cudaError_t k4_launch(const K4Geom &g, const SolveArgs &a, double *state, cudaStream_t stream) {
+    switch (g.rpw) {
+    case 1: k4_kernel<1, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
+    case 2: k4_kernel<2, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
+    case 4: k4_kernel<4, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
+    case 8: k4_kernel<8, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
+    case 16: k4_kernel<16, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
+    default: k4_kernel<32, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
+    }
+    return cudaPeekAtLastError();
 }
 
 }  // namespace
 
-// lane slots used for B ropes: one per rope up to a cap of about 48 GB of state
-long long k4_slots(int n, int64_t B) {
-    const long long per_slot = (long long)(n / 5) * k4::SPN * 8;
-    long long cap = (48LL << 30) / per_slot;
-    cap = cap / K4_BLOCK * K4_BLOCK;
-    if (cap < K4_BLOCK) cap = K4_BLOCK;
-    if (const char *e = std::getenv("BRDAE_K4_MAX_SLOTS")) {      // tests: fewer lane slots than ropes, so that lanes are refilled
-        const long long v = std::atoll(e) / K4_BLOCK * K4_BLOCK;
-        if (v >= K4_BLOCK && v < cap) cap = v;
-    }
-    long long G = (B + K4_BLOCK - 1) / K4_BLOCK * K4_BLOCK;
-    if (G < K4_BLOCK) G = K4_BLOCK;
-    return G < cap ? G : cap;
-}
-
-// workspace after the 256-byte work counter: atol[N] | var_index[N] | state [G/32][n/5][99][32]
-size_t k4_scratch_bytes(int n, int64_t B) {
-    const long long G = k4_slots(n, B);
-    return align8(sizeof(double) * n) + align8(sizeof(int32_t) * n) + (size_t)(n / 5) * k4::SPN * G * sizeof(double);
+// workspace after the 256-byte work counter: atol[N] | var_index[N] | state [warps][n/5][99][ropes per warp]
+size_t k4_scratch_bytes(int n, int64_t B, int sms) {
+    const K4Geom g = k4_geometry(n, B, sms);
+    return align8(sizeof(double) * n) + align8(sizeof(int32_t) * n) + (size_t)(n / 5) * k4::SPN * g.warps * g.rpw * sizeof(double);
 }
 
 int k4_chain(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, int sms, cudaStream_t stream, LaunchGeom *g, bool geom_only) {
-    (void)sms;
     const int N = a_in.n;
     if (N < 10 || N % 5 != 0) return BRDAE_ERR_BAD_ARGUMENT;
-    const long long G = k4_slots(N, a_in.B);
-    if (g) { g->grid = (int)(G / K4_BLOCK); g->block = K4_BLOCK; g->smem = 0; g->scratch_bytes = 0; }
+    const K4Geom kg = k4_geometry(N, a_in.B, sms);
+    if (g) { g->grid = (int)kg.warps; g->block = K4_BLOCK; g->smem = 0; g->scratch_bytes = 0; }
     if (geom_only) return BRDAE_OK;
     if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;      // the block elimination is the chain's own M and J
     SolveArgs a = a_in;
@@ -63,8 +100,9 @@ int k4_chain(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, int s
         if (cudaMemcpyAsync(vidx_d, b->var_index, sizeof(int32_t) * N, cudaMemcpyHostToDevice, stream) != cudaSuccess) return BRDAE_ERR_CUDA;
     } else if (cudaMemsetAsync(vidx_d, 0, sizeof(int32_t) * N, stream) != cudaSuccess) return BRDAE_ERR_CUDA;
     a.atol_dev = atol_d; a.var_index_dev = vidx_d;
-    k4_kernel<<<(int)(G / K4_BLOCK), K4_BLOCK, 0, stream>>>(a, state);
-    return cudaPeekAtLastError() == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;
+    const cudaError_t err = (kg.minb >= 32) ? k4_launch<32>(kg, a, state, stream)
+                            : (kg.minb >= 16) ? k4_launch<16>(kg, a, state, stream) : k4_launch<8>(kg, a, state, stream);
+    return err == cudaSuccess ? BRDAE_OK : BRDAE_ERR_CUDA;
 }
 
 }  // namespace brdae

@@ -26,7 +26,7 @@ int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int 
 size_t k2_scratch_bytes(int n, int sms, int64_t B);
 // lane-per-rope block-elimination kernel for the chain (k4_chain.cu, chain_k4.cuh)
 int k4_chain(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
-size_t k4_scratch_bytes(int n, int64_t B);
+size_t k4_scratch_bytes(int n, int64_t B, int sms);
 // which chain kernel a batch of B ropes with n unknowns uses (BRDAE_NPENDULUM_KERNEL=k2 selects the band kernel)
 bool npendulum_uses_k4(int n, int64_t B);
 

@@ -91,6 +91,9 @@ struct SolveArgs {
     // optional pipelined copy-in: input_ready[k] != 0 once y0/params of chunk k have arrived (written by a
     // host-to-device copy queued behind the chunk's data); a lane waits for its system's chunk before loading it
     const volatile int32_t *input_ready;
+    // set by the host (mapped memory) when the call is abandoned while lanes may still wait for input_ready: waiting
+    // lanes give up instead of spinning forever; a lane whose wait exceeds its bound raises work_counter[1] instead
+    const volatile int32_t *abort_flag;
     double *dense_t, *dense_y, *dense_q;   // optional per-step record (brdae.h), dense_cap steps per system
     int32_t dense_cap;
     // optional device-side events (brdae.h): g_e(y) = ev_coef[e] . y - ev_level[e]

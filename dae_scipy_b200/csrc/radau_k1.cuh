@@ -550,13 +550,32 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 if (got >= a.B) state = ST_EXIT;
                 else {
                     idx = got;
+                    bool input_lost = false;
 #if defined(__CUDA_ARCH__)
                     if (a.input_ready) {           // pipelined copy-in: this system's chunk may still be on its way
                         const volatile int32_t *ready = a.input_ready + idx / a.chunk_size;
-                        while (*ready == 0) __nanosleep(256);
+                        // bounded wait: the host raises abort_flag when it abandons the call, and a copy that has not
+                        // arrived after ~2^26 polls (tens of seconds) never will (a driver mode in which the launch
+                        // blocks the queueing of the copies): give the system up and tell the host
+                        unsigned spins = 0;
+                        while (*ready == 0) {
+                            if ((a.abort_flag && *a.abort_flag != 0) || ++spins > (1u << 26) ||
+                                *reinterpret_cast<volatile unsigned long long *>(a.work_counter + 1) != 0) { input_lost = true; break; }
+                            __nanosleep(256);
+                        }
                         __threadfence();
+                        if (input_lost) atomicExch(a.work_counter + 1, 1ull);
                     }
 #endif
+                    if (input_lost) {              // never integrated: no result is written, the host returns an error
+                        if (a.chunk_done) {
+#if defined(__CUDA_ARCH__)
+                            signal_chunk(a, idx);
+#endif
+                        }
+                        state = ST_IDLE;
+                        idx = -1;
+                    } else {
                     Prob::load(prm, a.params, a.par_sc, idx * a.par_sb);
                     t = a.t0;
 #pragma unroll
@@ -587,6 +606,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                             for (int c = 0; c < N; ++c) a.y_eval[ei * a.ye_st + c * a.ye_sc + idx * a.ye_sb] = y[c];
                         finish_status = BRDAE_STATUS_FINISHED;
                         state = ST_IDLE;
+                    }
                     }
                 }
             }

@@ -32,8 +32,8 @@ def shard_ensemble(ens: dict, world_size: int, rank: int) -> dict:
 
 def reduce_statistics(counters_sum, status_hist, dist=None, device=None):
     """Sum the per-rank statistics vectors over all ranks (all_reduce SUM).  `counters_sum` is the
-    int64 [9] sum of the per-system counters of the local shard, `status_hist` an int64 [4] vector
-    (finished, too-small-step, lu-failed, nmax-step)."""
+    int64 [9] sum of the per-system counters of the local shard, `status_hist` an int64 [5] vector
+    (finished, too-small-step, lu-failed, nmax-step, ended-by-a-terminal-event)."""
     import torch
     vec = torch.cat([torch.as_tensor(counters_sum, dtype=torch.int64).reshape(-1),
                      torch.as_tensor(status_hist, dtype=torch.int64).reshape(-1)])
@@ -68,10 +68,11 @@ def gather_results(local: dict, B_total: int, dist, dst: int = 0):
 
 
 def status_histogram(status):
-    """[finished, too-small-step, lu-failed, nmax-step] counts of a status vector."""
+    """[finished, too-small-step, lu-failed, nmax-step, terminal-event] counts of a status vector (BRDAE_STATUS_* 0, -1, -2,
+    2, 1): the bins sum to the number of systems."""
     import torch
     s = status if isinstance(status, torch.Tensor) else torch.as_tensor(np.asarray(status))
-    return torch.stack([(s == 0).sum(), (s == -1).sum(), (s == -2).sum(), (s == 2).sum()]).to(torch.int64)
+    return torch.stack([(s == 0).sum(), (s == -1).sum(), (s == -2).sum(), (s == 2).sum(), (s == 1).sum()]).to(torch.int64)
 
 
 def solve_ivp_sharded(problem, t_span, y0, params=None, *, dist=None, gather_dst=None, device=None, **kwargs):
@@ -82,7 +83,7 @@ def solve_ivp_sharded(problem, t_span, y0, params=None, *, dist=None, gather_dst
     ensemble order (NCCL over NVLink with the nccl backend).
 
     Returns a dict: `local` (this rank's BatchedOdeResult), `shard` (lo, hi), `counters_sum` [9] and
-    `status_histogram` [4] over the WHOLE ensemble (on every rank), and on `gather_dst` also `y` [B, n, T],
+    `status_histogram` [5] over the WHOLE ensemble (on every rank; the bins sum to B), and on `gather_dst` also `y` [B, n, T],
     `status`, `n_eval`, `t_final`, `y_final` [B, n], `counters` [B, 9] as device tensors (None elsewhere)."""
     import torch
     from .api import solve_ivp_batched

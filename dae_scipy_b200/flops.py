@@ -9,8 +9,14 @@ complex add 2.  Dense size n, z = nnz(M):
     F_err  = 2 n^2 + 15 n + 2 z                   one error estimate
     FLOPs  = nfev F_f + njev F_J + nlu (F_form + F_LU) + nlusolve F_newt + nlusolve_err F_err
              + naccpt 15 n + n_out (6 n + 3)
-For the banded CTA-per-system kernel 2/3 n^3 becomes 2 N kl (kl + ku) and 2 n^2 becomes
-2 N (2 kl + ku) with kl = 9, ku = 7.
+For the banded CTA-per-system kernel (K2) 2/3 n^3 becomes 2 N kl (kl + ku) and 2 n^2 becomes
+2 N (2 kl + ku) with kl = 9, ku = 7.  The chain kernel K4 does not run that algorithm: it eliminates the velocities and
+factorises 3 x 3 node blocks (csrc/chain_k4.cuh), and its model counts what that algorithm needs per node
+(`flop_constants("npendulum", n, chain_block=True)`):
+    factorisation (both systems)  ~700   (X = G U 18, E -= L X 36, Gauss-Jordan inverse ~75, block set-up ~10: 140 real, x 4 complex)
+    Newton iteration              ~610   (real solve 57, complex 4 x 57, residuals / stage combinations / norm / update 60 per unknown, 6 z)
+    error estimate                ~140   (real solve 57, 15 per unknown, 2 z)
+so the FP64 fraction of a chain run is quoted for the work the kernel actually has to do, not for the band LU it replaced.
 """
 from __future__ import annotations
 
@@ -21,7 +27,11 @@ F_JAC = {"pendulum3": 4, "pendulum2": 4, "pendulum1": 12, "robertson": 8, "trans
 MASS_NNZ = {"pendulum3": 4, "pendulum2": 4, "pendulum1": 4, "robertson": 2, "transistor": 9}
 
 
-def flop_constants(problem: str, n: int):
+def flop_constants(problem: str, n: int, chain_block: bool = False):
+    if problem == "npendulum" and chain_block:
+        nodes = n // 5
+        return dict(F_f=F_RHS[problem] * nodes, F_J=F_JAC[problem] * nodes, F_LU=690 * nodes, F_form=10 * nodes,
+                    F_newt=(5 * 57 + 60 * 5 + 6 * 4) * nodes, F_err=(57 + 15 * 5 + 2 * 4) * nodes)
     if problem == "npendulum":
         nodes = n // 5
         kl, ku = 9, 7
@@ -41,9 +51,9 @@ def flop_constants(problem: str, n: int):
                 F_err=2 * n * n + 15 * n + 2 * z)
 
 
-def algorithmic_flops(problem: str, n: int, counter_sums, n_out_total: int) -> float:
+def algorithmic_flops(problem: str, n: int, counter_sums, n_out_total: int, chain_block: bool = False) -> float:
     """counter_sums: the 9 counters summed over the ensemble, in _abi.COUNTER_NAMES order."""
-    c = flop_constants(problem, n)
+    c = flop_constants(problem, n, chain_block)
     nfev, njev, nlu, _nstep, naccpt, _nrej, _nfail, nsolve, nsolve_err = [float(x) for x in counter_sums]
     return (nfev * c["F_f"] + njev * c["F_J"] + nlu * (c["F_form"] + c["F_LU"]) + nsolve * c["F_newt"]
             + nsolve_err * c["F_err"] + naccpt * 15 * n + float(n_out_total) * (6 * n + 3))
@@ -54,3 +64,13 @@ def algorithmic_bytes(n: int, n_params: int, T: int, B: int) -> float:
     counters out."""
     per_sys = 8 * (n + n_params) + 8 * n * T + 8 * (n + 1) + 4 * (2 + 9)
     return float(per_sys) * B
+
+
+def chain_state_bytes_per_node_sweep() -> dict:
+    """HBM/L2 bytes the chain kernel K4 moves per node and sweep (8-byte slots of csrc/chain_k4.cuh), the bound of that
+    kernel: a Newton iteration reads y, W (twice: look-ahead and node), the rod quantities, the three inverse blocks, the
+    forward-substituted blocks, the scales, and writes z, the position rows and W."""
+    newton = 8 * (5 + 15 + 12 + 5 + 27 + 9 + 6 + 5 + 15 + 18 + 5 + 9 + 6) + 8 * (9 + 6 + 15)      # loads + stores
+    factor = 8 * (7 + 5) + 8 * 27
+    errest = 8 * (15 + 5 + 5 + 5 + 9 + 6 + 5 + 3 + 2 + 10) + 8 * (4 + 5 + 5)
+    return dict(newton=newton, factor=factor, error_estimate=errest)

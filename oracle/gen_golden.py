@@ -30,7 +30,8 @@ sys.path.insert(0, "/root/reference")
 warnings.filterwarnings("ignore")
 
 from scipy.integrate import solve_ivp  # noqa: E402
-from scipyDAE.radauDAE import RadauDAE  # noqa: E402  (the reference)
+from oracle import reference_runner  # noqa: E402
+RadauDAE = reference_runner.radau_class()  # the reference
 
 from dae_scipy_b200 import ensembles  # noqa: E402  (numpy-only input generators)
 from oracle import problems_numpy as prob  # noqa: E402
@@ -43,68 +44,9 @@ def build_system(problem, p, n=None):
 
 
 def run_reference_with_counters(ens, over=None):
-    """Same as run_reference but steps the solver object directly (the loop of scipy ivp.py:659-732)
-    to read nstep/naccpt/nrejct/nfailed/_nlusolve/_nlusolve_errorest from it."""
-    opts = dict(ens["options"])
-    opts.update(over or {})
-    mm = opts.pop("mass_matrix")
-    vi = opts.pop("var_index")
-    nmax_step = opts.pop("nmax_step", np.inf)
-    fd = "jac" in opts and opts.pop("jac") is None     # jac=None: the reference's finite-difference Jacobian
-    B, n = ens["y0"].shape
-    te = np.asarray(ens["t_eval"], dtype=float)
-    T = te.size
-    t0, tf = ens["t_span"]
-    y = np.full((B, n, T), np.nan)
-    status = np.zeros(B, dtype=np.int32)
-    n_eval = np.zeros(B, dtype=np.int32)
-    counters = np.zeros((B, 9), dtype=np.int32)
-    y_final = np.zeros((B, n))
-    t_final = np.zeros(B)
-    for i in range(B):
-        p = ens["params"][i] if ens["params"] is not None else ()
-        fun, jac, mass, _ = build_system(ens["problem"], p, n)
-        if not isinstance(mm, str):
-            mass = mm
-        if fd:
-            jac = None
-        with contextlib.redirect_stdout(io.StringIO()):
-            solver = RadauDAE(fun, t0, np.array(ens["y0"][i], dtype=float), tf, jac=jac, mass_matrix=mass,
-                              var_index=None if vi is None else np.asarray(vi, dtype=float), **opts)
-            ei = 0
-            st = None
-            nsteps = 0
-            while st is None:
-                nsteps += 1
-                if nsteps > nmax_step:
-                    st = 2
-                    break
-                solver.step()
-                if solver.status == 'finished':
-                    st = 0
-                elif solver.status == 'failed':
-                    st = -1
-                    break
-                t = solver.t
-                if tf > t0:
-                    ei_new = int(np.searchsorted(te, t, side='right'))
-                    pts = te[ei:ei_new]
-                else:
-                    # user order is decreasing: points >= t
-                    ei_new = ei
-                    while ei_new < T and te[ei_new] >= t:
-                        ei_new += 1
-                    pts = te[ei:ei_new]
-                if pts.size:
-                    y[i, :, ei:ei_new] = solver.dense_output()(pts)
-                    ei = ei_new
-        n_eval[i] = ei
-        status[i] = st
-        counters[i] = [solver.nfev, solver.njev, solver.nlu, solver.nstep, solver.naccpt, solver.nrejct,
-                       solver.nfailed, solver._nlusolve, solver._nlusolve_errorest]
-        y_final[i] = solver.y
-        t_final[i] = solver.t
-    return dict(y=y, status=status, n_eval=n_eval, counters=counters, y_final=y_final, t_final=t_final)
+    """The reference solver stepped like scipy's solve_ivp loop, counters read from the solver object
+    (oracle/reference_runner.py)."""
+    return reference_runner.run_reference(ens, over, build_system)
 
 
 ONLY = tuple(sys.argv[1:])       # optional name prefixes: regenerate just those fixtures

@@ -29,7 +29,7 @@ if rank == 0:
     assert np.array_equal(gathered["status"].numpy(), full["status"])
     assert np.array_equal(gathered["counters"].t().numpy(), full["counters"])
     assert np.array_equal(csum.numpy(), full["counters"].sum(axis=0))
-    assert hist.tolist() == [B, 0, 0, 0]
+    assert hist.tolist() == [B, 0, 0, 0, 0]
     print("rank0 ok")
 else:
     assert gathered is None

@@ -32,7 +32,7 @@ if rank == 0:
     assert torch.equal(out["counters"], full.counters.t()) and torch.equal(out["y_final"], full.y_final)
     assert torch.equal(out["n_eval"], full.n_eval) and torch.equal(out["t_final"], full.t_final)
     assert torch.equal(out["counters_sum"], full.counters.sum(dim=1, dtype=torch.int64))
-    assert out["status_histogram"].tolist() == [B, 0, 0, 0]
+    assert out["status_histogram"].tolist() == [B, 0, 0, 0, 0]
     print(f"rank0 ok: {B} Robertson systems over {world} GPUs, gathered over NCCL, bit-identical to one GPU")
 else:
     assert "y" not in out

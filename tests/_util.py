@@ -263,6 +263,15 @@ def run_numpy_oracle_parallel(ens, nproc=None):
     return {k: np.concatenate([o[k] for o in outs]) for k in outs[0]}
 
 
+def run_reference_or_port_parallel(ens):
+    """(result, kind): the UNMODIFIED reference over all host cores when it is importable (oracle/_ref travels with the
+    snapshot; /root/reference exists in the build container), else the numpy port that is bit-identical to it."""
+    from oracle import reference_runner
+    if reference_runner.reference_location() is not None:
+        return reference_runner.run_reference_parallel(ens), "reference"
+    return run_numpy_oracle_parallel(ens), "port"
+
+
 def parity_statistics(out, ref, rtol, atol, n_diff):
     """north_star acceptance numbers: fraction of systems with identical (naccpt, nrejct, nfailed); per-system max
     of |dy| / (atol + rtol |y_ref|) over the differential unknowns (first n_diff) and over the algebraic ones."""

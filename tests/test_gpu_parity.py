@@ -262,7 +262,34 @@ def test_gpu_parity_statistics_against_reference_port_at_scale():
     st = parity_statistics(run_gpu(ens), run_numpy_oracle_parallel(ens), 1e-6, 1e-8, n_diff=2)
     assert st["status_equal"]
     assert st["diff_err"].max() <= PARITY_FACTOR and st["alg_err"].max() <= PARITY_FACTOR
-    assert st["identical_counts"] >= 0.85      # measured 0.90: the reference itself reproduces 45/48 under ulp noise here
+    # The count criterion on this configuration is bounded by the reference's own reproducibility: run with another
+    # OpenBLAS kernel family (OPENBLAS_CORETYPE) the unmodified reference agrees with itself on 0.92-0.94 of these
+    # systems (profiles/r02_reference_selfconsistency.md, measured on the GPU box by profiles/tools/ref_selfconsistency.py);
+    # the kernels are inside that band.
+    assert st["identical_counts"] >= 0.88, st["identical_counts"]
+
+
+def test_gpu_transistor_bench_configuration_within_tolerance_of_the_reference():
+    """BASELINE configs[3]: the first 512 parameter sets of the 262,144-system transistor ensemble at the bench horizon
+    t_end = 0.2, CUDA path against the reference (the unmodified RadauDAE from oracle/_ref when it travelled with the
+    snapshot, else the numpy port that is bit-identical to it): every trajectory within 10 (atol + rtol |y|) at every
+    t_eval point.  Step counts: the reference does not reproduce its own counts on this problem under rounding noise
+    (0 of 256 systems identical between two OpenBLAS kernel families, profiles/r02_reference_selfconsistency.md), so the
+    agreement is reported and only the totals are bounded."""
+    from _util import run_reference_or_port_parallel
+    ens = E.transistor_ensemble(1 << 18, t_end=0.2)
+    k = 512
+    sub = dict(ens, y0=ens["y0"][:k], params=ens["params"][:k])
+    out, (ref, kind) = run_gpu(sub), run_reference_or_port_parallel(sub)
+    assert np.array_equal(out["status"], ref["status"]) and (out["status"] == 0).all()
+    assert np.array_equal(out["n_eval"], ref["n_eval"])
+    err = scaled_error(out["y"], ref["y"], 1e-5, 1e-5)
+    same = count_agreement(out["counters"], ref["counters"])
+    tot, tot_ref = out["counters"][:, 3:7].sum(axis=0), ref["counters"][:, 3:7].sum(axis=0)
+    print(f"transistor 512 x t_end=0.2 vs {kind}: max scaled error {err:.3f}, identical counts {same:.3f}, "
+          f"totals (nstep, naccpt, nrejct, nfailed) {tot.tolist()} vs {tot_ref.tolist()}")
+    assert err <= PARITY_FACTOR, err
+    assert np.all(np.abs(tot - tot_ref) <= 0.02 * np.maximum(tot_ref, 100))
 
 
 # ---------------------------------------------------------------- (3) properties at full size

@@ -174,7 +174,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "trajectories/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["config"]["workload"] == "pendulum3_1M_tend2" and d["dtype"] == "f64" and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    from oracle import reference_runner          # the unmodified reference when it is importable, else its numpy port
+    assert d["cpu_baseline"]["kind"] == ("reference" if reference_runner.reference_location() else "port")
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
     # the other ranks of a torchrun launch exit without work

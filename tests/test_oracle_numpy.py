@@ -12,7 +12,10 @@ import pytest
 from _util import (HAVE_REFERENCE, PARITY_FACTOR, count_agreement, golden_names, load_golden,
                    run_numpy_oracle, scaled_error, well_conditioned)
 
-FAST = [n for n in golden_names() if n not in ("ens_npendulum_n20", "g3_transistor_single", "script_pendulum3")]
+# the long chains (dense 250 x 250 / 500 x 500 LAPACK factorisations in the port) are pinned through the C oracle and the kernel
+# source instead (tests/test_oracle_c.py, tests/test_kernel_source_cpu.py)
+FAST = [n for n in golden_names() if n not in ("ens_npendulum_n20", "ens_npendulum_n50", "ens_npendulum_n100",
+                                               "g3_transistor_single", "script_pendulum3")]
 
 
 @pytest.mark.parametrize("name", FAST)
