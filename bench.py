@@ -403,7 +403,10 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind = _reference_kind()
-        per_core = 384 if gen_key != "npendulum" else max(1, 64 // gen_kw["n_nodes"])       # about 15-20 s of CPU work
+        # about 10-30 s of CPU work per workload (the reference integrates roughly 8 / 10 / 1.5 / 1.5 systems per second and core
+        # on the pendulum t_end = 2 / Robertson / transistor / pendulum t_end = 10 configurations, 1 rope per second at n = 20)
+        per_core = {"pendulum3_1M_tend2": 160, "robertson_4M": 160, "transistor_256k": 24, "pendulum3_1M_tend10": 24}.get(
+            args.workload, max(1, 64 // gen_kw.get("n_nodes", 64)))
         ns = args.cpu_sample or min(B, per_core * cores)
         rate, dt, nn = cpu_reference_rate(ens, ns, cores, kind)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,

@@ -17,7 +17,7 @@ COUNTER_NAMES = ("nfev", "njev", "nlu", "nstep", "naccpt", "nrejct", "nfailed", 
                  "nlusolve_errorest")
 NCOUNTERS = len(COUNTER_NAMES)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_EVENTS = 4
 STATUS_FINISHED = 0
 STATUS_EVENT = 1
@@ -64,7 +64,9 @@ class BrdaeBatch(C.Structure):
                 ("n_events", C.c_int32), ("event_cap", C.c_int32),
                 ("event_coef", C.c_void_p), ("event_level", C.c_void_p), ("event_direction", C.c_void_p),
                 ("event_terminal", C.c_void_p), ("event_count", C.c_void_p), ("event_t", C.c_void_p),
-                ("event_y", C.c_void_p), ("event_functor", C.c_void_p)]
+                ("event_y", C.c_void_p), ("event_functor", C.c_void_p),
+                ("report_cap", C.c_int32), ("reserved1", C.c_int32), ("report_count", C.c_void_p),
+                ("report_code", C.c_void_p), ("report_it", C.c_void_p), ("report_val", C.c_void_p)]
 
 
 # keyword -> (options field, default) : the RadauDAE constructor surface, radauDAE.py:263-278

@@ -135,6 +135,10 @@ class HostBatch:
                   "dense_t", "dense_y", "dense_q"):
             setattr(b, k, ptr.get(k))
         b.dense_cap = int(ptr.get("dense_cap") or 0)
+        b.report_cap = int(ptr.get("report_cap") or 0)
+        if b.report_cap:
+            for k in ("report_count", "report_code", "report_it", "report_val"):
+                setattr(b, k, ptr.get(k))
         if self.events is not None and ptr.get("event_cap"):
             coef, level, direction, terminal, functor = self.events
             b.n_events, b.event_cap = coef.shape[0], int(ptr["event_cap"])
@@ -218,6 +222,8 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
     elif callable(mass_matrix):
         raise ValueError("`mass_matrix` should be a constant matrix, but is callable")
     else:
+        if hasattr(mass_matrix, "toarray"):                # scipy.sparse matrix (radauDAE.py:452-457 keeps it as CSC; the
+            mass_matrix = mass_matrix.toarray()            # reference's own chain script passes one): the kernels take it dense
         mass = np.ascontiguousarray(np.asarray(mass_matrix, dtype=np.float64))
         if mass.shape != (n, n):
             raise ValueError("`mass_matrix` is expected to have shape {}, but actually has {}."
@@ -278,6 +284,7 @@ class BatchedOdeResult:
         self.t_events = self.y_events = None    # per system, per event (lists of arrays) when events were given
         self._event_cut = None                  # (terminated [B], t_stop [B], y_stop [B, n], ascending)
         self.event_count = self.event_t = self.event_y = None   # device-side events: [E, B], [E, cap, B], [E, cap, n, B]
+        self.reports = None                     # report=True: dict of device tensors, see solve_ivp_batched
         self.t = t
         self._y_eval = y_eval_tnb           # [T, n, B] as written by the kernel (coalesced SoA)
         self.n_eval = n_eval
@@ -319,6 +326,12 @@ class BatchedOdeResult:
             k = np.minimum(cnt, cap)
             out["t_events"] = [[out["event_t"][i, e, :k[e, i]] for e in range(cnt.shape[0])] for i in range(cnt.shape[1])]
             out["y_events"] = [[out["event_y"][i, e, :k[e, i]] for e in range(cnt.shape[0])] for i in range(cnt.shape[1])]
+        if self.reports is not None:            # the reference's solver.reports (bReport=True), one row per system
+            r = self.reports
+            out["reports"] = {"n": r["count"].cpu().numpy(), "code": r["code"].t().cpu().numpy(),
+                              "newton_iterations": r["it"][:, 0].t().cpu().numpy(), "bad_iterations": r["it"][:, 1].t().cpu().numpy(),
+                              "t": r["val"][:, 0].t().cpu().numpy(), "dt": r["val"][:, 1].t().cpu().numpy(),
+                              "err1": r["val"][:, 2].t().cpu().numpy(), "err2": r["val"][:, 3].t().cpu().numpy()}
         if self._event_cut is not None:         # a terminal event ends the reported result (scipy: status 1)
             term, t_stop, y_stop, asc = self._event_cut
             t = out["t"]
@@ -461,8 +474,8 @@ def _as_device_f64(x, device, torch):
 
 
 def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_eval=None,
-                      dense_output=False, max_dense_steps=None, events=None, max_events=8, device=None, stream=None,
-                      **options):
+                      dense_output=False, max_dense_steps=None, events=None, max_events=8, report=False, max_reports=4096,
+                      device=None, stream=None, **options):
     """Integrate B independent systems  M y' = f(t, y)  from t_span[0] to t_span[1] on one GPU.
 
     Parameters follow `scipy.integrate.solve_ivp(..., method=RadauDAE, **options)` of the
@@ -491,6 +504,10 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
                   scipy's solve_ivp; located on the host on the per-step record (implies dense_output=True, so
                   `max_dense_steps` is required); `result.t_events[i][e]`, `result.y_events[i][e]`, and a terminal
                   event cuts that system's reported result (status 1), see `find_events`.
+    report, max_reports : the reference's `bReport=True` (`solver.reports`, radauDAE.py:424-443): one record per factorisation,
+                  Jacobian update, non-converged attempt, rejected and accepted step (codes -10, -11, 5, 2, 0), the first
+                  `max_reports` per system, in `result.reports` (device tensors `count` [B], `code` [R, B], `it` [R, 2, B],
+                  `val` [R, 4, B] = t, h, err1, err2; `.numpy()["reports"]` gives the reference's keys, one row per system).
     dense_output, max_dense_steps : record every accepted step (up to `max_dense_steps` per system, required
                   with dense_output=True: the record takes 8 (4 n + 1) bytes per step and system) and return
                   `result.sol`, a BatchedOdeSolution.  Times known in advance are cheaper through `t_eval`.
@@ -550,6 +567,16 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
             dense_y = torch.empty((K, n, B), dtype=torch.float64, device=dev)
             dense_q = torch.empty((K, n, 3, B), dtype=torch.float64, device=dev)
             ptr.update(dense_cap=K, dense_t=dense_t.data_ptr(), dense_y=dense_y.data_ptr(), dense_q=dense_q.data_ptr())
+        if report:
+            R_ = int(max_reports)
+            if R_ < 1:
+                raise ValueError("`max_reports` must be at least 1.")
+            rep_count = torch.zeros(B, dtype=torch.int32, device=dev)
+            rep_code = torch.zeros((R_, B), dtype=torch.int32, device=dev)
+            rep_it = torch.full((R_, 2, B), -1, dtype=torch.int32, device=dev)
+            rep_val = torch.full((R_, 4, B), float("nan"), dtype=torch.float64, device=dev)
+            ptr.update(report_cap=R_, report_count=rep_count.data_ptr(), report_code=rep_code.data_ptr(),
+                       report_it=rep_it.data_ptr(), report_val=rep_val.data_ptr())
         if device_events:
             E_, cap = len(device_events), int(max_events)
             event_count = torch.zeros((E_, B), dtype=torch.int32, device=dev)
@@ -568,7 +595,7 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
             for ten in (y0_soa, par_soa, te_d, y_eval, n_eval, t_final, y_final, status, counters, ws):
                 if ten is not None:
                     ten.record_stream(cu_stream)
-            for name in ("dense_t", "dense_y", "dense_q", "event_count", "event_t", "event_y"):
+            for name in ("dense_t", "dense_y", "dense_q", "event_count", "event_t", "event_y", "rep_count", "rep_code", "rep_it", "rep_val"):
                 ten = locals().get(name)
                 if ten is not None:
                     ten.record_stream(cu_stream)
@@ -579,6 +606,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     res._keepalive = (y0_soa, par_soa, te_d, ws)
     if device_events:
         res.event_count, res.event_t, res.event_y = event_count, event_t, event_y
+    if report:
+        res.reports = {"count": rep_count, "code": rep_code, "it": rep_it, "val": rep_val}
     if dense_output:
         cu_stream.synchronize()
         y0_h = y0_d.cpu().numpy()

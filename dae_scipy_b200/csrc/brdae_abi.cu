@@ -138,7 +138,7 @@ int brdae_solve(const brdae_batch *b, const brdae_options *o, void *workspace, s
 int brdae_solve_host(const brdae_batch *hb, const brdae_options *o) {
     int rc = validate(hb, o);
     if (rc != BRDAE_OK) return rc;
-    if (hb->dense_cap > 0 || hb->n_events > 0) return BRDAE_ERR_UNSUPPORTED;   // the per-step record and events are device-buffer features
+    if (hb->dense_cap > 0 || hb->n_events > 0 || hb->report_cap > 0) return BRDAE_ERR_UNSUPPORTED;   // the per-step record, events and reports are device-buffer features
     const int64_t B = hb->n_systems;
     if (B == 0) return BRDAE_OK;
     const int n = hb->n, T = hb->n_t_eval, np = hb->n_params;
@@ -368,7 +368,7 @@ done:
 int brdae_solve_host_rows(const brdae_batch *hb, const brdae_options *o) {
     int rc = validate(hb, o);
     if (rc != BRDAE_OK) return rc;
-    if (hb->dense_cap > 0 || hb->n_events > 0) return BRDAE_ERR_UNSUPPORTED;
+    if (hb->dense_cap > 0 || hb->n_events > 0 || hb->report_cap > 0) return BRDAE_ERR_UNSUPPORTED;
     const int64_t B = hb->n_systems;
     if (B == 0) return BRDAE_OK;
     if (hb->problem != BRDAE_NPENDULUM && !std::getenv("BRDAE_ROWS_CHUNKED")) return host_rows_single_launch(hb, o);

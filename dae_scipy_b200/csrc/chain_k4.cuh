@@ -719,6 +719,7 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
                     h_abs_state = a.h0;
                     hist_state = false; current_jac = true; lu_valid = false; have_sol = false;
                     h_lu = 1.0; ei = 0; nsteps = 0;
+                    if (a.rep_cap > 0) a.rep_count[idx] = 0;
                     state = ST_SETUP; setup_kind = SETUP_STEP;
                     if (t == a.tb) {
                         for (; ei < a.T; ++ei)
@@ -742,13 +743,16 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
                 double error_norm = 0.0;
                 bool accepted = true;
                 if (!a.constant_dt) {
+                    double err1 = NAN, err2 = NAN;
                     for (int pass = 0;; ++pass) {
                         const double ssq = error_sweeps<STRIDE>(R, kc, a, pass, h, inv_h, h_lu, mrf);
                         cnt[CN_NSOLVE_ERR]++;
                         if (pass == 1) cnt[CN_NFEV]++;
                         error_norm = sqrt(ssq) * (a.zero_algebraic_error ? a.rsq_nondiff : a.rsqn);
+                        if (pass == 0) err1 = error_norm; else err2 = error_norm;
                         if (pass == 1 || !(error_norm > 1 && (a.always_2nd || rejected))) break;
                     }
+                    if (a.rep_cap > 0) report_event(a, idx, error_norm > 1 ? RC_REJECTED : RC_ACCEPTED, t, h, n_iter, nbad, err1, err2);
                     if (error_norm > 1) {
                         const double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller);
                         h_abs *= fmax(a.min_factor, safety * factor);
@@ -867,6 +871,7 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
                 mrf = mr; mcrf = mcr; mcif = mci;
                 factor_sweep<STRIDE>(R, kc, mr, mcr, mci);
                 cnt[CN_NLU]++;
+                if (a.rep_cap > 0) report_event(a, idx, RC_FACTORISATION, t, h, -1, -1, -1.0, -1.0);
                 lu_valid = true;
                 state = ST_NEWTON;
             }
@@ -920,6 +925,7 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
                         safety = a.safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter);
                         if (outcome == 1) state = ST_ERREST;
                         else if (current_jac) {
+                            if (a.rep_cap > 0) report_event(a, idx, RC_NON_CONV, t, h, n_iter, nbad, -1.0, -1.0);
                             cnt[CN_NFAIL]++;
                             h_abs *= a.nonconv_factor;
                             lu_valid = false;
@@ -927,6 +933,7 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
                         } else {
                             jac_sweep<STRIDE>(R, kc);
                             cnt[CN_NJEV]++;
+                            if (a.rep_cap > 0) report_event(a, idx, RC_JACOBIAN_UPDATE, t, h, -1, -1, -1.0, -1.0);
                             current_jac = true; lu_valid = false;
                             state = ST_SETUP; setup_kind = SETUP_GUESS;
                         }

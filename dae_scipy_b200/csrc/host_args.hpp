@@ -55,6 +55,7 @@ inline int validate(const brdae_batch *b, const brdae_options *o) {
             if (b->event_functor && b->event_functor[e] >= 0 && b->problem != BRDAE_USER) return BRDAE_ERR_UNSUPPORTED;   // the stock functors define none
         }
     }
+    if (b->report_cap < 0 || (b->report_cap > 0 && !(b->report_count && b->report_code && b->report_it && b->report_val))) return BRDAE_ERR_BAD_ARGUMENT;
     if (!(b->rtol > 0) || !(o->max_step > 0) || o->max_newton_ite < 1) return BRDAE_ERR_BAD_ARGUMENT;
     for (int c = 0; c < b->n; ++c) {
         if (!(b->atol[c] >= 0)) return BRDAE_ERR_BAD_ARGUMENT;
@@ -85,6 +86,7 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
         a.ev_functor[e] = b->event_functor ? b->event_functor[e] : -1;
         for (int c = 0; c < b->n && c < BRDAE_NMAX_SMALL; ++c) a.ev_coef[e][c] = b->event_coef[e * b->n + c];
     }
+    a.rep_cap = b->report_cap; a.rep_count = b->report_count; a.rep_code = b->report_code; a.rep_it = b->report_it; a.rep_val = b->report_val;
     a.work_counter = static_cast<unsigned long long *>(workspace);
     a.scratch = reinterpret_cast<double *>(static_cast<char *>(workspace) + kCounterBytes);
     a.t0 = b->t0; a.tb = b->t_bound;

@@ -32,7 +32,8 @@ int k1_launch_mode(const SolveArgs &a_in, int sms, cudaStream_t s, LaunchGeom *g
 template <class Prob, class Mass, int BLOCK, int MIN_BLOCKS, bool CTA_WIDE = false, bool COLD_GLOBAL = false>
 int k1_launch(const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only, int newton_reps = 3) {
     // device-side events (brdae_batch.n_events > 0) are their own instantiations: the event code costs the plain kernels nothing
-    if (a.n_events > 0) {
+    // ... and so is the per-attempt report (brdae_batch.report_cap > 0): the same instrumented instantiation writes it
+    if (a.n_events > 0 || a.rep_cap > 0) {
         if (a.jac_fd) return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, true, true>(a, sms, s, g, geom_only, newton_reps);
         return k1_launch_mode<Prob, Mass, BLOCK, MIN_BLOCKS, CTA_WIDE, COLD_GLOBAL, false, true>(a, sms, s, g, geom_only, newton_reps);
     }

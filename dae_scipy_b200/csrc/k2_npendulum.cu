@@ -798,6 +798,7 @@ int k2_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, i
     if (g) { g->grid = (int)grid; g->block = global_state ? K2G_BLOCK : K2_BLOCK; g->smem = (int)smem; g->scratch_bytes = 0; }
     if (geom_only) return BRDAE_OK;
     if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;   // band kernel: the problem's own M and J only
+    if (a_in.rep_cap > 0) return BRDAE_ERR_UNSUPPORTED;                   // the per-attempt report is written by K1 and K4
     SolveArgs a = a_in;
     char *ws = reinterpret_cast<char *>(a.work_counter) + kHeaderBytes;
     double *atol_d = reinterpret_cast<double *>(ws);

@@ -83,6 +83,16 @@ struct Pendulum {
         else if (INDEX == 2) f[4] = x * vx + y * vy;
         else f[4] = l * (x * x + y * y) * p.im + p.g * y - (vx * vx + vy * vy);
     }
+    // structural non-zeros of the Jacobian below (radau_k1.cuh: LuPattern)
+    static BRDAE_CX bool jac_nz(int r, int c) {
+        if (r == 0) return c == 2;
+        if (r == 1) return c == 3;
+        if (r == 2) return c == 0 || c == 4;
+        if (r == 3) return c == 1 || c == 4;
+        if (INDEX == 3) return c == 0 || c == 1;
+        if (INDEX == 2) return c < 4;
+        return true;
+    }
     static BRDAE_HD void jac(const P &p, double, const double (&X)[5], double (&J)[5][5]) {
         const double x = X[0], y = X[1], vx = X[2], vy = X[3], l = X[4];
 #pragma unroll

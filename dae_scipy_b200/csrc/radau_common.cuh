@@ -102,6 +102,10 @@ struct SolveArgs {
     double ev_level[BRDAE_MAX_EVENTS], ev_coef[BRDAE_MAX_EVENTS][BRDAE_NMAX_SMALL];
     int32_t *ev_count;
     double *ev_t, *ev_y;
+    // optional per-attempt report (brdae.h: report_*), rep_cap records per system
+    int32_t rep_cap;
+    int32_t *rep_count, *rep_code, *rep_it;
+    double *rep_val;
     unsigned long long *work_counter;
     double *scratch;  // per-CTA global scratch (K2)
     double t0, tb, dir, rtol;
@@ -125,5 +129,18 @@ struct SolveArgs {
 };
 
 enum : int { CN_NFEV = 0, CN_NJEV, CN_NLU, CN_NSTEP, CN_NACC, CN_NREJ, CN_NFAIL, CN_NSOLVE, CN_NSOLVE_ERR, CN_COUNT };
+
+// codes of the per-attempt report (radauDAE.py:24-28)
+enum : int { RC_FACTORISATION = -10, RC_JACOBIAN_UPDATE = -11, RC_NON_CONV = 5, RC_ACCEPTED = 0, RC_REJECTED = 2 };
+// append one record to system idx's report (the reference's RadauDAE._report, radauDAE.py:424-443)
+BRDAE_HD void report_event(const SolveArgs &a, long long idx, int code, double t, double h, int newt, int nbad, double e1, double e2) {
+    const int k = a.rep_count[idx];
+    a.rep_count[idx] = k + 1;
+    if (k >= a.rep_cap) return;
+    a.rep_code[(int64_t)k * a.B + idx] = code;
+    a.rep_it[((int64_t)k * 2 + 0) * a.B + idx] = newt; a.rep_it[((int64_t)k * 2 + 1) * a.B + idx] = nbad;
+    a.rep_val[((int64_t)k * 4 + 0) * a.B + idx] = t; a.rep_val[((int64_t)k * 4 + 1) * a.B + idx] = h;
+    a.rep_val[((int64_t)k * 4 + 2) * a.B + idx] = e1; a.rep_val[((int64_t)k * 4 + 3) * a.B + idx] = e2;
+}
 
 }  // namespace brdae

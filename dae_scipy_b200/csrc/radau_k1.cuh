@@ -34,6 +34,8 @@
 // non-convergence :635-658, error estimate :669-711, accept/reject :713-739, epilogue :742-784,
 // dense output :951-982, driver / t_eval slicing :1079-1157 (scipy ivp.py:659-732).
 #pragma once
+#include <type_traits>
+
 #include "problems.cuh"
 
 #ifndef BRDAE_K1_IDENT_FASTPATH
@@ -338,6 +340,240 @@ BRDAE_HD void solve_cplx_sm(const S &sm, int base_r, int base_i, int scratch, un
     }
 }
 
+// ---- compile-time sparsity of the factors (problems that declare the structure of their Jacobian) ---------------------
+// A functor may declare `static BRDAE_CX bool jac_nz(int r, int c)`, the structural non-zeros of its Jacobian.  Together with
+// the mass-matrix policy this gives the pattern of mu M - J and, by a symbolic elimination WITHOUT row exchanges, of its LU
+// factors (fill included).  The optimistic factorisation and the substitutions on compile-time addresses -- the paths taken
+// while nothing pivots -- then skip every operation on a structural zero: multiplying by an exact zero and adding the
+// product changes no bit of a finite result, so the factors and solutions are those of the dense routines (the index-3
+// pendulum keeps 21 of 45 multiply-adds of a substitution and a third of the elimination).  Entries outside the pattern
+// are never written by these paths; they are zeroed when a system is loaded, because the general (pivoting) routines,
+// which a neighbouring lane can force on the whole warp, read every entry.
+template <class P, class = void> struct trait_jac_nz { static BRDAE_CX bool get(int, int) { return true; } static constexpr bool declared = false; };
+template <class P> struct trait_jac_nz<P, decltype((void)P::jac_nz(0, 0))> {
+    static BRDAE_CX bool get(int r, int c) { return P::jac_nz(r, c); }
+    static constexpr bool declared = true;
+};
+template <class Prob, class Mass, bool DENSE>
+struct LuPattern {
+    static constexpr int N = Prob::N;
+    bool a[N][N];      // mu M - J
+    bool f[N][N];      // L (below the diagonal) and U (on and above it) of the elimination without row exchanges
+    BRDAE_CX LuPattern() : a{}, f{} {
+        for (int r = 0; r < N; ++r)
+            for (int c = 0; c < N; ++c) {
+                a[r][c] = DENSE || Mass::nz(r, c) || trait_jac_nz<Prob>::get(r, c);
+                f[r][c] = a[r][c] || r == c;
+            }
+        for (int k = 0; k < N; ++k)
+            for (int r = k + 1; r < N; ++r)
+                if (f[r][k])
+                    for (int c = k + 1; c < N; ++c)
+                        if (f[k][c]) f[r][c] = true;
+    }
+};
+template <class Prob, class Mass, bool DENSE>
+struct LuPat { static constexpr LuPattern<Prob, Mass, DENSE> v{}; };
+
+template <int I, int E, class F>
+BRDAE_HD void static_for(F &&f) {
+    if constexpr (I < E) { f(std::integral_constant<int, I>{}); static_for<I + 1, E>(f); }
+}
+template <int I, int E, class F>
+BRDAE_HD void static_for_down(F &&f) {      // I = E-1 ... 0 ... : indices E-1 down to I
+    if constexpr (I < E) { f(std::integral_constant<int, E - 1>{}); static_for_down<I, E - 1>(f); }
+}
+
+// columns of hscale (mu M - J), real and complex, on the structural non-zeros (entries outside the pattern: exact zeros);
+// a functor with explicit recursion rather than nested generic lambdas (those crash cudafe++ 12.9 inside the lane loop)
+template <class PAT, class Prob, class Mass, int N>
+struct PatColumns {
+    const typename Prob::P &prm;
+    const SolveArgs &a;
+    const double (&J)[N][N];
+    const double (&hs)[N];
+    double mr, mcr, mci;
+    template <int K, int R>
+    BRDAE_HD void real_rows(double (&col)[N]) const {
+        if constexpr (R < N) {
+            if constexpr (!PAT::v.a[R][K]) col[R] = 0.0;
+            else {
+                const double v = Mass::nz(R, K) ? fma(mr, Mass::get(prm, a, R, K), -J[R][K]) : -J[R][K];
+                col[R] = hs[R] * v;
+            }
+            real_rows<K, R + 1>(col);
+        }
+    }
+    template <int K, int R>
+    BRDAE_HD void cplx_rows(double (&cr)[N], double (&ci)[N]) const {
+        if constexpr (R < N) {
+            if constexpr (!PAT::v.a[R][K]) { cr[R] = 0.0; ci[R] = 0.0; }
+            else {
+                const bool nz = Mass::nz(R, K);
+                const double m = nz ? Mass::get(prm, a, R, K) : 0.0;
+                const double v = nz ? fma(mcr, m, -J[R][K]) : -J[R][K];
+                cr[R] = hs[R] * v;
+                ci[R] = nz ? hs[R] * (mci * m) : 0.0;
+            }
+            cplx_rows<K, R + 1>(cr, ci);
+        }
+    }
+    template <class KC>
+    BRDAE_HD void operator()(KC, double (&col)[N]) const { real_rows<KC::value, 0>(col); }
+    template <class KC>
+    BRDAE_HD void operator()(KC, double (&cr)[N], double (&ci)[N]) const { cplx_rows<KC::value, 0>(cr, ci); }
+};
+
+// zero the factor entries the pattern-aware paths never write (see above); called when a system is loaded
+template <class PAT, int N, class S>
+BRDAE_HD void zero_outside_pattern(const S &sm, int base_r, int base_cr, int base_ci) {
+    static_for<0, N>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        static_for<0, N>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            if constexpr (!PAT::v.f[r][c]) { sm(base_r + r * N + c) = 0.0; sm(base_cr + r * N + c) = 0.0; sm(base_ci + r * N + c) = 0.0; }
+        });
+    });
+}
+
+// lu_real_static / lu_cplx_static restricted to the pattern: `column(kc, cur)` fills the structurally non-zero entries of
+// column k (the others are not read).  Same operations, in the same order, on the entries that can be non-zero.
+template <class PAT, int N, class S, class ColFn>
+BRDAE_HD bool lu_real_static_p(const S &sm, int base, ColFn &&column) {
+    bool ok = true;
+    static_for<0, N>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        double cur[N];
+        column(kc, cur);
+        static_for<0, k>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (PAT::v.f[j][k]) {
+                const double cj = cur[j];
+                static_for<j + 1, N>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    if constexpr (PAT::v.f[r][j]) {
+                        cur[r] = fma(-sm(base + r * N + j), cj, cur[r]);
+                    }
+                });
+            }
+        });
+        const double best = fabs(cur[k]);
+        static_for<k + 1, N>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            if constexpr (PAT::v.f[r][k]) ok = ok && !(fabs(cur[r]) > best);
+        });
+        const double rcp = 1.0 / cur[k];
+        static_for<0, N>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (i != k && PAT::v.f[i][k]) sm(base + i * N + k) = (i < k) ? cur[i] : cur[i] * rcp;
+        });
+        sm(base + k * N + k) = rcp;
+    });
+    return ok;
+}
+template <class PAT, int N, class S, class ColFn>
+BRDAE_HD bool lu_cplx_static_p(const S &sm, int base_r, int base_i, ColFn &&column) {
+    bool ok = true;
+    static_for<0, N>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        double cr[N], ci[N];
+        column(kc, cr, ci);
+        static_for<0, k>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (PAT::v.f[j][k]) {
+                const double ur = cr[j], ui = ci[j];
+                static_for<j + 1, N>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    if constexpr (PAT::v.f[r][j]) {
+                        const double lr = sm(base_r + r * N + j), li = sm(base_i + r * N + j);
+                        double xr = cr[r], xi = ci[r];
+                        xr = fma(-lr, ur, xr); xr = fma(li, ui, xr);
+                        xi = fma(-lr, ui, xi); xi = fma(-li, ur, xi);
+                        cr[r] = xr; ci[r] = xi;
+                    }
+                });
+            }
+        });
+        const double best = fabs(cr[k]) + fabs(ci[k]);
+        static_for<k + 1, N>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            if constexpr (PAT::v.f[r][k]) ok = ok && !(fabs(cr[r]) + fabs(ci[r]) > best);
+        });
+        const double pr = cr[k], pi = ci[k];
+        const double invd = 1.0 / fma(pr, pr, pi * pi);
+        const double qr = pr * invd, qi = -(pi * invd);
+        static_for<0, N>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (PAT::v.f[i][k]) {
+                constexpr int dst = i * N + k;
+                if constexpr (i < k) { sm(base_r + dst) = cr[i]; sm(base_i + dst) = ci[i]; }
+                else if constexpr (i > k) {
+                    sm(base_r + dst) = fma(cr[i], qr, -(ci[i] * qi));
+                    sm(base_i + dst) = fma(cr[i], qi, ci[i] * qr);
+                }
+            }
+        });
+        sm(base_r + k * N + k) = qr; sm(base_i + k * N + k) = qi;
+    });
+    return ok;
+}
+// substitutions with identity permutation, restricted to the pattern (solve_real_sm<.., IDENT = true> on the non-zeros)
+template <class PAT, int N, class S>
+BRDAE_HD void solve_real_ident_p(const S &sm, int base, double (&b)[N]) {
+    static_for<0, N>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const double bk = b[k];
+        static_for<k + 1, N>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            if constexpr (PAT::v.f[r][k]) b[r] = fma(-sm(base + r * N + k), bk, b[r]);
+        });
+    });
+    static_for_down<0, N>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const double xk = b[k] * sm(base + k * N + k);
+        b[k] = xk;
+        static_for<0, k>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            if constexpr (PAT::v.f[r][k]) b[r] = fma(-sm(base + r * N + k), xk, b[r]);
+        });
+    });
+}
+template <class PAT, int N, class S>
+BRDAE_HD void solve_cplx_ident_p(const S &sm, int base_r, int base_i, double (&br)[N], double (&bi)[N]) {
+    static_for<0, N>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const double xr = br[k], xi = bi[k];
+        static_for<k + 1, N>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            if constexpr (PAT::v.f[r][k]) {
+                const double lr = sm(base_r + r * N + k), li = sm(base_i + r * N + k);
+                double yr = br[r], yi = bi[r];
+                yr = fma(-lr, xr, yr); yr = fma(li, xi, yr);
+                yi = fma(-lr, xi, yi); yi = fma(-li, xr, yi);
+                br[r] = yr; bi[r] = yi;
+            }
+        });
+    });
+    static_for_down<0, N>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const double qr = sm(base_r + k * N + k), qi = sm(base_i + k * N + k);
+        const double sr = br[k], si = bi[k];
+        const double xr = fma(sr, qr, -(si * qi));
+        const double xi = fma(sr, qi, si * qr);
+        br[k] = xr; bi[k] = xi;
+        static_for<0, k>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            if constexpr (PAT::v.f[r][k]) {
+                const double ur = sm(base_r + r * N + k), ui = sm(base_i + r * N + k);
+                double yr = br[r], yi = bi[r];
+                yr = fma(-ur, xr, yr); yr = fma(ui, xi, yr);
+                yi = fma(-ur, xi, yi); yi = fma(-ui, xr, yi);
+                br[r] = yr; bi[r] = yi;
+            }
+        });
+    });
+}
+
 // Slots of one lane.  HOT: the LU factors (+ N scratch slots for right-hand sides on their way into
 // pivoted order), always in shared memory.  COLD: f(t,y), y_old, the dense-output coefficients Q and the
 // point (t_J, y_J) of the last Jacobian -- touched once or twice per STEP, not per Newton iteration.
@@ -510,6 +746,11 @@ template <class Prob, class Mass, bool CTA_WIDE, bool COLD_GLOBAL, bool FD, bool
 BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const SG &gj, const double *t_eval) {
     constexpr int N = Prob::N;
     using L = K1Layout<Prob, COLD_GLOBAL, FD>;
+    // sparsity of the factors while nothing pivots (dense unless the functor declares jac_nz; finite-difference Jacobians and a
+    // user-supplied constant matrix have no declared structure)
+    constexpr bool PAT_DENSE = FD || !trait_jac_nz<Prob>::declared;
+    using PAT = LuPat<Prob, Mass, PAT_DENSE>;
+    const bool pat_ok = PAT_DENSE || !a.has_jac_const;
     typename Prob::P prm;
 
     // ---- lane state ---------------------------------------------------------------------
@@ -585,6 +826,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 #pragma unroll
                     for (int c = 0; c < N; ++c) { cd(L::C_F + c) = f0[c]; cd(L::C_YJ + c) = y[c]; }
                     cd(L::C_TJ) = t;                                     // J0 = jac(t0, y0) :483
+                    if constexpr (!PAT_DENSE) zero_outside_pattern<PAT, N>(sm, L::S_LUR, L::S_LCR, L::S_LCI);
 #pragma unroll
                     for (int q = 0; q < CN_COUNT; ++q) cnt[q] = 0;
                     cnt[CN_NFEV] = 1;
@@ -593,8 +835,10 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     hist_state = false; current_jac = true; lu_valid = false; have_sol = false; lu_static_ok = true;
                     inv_h_lu = 1.0; ei = 0; nsteps = 0;
                     state = ST_SETUP; setup_kind = SETUP_STEP;
-                    if (EVENTS)
+                    if (EVENTS) {
                         for (int e = 0; e < a.n_events; ++e) a.ev_count[e * a.B + idx] = 0;
+                        if (a.rep_cap > 0) a.rep_count[idx] = 0;
+                    }
                     if (FD && !a.has_jac_const) {                        // J0 = num_jac(t0, y0, f0) :475-481
 #pragma unroll
                         for (int c = 0; c < N; ++c) gj(L::G_FAC + c) = NJ_FACTOR0;
@@ -618,7 +862,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 
         // ================= error estimate, accept/reject, epilogue :660-784 ===================
         if (warp_any(state == ST_ERREST)) {
-            const bool ident_r = BRDAE_K1_IDENT_FASTPATH && warp_all(state != ST_ERREST || piv_r == perm_identity(N));
+            const bool ident_r = BRDAE_K1_IDENT_FASTPATH && pat_ok && warp_all(state != ST_ERREST || piv_r == perm_identity(N));
             if (state == ST_ERREST) {
                 double Z[3][N];
 #pragma unroll
@@ -646,8 +890,9 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     mass_mv<Mass>(prm, a, ze, mze);
 #pragma unroll
                     for (int c = 0; c < N; ++c) err[c] = cd(L::C_F + c) + mze[c];
+                    double err1 = NAN, err2 = NAN;          // per-attempt report only (instrumented instantiation)
                     for (int pass = 0;; ++pass) {
-                        if (ident_r) solve_real_sm<N, L::SELECT, true>(sm, L::S_LUR, L::S_B, piv_r, err);   // rhs NOT scaled by hscale
+                        if (ident_r) solve_real_ident_p<PAT, N>(sm, L::S_LUR, err);   // rhs NOT scaled by hscale
                         else solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, err);
                         cnt[CN_NSOLVE_ERR]++;
                         double s = 0.0;
@@ -657,6 +902,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                             else { const double v = err[c] * inv_es[c]; s = fma(v, v, s); }
                         }
                         error_norm = sqrt(s) * (a.zero_algebraic_error ? a.rsq_nondiff : a.rsqn);
+                        if (EVENTS) { if (pass == 0) err1 = error_norm; else err2 = error_norm; }
                         if (pass == 1 || !(error_norm > 1 && (a.always_2nd || rejected))) break;
                         double Y[N], F[N];
 #pragma unroll
@@ -666,6 +912,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 #pragma unroll
                         for (int c = 0; c < N; ++c) err[c] = F[c] + mze[c];
                     }
+                    if (EVENTS && a.rep_cap > 0)
+                        report_event(a, idx, error_norm > 1 ? RC_REJECTED : RC_ACCEPTED, t, h, n_iter, nbad, err1, err2);   // :719, :736
                     if (error_norm > 1) {                                               // :713-733
                         const double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, a.predictive_controller);
                         h_abs *= fmax(a.min_factor, safety * factor);
@@ -931,7 +1179,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
         }
         // ================= (re)factorisation :594-613 =========================================
         if (warp_any(state == ST_FACTOR)) {
-            const bool static_lu = BRDAE_K1_STATIC_LU && trait_static_lu<Prob>::value && warp_all(state != ST_FACTOR || lu_static_ok);
+            const bool static_lu = BRDAE_K1_STATIC_LU && trait_static_lu<Prob>::value && pat_ok && warp_all(state != ST_FACTOR || lu_static_ok);
             if (state == ST_FACTOR) {
                 if (a.scale_residuals) inv_h_lu = inv_h;
                 double J[N][N];
@@ -976,7 +1224,9 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 // factorisation with the general routine and switches the system over for good.
                 bool need_general = !static_lu;
                 if (static_lu) {
-                    const bool ok = lu_real_static<N>(sm, L::S_LUR, col_real) && lu_cplx_static<N>(sm, L::S_LCR, L::S_LCI, col_cplx);
+                    // the same columns on the structural non-zeros of mu M - J (entries outside the pattern: exact zeros)
+                    const PatColumns<PAT, Prob, Mass, N> colp{prm, a, J, hs, mr, mcr, mci};
+                    const bool ok = lu_real_static_p<PAT, N>(sm, L::S_LUR, colp) && lu_cplx_static_p<PAT, N>(sm, L::S_LCR, L::S_LCI, colp);
                     piv_r = piv_c = perm_identity(N);
                     BRDAE_SIM_COUNT(0);
                     if (!ok) { need_general = true; lu_static_ok = false; BRDAE_SIM_COUNT(1); }
@@ -987,6 +1237,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, col_cplx);
                 }
                 cnt[CN_NLU]++;
+                if (EVENTS && a.rep_cap > 0) report_event(a, idx, RC_FACTORISATION, t, h, -1, -1, -1.0, -1.0);   // :607
                 lu_valid = true;
                 state = ST_NEWTON;
             }
@@ -1001,7 +1252,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
             // no lane of the warp exchanged a row in its current factorisations (always, for the pendulum and Robertson
             // ensembles): the substitutions below run on compile-time addresses, without the permutation round trip
             const unsigned perm_id = perm_identity(N);
-            const bool ident = BRDAE_K1_IDENT_FASTPATH && warp_all(state != ST_NEWTON || (piv_r == perm_id && piv_c == perm_id));
+            const bool ident = BRDAE_K1_IDENT_FASTPATH && pat_ok && warp_all(state != ST_NEWTON || (piv_r == perm_id && piv_c == perm_id));
             // every Newton lane of the warp is at the first iteration of its attempt (the lanes phase-lock onto the cycle, so
             // this is the common case in the first pass): there is no previous increment norm, hence no rate, and the
             // division / power / reciprocal chain of the convergence test would only produce values nobody reads
@@ -1053,8 +1304,8 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     }
                     if (ident) {
                         BRDAE_SIM_COUNT(3);
-                        solve_real_sm<N, L::SELECT, true>(sm, L::S_LUR, L::S_B, piv_r, fr);
-                        solve_cplx_sm<N, L::SELECT, true>(sm, L::S_LCR, L::S_LCI, L::S_B, piv_c, fcr, fci);
+                        solve_real_ident_p<PAT, N>(sm, L::S_LUR, fr);
+                        solve_cplx_ident_p<PAT, N>(sm, L::S_LCR, L::S_LCI, fcr, fci);
                     } else {
                         BRDAE_SIM_COUNT(4);
                         solve_real_sm<N, L::SELECT>(sm, L::S_LUR, L::S_B, piv_r, fr);
@@ -1117,6 +1368,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                 if (outcome != 0) {
                     if (outcome == 1) state = ST_ERREST;
                     else if (current_jac) {                                            // :650-658
+                        if (EVENTS && a.rep_cap > 0) report_event(a, idx, RC_NON_CONV, t, h, n_iter, nbad, -1.0, -1.0);   // :654
                         cnt[CN_NFAIL]++;
                         h_abs *= a.nonconv_factor;
                         lu_valid = false;
@@ -1126,6 +1378,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                         for (int c = 0; c < N; ++c) cd(L::C_YJ + c) = y[c];
                         cd(L::C_TJ) = t;
                         cnt[CN_NJEV]++;
+                        if (EVENTS && a.rep_cap > 0) report_event(a, idx, RC_JACOBIAN_UPDATE, t, h, -1, -1, -1.0, -1.0);   // :644
                         current_jac = true; lu_valid = false;
                         state = FD ? ST_JACFD : ST_SETUP; setup_kind = SETUP_GUESS;
                     }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BRDAE_ABI_VERSION 3
+#define BRDAE_ABI_VERSION 4
 #define BRDAE_NMAX_SMALL 8 /* largest state size of the thread-per-system kernels */
 #define BRDAE_MAX_EVENTS 4 /* event functions located on the device per call */
 
@@ -156,6 +156,17 @@ typedef struct brdae_batch {
     const int32_t *event_functor;    /* [host] [E] or NULL: k >= 0 = event e is the k-th event function g_k(t, y) of the problem
                                         functor itself (plugin builds: UserProblem::event, any nonlinear function; coef and
                                         level of that event are ignored), -1 = the linear form above */
+    /* Optional PER-ATTEMPT REPORT, the reference's `bReport=True` (`RadauDAE._report`, radauDAE.py:424-443, codes :24-28):
+     * one record per factorisation (-10), Jacobian update after a non-converged Newton with a stale Jacobian (-11),
+     * non-converged attempt (5), rejected step (2) and accepted step (0), in the order the reference appends them.  A
+     * system records its first report_cap events; report_count counts all of them.  report_cap = 0 = off.  brdae_solve only. */
+    int32_t report_cap;       /* R */
+    int32_t reserved1;
+    int32_t *report_count;    /* [dev]  [B] */
+    int32_t *report_code;     /* [dev]  [R][B] */
+    int32_t *report_it;       /* [dev]  [R][2][B]: Newton iterations and bad iterations of the attempt (-1 for codes -10, -11) */
+    double *report_val;       /* [dev]  [R][4][B]: t, h, err1, err2 (the first / second error estimate: -1 where the reference
+                                        passes none, NaN for an estimate that was not computed) */
 } brdae_batch;
 
 int brdae_abi_version(void);

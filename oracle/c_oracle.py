@@ -103,6 +103,7 @@ class BatchResult:
     t_final: np.ndarray    # [B]
     y_final: np.ndarray    # [B, n]
     counters: np.ndarray   # [B, 9]
+    reports: dict | None = None   # report_cap > 0: n [B], code [B, K], newton_iterations / bad_iterations [B, K], t / dt / err1 / err2 [B, K]
 
     def counter(self, name):
         return self.counters[:, COUNTER_NAMES.index(name)]
@@ -113,8 +114,9 @@ def _dptr(a):
 
 
 def solve_batch(problem, t_span, y0, params, *, t_eval=None, rtol=1e-3, atol=1e-6, var_index=None,
-                mass_matrix=None, jac_const=None, nthreads=0, **options):
-    """y0: [B, n]; params: [B, p] (may be [B, 0]).  Returns BatchResult."""
+                mass_matrix=None, jac_const=None, nthreads=0, report_cap=0, **options):
+    """y0: [B, n]; params: [B, p] (may be [B, 0]).  Returns BatchResult.  `report_cap` > 0 also records the reference's
+    per-attempt report (`_report`, radauDAE.py:424-443) for the first `report_cap` events of every system."""
     L = lib()
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))
     B, n = y0.shape
@@ -136,16 +138,28 @@ def solve_batch(problem, t_span, y0, params, *, t_eval=None, rtol=1e-3, atol=1e-
     status = np.empty(B, dtype=np.int32)
     counters = np.zeros((9, B), dtype=np.int32)
     o = make_options(**options)
-    rc = L.orc_solve(C.c_int(PROBLEM_IDS[problem]), C.c_int(n), C.c_int(p), C.c_int64(B),
+    K = int(report_cap)
+    rep_count = np.zeros(B, dtype=np.int32)
+    rep_code = np.zeros((max(K, 1), B), dtype=np.int32)
+    rep_it = np.full((max(K, 1), 2, B), -1, dtype=np.int32)
+    rep_val = np.full((max(K, 1), 4, B), np.nan)
+    L.orc_solve_report.restype = C.c_int
+    rc = L.orc_solve_report(C.c_int(PROBLEM_IDS[problem]), C.c_int(n), C.c_int(p), C.c_int64(B),
                      _dptr(y0_soa), _dptr(par_soa), _dptr(M), _dptr(Jc),
                      vi.ctypes.data_as(C.POINTER(C.c_int32)), _dptr(at), C.c_double(rtol),
                      C.c_double(t0), C.c_double(tb), _dptr(te), C.c_int(T), C.byref(o),
                      _dptr(y_eval), n_eval.ctypes.data_as(C.POINTER(C.c_int32)), _dptr(t_final),
                      _dptr(y_final), status.ctypes.data_as(C.POINTER(C.c_int32)),
-                     counters.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(nthreads))
+                     counters.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(nthreads), C.c_int(K),
+                     rep_count.ctypes.data_as(C.POINTER(C.c_int32)), rep_code.ctypes.data_as(C.POINTER(C.c_int32)),
+                     rep_it.ctypes.data_as(C.POINTER(C.c_int32)), _dptr(rep_val))
     if rc != 0:
         raise RuntimeError(f"orc_solve failed with code {rc}")
-    return BatchResult(t=te, y=np.ascontiguousarray(y_eval[:T].transpose(2, 1, 0)), n_eval=n_eval,
+    reports = None
+    if K > 0:
+        reports = dict(n=rep_count, code=rep_code.T.copy(), newton_iterations=rep_it[:, 0].T.copy(), bad_iterations=rep_it[:, 1].T.copy(),
+                       t=rep_val[:, 0].T.copy(), dt=rep_val[:, 1].T.copy(), err1=rep_val[:, 2].T.copy(), err2=rep_val[:, 3].T.copy())
+    return BatchResult(reports=reports, t=te, y=np.ascontiguousarray(y_eval[:T].transpose(2, 1, 0)), n_eval=n_eval,
                        status=status, t_final=t_final, y_final=np.ascontiguousarray(y_final.T),
                        counters=np.ascontiguousarray(counters.T))
 

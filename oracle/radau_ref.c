@@ -888,13 +888,31 @@ static void num_jac_fd(const prob_ctx *pc, work *w, double t, const double *atol
     }
 }
 
+/* Per-attempt report, the reference's `_report` (radauDAE.py:424-443, codes :24-28; bReport=True): one record per
+ * factorisation (-10), Jacobian update after a failed Newton with a stale Jacobian (-11), non-converged attempt (5), rejected
+ * step (2) and accepted step (0), with t, h, the Newton iteration counts and the error norms where the reference passes them.
+ * Layouts: count [B]; code [cap][B]; it [cap][2][B] (newton iterations, bad iterations; -1 where not reported);
+ * val [cap][4][B] (t, h, err1, err2; err = -1 where not reported). */
+typedef struct { int cap; int32_t *count, *code, *it; double *val; } report_ctx;
+enum { RC_FACTORISATION = -10, RC_JACOBIAN_UPDATE = -11, RC_NON_CONV = 5, RC_ACCEPTED = 0, RC_REJECTED = 2 };
+static void report(const report_ctx *rc, int64_t B, int64_t sys, int code, double t, double h, int newt, int nbad, double e1, double e2) {
+    if (!rc || rc->cap <= 0) return;
+    int k = rc->count[sys]++;
+    if (k >= rc->cap) return;
+    rc->code[(int64_t)k * B + sys] = code;
+    rc->it[((int64_t)k * 2 + 0) * B + sys] = newt; rc->it[((int64_t)k * 2 + 1) * B + sys] = nbad;
+    rc->val[((int64_t)k * 4 + 0) * B + sys] = t; rc->val[((int64_t)k * 4 + 1) * B + sys] = h;
+    rc->val[((int64_t)k * 4 + 2) * B + sys] = e1; rc->val[((int64_t)k * 4 + 3) * B + sys] = e2;
+}
+
 /* Integrate one system.  Layout of the batch arrays is SoA: element (row, sys) at row*B+sys. */
 static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, const double *mass_in,
                           const double *jac_const, const int *var_index, const double *atol,
                           double rtol, double t0, double tb, const double *t_eval, int T, int64_t B,
                           int64_t sys, const double *y0, double *y_eval, int *n_eval_out,
-                          double *t_final, double *y_final, int *status_out, int *counters) {
+                          double *t_final, double *y_final, int *status_out, int *counters, const report_ctx *rc) {
     const int n = w->n;
+    if (rc && rc->cap > 0) rc->count[sys] = 0;
     int cnt[C_COUNT] = {0};
     const int MAXIT = o->max_newton_ite;
     const double dir = (tb != t0) ? (tb > t0 ? 1.0 : -1.0) : 1.0;
@@ -990,7 +1008,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 double hp = o->scale_newton_norm ? hpow(h, ve) : 1.0;
                 w->inv_ns[c] = hp / (atol[c] + fabs(w->y[c]) * rtol);
             }
-            int converged = 0;
+            int converged = 0, nbad_last = 0;
             for (;;) { /* convergence loop :591-647 */
                 /* starting guess :580-583 -> W = TI Z0 (recomputed on a retry: Z0 is never mutated) */
                 if (!have_sol || !o->extrapolated_guess) memset(w->W, 0, sizeof(double) * 3 * n);
@@ -1036,6 +1054,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     }
                     cnt[C_NLU]++;
                     trace_ev('F');
+                    report(rc, B, sys, RC_FACTORISATION, t, h, -1, -1, -1.0, -1.0);       /* :607 */
                     lu_valid = 1;
                 }
                 /* ------------- simplified Newton, :793-949 */
@@ -1116,15 +1135,18 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     dwn_old = dwn; have_old = 1;
                 }
                 n_iter = (k < MAXIT) ? k + 1 : MAXIT;
+                nbad_last = nbad;
                 safety = o->safety_factor * (2 * MAXIT + 1) / (2 * MAXIT + n_iter); /* :631 */
                 if (converged) break;
                 if (current_jac) break;                                            /* :638-641 */
                 if (fd) num_jac_fd(pc, w, t, atol); else if (chain) chain_jac(pc, w->y, w->ch.nd); else prob_jac(pc, t, w->y, w->J);
                 cnt[C_NJEV]++;                                                     /* :643 */
+                report(rc, B, sys, RC_JACOBIAN_UPDATE, t, h, -1, -1, -1.0, -1.0);  /* :644 */
                 current_jac = 1; lu_valid = 0;
             }
             if (!converged) {                                                      /* :650-658 */
                 cnt[C_NFAIL]++;
+                report(rc, B, sys, RC_NON_CONV, t, h, n_iter, nbad_last, -1.0, -1.0); /* :654 */
                 h_abs *= o->factor_on_non_convergence;
                 lu_valid = 0;
                 continue;
@@ -1144,6 +1166,7 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                 w->inv_es[c] = hp / (atol[c] + fmax(fabs(w->y[c]), fabs(ynew)) * rtol);
             }
             mass_mv(n, w->M, w->mlo, w->mhi, w->ze, w->mw0);
+            double err1 = NAN, err2 = NAN;
             for (int pass = 0; pass < 2; ++pass) {
                 if (pass == 0) for (int c = 0; c < n; ++c) w->err[c] = w->f[c] + w->mw0[c];
                 else {
@@ -1162,13 +1185,15 @@ static void integrate_one(const prob_ctx *pc, work *w, const orc_options *o, con
                     w->sq[c] = w->err[c] * w->inv_es[c];
                 }
                 error_norm = sqrt(chain ? chain_sum_squares(w->sq, n / 5, 1) : sum_squares(w->sq, n, n > 8)) * (o->zero_algebraic_error ? rsqdiff : rsqn);
+                if (pass == 0) err1 = error_norm; else err2 = error_norm;
                 if (!(error_norm > 1 && (o->always_2nd_estimate || rejected))) break;
             }
             if (error_norm > 1) {                                                   /* :713-733 */
                 double factor = gustafsson(h_abs, h_abs_old, error_norm, err_old, hist, o->predictive_controller);
+                report(rc, B, sys, RC_REJECTED, t, h, n_iter, nbad_last, err1, err2);   /* :719 */
                 h_abs *= fmax(o->min_factor, safety * factor);
                 lu_valid = 0; rejected = 1; cnt[C_NREJ]++;
-            } else { cnt[C_NACC]++; accepted = 1; }
+            } else { report(rc, B, sys, RC_ACCEPTED, t, h, n_iter, nbad_last, err1, err2); cnt[C_NACC]++; accepted = 1; }
         }
         if (status != 1) break;
         /* ---------------- epilogue, :742-784 */
@@ -1237,12 +1262,15 @@ int orc_trace(int problem, int n, int n_params, const double *y0, const double *
 
 /* Batch entry.  All pointers are host pointers; SoA layouts as in include/brdae.h.
  * mass / jac_const: [n][n] row-major shared by the batch, or NULL (problem's own). */
-int orc_solve(int problem, int n, int n_params, int64_t B, const double *y0, const double *params,
-              const double *mass, const double *jac_const, const int32_t *var_index,
-              const double *atol, double rtol, double t0, double t_bound, const double *t_eval,
-              int T, const orc_options *opts, double *y_eval, int32_t *n_eval, double *t_final,
-              double *y_final, int32_t *status, int32_t *counters, int nthreads) {
+int orc_solve_report(int problem, int n, int n_params, int64_t B, const double *y0, const double *params,
+                     const double *mass, const double *jac_const, const int32_t *var_index,
+                     const double *atol, double rtol, double t0, double t_bound, const double *t_eval,
+                     int T, const orc_options *opts, double *y_eval, int32_t *n_eval, double *t_final,
+                     double *y_final, int32_t *status, int32_t *counters, int nthreads,
+                     int report_cap, int32_t *report_count, int32_t *report_code, int32_t *report_it, double *report_val) {
     if (n <= 0 || B < 0) return -1;
+    report_ctx rctx = {report_cap, report_count, report_code, report_it, report_val};
+    const report_ctx *rc = (report_cap > 0 && report_count && report_code && report_it && report_val) ? &rctx : NULL;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #else
@@ -1259,10 +1287,19 @@ int orc_solve(int problem, int n, int n_params, int64_t B, const double *y0, con
         for (int64_t s = 0; s < B; ++s) {
             for (int k = 0; k < n_params; ++k) p[k] = params[(int64_t)k * B + s];
             integrate_one(&pc, &w, opts, mass, jac_const, var_index, atol, rtol, t0, t_bound, t_eval, T, B,
-                          s, y0, y_eval, n_eval, t_final, y_final, status, counters);
+                          s, y0, y_eval, n_eval, t_final, y_final, status, counters, rc);
         }
         free(p); free(pc.m); free(pc.inv_m); free(pc.r0s);
         work_free(&w);
     }
     return 0;
+}
+
+int orc_solve(int problem, int n, int n_params, int64_t B, const double *y0, const double *params,
+              const double *mass, const double *jac_const, const int32_t *var_index,
+              const double *atol, double rtol, double t0, double t_bound, const double *t_eval,
+              int T, const orc_options *opts, double *y_eval, int32_t *n_eval, double *t_final,
+              double *y_final, int32_t *status, int32_t *counters, int nthreads) {
+    return orc_solve_report(problem, n, n_params, B, y0, params, mass, jac_const, var_index, atol, rtol, t0, t_bound, t_eval, T,
+                            opts, y_eval, n_eval, t_final, y_final, status, counters, nthreads, 0, NULL, NULL, NULL, NULL);
 }

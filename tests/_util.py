@@ -67,7 +67,33 @@ def run_c_oracle(ens, nthreads=0, **over):
     r = c_oracle.solve_batch(ens["problem"], ens["t_span"], ens["y0"], params, t_eval=ens["t_eval"],
                              mass_matrix=None if isinstance(mm, str) else (np.eye(ens["y0"].shape[1]) if mm is None else mm),
                              nthreads=nthreads, **opts)
-    return dict(y=r.y, status=r.status, n_eval=r.n_eval, counters=r.counters, y_final=r.y_final, t_final=r.t_final)
+    out = dict(y=r.y, status=r.status, n_eval=r.n_eval, counters=r.counters, y_final=r.y_final, t_final=r.t_final)
+    if r.reports is not None:
+        out["reports"] = r.reports
+    return out
+
+
+def _report_buffers(B, cap):
+    """Host buffers of the per-attempt report in the kernel layout, and the conversion to the reference's keys."""
+    bufs = {"report_count": np.zeros(B, np.int32), "report_code": np.zeros((cap, B), np.int32),
+            "report_it": np.full((cap, 2, B), -1, np.int32), "report_val": np.full((cap, 4, B), np.nan)}
+
+    def as_dict():
+        return dict(n=bufs["report_count"], code=bufs["report_code"].T.copy(), newton_iterations=bufs["report_it"][:, 0].T.copy(),
+                    bad_iterations=bufs["report_it"][:, 1].T.copy(), t=bufs["report_val"][:, 0].T.copy(),
+                    dt=bufs["report_val"][:, 1].T.copy(), err1=bufs["report_val"][:, 2].T.copy(), err2=bufs["report_val"][:, 3].T.copy())
+    return bufs, as_dict
+
+
+def assert_reports_identical(a, b, what=""):
+    """Two per-attempt reports (dicts with the reference's keys, one row per system) agree bit for bit on the recorded part."""
+    assert np.array_equal(a["n"], b["n"]), f"{what}: report counts differ"
+    cap = a["code"].shape[1]
+    for i, k in enumerate(np.minimum(a["n"], cap)):
+        for key in ("code", "newton_iterations", "bad_iterations"):
+            assert np.array_equal(a[key][i, :k], b[key][i, :k]), f"{what}: system {i} {key}"
+        for key in ("t", "dt", "err1", "err2"):
+            assert np.array_equal(a[key][i, :k], b[key][i, :k], equal_nan=True), f"{what}: system {i} {key}"
 
 
 # ------------------------------------------------------------------ checker 2: numpy oracle
@@ -126,7 +152,7 @@ def _host_sim(problem):
     return _sims[path]
 
 
-def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, **over):
+def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, report_cap=0, **over):
     """tests/host_sim: the K1 kernel SOURCE compiled for the host, one lane.  With dense_cap > 0 the per-step
     record is requested too and returned as out["sol"] (a BatchedOdeSolution); with `events` (LinearEvents) the
     device-side event location runs and out["event_count" | "event_t" | "event_y"] are returned ([B, E, ...])."""
@@ -149,6 +175,9 @@ def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, **over
         dense = {"dense_t": np.full((dense_cap, B), np.nan), "dense_y": np.full((dense_cap, n, B), np.nan),
                  "dense_q": np.full((dense_cap, n, 3, B), np.nan)}
         ptr.update({k: v.ctypes.data for k, v in dense.items()}, dense_cap=dense_cap)
+    if report_cap:
+        rbufs, rdict = _report_buffers(B, report_cap)
+        ptr.update({k: v.ctypes.data for k, v in rbufs.items()}, report_cap=report_cap)
     if events:
         from dae_scipy_b200.api import pack_linear_events
         hb.events = pack_linear_events(events, n, hb.problem.n_event_functions)
@@ -160,6 +189,8 @@ def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, **over
     rc = _sim.sim_solve(C.byref(b), C.byref(hb.options))
     assert rc == 0, f"sim_solve returned {rc}"
     extra = {}
+    if report_cap:
+        extra["reports"] = rdict()
     if events:
         extra.update(event_count=evb["event_count"].T.copy(), event_t=evb["event_t"].transpose(2, 0, 1).copy(),
                      event_y=evb["event_y"].transpose(3, 0, 1, 2).copy())
@@ -171,7 +202,7 @@ def run_kernel_source_on_cpu(ens, dense_cap=0, events=None, max_events=8, **over
                 y_final=np.ascontiguousarray(out["y_final"].T), t_final=out["t_final"])
 
 
-def run_chain_kernel_source_on_cpu(ens, dense_cap=0, **over):
+def run_chain_kernel_source_on_cpu(ens, dense_cap=0, report_cap=0, **over):
     """tests/host_sim/k4_host_sim.cpp: the lane-per-rope chain kernel SOURCE (csrc/chain_k4.cuh) compiled for the host, one
     lane with slot stride 1, pulling the ropes of the batch one after the other from the work counter."""
     import dae_scipy_b200 as br
@@ -197,10 +228,15 @@ def run_chain_kernel_source_on_cpu(ens, dense_cap=0, **over):
         dense = {"dense_t": np.full((dense_cap, B), np.nan), "dense_y": np.full((dense_cap, n, B), np.nan),
                  "dense_q": np.full((dense_cap, n, 3, B), np.nan)}
         ptr.update({k: v.ctypes.data for k, v in dense.items()}, dense_cap=dense_cap)
+    if report_cap:
+        rbufs, rdict = _report_buffers(B, report_cap)
+        ptr.update({k: v.ctypes.data for k, v in rbufs.items()}, report_cap=report_cap)
     b = hb.struct(ptr)
     rc = _sims[path].sim_solve_chain(C.byref(b), C.byref(hb.options))
     assert rc == 0, f"sim_solve_chain returned {rc}"
     extra = {}
+    if report_cap:
+        extra["reports"] = rdict()
     if dense_cap:
         from dae_scipy_b200.api import make_ode_solution
         extra["sol"] = make_ode_solution(hb, y0, dense["dense_t"], dense["dense_y"], dense["dense_q"], out["status"], out["counters"])
@@ -210,7 +246,7 @@ def run_chain_kernel_source_on_cpu(ens, dense_cap=0, **over):
 
 
 # ------------------------------------------------------------------ the product (GPU)
-def run_gpu(ens, host_api=False, **over):
+def run_gpu(ens, host_api=False, report_cap=0, **over):
     import dae_scipy_b200 as br
     opts = dict(ens["options"])
     opts.update(over)
@@ -220,11 +256,15 @@ def run_gpu(ens, host_api=False, **over):
                     counters=np.ascontiguousarray(r["counters"]), y_final=np.ascontiguousarray(r["y_final"]),
                     t_final=r["t_final"].copy())
     import torch
-    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"], **opts)
+    res = br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], t_eval=ens["t_eval"],
+                               report=bool(report_cap), max_reports=max(int(report_cap), 1), **opts)
     torch.cuda.synchronize()
     o = res.numpy()
-    return dict(y=o["y"], status=o["status"], n_eval=o["n_eval"], counters=o["counters"], y_final=o["y_final"],
-                t_final=o["t_final"])
+    out = dict(y=o["y"], status=o["status"], n_eval=o["n_eval"], counters=o["counters"], y_final=o["y_final"],
+               t_final=o["t_final"])
+    if report_cap:
+        out["reports"] = o["reports"]
+    return out
 
 
 def assert_bit_identical(a, b, what=""):

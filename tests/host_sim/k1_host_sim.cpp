@@ -42,7 +42,7 @@ static void run(const SolveArgs &a) {
         using L = K1Layout<Prob, COLD, FD>;
         std::vector<double> hot(L::SHARED_SLOTS, 0.0), glob(L::GLOBAL_SLOTS + 1, 0.0);
         Slots<1> sm{hot.data()}, gj{glob.data()}, cd{COLD ? glob.data() : hot.data() + L::HOT};
-        if (a.n_events > 0) k1_lane_loop<Prob, Mass, false, COLD, FD, true>(a, sm, cd, gj, a.t_eval);     // device-side events
+        if (a.n_events > 0 || a.rep_cap > 0) k1_lane_loop<Prob, Mass, false, COLD, FD, true>(a, sm, cd, gj, a.t_eval);     // instrumented: events, reports
         else k1_lane_loop<Prob, Mass, false, COLD, FD, false>(a, sm, cd, gj, a.t_eval);
     };
     if (cold && a.jac_fd) go(std::true_type{}, std::true_type{});

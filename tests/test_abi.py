@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_abi.EXPORTED_SYMBOLS), declared ^ set(_abi.EXPORTED_SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.brdae_abi_version() == 3
+    assert lib.brdae_abi_version() == 4
 
 
 def test_ctypes_struct_layout_matches_header():

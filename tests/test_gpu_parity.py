@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import dae_scipy_b200 as br
-from _util import (PARITY_FACTOR, assert_bit_identical, count_agreement, golden_names, load_golden,
+from _util import (PARITY_FACTOR, assert_bit_identical, assert_reports_identical, count_agreement, golden_names, load_golden,
                    run_c_oracle, run_gpu, scaled_error, well_conditioned)
 
 pytestmark = pytest.mark.gpu
@@ -118,6 +118,24 @@ def test_gpu_npendulum_more_ropes_than_lane_slots(monkeypatch):
     assert_bit_identical(run_gpu(ens), ref, "npendulum 700 ropes")
     monkeypatch.setenv("BRDAE_K4_MAX_SLOTS", "64")        # 700 ropes through 64 lanes: every lane is refilled ten times
     assert_bit_identical(run_gpu(ens), ref, "npendulum 700 ropes, 64 lane slots")
+
+
+@pytest.mark.parametrize("make,over", [
+    (lambda: E.pendulum_ensemble(300), {}),
+    (lambda: E.pendulum_ensemble(64, index=2), dict(first_step=0.2, max_newton_ite=4, max_bad_ite=0)),
+    (lambda: E.robertson_ensemble(200), {}),
+    (lambda: E.npendulum_ensemble(40, n_nodes=6), {}),
+    (lambda: E.npendulum_ensemble(5, n_nodes=7), dict(first_step=0.05, max_newton_ite=4, max_bad_ite=0)),
+])
+def test_gpu_per_attempt_report_bit_identical_to_c_oracle(make, over):
+    """report=True (the reference's bReport: factorisations, Jacobian updates, non-converged / rejected / accepted attempts with
+    their Newton iteration counts and error norms) written by the kernels, against the same record of the scalar oracle --
+    which tests/test_kernel_source_cpu.py pins to `RadauDAE(bReport=True).reports` of the reference itself."""
+    ens = make()
+    out, ref = run_gpu(ens, report_cap=2500, **over), run_c_oracle(ens, report_cap=2500, **over)
+    assert_bit_identical(out, ref, "with the report switched on")
+    assert_reports_identical(out["reports"], ref["reports"], "GPU vs C oracle")
+    assert int(out["reports"]["n"].min()) > 10
 
 
 def test_gpu_constant_jacobian_mode():

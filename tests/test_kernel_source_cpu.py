@@ -6,8 +6,8 @@ import numpy as np
 import pytest
 
 import dae_scipy_b200 as br
-from _util import (PARITY_FACTOR, assert_bit_identical, count_agreement, golden_names, load_golden, run_c_oracle,
-                   run_chain_kernel_source_on_cpu, run_kernel_source_on_cpu, scaled_error)
+from _util import (PARITY_FACTOR, assert_bit_identical, assert_reports_identical, count_agreement, golden_names, load_golden,
+                   run_c_oracle, run_chain_kernel_source_on_cpu, run_kernel_source_on_cpu, scaled_error)
 
 E = br.ensembles
 
@@ -205,3 +205,59 @@ def test_chain_dense_output_record_of_the_kernel_source():
     np.testing.assert_allclose(sol(ens["t_eval"]), out["y"], rtol=1e-8, atol=1e-10)
     last = sol.ys[np.arange(3), :, sol.n_steps]
     assert np.array_equal(last, out["y_final"])
+
+
+# ---------------------------------------------------------------- per-attempt report (the reference's bReport=True)
+@pytest.mark.parametrize("make,over,chain", [
+    (lambda: E.pendulum_ensemble(12), {}, False),
+    (lambda: E.pendulum_ensemble(6, index=2), dict(first_step=0.2, max_newton_ite=4, max_bad_ite=0), False),   # failed attempts, Jacobian updates
+    (lambda: E.robertson_ensemble(12), {}, False),
+    (lambda: E.transistor_ensemble(3, t_end=0.02), {}, False),
+    (lambda: E.npendulum_ensemble(3, n_nodes=6), {}, True),
+    (lambda: E.npendulum_ensemble(2, n_nodes=7), dict(first_step=0.05, max_newton_ite=4, max_bad_ite=0), True),
+])
+def test_per_attempt_report_of_the_kernel_sources_equals_the_c_oracle(make, over, chain):
+    ens = make()
+    run = run_chain_kernel_source_on_cpu if chain else run_kernel_source_on_cpu
+    sim, orc = run(ens, report_cap=3000, **over), run_c_oracle(ens, report_cap=3000, **over)
+    assert_bit_identical(sim, orc, "with the report switched on")
+    assert_reports_identical(sim["reports"], orc["reports"], "kernel source vs C oracle")
+    codes = set(np.unique(np.concatenate([orc["reports"]["code"][i, :k] for i, k in enumerate(orc["reports"]["n"])])).tolist())
+    assert {0, -10} <= codes <= {0, 2, 5, -10, -11}
+    if over:
+        assert 5 in codes and -11 in codes                 # non-converged attempts and Jacobian updates were reported
+    # a capped report keeps the first records and still counts all of them
+    few = run(ens, report_cap=7, **over)["reports"]
+    assert np.array_equal(few["n"], sim["reports"]["n"]) and np.array_equal(few["code"], sim["reports"]["code"][:, :7])
+
+
+def test_per_attempt_report_reproduces_the_reference_report():
+    """`RadauDAE(bReport=True).reports` of the unmodified reference against the restatement's record on a well-conditioned
+    ensemble: the same events in the same order with the same Newton iteration counts; times, steps and error norms to
+    rounding.  (Runs where the reference is importable: /root/reference or oracle/_ref.)"""
+    import contextlib
+    import io
+    from oracle import problems_numpy as prob, reference_runner
+    if reference_runner.reference_location() is None:
+        pytest.skip("the reference is not importable here")
+    RadauDAE = reference_runner.radau_class()
+    ens = E.pendulum_ensemble(6)
+    sim = run_kernel_source_on_cpu(ens, report_cap=3000)["reports"]
+    opts = dict(ens["options"])
+    opts.pop("mass_matrix")
+    vi = opts.pop("var_index")
+    for i in range(6):
+        fun, jac, mass, _ = prob.build("pendulum3", ens["params"][i], 5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            s = RadauDAE(fun, 0.0, ens["y0"][i].copy(), 2.0, jac=jac, mass_matrix=mass, var_index=np.asarray(vi, float), bReport=True, **opts)
+            while s.status == "running":
+                s.step()
+        r, k = s.reports, int(sim["n"][i])
+        assert k == len(r["code"])
+        assert np.array_equal(np.array(r["code"]), sim["code"][i, :k])
+        assert np.array_equal(np.array(r["newton_iterations"]), sim["newton_iterations"][i, :k])
+        assert np.array_equal(np.array(r["bad_iterations"]), sim["bad_iterations"][i, :k])
+        np.testing.assert_allclose(sim["t"][i, :k], np.array(r["t"], float), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(sim["dt"][i, :k], np.array(r["dt"], float), rtol=1e-4, atol=1e-9)
+        acc = np.array(r["code"]) == 0
+        np.testing.assert_allclose(sim["err1"][i, :k][acc], np.array(r["err1"], float)[acc], rtol=2e-3, atol=1e-12)

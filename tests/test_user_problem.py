@@ -84,7 +84,7 @@ def test_plugin_library_builds_and_reports_its_problem():
     lib = _abi.load(prob.lib_path)
     for sym in _abi.EXPORTED_SYMBOLS:                              # a complete libbrdae: the same C ABI
         getattr(lib, sym)
-    assert lib.brdae_abi_version() == 3
+    assert lib.brdae_abi_version() == 4
     pid, n, npar = C.c_int32(-1), C.c_int32(-1), C.c_int32(-1)
     for name in (b"reactor", b"user"):
         assert lib.brdae_problem_lookup(name, C.byref(pid), C.byref(n), C.byref(npar)) == 0
