@@ -285,6 +285,7 @@ class BatchedOdeResult:
         self._event_cut = None                  # (terminated [B], t_stop [B], y_stop [B, n], ascending)
         self.event_count = self.event_t = self.event_y = None   # device-side events: [E, B], [E, cap, B], [E, cap, n, B]
         self.reports = None                     # report=True: dict of device tensors, see solve_ivp_batched
+        self.tsub = self.ysub = None            # return_substeps=True: stage points of every step (host arrays)
         self.t = t
         self._y_eval = y_eval_tnb           # [T, n, B] as written by the kernel (coalesced SoA)
         self.n_eval = n_eval
@@ -413,6 +414,26 @@ class BatchedOdeSolution:
     def system(self, i):
         return lambda t: self(np.atleast_1d(t))[i] if np.ndim(t) else self([t])[i, :, 0]
 
+    def substeps(self):
+        """The collocation (stage) points of every recorded step -- what the reference returns with `return_substeps=True`
+        (radauDAE.py:661-663, 1097-1134, 1175-1191: `tsub`, `ysub`): `tsub` [B, 3 K] = t_old + h C and `ysub` [B, n, 3 K] =
+        y_old + Z_i for the three Radau IIA stages of each step, NaN beyond a system's last step.  The stage values are
+        recovered from the step's interpolation coefficients, Z^T = Q P^-1, i.e. the step's cubic evaluated at x = C_i (the
+        third stage is the end of the step exactly)."""
+        C = np.array([(4 - 6 ** 0.5) / 10, (4 + 6 ** 0.5) / 10, 1.0])          # radauDAE.py:14
+        B, K1 = self.ts.shape
+        K = K1 - 1
+        h = self.ts[:, 1:] - self.ts[:, :-1]                                       # [B, K]
+        tsub = self.ts[:, :-1, None] + h[:, :, None] * C[None, None, :]            # [B, K, 3]
+        X = np.stack([C, C * C, C * C * C])                                        # [3 powers, 3 stages]
+        ysub = np.einsum("bknp,ps->bkns", self.Q, X) + np.moveaxis(self.ys, 2, 1)[:, :-1, :, None]     # [B, K, n, 3]
+        ysub[:, :, :, 2] = np.moveaxis(self.ys, 2, 1)[:, 1:, :]                    # C_3 = 1: the recorded end state itself
+        beyond = np.arange(K)[None, :] >= self.n_steps[:, None]
+        tsub[beyond] = np.nan
+        ysub[beyond] = np.nan
+        n = ysub.shape[2]
+        return tsub.reshape(B, 3 * K), np.ascontiguousarray(np.moveaxis(ysub, 2, 1)).reshape(B, n, 3 * K)
+
     def step(self, i, k):
         """The cubic of step k of system i as a callable t -> y[n] (RadauDenseOutput, radauDAE.py:959-982)."""
         t_old, h = self.ts[i, k], self.ts[i, k + 1] - self.ts[i, k]
@@ -475,7 +496,7 @@ def _as_device_f64(x, device, torch):
 
 def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_eval=None,
                       dense_output=False, max_dense_steps=None, events=None, max_events=8, report=False, max_reports=4096,
-                      device=None, stream=None, **options):
+                      return_substeps=False, device=None, stream=None, **options):
     """Integrate B independent systems  M y' = f(t, y)  from t_span[0] to t_span[1] on one GPU.
 
     Parameters follow `scipy.integrate.solve_ivp(..., method=RadauDAE, **options)` of the
@@ -508,6 +529,9 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
                   Jacobian update, non-converged attempt, rejected and accepted step (codes -10, -11, 5, 2, 0), the first
                   `max_reports` per system, in `result.reports` (device tensors `count` [B], `code` [R, B], `it` [R, 2, B],
                   `val` [R, 4, B] = t, h, err1, err2; `.numpy()["reports"]` gives the reference's keys, one row per system).
+    return_substeps : as in the reference's solve_ivp_custom (radauDAE.py:992, 1175-1191): also return the collocation points of
+                  every step, `result.tsub` [B, 3 K] and `result.ysub` [B, n, 3 K] (implies dense_output=True; see
+                  `BatchedOdeSolution.substeps`).
     dense_output, max_dense_steps : record every accepted step (up to `max_dense_steps` per system, required
                   with dense_output=True: the record takes 8 (4 n + 1) bytes per step and system) and return
                   `result.sol`, a BatchedOdeSolution.  Times known in advance are cheaper through `t_eval`.
@@ -523,8 +547,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
         device_events, events = tuple(events), None       # located by the kernel; nothing to do on the host
         if int(max_events) < 1:
             raise ValueError("`max_events` (occurrences recorded per event and system) must be at least 1.")
-    if events and not dense_output:
-        dense_output = True                    # Python event functions are located on the per-step record
+    if (events or return_substeps) and not dense_output:
+        dense_output = True                    # Python event functions are located on the per-step record; so are the stage points
     if dense_output and (max_dense_steps is None or int(max_dense_steps) < 1):
         raise ValueError("dense_output=True (and events) need `max_dense_steps` (steps recorded per system).")
     if not torch.cuda.is_available():
@@ -613,6 +637,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
         y0_h = y0_d.cpu().numpy()
         res.sol = make_ode_solution(hb, y0_h, dense_t.cpu().numpy(), dense_y.cpu().numpy(),
                                     dense_q.cpu().numpy(), status.cpu().numpy(), counters.cpu().numpy())
+        if return_substeps:
+            res.tsub, res.ysub = res.sol.substeps()
         if events:
             if res.sol.truncated.any():
                 raise RuntimeError("`max_dense_steps` is too small for event location: a system took more steps than recorded.")

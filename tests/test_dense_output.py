@@ -70,3 +70,38 @@ def test_dense_output_needs_a_cap_and_host_entry_refuses_it():
     ens = E.pendulum_ensemble(2)
     with pytest.raises(ValueError, match="max_dense_steps"):
         br.solve_ivp_batched(ens["problem"], ens["t_span"], ens["y0"], ens["params"], dense_output=True, **ens["options"])
+
+
+def test_substeps_reproduce_the_reference_stage_points():
+    """return_substeps (radauDAE.py:661-663, 1175-1191): the collocation points recovered from the step record against
+    `solver.t_substeps` / `solver.y_substeps` of the reference itself, stepped like solve_ivp (reference importable only)."""
+    import contextlib
+    import io
+    import dae_scipy_b200 as br
+    from _util import run_kernel_source_on_cpu
+    from oracle import problems_numpy as prob, reference_runner
+    if reference_runner.reference_location() is None:
+        pytest.skip("the reference is not importable here")
+    RadauDAE = reference_runner.radau_class()
+    ens = br.ensembles.pendulum_ensemble(3, t_end=1.0)
+    sol = run_kernel_source_on_cpu(ens, dense_cap=400)["sol"]
+    tsub, ysub = sol.substeps()
+    assert tsub.shape == (3, 1200) and ysub.shape == (3, 5, 1200)
+    opts = dict(ens["options"])
+    opts.pop("mass_matrix")
+    vi = opts.pop("var_index")
+    for i in range(3):
+        fun, jac, mass, _ = prob.build("pendulum3", ens["params"][i], 5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            s = RadauDAE(fun, 0.0, ens["y0"][i].copy(), 1.0, jac=jac, mass_matrix=mass, var_index=np.asarray(vi, float), **opts)
+            ts, ys = [], []
+            while s.status == "running":
+                s.step()
+                ts.extend(s.t_substeps)
+                ys.extend(s.y_substeps)
+        ts, ys = np.array(ts), np.array(ys).T
+        k = ts.size
+        assert k == 3 * sol.n_steps[i] and np.isnan(tsub[i, k:]).all() and np.isnan(ysub[i, :, k:]).all()
+        np.testing.assert_allclose(tsub[i, :k], ts, rtol=0, atol=1e-6)
+        assert np.max(np.abs(ysub[i, :, :k] - ys) / (1e-6 + 1e-6 * np.abs(ys))) <= 10.0        # the north_star tolerance
+        assert np.array_equal(ysub[i, :, 2:k:3], sol.ys[i, :, 1:sol.n_steps[i] + 1])            # third stage = end of the step
