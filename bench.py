@@ -126,6 +126,12 @@ def _cpu_worker(args):
     kind, ens = args
     # one BLAS thread per process: the pool already uses every core, and the LAPACK calls of the chain problems
     # (N = 100..500) would otherwise start a full OpenBLAS thread team in each forked worker (measured: 50x slower)
+    # The limit only reaches libraries that are loaded when it is set: scipy brings its own OpenBLAS, so import it first
+    # (a first call that loaded scipy under the limit ran 16 x 16 spinning threads: 240 s instead of 0.3 s per rope).
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    import scipy.linalg  # noqa: F401
+    import scipy.sparse.linalg  # noqa: F401
     try:
         from threadpoolctl import threadpool_limits
         limit = threadpool_limits(limits=1)
@@ -167,6 +173,11 @@ def cpu_reference_rate(ens, n_systems, cores, kind):
     return n / dt, dt, n
 
 
+# about what the reference needs for one system on one core (measured, 1 BLAS thread): sizes the bounded CPU samples
+_REF_SECONDS_PER_SYSTEM = {"pendulum3_1M_tend2": 0.12, "robertson_4M": 0.1, "transistor_256k": 0.7, "pendulum3_1M_tend10": 0.7,
+                           "npendulum_n20_16k": 0.8, "npendulum_n50_16k": 3.0, "npendulum_n100_16k": 20.0}
+
+
 def _kind_text(kind):
     return ("the unmodified reference (scipyDAE.radauDAE.RadauDAE installed under oracle/_ref), stepped like scipy's solve_ivp"
             if kind == "reference" else "numpy restatement of the reference (oracle/radau_numpy.py; the reference itself is not importable here)")
@@ -178,7 +189,8 @@ def run_reference_arm(args, ens, wl_name):
         return
     kind = _reference_kind()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    per_step = max(cores, min(args.ref_sample, 64 * cores))
+    # a bounded sample per step: at most 64 systems per core, fewer where one system costs the reference seconds (chains)
+    per_step = max(cores, min(args.ref_sample, cores * min(64, max(1, int(25.0 / _REF_SECONDS_PER_SYSTEM.get(wl_name, 0.2))))))
     for _ in range(args.warmup):
         cpu_reference_rate(ens, min(per_step, 2 * cores), cores, kind)
     total_n, total_t = 0, 0.0
@@ -406,7 +418,7 @@ def main():
         # about 10-30 s of CPU work per workload (the reference integrates roughly 8 / 10 / 1.5 / 1.5 systems per second and core
         # on the pendulum t_end = 2 / Robertson / transistor / pendulum t_end = 10 configurations, 1 rope per second at n = 20)
         per_core = {"pendulum3_1M_tend2": 160, "robertson_4M": 160, "transistor_256k": 24, "pendulum3_1M_tend10": 24}.get(
-            args.workload, max(1, 64 // gen_kw.get("n_nodes", 64)))
+            args.workload, max(1, int(15.0 / _REF_SECONDS_PER_SYSTEM.get(args.workload, 1.0))))
         ns = args.cpu_sample or min(B, per_core * cores)
         rate, dt, nn = cpu_reference_rate(ens, ns, cores, kind)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,

@@ -46,6 +46,37 @@ struct Rope {
 };
 #define K4S(nb, s) (nb)[(s) * STRIDE]
 
+// Software prefetch of slots [s0, s0 + ns) of one node into L1, issued one node ahead of the sweep that reads them.  The
+// kernel is bound by the latency of its global loads (profiles/r02_k4_ncu_summary.md) and has no registers left to issue
+// the next node's loads early, so the lines are requested without a destination register: the active lanes of the block
+// share the lines of the warp's region among themselves (line j of the range goes to the lane of rank j mod #active).
+#ifndef BRDAE_K4_PREFETCH
+#define BRDAE_K4_PREFETCH 1      // 0 off, 1 into L1, 2 into L2 only
+#endif
+#ifndef BRDAE_K4_PFD
+#define BRDAE_K4_PFD 2           // nodes ahead of the sweep
+#endif
+constexpr int K4_PFD = BRDAE_K4_PFD;
+template <int STRIDE>
+BRDAE_HD void prefetch_slots(const double *nb, int s0, int ns) {
+#if defined(__CUDA_ARCH__) && BRDAE_K4_PREFETCH
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m = __activemask();
+    const int cnt = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+    const char *base = reinterpret_cast<const char *>(nb - (lane < (unsigned)STRIDE ? lane : 0u) + (size_t)s0 * STRIDE);
+    const int lines = (ns * STRIDE * 8 + 127) / 128;
+    for (int j = rank; j < lines; j += cnt) {
+#if BRDAE_K4_PREFETCH == 1
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + 128 * j));
+#else
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 128 * j));
+#endif
+    }
+#else
+    (void)nb; (void)s0; (void)ns;
+#endif
+}
+
 struct Rod { double a, b, rs; };
 // lambda dx / rs, lambda dy / rs with one reciprocal per rod (oracle npe_rhs)
 BRDAE_HD Rod rod(double dx, double dy, double l) {
@@ -100,6 +131,7 @@ template <int STRIDE>
 BRDAE_HD void jac_sweep(const Rope<STRIDE> &R, const Consts &k) {
     double xp = 0, yp = 0;
     for (int i = 0; i < k.nn; ++i) {
+        if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 5); }
         double *nb = R.node(i);
         const double x = K4S(nb, O_Y), y = K4S(nb, O_Y + 1), l = K4S(nb, O_Y + 4);
         const double dx = (i == 0) ? x : x - xp, dy = (i == 0) ? y : y - yp;
@@ -223,6 +255,7 @@ BRDAE_HD void factor_sweep(const Rope<STRIDE> &R, const Consts &k, double mr, do
     double adx = K4S(nb, O_ND + ND_ADX), ady = K4S(nb, O_ND + ND_ADY), bdy = K4S(nb, O_ND + ND_BDY);
     double al = K4S(nb, O_ND + ND_AL), bl = K4S(nb, O_ND + ND_BL), dx2 = K4S(nb, O_ND + ND_DX2), dy2 = K4S(nb, O_ND + ND_DY2);
     for (int i = 0; i < k.nn; ++i) {
+        if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 45, 7); }
         nb = R.node(i);
         const double im = node_im(k, i);
         double sxx = im * adx, sxy = im * ady, syy = im * bdy;
@@ -343,6 +376,7 @@ BRDAE_HD bool newton_sweeps(const Rope<STRIDE> &R, const Consts &k, double mr, d
             cur[0] = rod(cx[0], cy[0], l0); cur[1] = rod(cx[1], cy[1], l1); cur[2] = rod(cx[2], cy[2], l2);
         }
         for (int i = 0; i < k.nn; ++i) {
+            if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 5); prefetch_slots<STRIDE>(pn_, 30, 54); }
             double *nb = R.node(i);
             const bool last = (i == k.nn - 1);
             Rod nxt[3] = {cur[0], cur[1], cur[2]};
@@ -433,6 +467,7 @@ BRDAE_HD bool newton_sweeps(const Rope<STRIDE> &R, const Consts &k, double mr, d
         double u[3] = {0, 0, 0}, ur[3] = {0, 0, 0}, ui[3] = {0, 0, 0};
         double s5[5] = {0, 0, 0, 0, 0};
         for (int i = k.nn - 1; i >= 0; --i) {
+            if (i - K4_PFD >= 0) { const double *pn_ = R.node(i - K4_PFD); prefetch_slots<STRIDE>(pn_, 30, 69); }
             double *nb = R.node(i);
             const double *nbn = R.node(i + 1 < k.nn ? i + 1 : i);
             double d0[5], d1[5], d2[5];
@@ -488,6 +523,7 @@ BRDAE_HD bool newton_sweeps(const Rope<STRIDE> &R, const Consts &k, double mr, d
 template <int STRIDE>
 BRDAE_HD void scale_sweep(const Rope<STRIDE> &R, const Consts &k, const SolveArgs &a, double h) {
     for (int i = 0; i < k.nn; ++i) {
+        if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 5); }
         double *nb = R.node(i);
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
@@ -508,6 +544,7 @@ BRDAE_HD void guess_sweep(const Rope<STRIDE> &R, const Consts &k, bool zero, dou
         x[s] = (tt - t_sol_old) * inv_h_sol; x2[s] = x[s] * x[s]; x3[s] = x2[s] * x[s];
     }
     for (int i = 0; i < k.nn; ++i) {
+        if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 30); }
         double *nb = R.node(i);
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
@@ -544,6 +581,7 @@ BRDAE_HD double error_sweeps(const Rope<STRIDE> &R, const Consts &k, const Solve
     };
     if (pass == 0) {
         for (int i = 0; i < k.nn; ++i) {
+            if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 5, 5); prefetch_slots<STRIDE>(pn_, 30, 36); }
             double *nb = R.node(i);
             double e[5];
 #pragma unroll
@@ -569,6 +607,7 @@ BRDAE_HD double error_sweeps(const Rope<STRIDE> &R, const Consts &k, const Solve
             cur = rod(x, y, K4S(nb, O_Y + 4) + K4S(nb, O_ERR + 4));
         }
         for (int i = 0; i < k.nn; ++i) {
+            if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 5); prefetch_slots<STRIDE>(pn_, 45, 21); prefetch_slots<STRIDE>(pn_, 84, 15); }
             double *nb = R.node(i);
             const bool last = (i == k.nn - 1);
             Rod nxt = cur;
@@ -596,6 +635,7 @@ BRDAE_HD double error_sweeps(const Rope<STRIDE> &R, const Consts &k, const Solve
     }
     double u[3] = {0, 0, 0}, s5[5] = {0, 0, 0, 0, 0};
     for (int i = k.nn - 1; i >= 0; --i) {
+        if (i - K4_PFD >= 0) { const double *pn_ = R.node(i - K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 5); prefetch_slots<STRIDE>(pn_, 30, 36); prefetch_slots<STRIDE>(pn_, 84, 15); }
         double *nb = R.node(i);
         const double *nbn = R.node(i + 1 < k.nn ? i + 1 : i);
         double d[5];
@@ -633,6 +673,7 @@ BRDAE_HD void accept_sweep(const Rope<STRIDE> &R, const Consts &k, bool recomput
         cur = rod(dx, dy, l);
     }
     for (int i = 0; i < k.nn; ++i) {
+        if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 5); prefetch_slots<STRIDE>(pn_, 30, 15); }
         double *nb = R.node(i);
         const bool last = (i == k.nn - 1);
         Rod nxt = cur;
@@ -878,9 +919,16 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
         }
         warp_converge();
         // ---------------- simplified-Newton iterations :846-940
+        // At least a.newton_reps passes (while any rope iterates); beyond that for as long as more than newton_vote / 32 of
+        // the live ropes of the warp still iterate: the chain refactorises at every step and needs 4-5 iterations per
+        // attempt, so with a fixed count most ropes wait a whole trip of the other blocks for their last iteration
+        // (profiles/tools/k4_sched_sim.py: lane efficiency 0.42 -> 0.56).  Scheduling only: results do not depend on it.
 #pragma unroll 1
-        for (int rep = 0; rep < a.newton_reps; ++rep) {
-            if (warp_any(state == ST_NEWTON)) {
+        for (int rep = 0;; ++rep) {
+            const int iterating = warp_count(state == ST_NEWTON);
+            if (iterating == 0) break;
+            if (rep >= a.newton_reps && (a.newton_vote <= 0 || 32 * iterating <= a.newton_vote * warp_count(state != ST_EXIT))) break;
+            {
                 if (state == ST_NEWTON) {
                     double ssq = 0;
                     const bool finite = newton_sweeps<STRIDE>(R, kc, mr, mcr, mci, mrf, mcrf, mcif, ssq);

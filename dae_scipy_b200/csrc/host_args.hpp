@@ -116,6 +116,7 @@ inline void fill_common(SolveArgs &a, const brdae_batch *b, const brdae_options 
     a.all_newton = o->all_newton_iterations; a.constant_dt = o->constant_dt;
     a.has_jac_const = b->jac_const != nullptr;
     a.newton_reps = 3;
+    a.newton_vote = 0;
     a.jac_fd = (o->jac_finite_differences && !b->jac_const) ? 1 : 0;
     if (b->n <= BRDAE_NMAX_SMALL) {
         for (int c = 0; c < b->n; ++c) {

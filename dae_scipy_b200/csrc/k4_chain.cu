@@ -13,6 +13,7 @@ namespace {
 constexpr int K4_BLOCK = 32;             // one warp per CTA: the warps of an SM run different blocks of the step at the same time
 constexpr size_t kHeaderBytes = 256;
 size_t align8(size_t x) { return (x + 7) / 8 * 8; }
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }       // the state starts on a line boundary (the header is 256 bytes)
 
 // RPW ropes per warp (lanes RPW..31 idle), at least MINB warps resident per SM.  The kernel is bound by the latency of
 // its global-memory accesses (one warp per SM measured 63 % long-scoreboard stalls and 3 % of the issue slots used,
@@ -79,7 +80,7 @@ cudaError_t k4_launch(const K4Geom &g, const SolveArgs &a, double *state, cudaSt
 // workspace after the 256-byte work counter: atol[N] | var_index[N] | state [warps][n/5][99][ropes per warp]
 size_t k4_scratch_bytes(int n, int64_t B, int sms) {
     const K4Geom g = k4_geometry(n, B, sms);
-    return align8(sizeof(double) * n) + align8(sizeof(int32_t) * n) + (size_t)(n / 5) * k4::SPN * g.warps * g.rpw * sizeof(double);
+    return align256(align8(sizeof(double) * n) + align8(sizeof(int32_t) * n)) + (size_t)(n / 5) * k4::SPN * g.warps * g.rpw * sizeof(double);
 }
 
 int k4_chain(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, int sms, cudaStream_t stream, LaunchGeom *g, bool geom_only) {
@@ -91,10 +92,11 @@ int k4_chain(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, int s
     if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;      // the block elimination is the chain's own M and J
     SolveArgs a = a_in;
     if (const char *e = std::getenv("BRDAE_NEWTON_REPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) a.newton_reps = v; }
+    a.newton_vote = env_int("BRDAE_K4_VOTE", 0, 32, 1);     // keep iterating until at most 1/32 of the live ropes still do
     char *ws = reinterpret_cast<char *>(a.work_counter) + kHeaderBytes;
     double *atol_d = reinterpret_cast<double *>(ws);
     int32_t *vidx_d = reinterpret_cast<int32_t *>(ws + align8(sizeof(double) * N));
-    double *state = reinterpret_cast<double *>(ws + align8(sizeof(double) * N) + align8(sizeof(int32_t) * N));
+    double *state = reinterpret_cast<double *>(ws + align256(align8(sizeof(double) * N) + align8(sizeof(int32_t) * N)));
     if (cudaMemcpyAsync(atol_d, b->atol, sizeof(double) * N, cudaMemcpyHostToDevice, stream) != cudaSuccess) return BRDAE_ERR_CUDA;
     if (b->var_index) {
         if (cudaMemcpyAsync(vidx_d, b->var_index, sizeof(int32_t) * N, cudaMemcpyHostToDevice, stream) != cudaSuccess) return BRDAE_ERR_CUDA;

@@ -118,6 +118,7 @@ struct SolveArgs {
     int32_t has_jac_const;
     int32_t jac_fd;        // K1: finite-difference Jacobian (jac=None of the reference)
     int32_t newton_reps;   // K1: Newton passes per cycle (scheduling only, results do not depend on it)
+    int32_t newton_vote;   // K4: after newton_reps passes, keep iterating while more than newton_vote/32 of the live ropes do (0: never)
     // small-problem (n <= BRDAE_NMAX_SMALL) uniform vectors; K2 reads its own from global memory
     double atol[BRDAE_NMAX_SMALL];
     int32_t var_index[BRDAE_NMAX_SMALL];

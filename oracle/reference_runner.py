@@ -135,6 +135,8 @@ def run_reference(ens, over=None, build_system=None):
 def _worker(args):
     import warnings
     warnings.filterwarnings("ignore")
+    import scipy.linalg  # noqa: F401  (scipy's own OpenBLAS must be loaded before the limit is set, or it is not limited)
+    import scipy.sparse.linalg  # noqa: F401
     try:
         from threadpoolctl import threadpool_limits
         limit = threadpool_limits(limits=1)      # one BLAS thread per process: the pool already uses every core
