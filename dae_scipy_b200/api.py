@@ -22,13 +22,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _abi
+from .ode_solver import DeviceFun, RadauDAE          # RadauDAE: the `method=` marker, and a scipy OdeSolver for one system
 from .problems import Problem, get_problem
-
-
-class RadauDAE:
-    """Marker for `method=`: the batched Radau IIA(5) DAE solver (reference class
-    scipyDAE/radauDAE.py:126).  It only names the method; the stepping lives in the kernels."""
-    name = "RadauDAE"
 
 
 class LinearEvent:

@@ -50,6 +50,9 @@
 #ifndef BRDAE_SIM_COUNT
 #define BRDAE_SIM_COUNT(i)      // tests/host_sim counts how often the fast paths and their fall-backs run; nothing on the device
 #endif
+#ifndef BRDAE_SIM_NEIGHBOUR
+#define BRDAE_SIM_NEIGHBOUR() true   // tests/host_sim (a warp of ONE lane) lets an imaginary neighbouring lane veto the warp-wide fast paths at random
+#endif
 #ifndef K1_TEVAL_SHARED
 #define K1_TEVAL_SHARED 256      // output grids up to this many points are staged in shared memory
 #endif
@@ -865,7 +868,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
 
         // ================= error estimate, accept/reject, epilogue :660-784 ===================
         if (warp_any(state == ST_ERREST)) {
-            const bool ident_r = BRDAE_K1_IDENT_FASTPATH && pat_ok && warp_all(state != ST_ERREST || piv_r == perm_identity(N));
+            const bool ident_r = BRDAE_K1_IDENT_FASTPATH && pat_ok && warp_all(state != ST_ERREST || piv_r == perm_identity(N)) && BRDAE_SIM_NEIGHBOUR();
             if (state == ST_ERREST) {
                 double Z[3][N];
 #pragma unroll
@@ -1182,7 +1185,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
         }
         // ================= (re)factorisation :594-613 =========================================
         if (warp_any(state == ST_FACTOR)) {
-            const bool static_lu = BRDAE_K1_STATIC_LU && trait_static_lu<Prob>::value && pat_ok && warp_all(state != ST_FACTOR || lu_static_ok);
+            const bool static_lu = BRDAE_K1_STATIC_LU && trait_static_lu<Prob>::value && pat_ok && warp_all(state != ST_FACTOR || lu_static_ok) && BRDAE_SIM_NEIGHBOUR();
             if (state == ST_FACTOR) {
                 if (a.scale_residuals) inv_h_lu = inv_h;
                 double J[N][N];
@@ -1238,6 +1241,10 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
                     BRDAE_SIM_COUNT(2);
                     piv_r = lu_real_left<N>(sm, L::S_LUR, col_real);
                     piv_c = lu_cplx_left<N>(sm, L::S_LCR, L::S_LCI, col_cplx);
+                    // A system that exchanged rows here -- also when a NEIGHBOUR forced the general routine on the warp -- stays
+                    // on it: the exchange leaves fill outside the no-exchange pattern, which the pattern-restricted optimistic
+                    // factorisation would not overwrite and a later general substitution (forced by a neighbour again) would read.
+                    if (piv_r != perm_identity(N) || piv_c != perm_identity(N)) lu_static_ok = false;
                 }
                 cnt[CN_NLU]++;
                 if (EVENTS && a.rep_cap > 0) report_event(a, idx, RC_FACTORISATION, t, h, -1, -1, -1.0, -1.0);   // :607
@@ -1255,7 +1262,7 @@ BRDAE_HD void k1_lane_loop(const SolveArgs &a, const S &sm, const SC &cd, const 
             // no lane of the warp exchanged a row in its current factorisations (always, for the pendulum and Robertson
             // ensembles): the substitutions below run on compile-time addresses, without the permutation round trip
             const unsigned perm_id = perm_identity(N);
-            const bool ident = BRDAE_K1_IDENT_FASTPATH && pat_ok && warp_all(state != ST_NEWTON || (piv_r == perm_id && piv_c == perm_id));
+            const bool ident = BRDAE_K1_IDENT_FASTPATH && pat_ok && warp_all(state != ST_NEWTON || (piv_r == perm_id && piv_c == perm_id)) && BRDAE_SIM_NEIGHBOUR();
             // every Newton lane of the warp is at the first iteration of its attempt (the lanes phase-lock onto the cycle, so
             // this is the common case in the first pass): there is no previous increment norm, hence no rate, and the
             // division / power / reciprocal chain of the convergence test would only produce values nobody reads

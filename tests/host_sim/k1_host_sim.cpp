@@ -16,6 +16,17 @@
 static long g_sim_counts[8];
 extern "C" long *sim_counts() { return g_sim_counts; }
 #define BRDAE_SIM_COUNT(i) (++g_sim_counts[i])
+// The harness runs a warp of one lane, so the warp-wide votes of the kernel (every lane static? nobody pivoted?) only ever see
+// that lane.  On the device a neighbouring lane can veto a fast path for the whole warp at any time; with sim_neighbour(p) set,
+// an imaginary neighbour does so with probability p / 256 per vote (results must not depend on it).
+static unsigned g_sim_neighbour_p = 0, g_sim_lcg = 12345u;
+extern "C" void sim_neighbour(unsigned p, unsigned seed) { g_sim_neighbour_p = p; g_sim_lcg = seed; }
+static inline bool sim_neighbour_agrees() {
+    if (g_sim_neighbour_p == 0) return true;
+    g_sim_lcg = g_sim_lcg * 1664525u + 1013904223u;
+    return ((g_sim_lcg >> 16) & 255u) >= g_sim_neighbour_p;
+}
+#define BRDAE_SIM_NEIGHBOUR() sim_neighbour_agrees()
 #include "../../dae_scipy_b200/csrc/host_args.hpp"
 #include "../../dae_scipy_b200/csrc/radau_k1.cuh"
 #ifdef BRDAE_USER_HEADER        // a user problem (dae_scipy_b200/plugin.py): the same generated functor header as the plugin build

@@ -261,3 +261,25 @@ def test_per_attempt_report_reproduces_the_reference_report():
         np.testing.assert_allclose(sim["dt"][i, :k], np.array(r["dt"], float), rtol=1e-4, atol=1e-9)
         acc = np.array(r["code"]) == 0
         np.testing.assert_allclose(sim["err1"][i, :k][acc], np.array(r["err1"], float)[acc], rtol=2e-3, atol=1e-12)
+
+
+@pytest.mark.parametrize("make,p", [(lambda: E.pendulum_ensemble(96, index=2), 64), (lambda: E.pendulum_ensemble(96, index=2), 200),
+                                    (lambda: E.pendulum_ensemble(48, index=1), 64), (lambda: E.pendulum_ensemble(48), 64),
+                                    (lambda: E.robertson_ensemble(48), 64), (lambda: E.robertson_ensemble(64, rtol=1e-3, atol=1e-4), 100)])
+def test_fast_paths_vetoed_by_a_neighbouring_lane_stay_bit_identical(make, p):
+    """On the device the fast paths (optimistic LU, pattern-restricted substitutions) are warp-wide votes: a neighbouring lane
+    that pivoted sends every lane of the warp through the general code for that block.  The harness (one lane per warp)
+    emulates that neighbour at random; whatever mix of paths a system sees, its bits must not change.  (Regression: a system
+    that pivoted inside a general factorisation forced by a neighbour went back to the pattern-restricted optimistic
+    factorisation, which left the earlier fill outside the pattern in place -- GPU run of pendulum2_1024, round 2.)"""
+    import ctypes as C
+    from _util import _host_sim
+    ens = make()
+    sim = _host_sim(br.get_problem(ens["problem"]))
+    ref = run_c_oracle(ens)
+    try:
+        for seed in (1, 2, 3):
+            sim.sim_neighbour(C.c_uint(p), C.c_uint(seed))
+            assert_bit_identical(run_kernel_source_on_cpu(ens), ref, f"neighbour veto p={p} seed={seed}")
+    finally:
+        sim.sim_neighbour(C.c_uint(0), C.c_uint(0))
