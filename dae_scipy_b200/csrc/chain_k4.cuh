@@ -519,24 +519,11 @@ BRDAE_HD bool newton_sweeps(const Rope<STRIDE> &R, const Consts &k, double mr, d
     return true;
 }
 
-// attempt set-up (:564-588): Newton scales
+// attempt set-up in ONE sweep: the Newton scales (:564-588, when the step size is new) and the starting guess W = TI Z0
+// (:580-583), Z0 from the previous step's cubic evaluated beyond its interval
 template <int STRIDE>
-BRDAE_HD void scale_sweep(const Rope<STRIDE> &R, const Consts &k, const SolveArgs &a, double h) {
-    for (int i = 0; i < k.nn; ++i) {
-        if (i + K4_PFD < k.nn) { const double *pn_ = R.node(i + K4_PFD); prefetch_slots<STRIDE>(pn_, 0, 5); }
-        double *nb = R.node(i);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const int vi = a.var_index_dev[5 * i + c];
-            const int ve = vi > 1 ? vi - 1 : 0;
-            const double hp = a.scale_newton_norm ? hpow(h, ve) : 1.0;
-            K4S(nb, O_NS + c) = hp / (a.atol_dev[5 * i + c] + fabs(K4S(nb, O_Y + c)) * a.rtol);
-        }
-    }
-}
-// starting guess W = TI Z0 (:580-583), Z0 from the previous step's cubic evaluated beyond its interval
-template <int STRIDE>
-BRDAE_HD void guess_sweep(const Rope<STRIDE> &R, const Consts &k, bool zero, double t, double h, double t_sol_old, double inv_h_sol) {
+BRDAE_HD void setup_sweep(const Rope<STRIDE> &R, const Consts &k, const SolveArgs &a, bool scale, bool zero, double t, double h,
+                          double t_sol_old, double inv_h_sol) {
     double x[3], x2[3], x3[3];
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
@@ -548,9 +535,16 @@ BRDAE_HD void guess_sweep(const Rope<STRIDE> &R, const Consts &k, bool zero, dou
         double *nb = R.node(i);
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
+            const double yc = K4S(nb, O_Y + c);
+            if (scale) {
+                const int vi = a.var_index_dev[5 * i + c];
+                const int ve = vi > 1 ? vi - 1 : 0;
+                const double hp = a.scale_newton_norm ? hpow(h, ve) : 1.0;
+                K4S(nb, O_NS + c) = hp / (a.atol_dev[5 * i + c] + fabs(yc) * a.rtol);
+            }
             if (zero) { K4S(nb, O_W + c) = 0.0; K4S(nb, O_W + 5 + c) = 0.0; K4S(nb, O_W + 10 + c) = 0.0; continue; }
             const double q0 = K4S(nb, O_Q + 3 * c), q1 = K4S(nb, O_Q + 3 * c + 1), q2 = K4S(nb, O_Q + 3 * c + 2);
-            const double yo = K4S(nb, O_YO + c), yc = K4S(nb, O_Y + c);
+            const double yo = K4S(nb, O_YO + c);
             double z[3];
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
@@ -869,6 +863,7 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
                         rejected = false;
                     }
                 }
+                bool new_scales = false;
                 if (finish_status == RUNNING && setup_kind <= SETUP_ATTEMPT) {
                     if (h_abs < min_step) finish_status = BRDAE_STATUS_TOO_SMALL_STEP;
                     else {
@@ -878,12 +873,12 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
                         h = t_new - t;
                         h_abs = fabs(h);
                         inv_h = 1.0 / h;
-                        scale_sweep<STRIDE>(R, kc, a, h);
+                        new_scales = true;
                         mr = MU_REAL * inv_h; mcr = MU_CR * inv_h; mci = MU_CI * inv_h;
                     }
                 }
                 if (finish_status == RUNNING) {
-                    guess_sweep<STRIDE>(R, kc, !have_sol || !a.extrapolate, t, h, t_sol_old, inv_h_sol);
+                    setup_sweep<STRIDE>(R, kc, a, new_scales, !have_sol || !a.extrapolate, t, h, t_sol_old, inv_h_sol);
                     kit = 0; nbad = 0; have_old = false; have_rate = false; rate = 0; dwn_old = 0;
                     state = lu_valid ? ST_NEWTON : ST_FACTOR;
                 }
