@@ -23,13 +23,20 @@ size_t align256(size_t x) { return (x + 255) / 256 * 256; }       // the state s
 template <int RPW, int MINB>
 __global__ void __launch_bounds__(K4_BLOCK, MINB) k4_kernel(const __grid_constant__ SolveArgs a, double *state) {
     // [warp][node][slot][rope of the warp]: the state of the ropes of a warp is one contiguous region
+    extern __shared__ __align__(128) unsigned char k4_smem[];      // the warp's ring of staged node blocks (chain_k4.cuh: Stager)
     const size_t warp = blockIdx.x;
     const bool have = threadIdx.x < RPW;
     k4::Rope<RPW> R{state + warp * ((size_t)(a.n / 5) * k4::SPN * RPW) + (have ? threadIdx.x : 0)};
-    k4::k4_lane_loop<RPW>(a, R, have);
+    constexpr bool STAGED = BRDAE_K4_STAGED && RPW >= 2;            // bulk copies move multiples of 16 bytes
+    k4::Stager<RPW, STAGED> S;
+    if constexpr (STAGED) S.init(k4_smem);
+    k4::k4_lane_loop<RPW>(a, R, have, S);
 }
+template <int RPW>
+constexpr int k4_smem_bytes() { return (BRDAE_K4_STAGED && RPW >= 2) ? k4::STAGE_SLOTS * RPW * 8 * 3 + 64 : 0; }
 
 struct K4Geom { int rpw, minb; long long warps; };
+int k4_smem_for(int rpw);
 
 int env_int(const char *name, int lo, int hi, int dflt) {
     if (const char *e = std::getenv(name)) { const int v = std::atoi(e); if (v >= lo && v <= hi) return v; }
@@ -43,13 +50,23 @@ K4Geom k4_geometry(int n, int64_t B, int sms) {
     K4Geom g;
     const int mb = env_int("BRDAE_K4_MINB", 1, 32, 8);      // 252 registers, no spills: measured best (profiles/r02_k4_geometry.md)
     g.minb = mb >= 24 ? 32 : (mb >= 12 ? 16 : 8);
-    const long long resident = (long long)nsm * g.minb;
+    // warps that stay resident on an SM: the register budget (minb) and the staged node ring in shared memory (k4_smem_for)
+    auto resident_for = [&](int rpw) {
+        const int by_smem = (int)((227 * 1024) / (k4_smem_for(rpw) + 1024));
+        return (long long)nsm * (g.minb < by_smem ? g.minb : by_smem);
+    };
     int rpw = 1;
-    while (rpw < 32 && (long long)rpw * resident < B) rpw *= 2;
+    while (rpw < 32 && (long long)rpw * resident_for(rpw) < B) rpw *= 2;
+    // With the node stream staged in shared memory a warp no longer waits on global loads, and a warp instruction costs the
+    // same for 32 ropes as for 8: as many ropes per warp as leave about two warps per SM (16,384 ropes, n = 20: 32 ropes per
+    // warp 171 ms, 16: 258 ms, 8: 418 ms; the unstaged kernel preferred 16: 317 ms -- profiles/r02_k4_ncu_summary.md).
+    if (BRDAE_K4_STAGED)
+        while (rpw < 32 && B / (2 * rpw) >= 2LL * nsm) rpw *= 2;
     rpw = env_int("BRDAE_K4_RPW", 1, 32, rpw);
     int p2 = 1;
     while (p2 < rpw) p2 *= 2;
     g.rpw = p2;
+    const long long resident = resident_for(g.rpw);
     long long warps = (B + g.rpw - 1) / g.rpw;
     if (warps > resident) warps = resident;
     // memory cap (about 48 GB of state) and the test hook that forces refills
@@ -62,17 +79,34 @@ K4Geom k4_geometry(int n, int64_t B, int sms) {
     return g;
 }
 
+template <int RPW, int MINB>
+void k4_launch_one(const K4Geom &g, const SolveArgs &a, double *state, cudaStream_t stream) {
+    constexpr int smem = k4_smem_bytes<RPW>();
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k4_kernel<RPW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k4_kernel<RPW, MINB><<<(int)g.warps, K4_BLOCK, smem, stream>>>(a, state);
+}
 template <int MINB>
 cudaError_t k4_launch(const K4Geom &g, const SolveArgs &a, double *state, cudaStream_t stream) {
     switch (g.rpw) {
-    case 1: k4_kernel<1, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
-    case 2: k4_kernel<2, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
-    case 4: k4_kernel<4, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
-    case 8: k4_kernel<8, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
-    case 16: k4_kernel<16, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
-    default: k4_kernel<32, MINB><<<(int)g.warps, K4_BLOCK, 0, stream>>>(a, state); break;
+    case 1: k4_launch_one<1, MINB>(g, a, state, stream); break;
+    case 2: k4_launch_one<2, MINB>(g, a, state, stream); break;
+    case 4: k4_launch_one<4, MINB>(g, a, state, stream); break;
+    case 8: k4_launch_one<8, MINB>(g, a, state, stream); break;
+    case 16: k4_launch_one<16, MINB>(g, a, state, stream); break;
+    default: k4_launch_one<32, MINB>(g, a, state, stream); break;
     }
     return cudaPeekAtLastError();
+}
+
+int k4_smem_for(int rpw) {
+    switch (rpw) {
+    case 1: return k4_smem_bytes<1>();
+    case 2: return k4_smem_bytes<2>();
+    case 4: return k4_smem_bytes<4>();
+    case 8: return k4_smem_bytes<8>();
+    case 16: return k4_smem_bytes<16>();
+    default: return k4_smem_bytes<32>();
+    }
 }
 
 }  // namespace
@@ -87,7 +121,7 @@ int k4_chain(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, int s
     const int N = a_in.n;
     if (N < 10 || N % 5 != 0) return BRDAE_ERR_BAD_ARGUMENT;
     const K4Geom kg = k4_geometry(N, a_in.B, sms);
-    if (g) { g->grid = (int)kg.warps; g->block = K4_BLOCK; g->smem = 0; g->scratch_bytes = 0; }
+    if (g) { g->grid = (int)kg.warps; g->block = K4_BLOCK; g->smem = k4_smem_for(kg.rpw); g->scratch_bytes = 0; }
     if (geom_only) return BRDAE_OK;
     if (dense_mass || a_in.has_jac_const) return BRDAE_ERR_UNSUPPORTED;      // the block elimination is the chain's own M and J
     SolveArgs a = a_in;

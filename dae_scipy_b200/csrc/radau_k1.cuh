@@ -695,6 +695,8 @@ BRDAE_HD double functor_event(const typename Prob::P &prm, int k, double t, cons
 BRDAE_D bool warp_all(bool x) { return __all_sync(0xffffffffu, x); }
 BRDAE_D bool warp_any(bool x) { return __any_sync(0xffffffffu, x); }
 BRDAE_D int warp_count(bool x) { return __popc(__ballot_sync(0xffffffffu, x)); }
+BRDAE_D unsigned warp_ballot(bool x) { return __ballot_sync(0xffffffffu, x); }
+BRDAE_D unsigned warp_ballot_in(unsigned mask, bool x) { return __ballot_sync(mask, x); }     // among the lanes of `mask` (all of them call)
 // Once per cycle: is any lane of the scope still alive?  CTA-wide this is the one barrier of the
 // cycle (BAR.RED.OR): it keeps the warps of the SM in step, so that they walk through the same block
 // at the same time and share its instruction-cache lines (with free-running warps the kernel was
@@ -734,6 +736,8 @@ BRDAE_D void signal_chunk(const SolveArgs &a, long long idx) {
 inline bool warp_all(bool x) { return x; }
 inline bool warp_any(bool x) { return x; }
 inline int warp_count(bool x) { return x ? 1 : 0; }
+inline unsigned warp_ballot(bool x) { return x ? 1u : 0u; }
+inline unsigned warp_ballot_in(unsigned, bool x) { return x ? 1u : 0u; }
 template <bool CTA_WIDE>
 inline bool cycle_sync(bool alive) { return alive; }
 inline void warp_converge() {}

@@ -27,6 +27,7 @@ extern "C" int sim_solve_chain(const brdae_batch *b, const brdae_options *o) {
     if (const char *e = std::getenv("BRDAE_NEWTON_REPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) a.newton_reps = v; }
     std::vector<double> state((size_t)(b->n / 5) * k4::SPN, 0.0);
     k4::Rope<1> R{state.data()};
-    k4::k4_lane_loop<1>(a, R, true);        // the one lane pulls ropes from the work counter until none is left
+    k4::Stager<1, false> S;                 // the harness reads the nodes in place (staging is a device-side data movement)
+    k4::k4_lane_loop<1>(a, R, true, S);        // the one lane pulls ropes from the work counter until none is left
     return BRDAE_OK;
 }
