@@ -52,7 +52,7 @@ NCU_DRAM_BYTES_PER_SYSTEM = {
     "pendulum3_1M_tend10": ((158.95e6 + 334.40e6) / 262144, "profiles/r01_k1_fastpaths.md (same kernel and output grid as t_end = 2)"),
     "robertson_4M": ((18.2e6 + 71.0e6) / 262144, "profiles/r01_k1_ncu_summary.md (Robertson, 262,144 systems: part of that launch's output was still in L2 at kernel end)"),
     "transistor_256k": ((10.8e6 + 12.9e6) / 65536, "profiles/r01_k1_ncu_summary.md (transistor, 65,536 systems: that launch's output was still in L2 at kernel end)"),
-    "npendulum_n20_16k": ((96.3e6 + 13.80e9) / 4096, "profiles/r02_k4_ncu_summary.md (K4, n = 20, 4,096 ropes)"),
+    "npendulum_n20_16k": ((557.1e9 + 186.1e9) / 16384, "profiles/r02_k4_ncu_summary.md (K4 staged, n = 20, 16,384 ropes)"),
 }
 
 
@@ -373,14 +373,22 @@ def main():
                 "hbm": {"algorithmic_bytes": abytes, "achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak,
                         "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src}}
     if chain:
-        # the chain kernel streams its per-rope state (99 doubles per node) through L2/HBM once per sweep: the bytes that
-        # algorithm has to move, from the counters (flops.chain_state_bytes_per_node_sweep), against the measured HBM peak
+        # The chain kernel is bound by HBM, not by the FP64 pipe: it streams the state of every rope (99 doubles per node) through
+        # shared memory once per sweep (TMA bulk copies, csrc/chain_k4.cuh: Stager).  Algorithmic bytes = what the block-elimination
+        # sweeps of this run stage and store per rope (flops.chain_state_bytes_per_node_sweep x the run's own counters), i.e. the
+        # traffic if every lane of a warp were busy in every sweep; `traffic` is the DRAM traffic ncu measured for this workload.
         per = flops.chain_state_bytes_per_node_sweep()
         nodes = n // 5
-        state_bytes = nodes * (float(out_counts[7]) * per["newton"] + float(out_counts[2]) * per["factor"] + float(out_counts[8]) * per["error_estimate"])
-        roofline["state_stream"] = {"bytes_per_launch": state_bytes, "achieved_gbs": state_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                                    "frac": state_bytes / (kms * 1e-3) / 1e9 / hbm_peak,
-                                    "note": "state traffic of the block-elimination sweeps (served by L2 while the resident ropes fit it); the kernel is bound by the latency of this stream, see profiles/r02_k4_ncu_summary.md"}
+        attempts = float(out_counts[4] + out_counts[5] + out_counts[6])         # accepted + rejected + failed: one set-up sweep each
+        state_bytes = nodes * (float(out_counts[7]) * per["newton"] + float(out_counts[2]) * per["factor"] + float(out_counts[8]) * per["error_estimate"]
+                               + attempts * per["setup"] + float(out_counts[4]) * per["accept"]) + abytes
+        gbs = state_bytes / (kms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": None if traffic is None else traffic * B, "traffic_source": traffic_src, "peak_source": hbm_src,
+                    "kernel": kernel_name, "kernel_ms": kms, "bytes_per_launch": state_bytes, "bytes_per_trajectory": state_bytes / B,
+                    "fp64": {"achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                             "flops_per_launch": fl, "peak_source": "measured in this run: dependent-chain DFMA probe (brdae_fp64_peak_probe)"},
+                    "note": "rope state staged into shared memory and stored by the sweeps, from the run's counters; see profiles/r02_k4_ncu_summary.md"}
 
     statuses = hist.cpu().numpy().tolist()
 

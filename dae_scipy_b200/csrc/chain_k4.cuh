@@ -757,8 +757,11 @@ BRDAE_HD double error_sweeps(STG &S, const Rope<STRIDE> &R, const Consts &k, con
 }
 
 // accepted step (:742-784): y_old = y, y += Z_2, Q = Z^T P, f = rhs(y), optionally the Jacobian's rod quantities at the new y
+// `out` != nullptr: the first output point of this step is evaluated here, from the coefficients while they are in registers
+// (out[(5 i + c) out_stride] = y_old + Q [x, x^2, x^3], the arithmetic of the output loop of the lane loop)
 template <int STRIDE, class STG>
-BRDAE_HD void accept_sweep(STG &S, const Rope<STRIDE> &R, const Consts &k, bool recompute, unsigned m) {
+BRDAE_HD void accept_sweep(STG &S, const Rope<STRIDE> &R, const Consts &k, bool recompute, unsigned m, double *out, int64_t out_stride,
+                           double ox, double ox2, double ox3) {
     // new state of a node: y + (W0 + W1)
     auto ynew = [&](const NodeRef &nb, int c) { return K4L(nb, O_Y + c) + (K4L(nb, O_W + c) + K4L(nb, O_W + 5 + c)); };
     double x, y, l, dx, dy;
@@ -792,9 +795,18 @@ BRDAE_HD void accept_sweep(STG &S, const Rope<STRIDE> &R, const Consts &k, bool 
             K4W(nb, O_YO + c) = yo;
             yn5[c] = yo + z2;
             K4W(nb, O_Y + c) = yn5[c];
-            K4W(nb, O_Q + 3 * c) = fma(z2, P20, fma(z1, P10, z0 * P00));
-            K4W(nb, O_Q + 3 * c + 1) = fma(z2, P21, fma(z1, P11, z0 * P01));
-            K4W(nb, O_Q + 3 * c + 2) = fma(z2, P22, fma(z1, P12, z0 * P02));
+            const double q0 = fma(z2, P20, fma(z1, P10, z0 * P00));
+            const double q1 = fma(z2, P21, fma(z1, P11, z0 * P01));
+            const double q2 = fma(z2, P22, fma(z1, P12, z0 * P02));
+            K4W(nb, O_Q + 3 * c) = q0;
+            K4W(nb, O_Q + 3 * c + 1) = q1;
+            K4W(nb, O_Q + 3 * c + 2) = q2;
+            if (out) {
+                double v = q0 * ox;
+                v = fma(q1, ox2, v);
+                v = fma(q2, ox3, v);
+                out[(int64_t)(5 * i + c) * out_stride] = v + yo;
+            }
         }
         const double m = node_m(k, i), im = node_im(k, i);
         K4W(nb, O_F) = yn5[2];
@@ -922,7 +934,19 @@ BRDAE_HD void k4_lane_loop(const SolveArgs &a, const Rope<STRIDE> &R, bool have_
             }
             const unsigned ma = warp_ballot(accepted);
             if (accepted) {
-                accept_sweep<STRIDE>(S, R, kc, recompute, ma);
+                // an output point inside this step (usually at most one) is produced by the sweep itself; reading the
+                // coefficients back from global memory for it was 15 % of the stall samples (profiles/r02_k4_ncu_summary.md)
+                double *out = nullptr;
+                double ox = 0, ox2 = 0, ox3 = 0;
+                if (ei < a.T) {
+                    const double te = a.t_eval[ei];
+                    if (dir > 0 ? te <= t_new : te >= t_new) {
+                        out = a.y_eval + (int64_t)ei * N * a.B + idx;
+                        ox = (te - t) * inv_h; ox2 = ox * ox; ox3 = ox2 * ox;
+                    }
+                }
+                accept_sweep<STRIDE>(S, R, kc, recompute, ma, out, a.B, ox, ox2, ox3);
+                if (out) ++ei;
                 cnt[CN_NFEV]++;
                 if (recompute) { cnt[CN_NJEV]++; current_jac = true; }
                 else current_jac = false;

@@ -48,7 +48,7 @@ int env_int(const char *name, int lo, int hi, int dflt) {
 K4Geom k4_geometry(int n, int64_t B, int sms) {
     const int nsm = sms > 0 ? sms : 148;
     K4Geom g;
-    const int mb = env_int("BRDAE_K4_MINB", 1, 32, 8);      // 252 registers, no spills: measured best (profiles/r02_k4_geometry.md)
+    const int mb = env_int("BRDAE_K4_MINB", 1, 32, 8);      // 252 registers, no spills: measured best (profiles/r02_k4_ncu_summary.md, "Geometry")
     g.minb = mb >= 24 ? 32 : (mb >= 12 ? 16 : 8);
     // warps that stay resident on an SM: the register budget (minb) and the staged node ring in shared memory (k4_smem_for)
     auto resident_for = [&](int rpw) {

@@ -67,10 +67,12 @@ def algorithmic_bytes(n: int, n_params: int, T: int, B: int) -> float:
 
 
 def chain_state_bytes_per_node_sweep() -> dict:
-    """HBM/L2 bytes the chain kernel K4 moves per node and sweep (8-byte slots of csrc/chain_k4.cuh), the bound of that
-    kernel: a Newton iteration reads y, W (twice: look-ahead and node), the rod quantities, the three inverse blocks, the
-    forward-substituted blocks, the scales, and writes z, the position rows and W."""
-    newton = 8 * (5 + 15 + 12 + 5 + 27 + 9 + 6 + 5 + 15 + 18 + 5 + 9 + 6) + 8 * (9 + 6 + 15)      # loads + stores
-    factor = 8 * (7 + 5) + 8 * 27
-    errest = 8 * (15 + 5 + 5 + 5 + 9 + 6 + 5 + 3 + 2 + 10) + 8 * (4 + 5 + 5)
-    return dict(newton=newton, factor=factor, error_estimate=errest)
+    """Bytes of rope state the chain kernel K4 moves per node (and per rope) in each kind of sweep: the slot range the sweep
+    stages in shared memory (TMA bulk copy of slots [lo, hi) of the node, csrc/chain_k4.cuh: Stager) plus the slots it
+    stores.  8-byte slots; the figures are the `S.begin(R, lo, count, ...)` ranges of the sweeps."""
+    newton = 8 * (54 + 69) + 8 * (15 + 15)          # forward [O_Y, O_Z) + backward [O_W, SPN); stores z, position rows | W
+    factor = 8 * 7 + 8 * 27                         # rod quantities in, three inverse blocks out
+    errest = 8 * (41 + 65) + 8 * (9 + 5)            # first estimate: forward [O_F, O_VCR) + backward [O_Y, O_RP + 2)
+    setup = 8 * 30 + 8 * 20                         # [O_Q, O_W) in; W and the Newton scales out
+    accept = 8 * 20 + 8 * 37                        # [O_Y, O_ND) in; y_old, y, Q, f and the rod quantities out
+    return dict(newton=newton, factor=factor, error_estimate=errest, setup=setup, accept=accept)
