@@ -417,6 +417,25 @@ def main():
                        "page-locked buffers and the final synchronisation are all inside the timed region",
                "all_finished": bool((out["status"] == 0).all())}
 
+        # what bounds the end-to-end rate with several ranks on one host: the plain device-to-host copy rate of a buffer of the
+        # result's size into page-locked memory, all ranks copying at the same time (no kernel, no host work)
+        try:
+            probe_d = torch.empty(d2h // 8, dtype=torch.float64, device=dev)
+            probe_h = torch.empty(d2h // 8, dtype=torch.float64, pin_memory=True)
+            probe_h.copy_(probe_d, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                probe_h.copy_(probe_d, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            dtp = max_over_ranks(time.perf_counter() - t0)
+            e2e["d2h_copy_probe_gbs_all_ranks"] = 3 * d2h * world / dtp / 1e9
+            e2e["d2h_bound_on_e2e"] = systems_all / (d2h * world / (e2e["d2h_copy_probe_gbs_all_ranks"] * 1e9))
+            del probe_d, probe_h
+        except Exception as exc:
+            e2e["d2h_copy_probe_gbs_all_ranks"] = None
+            e2e["d2h_probe_error"] = repr(exc)
+
     clk.__exit__(None, None, None)
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)

@@ -237,9 +237,9 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
     elif jac is None:
         # the reference's default (radauDAE.py:468-481): scipy num_jac forward differences of the RHS
         # functor with adaptive column factors, on the device (thread-per-system problems)
-        if prob.name == "npendulum":
-            raise NotImplementedError("finite-difference Jacobians are not available for the n-pendulum chain "
-                                      "kernels; use jac='analytic'.")
+        # (the n-pendulum chain: the reference's own default for that problem, recursive_pendulum.py:128, 165 -- runs on the
+        # band kernel with one right-hand-side evaluation per group of 17 columns; jac='analytic' selects the much faster
+        # block-elimination kernel)
         fd = True
     elif callable(jac):
         raise ValueError("Python Jacobian callables cannot run on the device; use jac='analytic'.")

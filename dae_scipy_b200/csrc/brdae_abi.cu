@@ -75,9 +75,11 @@ void brdae_default_options(brdae_options *o) {
 size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *o) {
     if (!b) return 0;
     size_t bytes = kCounterBytes;
-    if (b->problem == BRDAE_NPENDULUM)
-        bytes += npendulum_uses_k4(b->n, b->n_systems) ? k4_scratch_bytes(b->n, b->n_systems, sm_count()) : k2_scratch_bytes(b->n, sm_count(), b->n_systems);
-    else {      // K1: per-CTA slice of cold per-lane state (kernels that keep it in shared memory need none)
+    if (b->problem == BRDAE_NPENDULUM) {
+        const bool fd = o && o->jac_finite_differences && !b->jac_const;      // finite differences: the band kernel
+        bytes += (!fd && npendulum_uses_k4(b->n, b->n_systems)) ? k4_scratch_bytes(b->n, b->n_systems, sm_count())
+                                                                  : k2_scratch_bytes(b->n, sm_count(), b->n_systems, fd);
+    } else {      // K1: per-CTA slice of cold per-lane state (kernels that keep it in shared memory need none)
         LaunchGeom g{};
         const bool fd = o && o->jac_finite_differences && !b->jac_const;
         if (launch_geometry(b->problem, b->mass != nullptr, fd, b->n, b->n_systems, sm_count(), &g) == BRDAE_OK) bytes += g.scratch_bytes;

@@ -25,7 +25,9 @@ static int route(int problem, bool dense_mass, const SolveArgs &a, const brdae_b
     case BRDAE_ROBERTSON: return k1_robertson(dense_mass, a, sms, s, g, geom_only);
     case BRDAE_TRANSISTOR: return k1_transistor(dense_mass, a, sms, s, g, geom_only);
     case BRDAE_NPENDULUM:
-        if (npendulum_uses_k4(a.n, a.B)) return k4_chain(dense_mass, a, b, sms, s, g, geom_only);
+        // the block elimination of K4 is built on the chain's analytic Jacobian; jac=None (finite differences, the
+        // reference's default for this problem) runs on the general band kernel
+        if (!a.jac_fd && npendulum_uses_k4(a.n, a.B)) return k4_chain(dense_mass, a, b, sms, s, g, geom_only);
         return k2_npendulum(dense_mass, a, b, sms, s, g, geom_only);
     case BRDAE_ROBERTSON_ODE: case BRDAE_JAY: case BRDAE_POLYDAE2: case BRDAE_LINEAR7:
         return k1_extra(problem, dense_mass, a, sms, s, g, geom_only);

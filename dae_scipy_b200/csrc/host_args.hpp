@@ -62,7 +62,6 @@ inline int validate(const brdae_batch *b, const brdae_options *o) {
         if (b->var_index && (b->var_index[c] < 0 || b->var_index[c] > 3)) return BRDAE_ERR_BAD_ARGUMENT;
     }
     if (o->first_step > 0 && o->first_step > std::fabs(b->t_bound - b->t0)) return BRDAE_ERR_BAD_ARGUMENT;
-    if (o->jac_finite_differences && !b->jac_const && b->problem == BRDAE_NPENDULUM) return BRDAE_ERR_UNSUPPORTED;
     return BRDAE_OK;
 }
 

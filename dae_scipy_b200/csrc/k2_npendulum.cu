@@ -40,6 +40,7 @@ struct K2Cfg {
     int complex_in_smem;          // complex LU factors in shared memory?
     int state_in_global;          // ALL per-rope state in the (L2-resident) global scratch: more ropes in flight
     size_t scratch_stride;        // doubles per CTA in the global scratch
+    size_t fd_offset;             // finite-difference mode: offset of its state inside the CTA's slice
 };
 
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
@@ -327,7 +328,13 @@ struct Rope {           // shared-memory views of one CTA
     double *mass_m, *inv_m, *r0s, *atol, *red;
     int *vidx, *pivr, *pivc;
     double *lur, *lcr, *lci;
+    // finite-difference Jacobian (jac=None): the band of J (row r, column c at jb[r * JW + c - r + KL]), the column factors of
+    // scipy's num_jac (kept from one evaluation to the next), step, largest difference and its scale of every column
+    double *jb, *jfac, *jh, *jmd, *jsc;
+    int *jflag;
 };
+constexpr int JW = KL + KU + 1;            // 17 entries per row; columns 17 apart share no row: 17 column groups
+#define JB(jb, r, c) (jb)[(r) * JW + ((c) - (r) + KL)]
 
 // f = rhs(Y): recursive_pendulum.py:93-118.  Node-parallel, two phases (the (i+1) term).
 __device__ void rope_rhs(const Rope &s, const double *Y, double *F) {
@@ -374,11 +381,105 @@ __device__ __forceinline__ NodeJac node_jac(const double *X, int i) {
     return j;
 }
 
+// Finite-difference Jacobian, the reference's default for this problem (recursive_pendulum.py:128, 165: jac=None with the
+// banded `jac_sparsity`; radauDAE.py:475-480 -> scipy num_jac with column groups, common.py:268-452).  Columns 17 apart
+// touch disjoint rows, so one right-hand-side evaluation per group of columns gives every column of the group: 17
+// evaluations per Jacobian (plus one per group in which a difference was too small and is repeated with a ten times larger
+// factor).  Per column the arithmetic is that of the scalar oracle's column-by-column restatement (num_jac_fd): forward
+// difference with step h = (y + factor * y_scale) - y, largest difference (first maximum) and its scale, repetition rule,
+// entries (f(y + h e_c) - f) * (1 / h), factor update.  Evaluations made here are not counted in nfev (as in scipy).
+constexpr double NJ_FACTOR0 = 0x1.0000000000000p-26, NJ_DIFF_REJECT = 0x1.6a09e667f3bcdp-46, NJ_DIFF_SMALL = 0x1.0000000000000p-39,
+                 NJ_DIFF_BIG = 0x1.0000000000000p-13, NJ_MIN_FACTOR = 0x1.f400000000000p-43;
+// largest |Ft - f| over the rows of column c (first maximum over ALL rows: row 0 when the column does not move anything)
+__device__ __forceinline__ void fd_column_max(const Rope &s, int c, int &mi, double &md) {
+    const int lo = imax(0, c - KU), hi = imin(s.N - 1, c + KL);
+    mi = 0; md = (lo == 0) ? fabs(s.Ft[0] - s.f[0]) : 0.0;
+    for (int r = imax(lo, 1); r <= hi; ++r) { const double d = fabs(s.Ft[r] - s.f[r]); if (d > md) { md = d; mi = r; } }
+}
+__device__ void rope_num_jac(const Rope &s) {
+    const int N = s.N, tid = threadIdx.x, nthr = blockDim.x;
+    for (int c = tid; c < N; c += nthr) {
+        const double ys = (s.f[c] >= 0 ? 1.0 : -1.0) * fmax(s.atol[c], fabs(s.y[c]));
+        double fac = s.jfac[c];
+        double h = (s.y[c] + fac * ys) - s.y[c];
+        while (h == 0) { fac *= 10; h = (s.y[c] + fac * ys) - s.y[c]; }
+        s.jfac[c] = fac; s.jh[c] = h;
+    }
+    __syncthreads();
+    for (int g = 0; g < JW; ++g) {
+        for (int c = tid; c < N; c += nthr) s.Yt[c] = s.y[c] + ((c % JW == g) ? s.jh[c] : 0.0);
+        __syncthreads();
+        rope_rhs(s, s.Yt, s.Ft);
+        bool small = false;
+        for (int c = g + JW * tid; c < N; c += JW * nthr) {
+            int mi; double md;
+            fd_column_max(s, c, mi, md);
+            const double scale = fmax(fabs(s.f[mi]), fabs(s.Ft[mi]));
+            const int lo = imax(0, c - KU), hi = imin(N - 1, c + KL);
+            for (int r = lo; r <= hi; ++r) JB(s.jb, r, c) = s.Ft[r] - s.f[r];
+            s.jmd[c] = md; s.jsc[c] = scale;
+            const bool ts = md < NJ_DIFF_REJECT * scale;
+            s.jflag[c] = ts ? 1 : 0;
+            small = small || ts;
+        }
+        if (__syncthreads_or(small)) {       // repeat the too-small columns of this group with ten times the factor
+            for (int c = tid; c < N; c += nthr) {
+                double v = s.y[c];
+                if (c % JW == g && s.jflag[c]) {
+                    const double ys = (s.f[c] >= 0 ? 1.0 : -1.0) * fmax(s.atol[c], fabs(s.y[c]));
+                    v = s.y[c] + ((s.y[c] + (10 * s.jfac[c]) * ys) - s.y[c]);
+                }
+                s.Yt[c] = v;
+            }
+            __syncthreads();
+            rope_rhs(s, s.Yt, s.Ft);
+            for (int c = g + JW * tid; c < N; c += JW * nthr) {
+                if (!s.jflag[c]) continue;
+                const double ys = (s.f[c] >= 0 ? 1.0 : -1.0) * fmax(s.atol[c], fabs(s.y[c]));
+                const double fac_new = 10 * s.jfac[c];
+                const double h_new = (s.y[c] + fac_new * ys) - s.y[c];
+                int mi2; double md2;
+                fd_column_max(s, c, mi2, md2);
+                const double scale2 = fmax(fabs(s.f[mi2]), fabs(s.Ft[mi2]));
+                if (s.jmd[c] * scale2 < md2 * s.jsc[c]) {
+                    s.jfac[c] = fac_new; s.jh[c] = h_new; s.jsc[c] = scale2; s.jmd[c] = md2;
+                    const int lo = imax(0, c - KU), hi = imin(N - 1, c + KL);
+                    for (int r = lo; r <= hi; ++r) JB(s.jb, r, c) = s.Ft[r] - s.f[r];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int c = tid; c < N; c += nthr) {
+        const double rh = 1.0 / s.jh[c];
+        const int lo = imax(0, c - KU), hi = imin(N - 1, c + KL);
+        for (int r = lo; r <= hi; ++r) JB(s.jb, r, c) = JB(s.jb, r, c) * rh;
+        double fac = s.jfac[c];
+        const double md = s.jmd[c], scale = s.jsc[c];
+        if (md < NJ_DIFF_SMALL * scale) fac *= 10;
+        if (md > NJ_DIFF_BIG * scale) fac *= 0.1;
+        s.jfac[c] = fmax(fac, NJ_MIN_FACTOR);
+    }
+    __syncthreads();
+}
+
 // iteration matrices hscale (mu/h M - J) in band storage, then both LUs (radauDAE.py:594-613)
+template <bool FD>
 __device__ void rope_factor(const Rope &s, const SolveArgs &a, double mr, double mcr, double mci, double inv_h_lu) {
     const int N = s.N;
     for (int e = threadIdx.x; e < N * WB; e += blockDim.x) { s.lur[e] = 0.0; s.lcr[e] = 0.0; s.lci[e] = 0.0; }
     __syncthreads();
+    if (FD) {       // every band entry from the stored finite-difference Jacobian; mass diag(1,1,1,1,0) per node
+        for (int e = threadIdx.x; e < N * JW; e += blockDim.x) {
+            const int row = e / JW, col = row - KL + e % JW;
+            if (col < 0 || col >= N) continue;
+            const double h = (a.scale_residuals && s.vidx[row] >= 1) ? inv_h_lu : 1.0;
+            const double m = (row == col && row % 5 != 4) ? 1.0 : 0.0, jv = s.jb[e];
+            AB(s.lur, row, col) = h * fma(mr, m, -jv);
+            AB(s.lcr, row, col) = h * fma(mcr, m, -jv);
+            AB(s.lci, row, col) = h * (mci * m);
+        }
+    } else
     for (int i = threadIdx.x; i < s.nn; i += blockDim.x) {
         const NodeJac me = node_jac(s.yJ, i);
         const int r = 5 * i;
@@ -420,7 +521,7 @@ __device__ void rope_factor(const Rope &s, const SolveArgs &a, double mr, double
 template <int I>
 __device__ __forceinline__ double zstage(const double *W, int N, int c) { return stage_z<I>(W[c], W[N + c], W[2 * N + c]); }
 
-template <int BLOCK, int MINB>
+template <int BLOCK, int MINB, bool FD>
 __global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__ SolveArgs a, const K2Cfg cfg) {
     extern __shared__ double sm[];
     __shared__ long long next_idx;
@@ -437,6 +538,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__
     if (cfg.complex_in_smem || cfg.state_in_global) { s.lcr = p; p += (size_t)N * WB; s.lci = p; p += (size_t)N * WB; }
     else { s.lcr = a.scratch + (size_t)blockIdx.x * cfg.scratch_stride; s.lci = s.lcr + (size_t)N * WB; }
     s.vidx = reinterpret_cast<int *>(p); s.pivr = s.vidx + N; s.pivc = s.pivr + N;
+    s.jb = s.jfac = s.jh = s.jmd = s.jsc = nullptr; s.jflag = nullptr;
+    if (FD) {       // the finite-difference mode keeps its state behind the regular per-CTA slice (host: k2_fd_doubles)
+        double *q = a.scratch + (size_t)blockIdx.x * cfg.scratch_stride + cfg.fd_offset;
+        s.jb = q; q += (size_t)N * JW; s.jfac = q; q += N; s.jh = q; q += N; s.jmd = q; q += N; s.jsc = q; q += N;
+        s.jflag = reinterpret_cast<int *>(q);
+    }
 
     for (int c = tid; c < N; c += nthr) { s.atol[c] = a.atol_dev[c]; s.vidx[c] = a.var_index_dev[c]; }
     for (int i = tid; i < nn; i += nthr) {       // recursive_pendulum.py:63-73
@@ -465,6 +572,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__
         __syncthreads();
         rope_rhs(s, s.y, s.f);
         cnt[CN_NFEV] = 1; cnt[CN_NJEV] = 1;
+        if (FD) {
+            for (int c = tid; c < N; c += nthr) s.jfac[c] = NJ_FACTOR0;
+            __syncthreads();
+            rope_num_jac(s);                                              // :475-481
+        }
         double h_abs_state = a.h0, h_abs_old_state = 0, err_old_state = 0;
         bool hist_state = false, current_jac = true, lu_valid = false, have_sol = false;
         double inv_h_sol = 0, t_sol_old = 0, inv_h_lu = 1.0;
@@ -537,7 +649,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__
                     __syncthreads();
                     if (!lu_valid) {
                         if (a.scale_residuals) inv_h_lu = inv_h;
-                        rope_factor(s, a, mr, mcr, mci, inv_h_lu);
+                        rope_factor<FD>(s, a, mr, mcr, mci, inv_h_lu);
                         cnt[CN_NLU]++;
                         lu_valid = true;
                     }
@@ -619,6 +731,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__
                     if (current_jac) break;
                     for (int c = tid; c < N; c += nthr) s.yJ[c] = s.y[c];     // J = jac(t, y) (:643)
                     __syncthreads();
+                    if (FD) rope_num_jac(s);
                     cnt[CN_NJEV]++;
                     current_jac = true; lu_valid = false;
                 }
@@ -695,6 +808,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k2_kernel(const __grid_constant__
             if (recompute) {
                 for (int c = tid; c < N; c += nthr) s.yJ[c] = s.y[c];
                 __syncthreads();
+                if (FD) rope_num_jac(s);
                 cnt[CN_NJEV]++;
                 current_jac = true;
             } else current_jac = false;
@@ -769,9 +883,13 @@ bool k2_use_global(int64_t B, int sms) {
     return B >= (int64_t)(sms > 0 ? sms : 148) * 4;
 }
 
-size_t k2_scratch_bytes(int n, int sms, int64_t B) {
+// finite-difference mode: band of J, four vectors, flags (per CTA, behind its regular slice)
+size_t k2_fd_doubles(int N) { return (size_t)N * (KL + KU + 1) + 4 * (size_t)N + ((size_t)N * sizeof(int) + 7) / 8 + 1; }
+
+size_t k2_scratch_bytes(int n, int sms, int64_t B, bool fd) {
     size_t bytes = sizeof(double) * n + ((sizeof(int32_t) * n + 7) / 8) * 8;
     const int nsm = sms > 0 ? sms : 148;
+    if (fd) return bytes + (size_t)nsm * K2G_PER_SM * (k2_smem_doubles(n, true) + k2_fd_doubles(n)) * sizeof(double);
     if (k2_use_global(B, sms)) bytes += (size_t)nsm * K2G_PER_SM * k2_smem_doubles(n, true) * sizeof(double);
     else if (!k2_complex_fits(n)) bytes += (size_t)nsm * 2 * n * WB * sizeof(double);
     return bytes;
@@ -782,7 +900,8 @@ int k2_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, i
     const int N = a_in.n;
     if (N <= 0 || N % 5 != 0 || N < 10) return BRDAE_ERR_BAD_ARGUMENT;
     const int nsm = sms > 0 ? sms : 148;
-    const bool global_state = k2_use_global(a_in.B, sms);
+    const bool fd = a_in.jac_fd != 0;
+    const bool global_state = fd || k2_use_global(a_in.B, sms);      // the finite-difference mode always keeps its state in global memory
     const bool cfits = k2_complex_fits(N);
     size_t smem = global_state ? 0 : k2_smem_doubles(N, cfits) * 8;
     if (smem > kSmemBudget) return BRDAE_ERR_UNSUPPORTED;          // more than ~170 nodes in shared-memory mode
@@ -812,11 +931,14 @@ int k2_npendulum(bool dense_mass, const SolveArgs &a_in, const brdae_batch *b, i
     K2Cfg cfg;
     cfg.complex_in_smem = cfits ? 1 : 0;
     cfg.state_in_global = global_state ? 1 : 0;
-    cfg.scratch_stride = global_state ? k2_smem_doubles(N, true) : (size_t)2 * N * WB;
-    if (global_state) {
-        k2_kernel<K2G_BLOCK, K2G_PER_SM><<<(int)grid, K2G_BLOCK, 0, stream>>>(a, cfg);
+    cfg.scratch_stride = global_state ? k2_smem_doubles(N, true) + (fd ? k2_fd_doubles(N) : 0) : (size_t)2 * N * WB;
+    cfg.fd_offset = k2_smem_doubles(N, true);
+    if (fd) {
+        k2_kernel<K2G_BLOCK, K2G_PER_SM, true><<<(int)grid, K2G_BLOCK, 0, stream>>>(a, cfg);
+    } else if (global_state) {
+        k2_kernel<K2G_BLOCK, K2G_PER_SM, false><<<(int)grid, K2G_BLOCK, 0, stream>>>(a, cfg);
     } else {
-        auto kern = k2_kernel<K2_BLOCK, 1>;
+        auto kern = k2_kernel<K2_BLOCK, 1, false>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BRDAE_ERR_CUDA;
         kern<<<(int)grid, K2_BLOCK, smem, stream>>>(a, cfg);
     }

@@ -23,7 +23,7 @@ int k1_extra(int problem, bool dense_mass, const SolveArgs &a, int sms, cudaStre
 int k1_user(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 // CTA-per-system banded kernel for the n-pendulum chain (k2_npendulum.cu)
 int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
-size_t k2_scratch_bytes(int n, int sms, int64_t B);
+size_t k2_scratch_bytes(int n, int sms, int64_t B, bool fd);
 // lane-per-rope block-elimination kernel for the chain (k4_chain.cu, chain_k4.cuh)
 int k4_chain(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 size_t k4_scratch_bytes(int n, int64_t B, int sms);

@@ -214,6 +214,9 @@ def main():
     save("fd_pendulum2", E.pendulum_ensemble(8, t_end=1.0, index=2), dict(jac=None))
     save("fd_robertson", E.robertson_ensemble(8, t_end=1e3), dict(jac=None))
     save("fd_transistor", E.transistor_ensemble(4, t_end=0.05), dict(jac=None))
+    # the reference's OWN chain configuration: jac=None with the banded jac_sparsity (recursive_pendulum.py:128, 165-166)
+    save("fd_npendulum_n4", E.npendulum_ensemble(3, n_nodes=4), dict(jac=None))
+    save("fd_npendulum_n20", E.npendulum_ensemble(2, n_nodes=20), dict(jac=None))
     # --- a user problem (plugin path): the batch reactor of the reference's tests/reactor.py with the script's
     #     options, analytic Jacobian and the script's own jac=None
     save("user_reactor", E.reactor_ensemble(8))

@@ -93,6 +93,11 @@ def run_reference(ens, over=None, build_system=None):
             mass = mm
         if fd:
             jac = None
+            if ens["problem"] == "npendulum" and "jac_sparsity" not in opts:
+                # the reference's own chain run: banded sparsity for num_jac's column groups (recursive_pendulum.py:165-166)
+                import scipy.sparse
+                opts["jac_sparsity"] = scipy.sparse.diags(diagonals=[np.ones(n - abs(k)) for k in range(-10, 10)],
+                                                          offsets=list(range(-10, 10)), format="csc")
         with contextlib.redirect_stdout(io.StringIO()):
             solver = RadauDAE(fun, t0, np.array(ens["y0"][i], dtype=float), tf, jac=jac, mass_matrix=mass,
                               var_index=None if vi is None else np.asarray(vi, dtype=float), **opts)

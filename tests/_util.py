@@ -281,6 +281,7 @@ def well_conditioned(name):
                     "ens_pendulum1_tend2", "opt_pendulum3_max_step", "opt_pendulum3_nmax_step",
                     "opt_pendulum3_dense_mass", "opt_pendulum3_backward", "opt_pendulum3_controller_off",
                     "ens_npendulum_n4", "ens_npendulum_n10", "ens_npendulum_n20", "ens_npendulum_n50", "ens_npendulum_n100",
+                    "fd_npendulum_n4", "fd_npendulum_n20",
                     "script_robertson",
                     "kat_jay", "kat_polydae2", "kat_linear7_with_mass", "kat_linear7_without_mass", "kat_robertson_ode")
 

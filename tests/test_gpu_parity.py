@@ -51,6 +51,10 @@ def _need_gpu():
     ("fd_jacobian_pendulum1", lambda: E.pendulum_ensemble(128, index=1), dict(jac=None)),
     ("fd_jacobian_robertson", lambda: E.robertson_ensemble(512, t_end=1e3), dict(jac=None)),
     ("fd_jacobian_dense_mass", lambda: E.pendulum_ensemble(64), dict(jac=None, mass_matrix=np.diag([1., 1, 1, 1, 0]) * 1.5)),
+    # the chain with the reference's own default, jac=None: banded finite differences on the band kernel (17 column groups)
+    ("fd_jacobian_npendulum_n6", lambda: E.npendulum_ensemble(40, n_nodes=6, t_end=1.0), dict(jac=None)),
+    ("fd_jacobian_npendulum_n20", lambda: E.npendulum_ensemble(3, n_nodes=20, t_end=1.5), dict(jac=None)),
+    ("fd_jacobian_npendulum_n50", lambda: E.npendulum_ensemble(2, n_nodes=50, t_end=0.3), dict(jac=None)),
     ("pendulum3_long_t_eval", lambda: E.pendulum_ensemble(128, n_t_eval=401), {}),   # > K1_TEVAL_SHARED points
     ("ragged_sizes_1", lambda: E.pendulum_ensemble(1), {}),
     ("ragged_sizes_33", lambda: E.pendulum_ensemble(33), {}),
