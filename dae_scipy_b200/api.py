@@ -259,8 +259,10 @@ def prepare(problem, t_span, y0_shape, *, t_eval=None, rtol=1e-3, atol=1e-6, mas
     extraneous = {k: options.pop(k) for k in list(options) if k not in _abi.SOLVER_OPTION_NAMES}
     warn_extraneous(extraneous)
     opts = _abi.make_options(jac_finite_differences=fd, **options)
-    if n > 8 and prob.name != "npendulum":
-        raise ValueError("thread-per-system kernels support at most 8 unknowns.")
+    if n > 8 and prob.name != "npendulum" and prob.band is None:
+        raise ValueError("thread-per-system kernels support at most 8 unknowns (larger banded systems: compile_band_problem).")
+    if prob.band is not None and (mass is not None or jac_const is not None):
+        raise ValueError("a band problem runs with its own diag(0/1) mass matrix and a finite-difference Jacobian.")
     return HostBatch(problem=prob, n=n, B=B, t0=t0, t_bound=tf, t_eval=te, rtol=rtol, atol=at,
                      var_index=vi, mass=mass, jac_const=jac_const, options=opts)
 
@@ -538,7 +540,8 @@ def solve_ivp_batched(problem, t_span, y0, params=None, *, method=RadauDAE, t_ev
     if callable(events):
         events = (events,)
     device_events = None
-    if events and all(isinstance(ev, (LinearEvent, FunctorEvent)) for ev in events) and get_problem(problem).name != "npendulum":
+    if (events and all(isinstance(ev, (LinearEvent, FunctorEvent)) for ev in events) and get_problem(problem).name != "npendulum"
+            and get_problem(problem).band is None):
         device_events, events = tuple(events), None       # located by the kernel; nothing to do on the host
         if int(max_events) < 1:
             raise ValueError("`max_events` (occurrences recorded per event and system) must be at least 1.")

@@ -18,8 +18,9 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbrdae.so")
 
 SOURCES = ["brdae_abi.cu", "dispatch.cu", "k1_pendulum.cu", "k1_robertson.cu", "k1_transistor.cu", "k1_extra.cu",
-           "k2_npendulum.cu", "k4_chain.cu", "fp64_peak.cu", "layout.cu", "k1_user.cu"]
+           "k2_npendulum.cu", "k4_chain.cu", "fp64_peak.cu", "layout.cu", "k1_user.cu", "k2_user.cu"]
 USER_TU = "k1_user.cu"       # stub in the stock library, the user's functor in a plugin build
+USER_BAND_TU = "k2_user.cu"  # the same for a band problem with more than 8 unknowns (K2)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -76,12 +77,14 @@ def build_variant(tag: str, defines: dict) -> str:
     return lib
 
 
-def build_plugin(header: str, lib: str) -> str:
-    """Plugin build: compile k1_user.cu WITH the user's problem header and link it, in place of the stub,
-    with the stock objects into `lib` -- a complete libbrdae whose problem BRDAE_USER is that functor."""
+def build_plugin(header: str, lib: str, band: bool = False) -> str:
+    """Plugin build: compile k1_user.cu (band problems: k2_user.cu) WITH the user's problem header and link it, in place of
+    the stub, with the stock objects into `lib` -- a complete libbrdae whose problem BRDAE_USER is that functor."""
     build()                                                  # the stock objects (no-op when up to date)
-    obj = os.path.splitext(lib)[0] + ".k1_user.o"
-    cmd = [_nvcc(), *NVCC_FLAGS, f'-DBRDAE_USER_HEADER="{os.path.abspath(header)}"', "-c",
+    USER_TU = USER_BAND_TU if band else globals()["USER_TU"]
+    macro = "BRDAE_USER_BAND_HEADER" if band else "BRDAE_USER_HEADER"
+    obj = os.path.splitext(lib)[0] + "." + USER_TU.replace(".cu", ".o")
+    cmd = [_nvcc(), *NVCC_FLAGS, f'-D{macro}="{os.path.abspath(header)}"', "-c",
            os.path.join(CSRC, USER_TU), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -51,7 +51,7 @@ int brdae_problem_lookup(const char *name, int32_t *problem, int32_t *n, int32_t
             if (n_params) *n_params = p.n_params;
             return BRDAE_OK;
         }
-    if (const ProblemInfo *u = user_problem_info())        // plugin build: "user" or the functor's own name
+    if (const ProblemInfo *u = find_problem(BRDAE_USER))   // plugin build: "user" or the functor's own name
         if (std::strcmp(name, "user") == 0 || std::strcmp(name, u->name) == 0) {
             if (problem) *problem = u->id;
             if (n) *n = u->n;
@@ -79,6 +79,8 @@ size_t brdae_workspace_bytes(const brdae_batch *b, const brdae_options *o) {
         const bool fd = o && o->jac_finite_differences && !b->jac_const;      // finite differences: the band kernel
         bytes += (!fd && npendulum_uses_k4(b->n, b->n_systems)) ? k4_scratch_bytes(b->n, b->n_systems, sm_count())
                                                                   : k2_scratch_bytes(b->n, sm_count(), b->n_systems, fd);
+    } else if (is_large_problem(b->problem)) {      // user band problem
+        bytes += k2_user_scratch_bytes(b->n, sm_count(), b->n_systems, o && o->jac_finite_differences && !b->jac_const);
     } else {      // K1: per-CTA slice of cold per-lane state (kernels that keep it in shared memory need none)
         LaunchGeom g{};
         const bool fd = o && o->jac_finite_differences && !b->jac_const;
@@ -111,7 +113,7 @@ static int solve_impl(const brdae_batch *b, const brdae_options *o, void *worksp
     SolveArgs a;
     fill_common(a, b, o, workspace);
     if (rows) {
-        if (b->problem == BRDAE_NPENDULUM) return BRDAE_ERR_UNSUPPORTED;      // the chain kernels are structure-of-arrays only
+        if (is_large_problem(b->problem)) return BRDAE_ERR_UNSUPPORTED;       // the chain / band kernels are structure-of-arrays only
         const int64_t n = b->n, T = b->n_t_eval;
         a.y0_sc = 1; a.y0_sb = n; a.par_sc = 1; a.par_sb = b->n_params;
         a.ye_st = n; a.ye_sc = 1; a.ye_sb = n * T;      // the n unknowns of an output point are one 8n-byte run
@@ -373,7 +375,7 @@ int brdae_solve_host_rows(const brdae_batch *hb, const brdae_options *o) {
     if (hb->dense_cap > 0 || hb->n_events > 0 || hb->report_cap > 0) return BRDAE_ERR_UNSUPPORTED;
     const int64_t B = hb->n_systems;
     if (B == 0) return BRDAE_OK;
-    if (hb->problem != BRDAE_NPENDULUM && !std::getenv("BRDAE_ROWS_CHUNKED")) return host_rows_single_launch(hb, o);
+    if (!is_large_problem(hb->problem) && !std::getenv("BRDAE_ROWS_CHUNKED")) return host_rows_single_launch(hb, o);
     const int n = hb->n, T = hb->n_t_eval, np = hb->n_params;
     const int64_t in_rows = (int64_t)(n > np ? n : np);
     // Chunked pipeline: about 128k systems per chunk (at most 16 chunks), three buffer sets, two compute

@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "host_args.hpp"
 #include "kernels.cuh"
 
 namespace brdae {
@@ -31,7 +32,9 @@ static int route(int problem, bool dense_mass, const SolveArgs &a, const brdae_b
         return k2_npendulum(dense_mass, a, b, sms, s, g, geom_only);
     case BRDAE_ROBERTSON_ODE: case BRDAE_JAY: case BRDAE_POLYDAE2: case BRDAE_LINEAR7:
         return k1_extra(problem, dense_mass, a, sms, s, g, geom_only);
-    case BRDAE_USER: return k1_user(dense_mass, a, sms, s, g, geom_only);
+    case BRDAE_USER:
+        if (user_band_problem_info()) return k2_user(dense_mass, a, b, sms, s, g, geom_only);      // band problem of a plugin build
+        return k1_user(dense_mass, a, sms, s, g, geom_only);
     }
     return BRDAE_ERR_UNKNOWN_PROBLEM;
 }

@@ -21,12 +21,15 @@ static const ProblemInfo kProblems[] = {
     {"polydae2", BRDAE_POLYDAE2, 2, 5}, {"linear7", BRDAE_LINEAR7, 7, 7},
 };
 
-// the problem of a plugin build (k1_user.cu), nullptr in the stock library
+// the problem of a plugin build: thread-per-system functor (k1_user.cu) or band problem (k2_user.cu); nullptr in the stock library
 const ProblemInfo *user_problem_info();
+const ProblemInfo *user_band_problem_info();
+// problems whose state does not fit a lane: CTA-per-system / lane-per-rope kernels, structure-of-arrays batches only
+inline bool is_large_problem(int32_t id) { return id == BRDAE_NPENDULUM || (id == BRDAE_USER && user_band_problem_info() != nullptr); }
 
 inline const ProblemInfo *find_problem(int32_t id) {
     for (const auto &p : kProblems) if (p.id == id) return &p;
-    if (id == BRDAE_USER) return user_problem_info();
+    if (id == BRDAE_USER) return user_band_problem_info() ? user_band_problem_info() : user_problem_info();
     return nullptr;
 }
 
@@ -47,7 +50,7 @@ inline int validate(const brdae_batch *b, const brdae_options *o) {
     if (b->dense_cap < 0 || (b->dense_cap > 0 && !(b->dense_t && b->dense_y && b->dense_q))) return BRDAE_ERR_BAD_ARGUMENT;
     if (b->n_events < 0 || b->n_events > BRDAE_MAX_EVENTS) return BRDAE_ERR_BAD_ARGUMENT;
     if (b->n_events > 0) {
-        if (b->problem == BRDAE_NPENDULUM) return BRDAE_ERR_UNSUPPORTED;      // thread-per-system kernels only
+        if (is_large_problem(b->problem)) return BRDAE_ERR_UNSUPPORTED;       // thread-per-system kernels only
         if (b->event_cap < 1 || !b->event_coef || !b->event_level || !b->event_direction || !b->event_terminal) return BRDAE_ERR_BAD_ARGUMENT;
         if (b->n_systems > 0 && (!b->event_count || !b->event_t)) return BRDAE_ERR_BAD_ARGUMENT;
         for (int e = 0; e < b->n_events; ++e) {

@@ -109,5 +109,35 @@ def reactor_ensemble(B, t_end=20.0, n_t_eval=21, seed=4):
                              mass_matrix="problem", var_index=np.array([0, 1, 1], dtype=np.int32)))
 
 
+# ---------------------------------------------------------------- a USER BAND problem (more than 8 unknowns, CTA-per-system kernel)
+# A reaction-diffusion rod by the method of lines with algebraic boundary rows (an index-1 DAE, tridiagonal Jacobian):
+#   0 = u_0 - (1 + a sin(w t));   u_i' = D (n-1)^2 (u_{i-1} - 2 u_i + u_{i+1}) - k u_i^3;   0 = u_{n-1} - u_{n-2}
+ROD_N = 48
+ROD_RHS_ROW = """if (i == 0) return y[0] - (1.0 + p[2] * sin(p[3] * t));
+                 if (i == n - 1) return y[n - 1] - y[n - 2];
+                 const double s = (double)(n - 1) * (double)(n - 1);
+                 return (p[0] * s) * ((y[i - 1] - 2.0 * y[i]) + y[i + 1]) - p[1] * ((y[i] * y[i]) * y[i]);"""
+
+
+def rod_problem():
+    """Compile (once, cached) and register the rod as a band problem (kl = ku = 1, jac=None); returns its `Problem`."""
+    from .plugin import compile_band_problem
+    diag = (0,) + (1,) * (ROD_N - 2) + (0,)
+    return compile_band_problem("rod", ROD_N, 1, 1, ROD_RHS_ROW, mass_row="i != 0 && i != n - 1", mass_diag=diag,
+                                param_names=("D", "k", "a", "w"), param_defaults=(0.05, 2.0, 0.5, 6.0), t_span=(0.0, 2.0))
+
+
+def rod_ensemble(B, t_end=2.0, n_t_eval=11, seed=5):
+    """D = 0.05 * 10**U(-0.5, 0.5), k = 2 * 10**U(-0.5, 0.5), a = U(0.2, 0.8), w = U(3, 9); u(0) = 1 (consistent)."""
+    rng = np.random.default_rng(seed)
+    u = rng.random((B, 4))
+    params = np.stack([0.05 * 10.0 ** (u[:, 0] - 0.5), 2.0 * 10.0 ** (u[:, 1] - 0.5), 0.2 + 0.6 * u[:, 2], 3.0 + 6.0 * u[:, 3]], axis=1)
+    vi = np.zeros(ROD_N, dtype=np.int32)
+    vi[0] = vi[-1] = 1
+    return dict(problem="rod", t_span=(0.0, float(t_end)), y0=np.ones((B, ROD_N)), params=params,
+                t_eval=np.linspace(0.0, t_end, n_t_eval),
+                options=dict(rtol=1e-6, atol=1e-8, first_step=1e-6, jac=None, mass_matrix="problem", var_index=vi))
+
+
 ENSEMBLES = {"pendulum": pendulum_ensemble, "robertson": robertson_ensemble,
              "transistor": transistor_ensemble, "npendulum": npendulum_ensemble}

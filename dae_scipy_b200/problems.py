@@ -36,6 +36,7 @@ class Problem:
     lib_path: str | None = None
     header_path: str | None = None
     n_event_functions: int = 0      # (nonlinear) event functions compiled into the functor: FunctorEvent(k), k < this
+    band: tuple | None = None       # user band problem (more than 8 unknowns, CTA-per-system kernel): (kl, ku) of df/dy
 
     @property
     def n_params(self):

@@ -221,6 +221,8 @@ def main():
     #     options, analytic Jacobian and the script's own jac=None
     save("user_reactor", E.reactor_ensemble(8))
     save("user_reactor_fd", E.reactor_ensemble(8), dict(jac=None))
+    # --- a user BAND problem (48 unknowns, tridiagonal Jacobian by finite differences with jac_sparsity)
+    save("user_rod", E.rod_ensemble(6))
     # --- events (scipy's solve_ivp driving the reference solver)
     save_events("events_pendulum3", E.pendulum_ensemble(6, t_end=3.0, n_t_eval=31))
     # --- n-pendulum chains (dense analytic Jacobian handed to the reference)

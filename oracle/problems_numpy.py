@@ -143,6 +143,25 @@ def reactor(k=1.47, Ca0=0.0209, Cb0=0.0209 / 3):
     return fun, jac, mass, np.array([0, 1, 1])
 
 
+# ------------------------------------------------------------------------- reaction-diffusion rod (user band problem)
+def rod(D=0.05, k=2.0, a=0.5, w=6.0, n=48):
+    """The band example of dae_scipy_b200.ensembles (ROD_RHS_ROW) as a numpy closure: method of lines with algebraic boundary
+    rows; no analytic Jacobian (jac=None with a tridiagonal `jac_sparsity`, like the reference's own chain script)."""
+    diag = np.ones(n)
+    diag[0] = diag[-1] = 0.0
+    s = float(n - 1) * float(n - 1)
+
+    def fun(t, y):
+        f = np.empty_like(y)
+        f[0] = y[0] - (1.0 + a * np.sin(w * t))
+        f[-1] = y[-1] - y[-2]
+        f[1:-1] = (D * s) * ((y[:-2] - 2.0 * y[1:-1]) + y[2:]) - k * ((y[1:-1] * y[1:-1]) * y[1:-1])
+        return f
+    vi = np.zeros(n, dtype=int)
+    vi[0] = vi[-1] = 1
+    return fun, None, np.diag(diag), vi
+
+
 # ------------------------------------------------------------------------- Jay 1995
 def jay(nonlinear=1.0):
     """Index-3 DAE of Jay 1995, jay_dae.py:22-68 (y1, y2, z1, z2, lambda).  The reference has no
@@ -392,4 +411,6 @@ def build(problem, params=(), n=None):
         return linear7(*params)
     if problem == "reactor":
         return reactor(*params)
+    if problem == "rod":
+        return rod(*params, n=n)
     raise ValueError(problem)

@@ -93,6 +93,9 @@ def run_reference(ens, over=None, build_system=None):
             mass = mm
         if fd:
             jac = None
+            if ens["problem"] == "rod" and "jac_sparsity" not in opts:      # the band example: tridiagonal
+                import scipy.sparse
+                opts["jac_sparsity"] = scipy.sparse.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1], format="csc")
             if ens["problem"] == "npendulum" and "jac_sparsity" not in opts:
                 # the reference's own chain run: banded sparsity for num_jac's column groups (recursive_pendulum.py:165-166)
                 import scipy.sparse

@@ -36,9 +36,10 @@ const ProblemInfo *user_problem_info() {
     static const ProblemInfo pi{UserProblem::name(), BRDAE_USER, UserProblem::N, UserProblem::NP};
     return &pi;
 }
+const ProblemInfo *user_band_problem_info() { return nullptr; }
 }
 #else
-namespace brdae { const ProblemInfo *user_problem_info() { return nullptr; } }
+namespace brdae { const ProblemInfo *user_problem_info() { return nullptr; } const ProblemInfo *user_band_problem_info() { return nullptr; } }
 #endif
 
 using namespace brdae;

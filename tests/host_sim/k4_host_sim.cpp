@@ -10,7 +10,7 @@
 #include "../../dae_scipy_b200/csrc/host_args.hpp"
 #include "../../dae_scipy_b200/csrc/chain_k4.cuh"
 
-namespace brdae { const ProblemInfo *user_problem_info() { return nullptr; } }
+namespace brdae { const ProblemInfo *user_problem_info() { return nullptr; } const ProblemInfo *user_band_problem_info() { return nullptr; } }
 using namespace brdae;
 
 extern "C" int sim_solve_chain(const brdae_batch *b, const brdae_options *o) {

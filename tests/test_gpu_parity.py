@@ -393,6 +393,34 @@ def test_gpu_user_problem_plugin_against_kernel_source_and_reference_fixture():
     assert scaled_error(dense["y"], sim["y"], 1e-6, 1e-7) <= PARITY_FACTOR
 
 
+def test_gpu_user_band_problem_against_the_reference():
+    """A user problem with MORE THAN 8 unknowns (compile_band_problem: 48-unknown reaction-diffusion rod with algebraic
+    boundary rows, tridiagonal Jacobian by finite differences) on the CTA-per-system band kernel: the reference's own run
+    of the same problem (fixture user_rod.npz, generated with jac=None + jac_sparsity) within tolerance and with identical
+    step counts, and a larger ensemble against the numpy restatement of the reference."""
+    from test_user_problem import rod_numpy_oracle
+    E.rod_problem()
+    ens, ref = load_golden("user_rod")
+    out = run_gpu(ens)
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["n_eval"], ref["n_eval"])
+    err = scaled_error(out["y"], ref["y"], 1e-6, 1e-8)
+    same = count_agreement(out["counters"], ref["counters"])
+    print(f"rod fixture: max scaled error {err:.3g}, identical counts {same:.3f}, nfev/njev/nlu {out['counters'][:, :3].tolist()} vs {ref['counters'][:, :3].tolist()}")
+    assert err <= PARITY_FACTOR and same >= 0.99
+    ens = E.rod_ensemble(300)                      # more systems than resident CTAs of a small launch: refills
+    out = run_gpu(ens)
+    assert (out["status"] == 0).all() and (out["n_eval"] == len(ens["t_eval"])).all()
+    y = out["y"]
+    t = ens["t_eval"][None, :]
+    a, w = ens["params"][:, 2:3], ens["params"][:, 3:4]
+    assert np.abs(y[:, 0, :] - (1.0 + a * np.sin(w * t))).max() < 1e-5          # the algebraic boundary rows hold
+    assert np.abs(y[:, -1, :] - y[:, -2, :]).max() < 1e-5
+    first = dict(ens, y0=ens["y0"][:24], params=ens["params"][:24])
+    orc = rod_numpy_oracle(first)
+    assert scaled_error(out["y"][:24], orc["y"], 1e-6, 1e-8) <= PARITY_FACTOR
+    assert count_agreement(out["counters"][:24], orc["counters"]) >= 0.95
+
+
 def test_gpu_user_problem_stiff_forced_oscillator_against_numpy_oracle():
     """A user functor with a time-dependent right-hand side and a libm call (device sin differs from glibc by <= 2 ulp:
     tolerance, not bits) against the reference-equivalent numpy oracle driven by the closure form of the problem."""

@@ -192,3 +192,61 @@ def test_user_event_functions_are_located_by_the_kernel():
     assert out["event_count"][:, 1].sum() > 0             # the observer fired too
     with pytest.raises(ValueError):
         U.run_kernel_source_on_cpu(ens, events=[FunctorEvent(2)])          # only two event functions were compiled
+
+
+# ---------------------------------------------------------------- band problems with more than 8 unknowns (CTA-per-system kernel)
+def rod_numpy_oracle(ens):
+    """The numpy restatement of the reference on the rod ensemble (finite-difference Jacobian, like the fixture)."""
+    from oracle import radau_numpy as orc, problems_numpy as prob
+    B, n = ens["y0"].shape
+    T = len(ens["t_eval"])
+    o = dict(ens["options"])
+    o.pop("mass_matrix"); vi = o.pop("var_index"); o.pop("jac")
+    out = dict(y=np.full((B, n, T), np.nan), counters=np.zeros((B, 9), np.int32), status=np.zeros(B, np.int32), n_eval=np.zeros(B, np.int32))
+    for i in range(B):
+        fun, _, mass, _ = prob.build("rod", ens["params"][i], n)
+        r = orc.solve(fun, ens["t_span"], ens["y0"][i], jac=None, mass_matrix=mass, var_index=np.asarray(vi, float),
+                      t_eval=ens["t_eval"], **o)
+        out["y"][i, :, :r.y.shape[1]] = r.y
+        out["counters"][i] = r.counters.as_array()
+        out["status"][i] = r.status
+        out["n_eval"][i] = r.y.shape[1]
+    return out
+
+
+def test_band_problem_header_build_and_abi():
+    text = plugin.generate_band_header("rod", 48, 4, 1, 1, E.ROD_RHS_ROW, "i != 0 && i != n - 1")
+    assert "struct UserBand" in text and "KL = 1, KU = 1" in text and "N = 48, NP = 4" in text
+    with pytest.raises(ValueError):
+        plugin.generate_band_header("rod", 48, 0, 20, 12, "return 0.0;")        # kl + ku > 31
+    with pytest.raises(ValueError):
+        plugin.generate_band_header("rod", 48, 0, 1, 1, "y[i];")                # nothing returned
+    prob = E.rod_problem()
+    assert prob.problem_id == plugin.BRDAE_USER and prob.n == 48 and prob.band == (1, 1) and not prob.has_jac
+    lib = _abi.load(prob.lib_path)
+    for sym in _abi.EXPORTED_SYMBOLS:                                           # a complete libbrdae: the same C ABI
+        getattr(lib, sym)
+    pid, n, npar = C.c_int32(-1), C.c_int32(-1), C.c_int32(-1)
+    for name in (b"rod", b"user"):
+        assert lib.brdae_problem_lookup(name, C.byref(pid), C.byref(n), C.byref(npar)) == 0
+        assert (pid.value, n.value, npar.value) == (100, 48, 4)
+    assert lib.brdae_problem_lookup(b"npendulum", C.byref(pid), C.byref(n), C.byref(npar)) == 0       # the stock problems are still there
+    ens = E.rod_ensemble(4)
+    hb = br.prepare(prob, ens["t_span"], ens["y0"].shape, t_eval=ens["t_eval"], **ens["options"])
+    assert hb.n == 48 and hb.options.jac_finite_differences == 1 and hb.mass is None
+    assert hb.var_index.tolist() == [1] + [0] * 46 + [1]
+    with pytest.raises(ValueError, match="finite-difference"):
+        br.prepare(prob, ens["t_span"], ens["y0"].shape, **dict(ens["options"], mass_matrix=np.eye(48)))
+    with pytest.raises(ValueError, match="8 unknowns"):                         # a thread-per-system functor stays at n <= 8
+        plugin.generate_header("big", 9, 0, "f[0] = 0;")
+
+
+def test_rod_numpy_oracle_reproduces_the_reference_fixture():
+    """The band example's fixture comes from the reference itself (jac=None with the tridiagonal jac_sparsity); the numpy
+    restatement with the dense finite-difference Jacobian gives the same run: bands of a finite-difference Jacobian do not
+    depend on how the columns are grouped."""
+    ens, ref = U.load_golden("user_rod")
+    out = rod_numpy_oracle(ens)
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["n_eval"], ref["n_eval"])
+    assert U.scaled_error(out["y"], ref["y"], 1e-6, 1e-8) <= 1.0
+    assert U.count_agreement(out["counters"], ref["counters"]) == 1.0
