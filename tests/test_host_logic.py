@@ -69,9 +69,9 @@ def test_option_defaults_follow_the_reference_constructor():
     assert _prep(var_index=None).var_index.tolist() == [0] * 5
     assert o.jac_finite_differences == 0
     assert _prep(jac=None).options.jac_finite_differences == 1      # reference default: finite differences
-    with pytest.raises(NotImplementedError):                        # not for the chain kernels
-        e = br.ensembles.npendulum_ensemble(2, n_nodes=4)
-        br.prepare(e["problem"], e["t_span"], e["y0"].shape, t_eval=e["t_eval"], **dict(e["options"], jac=None))
+    e = br.ensembles.npendulum_ensemble(2, n_nodes=4)               # the chain too (band kernel, the reference's own default)
+    hbc = br.prepare(e["problem"], e["t_span"], e["y0"].shape, t_eval=e["t_eval"], **dict(e["options"], jac=None))
+    assert hbc.options.jac_finite_differences == 1
 
 
 def test_ensembles_are_seeded_and_prefix_stable():
