@@ -60,11 +60,17 @@ struct NodeRef { const double *ld; double *st; };
 // long scoreboard, 252 registers -- none left to issue the next node's loads early; L1/L2 prefetch instructions gained 6 %,
 // profiles/r02_k4_ncu_summary.md).  Here the warp's elected lane asks the TMA unit for the block of the node(s) ahead
 // (cp.async.bulk global -> shared, completion on an mbarrier) while the lanes compute the current node out of shared memory:
-// a ring of three node buffers per warp -- current, look-ahead (forward sweeps read the next node's state early; backward
-// sweeps the previous node's rod quantities), in flight.  Stores go straight to global memory; a sweep begins with
+// a ring of three node buffers per warp -- current and two ahead (forward sweeps read the next node's state during a visit; backward
+// sweeps carry what they need of the previous node in registers).  Stores go straight to global memory; a sweep begins with
 // fence.proxy.async so that the stores of the sweeps before it are ordered before its bulk reads.
 // Buffer b's k-th use completes phase k of its mbarrier; the use counts live next to the barriers in shared memory because the
 // set of active lanes (and with it the elected lane) changes from sweep to sweep.
+#ifndef BRDAE_K4_UNROLL
+#define BRDAE_K4_UNROLL 1        // node loops of the Newton sweeps: 1 = rolled
+#endif
+#define K4_STR2(x) #x
+#define K4_STR(x) K4_STR2(x)
+#define K4_NEWTON_UNROLL K4_STR(unroll BRDAE_K4_UNROLL)
 #ifndef BRDAE_K4_STAGED
 #define BRDAE_K4_STAGED 1
 #endif
@@ -141,7 +147,7 @@ struct Stager<STRIDE, true> {
         asm volatile("fence.proxy.async.global;" ::: "memory");     // this lane's earlier stores before the bulk reads below
         __syncwarp(mask);
         next = first; waited = first - dir_;
-        fill(first + dir_);
+        fill(first + dir_);          // (the third buffer is requested by the first step())
     }
     __device__ void fill(int upto) {            // issue every node up to `upto` (inclusive) that has not been issued yet
         while (dir > 0 ? (next <= upto && next < nn) : (next >= upto && next >= 0)) {
@@ -149,11 +155,12 @@ struct Stager<STRIDE, true> {
             next += dir;
         }
     }
-    // top of the visit of node i: the buffer of the node left two visits ago is free; forward sweeps keep two nodes ahead
-    // (the next one is read during this visit), backward sweeps one (the previous node's buffer is still read)
+    // top of the visit of node i: the buffer of the node visited before is free (what backward sweeps still need of it, its
+    // rod quantities, they carry in registers): two nodes ahead are in flight while this one is computed; forward sweeps read
+    // the next node during this visit (look-ahead), so that one must have arrived
     __device__ void step(int i) {
         __syncwarp(mask);
-        fill(dir > 0 ? i + 2 : i - 1);
+        fill(dir > 0 ? i + 2 : i - 2);
         __syncwarp(mask);                       // the use counts written by the elected lane
         const int need = dir > 0 ? (i + 1 < nn ? i + 1 : i) : i;
         while (waited != need) { waited += dir; wait(waited); }
@@ -426,15 +433,17 @@ BRDAE_HD void fwd_real(const NodeRef &nb, const Consts &k, int i, double mrf, co
 // one step of the real back substitution at node i: u = solution block of node i+1 on entry, of node i on exit;
 // d = (dx, dy, dvx, dvy, dlambda) of node i
 template <int STRIDE>
-BRDAE_HD void bwd_real(const NodeRef &nb, const NodeRef &nbn, const Consts &k, int i, double mrf, double (&u)[3], double (&d)[5]) {
+// `rn` = the rod quantities (adx, ady, bdy, al, bl) of node i+1, carried in registers from its visit: its buffer is already
+// being refilled with the node two visits ahead
+BRDAE_HD void bwd_real(const NodeRef &nb, const double (&rn)[5], const Consts &k, int i, double mrf, double (&u)[3], double (&d)[5]) {
     double un[3];
     if (i == k.nn - 1) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) un[q] = K4L(nb, O_Z + q);
     } else {
         const double im = node_im(k, i);
-        const double adx = K4L(nbn, O_ND + ND_ADX), ady = K4L(nbn, O_ND + ND_ADY), bdy = K4L(nbn, O_ND + ND_BDY);
-        const double U[2][3] = {{im * adx, im * ady, im * K4L(nbn, O_ND + ND_AL)}, {im * ady, im * bdy, im * K4L(nbn, O_ND + ND_BL)}};
+        const double adx = rn[0], ady = rn[1], bdy = rn[2];
+        const double U[2][3] = {{im * adx, im * ady, im * rn[3]}, {im * ady, im * bdy, im * rn[4]}};
         const double w0 = fma(U[0][2], u[2], fma(U[0][1], u[1], U[0][0] * u[0]));
         const double w1 = fma(U[1][2], u[2], fma(U[1][1], u[1], U[1][0] * u[0]));
 #pragma unroll
@@ -470,6 +479,7 @@ BRDAE_HD bool newton_sweeps(STG &S, const Rope<STRIDE> &R, const Consts &k, doub
             const double l0 = y4 + stage_z<0>(w04, w14, w24), l1 = y4 + stage_z<1>(w04, w14, w24), l2 = y4 + stage_z<2>(w04, w14, w24);
             cur[0] = rod(cx[0], cy[0], l0); cur[1] = rod(cx[1], cy[1], l1); cur[2] = rod(cx[2], cy[2], l2);
         }
+_Pragma(K4_NEWTON_UNROLL)
         for (int i = 0; i < k.nn; ++i) {
             S.step(i);
             const NodeRef nb = S.ref(i);
@@ -562,13 +572,14 @@ BRDAE_HD bool newton_sweeps(STG &S, const Rope<STRIDE> &R, const Consts &k, doub
     {   // ---------- backward: block back substitution, velocities, norm, W += dW
         double u[3] = {0, 0, 0}, ur[3] = {0, 0, 0}, ui[3] = {0, 0, 0};
         double s5[5] = {0, 0, 0, 0, 0};
+        double rn[5] = {0, 0, 0, 0, 0};
         S.begin(R, O_W, SPN - O_W, k.nn - 1, -1, k.nn, mb);
+_Pragma(K4_NEWTON_UNROLL)
         for (int i = k.nn - 1; i >= 0; --i) {
             S.step(i);
             const NodeRef nb = S.ref(i);
-            const NodeRef nbn = S.ref(i + 1 < k.nn ? i + 1 : i);
             double d0[5], d1[5], d2[5];
-            bwd_real<STRIDE>(nb, nbn, k, i, mrf, u, d0);
+            bwd_real<STRIDE>(nb, rn, k, i, mrf, u, d0);
             {
                 double nr[3], ni[3];
                 if (i == k.nn - 1) {
@@ -576,8 +587,8 @@ BRDAE_HD bool newton_sweeps(STG &S, const Rope<STRIDE> &R, const Consts &k, doub
                     for (int q = 0; q < 3; ++q) { nr[q] = K4L(nb, O_Z + 3 + q); ni[q] = K4L(nb, O_Z + 6 + q); }
                 } else {
                     const double im = node_im(k, i);
-                    const double adx = K4L(nbn, O_ND + ND_ADX), ady = K4L(nbn, O_ND + ND_ADY), bdy = K4L(nbn, O_ND + ND_BDY);
-                    const double U[2][3] = {{im * adx, im * ady, im * K4L(nbn, O_ND + ND_AL)}, {im * ady, im * bdy, im * K4L(nbn, O_ND + ND_BL)}};
+                    const double adx = rn[0], ady = rn[1], bdy = rn[2];
+                    const double U[2][3] = {{im * adx, im * ady, im * rn[3]}, {im * ady, im * bdy, im * rn[4]}};
                     const double w0r = fma(U[0][2], ur[2], fma(U[0][1], ur[1], U[0][0] * ur[0]));
                     const double w0i = fma(U[0][2], ui[2], fma(U[0][1], ui[1], U[0][0] * ui[0]));
                     const double w1r = fma(U[1][2], ur[2], fma(U[1][1], ur[1], U[1][0] * ur[0]));
@@ -610,6 +621,7 @@ BRDAE_HD bool newton_sweeps(STG &S, const Rope<STRIDE> &R, const Consts &k, doub
                 x = d2[c] * sc; s5[c] = fma(x, x, s5[c]);
                 K4W(nb, O_W + c) = K4L(nb, O_W + c) + d0[c]; K4W(nb, O_W + 5 + c) = K4L(nb, O_W + 5 + c) + d1[c]; K4W(nb, O_W + 10 + c) = K4L(nb, O_W + 10 + c) + d2[c];
             }
+            rn[0] = K4L(nb, O_ND + ND_ADX); rn[1] = K4L(nb, O_ND + ND_ADY); rn[2] = K4L(nb, O_ND + ND_BDY); rn[3] = K4L(nb, O_ND + ND_AL); rn[4] = K4L(nb, O_ND + ND_BL);       // for the visit of node i - 1
         }
         ss = ((s5[0] + s5[1]) + (s5[2] + s5[3])) + s5[4];
     }
@@ -729,14 +741,13 @@ BRDAE_HD double error_sweeps(STG &S, const Rope<STRIDE> &R, const Consts &k, con
             x = xn; y = yn; cur = nxt;
         }
     }
-    double u[3] = {0, 0, 0}, s5[5] = {0, 0, 0, 0, 0};
+    double u[3] = {0, 0, 0}, s5[5] = {0, 0, 0, 0, 0}, rn[5] = {0, 0, 0, 0, 0};
     S.begin(R, O_Y, O_RP + 2 - O_Y, k.nn - 1, -1, k.nn, m);
     for (int i = k.nn - 1; i >= 0; --i) {
         S.step(i);
         const NodeRef nb = S.ref(i);
-        const NodeRef nbn = S.ref(i + 1 < k.nn ? i + 1 : i);
         double d[5];
-        bwd_real<STRIDE>(nb, nbn, k, i, mrf, u, d);
+        bwd_real<STRIDE>(nb, rn, k, i, mrf, u, d);
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
             const int vi = a.var_index_dev[5 * i + c];
@@ -752,6 +763,7 @@ BRDAE_HD double error_sweeps(STG &S, const Rope<STRIDE> &R, const Consts &k, con
             s5[c] = fma(sq, sq, s5[c]);
             K4W(nb, O_ERR + c) = d[c];
         }
+        rn[0] = K4L(nb, O_ND + ND_ADX); rn[1] = K4L(nb, O_ND + ND_ADY); rn[2] = K4L(nb, O_ND + ND_BDY); rn[3] = K4L(nb, O_ND + ND_AL); rn[4] = K4L(nb, O_ND + ND_BL);
     }
     return ((s5[0] + s5[1]) + (s5[2] + s5[3])) + s5[4];
 }

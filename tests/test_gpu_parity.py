@@ -91,6 +91,19 @@ def test_gpu_npendulum_many_ropes_with_refill_and_ragged_warps():
     assert_bit_identical(run_gpu(ens), run_c_oracle(ens), "k4 n=100")
 
 
+@pytest.mark.parametrize("rpw", [1, 2, 4, 8, 16, 32])
+def test_gpu_npendulum_every_ropes_per_warp_geometry(rpw, monkeypatch):
+    """K4 geometries: 1 rope per warp reads its nodes in place, 2 ... 32 ropes per warp stage them through shared memory with
+    TMA bulk copies (ring of three node buffers, csrc/chain_k4.cuh: Stager); partially filled warps, lanes refilled from the
+    work counter (more ropes than lane slots), and an ensemble whose ropes take different numbers of steps."""
+    monkeypatch.setenv("BRDAE_K4_RPW", str(rpw))
+    monkeypatch.setenv("BRDAE_K4_MAX_SLOTS", str(2 * rpw + (rpw > 1)))      # two warps (the second ragged): every lane is refilled
+    ens = E.npendulum_ensemble(71, n_nodes=7, t_end=1.2)
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), f"k4, {rpw} ropes per warp")
+    ens = E.npendulum_ensemble(5, n_nodes=2, t_end=0.5)                       # the shortest chain: every node is first or last
+    assert_bit_identical(run_gpu(ens), run_c_oracle(ens), f"k4 n=2, {rpw} ropes per warp")
+
+
 def test_gpu_npendulum_bench_configurations_first_ropes_bit_identical():
     """BASELINE configs[4] (16,384 ropes, n = 20 / 50 / 100): the first 64 ropes of each bench ensemble, full t_end,
     bit-identical to the scalar oracle (which reproduces the reference's step counts on ens_npendulum_n*.npz)."""
