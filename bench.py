@@ -48,8 +48,8 @@ WORKLOADS = {
 # DRAM traffic of one launch, per system: dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set full` capture of the
 # workload's kernel divided by the systems of the profiled launch; each entry names the committed summary it comes from.
 NCU_DRAM_BYTES_PER_SYSTEM = {
-    "pendulum3_1M_tend2": ((158.95e6 + 334.40e6) / 262144, "profiles/r01_k1_fastpaths.md (v8, 262,144 systems)"),
-    "pendulum3_1M_tend10": ((158.95e6 + 334.40e6) / 262144, "profiles/r01_k1_fastpaths.md (same kernel and output grid as t_end = 2)"),
+    "pendulum3_1M_tend2": ((160.46e6 + 333.03e6) / 262144, "profiles/r02_k1_ncu_summary.md (v9, 262,144 systems)"),
+    "pendulum3_1M_tend10": ((160.46e6 + 333.03e6) / 262144, "profiles/r02_k1_ncu_summary.md (same kernel and output grid as t_end = 2)"),
     "robertson_4M": ((18.2e6 + 71.0e6) / 262144, "profiles/r01_k1_ncu_summary.md (Robertson, 262,144 systems: part of that launch's output was still in L2 at kernel end)"),
     "transistor_256k": ((10.8e6 + 12.9e6) / 65536, "profiles/r01_k1_ncu_summary.md (transistor, 65,536 systems: that launch's output was still in L2 at kernel end)"),
     "npendulum_n20_16k": ((557.1e9 + 186.1e9) / 16384, "profiles/r02_k4_ncu_summary.md (K4 staged, n = 20, 16,384 ropes)"),
