@@ -22,18 +22,71 @@
 
 namespace brdae {
 
-constexpr double RC0 = 0x1.3d8b64657caeap-3, RC1 = 0x1.4a36c0803a6dfp-1;
-constexpr double RE0 = -0x1.418fd8baffe05p+3, RE1 = 0x1.61d41b2d54580p+0, RE2 = -0x1.5555555555555p-2;
-constexpr double MU_REAL = 0x1.d1a48d83e731dp+1;
-constexpr double MU_CR = 0x1.572db93e0c672p+1, MU_CI = -0x1.86747f2c3fcb6p+1;
-constexpr double T00 = 0x1.82d23845d677bp-4, T01 = -0x1.214a74c403bf7p-3, T02 = 0x1.ebff91a6d688ep-6;
-constexpr double T10 = 0x1.0037de70aa1edp-2, T11 = 0x1.a20e91e20b551p-3, T12 = -0x1.8821fa2a36dedp-2;
-constexpr double TI00 = 0x1.0b70201a79c46p+2, TI01 = 0x1.4f8c15da84e86p-2, TI02 = 0x1.0bf7ff59d56efp-1;
-constexpr double TI10 = -0x1.0b70201a79c46p+2, TI11 = -0x1.4f8c15da84e86p-2, TI12 = 0x1.e810014c55221p-2;
-constexpr double TI20 = 0x1.017885a24a7f2p-1, TI21 = -0x1.4934e6fcaa598p+1, TI22 = 0x1.312c0cf7bdfd1p-1;
-constexpr double P00 = 0x1.418fd8baffe05p+3, P01 = -0x1.9a12ce7b30915p+4, P02 = 0x1.f295c43b61425p+3;
-constexpr double P10 = -0x1.61d41b2d54580p+0, P11 = 0x1.497af24bb677ep+3, P12 = -0x1.1d406ee60becfp+3;
-constexpr double P20 = 0x1.5555555555555p-2, P21 = -0x1.5555555555555p+1, P22 = 0x1.aaaaaaaaaaaabp+1;
+constexpr double c_RC0 = 0x1.3d8b64657caeap-3, c_RC1 = 0x1.4a36c0803a6dfp-1;
+constexpr double c_RE0 = -0x1.418fd8baffe05p+3, c_RE1 = 0x1.61d41b2d54580p+0, c_RE2 = -0x1.5555555555555p-2;
+constexpr double c_MU_REAL = 0x1.d1a48d83e731dp+1;
+constexpr double c_MU_CR = 0x1.572db93e0c672p+1, c_MU_CI = -0x1.86747f2c3fcb6p+1;
+constexpr double c_T00 = 0x1.82d23845d677bp-4, c_T01 = -0x1.214a74c403bf7p-3, c_T02 = 0x1.ebff91a6d688ep-6;
+constexpr double c_T10 = 0x1.0037de70aa1edp-2, c_T11 = 0x1.a20e91e20b551p-3, c_T12 = -0x1.8821fa2a36dedp-2;
+constexpr double c_TI00 = 0x1.0b70201a79c46p+2, c_TI01 = 0x1.4f8c15da84e86p-2, c_TI02 = 0x1.0bf7ff59d56efp-1;
+constexpr double c_TI10 = -0x1.0b70201a79c46p+2, c_TI11 = -0x1.4f8c15da84e86p-2, c_TI12 = 0x1.e810014c55221p-2;
+constexpr double c_TI20 = 0x1.017885a24a7f2p-1, c_TI21 = -0x1.4934e6fcaa598p+1, c_TI22 = 0x1.312c0cf7bdfd1p-1;
+constexpr double c_P00 = 0x1.418fd8baffe05p+3, c_P01 = -0x1.9a12ce7b30915p+4, c_P02 = 0x1.f295c43b61425p+3;
+constexpr double c_P10 = -0x1.61d41b2d54580p+0, c_P11 = 0x1.497af24bb677ep+3, c_P12 = -0x1.1d406ee60becfp+3;
+constexpr double c_P20 = 0x1.5555555555555p-2, c_P21 = -0x1.5555555555555p+1, c_P22 = 0x1.aaaaaaaaaaaabp+1;
+
+
+// On the device the tableau constants are read from constant memory (LDCU.128 into uniform registers, two constants per
+// instruction) instead of being written into the code as immediates, which ptxas materialised with two UMOVs per constant and
+// use inside the rolled Newton loops (5.5 percent of the warp instructions of the pendulum kernel).  Same values, same bits.
+// Measured (GPU call 14 of round 2, constant memory against immediates): pendulum 58.03 / 57.96 ms, Robertson 127.0 / 128.6 ms,
+// transistor 134.9 / 135.5 ms, chain n = 20 161.1 / 165.1 ms -- the kernels are latency-bound, not issue-bound, so the saved
+// instructions buy 0-2 percent.  BRDAE_CONST_BANK=0 restores the immediates (A/B builds).
+#ifndef BRDAE_CONST_BANK
+#define BRDAE_CONST_BANK 1
+#endif
+#if defined(__CUDACC__) && BRDAE_CONST_BANK
+__constant__ double kTableau[32] = {c_RC0, c_RC1, c_RE0, c_RE1, c_RE2, c_MU_REAL, c_MU_CR, c_MU_CI, c_T00, c_T01, c_T02, c_T10, c_T11, c_T12, c_TI00, c_TI01, c_TI02, c_TI10, c_TI11, c_TI12, c_TI20, c_TI21, c_TI22, c_P00, c_P01, c_P02, c_P10, c_P11, c_P12, c_P20, c_P21, c_P22};
+#if defined(__CUDA_ARCH__)
+#define BRDAE_K(name, i) (::brdae::kTableau[i])
+#else
+#define BRDAE_K(name, i) (::brdae::name)
+#endif
+#else
+#define BRDAE_K(name, i) (::brdae::name)
+#endif
+#define RC0 BRDAE_K(c_RC0, 0)
+#define RC1 BRDAE_K(c_RC1, 1)
+#define RE0 BRDAE_K(c_RE0, 2)
+#define RE1 BRDAE_K(c_RE1, 3)
+#define RE2 BRDAE_K(c_RE2, 4)
+#define MU_REAL BRDAE_K(c_MU_REAL, 5)
+#define MU_CR BRDAE_K(c_MU_CR, 6)
+#define MU_CI BRDAE_K(c_MU_CI, 7)
+#define T00 BRDAE_K(c_T00, 8)
+#define T01 BRDAE_K(c_T01, 9)
+#define T02 BRDAE_K(c_T02, 10)
+#define T10 BRDAE_K(c_T10, 11)
+#define T11 BRDAE_K(c_T11, 12)
+#define T12 BRDAE_K(c_T12, 13)
+#define TI00 BRDAE_K(c_TI00, 14)
+#define TI01 BRDAE_K(c_TI01, 15)
+#define TI02 BRDAE_K(c_TI02, 16)
+#define TI10 BRDAE_K(c_TI10, 17)
+#define TI11 BRDAE_K(c_TI11, 18)
+#define TI12 BRDAE_K(c_TI12, 19)
+#define TI20 BRDAE_K(c_TI20, 20)
+#define TI21 BRDAE_K(c_TI21, 21)
+#define TI22 BRDAE_K(c_TI22, 22)
+#define P00 BRDAE_K(c_P00, 23)
+#define P01 BRDAE_K(c_P01, 24)
+#define P02 BRDAE_K(c_P02, 25)
+#define P10 BRDAE_K(c_P10, 26)
+#define P11 BRDAE_K(c_P11, 27)
+#define P12 BRDAE_K(c_P12, 28)
+#define P20 BRDAE_K(c_P20, 29)
+#define P21 BRDAE_K(c_P21, 30)
+#define P22 BRDAE_K(c_P22, 31)
 
 // the same transforms as tables, for loops that are deliberately not unrolled
 #if defined(__CUDACC__)
@@ -41,9 +94,9 @@ constexpr double P20 = 0x1.5555555555555p-2, P21 = -0x1.5555555555555p+1, P22 = 
 #else
 #define BRDAE_TABLE static const double
 #endif
-BRDAE_TABLE kStageT[3][3] = {{T00, T01, T02}, {T10, T11, T12}, {1.0, 1.0, 0.0}};
-BRDAE_TABLE kStageTI[3][3] = {{TI00, TI01, TI02}, {TI10, TI11, TI12}, {TI20, TI21, TI22}};
-BRDAE_TABLE kStageC[3] = {RC0, RC1, 1.0};
+BRDAE_TABLE kStageT[3][3] = {{c_T00, c_T01, c_T02}, {c_T10, c_T11, c_T12}, {1.0, 1.0, 0.0}};
+BRDAE_TABLE kStageTI[3][3] = {{c_TI00, c_TI01, c_TI02}, {c_TI10, c_TI11, c_TI12}, {c_TI20, c_TI21, c_TI22}};
+BRDAE_TABLE kStageC[3] = {c_RC0, c_RC1, 1.0};
 
 // (T W)_i for one component: fma chain over the stages 0,1,2; T[2] = (1, 1, 0)
 template <int I>
