@@ -186,6 +186,9 @@ EXPORTED_SYMBOLS = ("brdae_abi_version", "brdae_strerror", "brdae_problem_lookup
                     "brdae_alloc_pinned", "brdae_free_pinned")
 
 
+ERR_NONFINITE_Y0 = 6          # include/brdae.h
+
+
 def check(rc: int, what: str = "brdae call"):
     if rc != 0:
         msg = load().brdae_strerror(rc).decode()

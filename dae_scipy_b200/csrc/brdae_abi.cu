@@ -38,6 +38,7 @@ const char *brdae_strerror(int code) {
     case BRDAE_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
     case BRDAE_ERR_CUDA: return "CUDA runtime error";
     case BRDAE_ERR_UNSUPPORTED: return "unsupported configuration";
+    case BRDAE_ERR_NONFINITE_Y0: return "all components of the initial state y0 must be finite";
     }
     return "unknown error code";
 }
@@ -331,11 +332,15 @@ static int host_rows_single_launch(const brdae_batch *hb, const brdae_options *o
         CK(cudaMemcpyAsync(hb->status + b0, dst + b0, sizeof(int32_t) * bn, cudaMemcpyDeviceToHost, s_copy));
     }
     if (cudaGetLastError() != cudaSuccess) rc = BRDAE_ERR_CUDA;
-    if (!serial_in) {      // did any lane give up waiting for its input? (word 1 of the workspace header)
-        unsigned long long lost = 0;
-        CK(cudaMemcpyAsync(&lost, static_cast<char *>(ws) + 8, sizeof(lost), cudaMemcpyDeviceToHost, s));
+    {   // words 1 and 2 of the workspace header: did any lane give up waiting for its input?  does y0 hold NaN / inf?  (the
+        // finiteness check scipy makes on the host, base.py:14-17, runs on the device copy behind the kernel: every chunk
+        // has arrived by then)
+        unsigned long long flags2[2] = {0, 0};
+        count_nonfinite(dy0, (int64_t)n * B, reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 16), s);
+        CK(cudaMemcpyAsync(flags2, static_cast<char *>(ws) + 8, sizeof(flags2), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        if (lost != 0) rc = BRDAE_ERR_CUDA;
+        if (!serial_in && flags2[0] != 0) rc = BRDAE_ERR_CUDA;
+        else if (flags2[1] != 0) rc = BRDAE_ERR_NONFINITE_Y0;
     }
     if (timing) {
         CK(cudaEventRecord(ev[3], s_copy));

@@ -25,6 +25,7 @@ int k1_user(bool dense_mass, const SolveArgs &a, int sms, cudaStream_t s, Launch
 int k2_npendulum(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 size_t k2_scratch_bytes(int n, int sms, int64_t B, bool fd);
 // the same kernel for a user band problem with more than 8 unknowns (k2_user.cu; a stub in the stock library)
+void count_nonfinite(const double *v, int64_t n, unsigned long long *count, cudaStream_t s);
 int k2_user(bool dense_mass, const SolveArgs &a, const brdae_batch *b, int sms, cudaStream_t s, LaunchGeom *g, bool geom_only);
 size_t k2_user_scratch_bytes(int n, int sms, int64_t B, bool fd);
 // lane-per-rope block-elimination kernel for the chain (k4_chain.cu, chain_k4.cuh)

@@ -70,7 +70,8 @@ enum {
 /* error codes */
 enum {
     BRDAE_OK = 0, BRDAE_ERR_BAD_ARGUMENT = 1, BRDAE_ERR_UNKNOWN_PROBLEM = 2,
-    BRDAE_ERR_WORKSPACE_TOO_SMALL = 3, BRDAE_ERR_CUDA = 4, BRDAE_ERR_UNSUPPORTED = 5
+    BRDAE_ERR_WORKSPACE_TOO_SMALL = 3, BRDAE_ERR_CUDA = 4, BRDAE_ERR_UNSUPPORTED = 5,
+    BRDAE_ERR_NONFINITE_Y0 = 6      /* brdae_solve_host_rows: y0 holds NaN or inf (scipy raises ValueError for it, base.py:14-17) */
 };
 
 /* POD mirror of the RadauDAE constructor keywords (radauDAE.py:263-278) plus solve_ivp_custom's

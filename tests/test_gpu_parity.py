@@ -209,12 +209,25 @@ def test_host_buffer_entry_equals_device_entry():
     assert np.array_equal(r1["y"], ref["y"]) and np.array_equal(r1["counters"], ref["counters"])
 
 
+@pytest.mark.gpu
 def test_invalid_y0_raises_like_scipy():
     ens = E.pendulum_ensemble(4)
     y0 = ens["y0"].copy()
     y0[2, 1] = np.nan
     with pytest.raises(ValueError, match="must be finite"):
         br.solve_ivp_batched(ens["problem"], ens["t_span"], y0, ens["params"], t_eval=ens["t_eval"], **ens["options"])
+    # the host-buffer entry makes the same check on the device copy of y0 (BRDAE_ERR_NONFINITE_Y0), NaN and inf, any position
+    for bad, where in ((np.nan, (2, 1)), (np.inf, (3, 4)), (-np.inf, (0, 0))):
+        y0 = E.pendulum_ensemble(70000)["y0"]
+        ens_b = E.pendulum_ensemble(70000)
+        y0[(where[0] * 17001) % 70000, where[1]] = bad
+        with pytest.raises(ValueError, match="must be finite"):
+            br.solve_ivp_batched_host(ens_b["problem"], ens_b["t_span"], y0, ens_b["params"], t_eval=ens_b["t_eval"], **ens_b["options"])
+    ens_c = E.npendulum_ensemble(3, n_nodes=4)
+    y0 = ens_c["y0"].copy()
+    y0[1, 7] = np.nan
+    with pytest.raises(ValueError, match="must be finite"):                   # chunked entry of the chain: host-side check
+        br.solve_ivp_batched_host(ens_c["problem"], ens_c["t_span"], y0, None, t_eval=ens_c["t_eval"], **ens_c["options"])
 
 
 def test_gpu_dense_output_record_equals_kernel_source_and_t_eval():
