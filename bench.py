@@ -297,9 +297,6 @@ def main():
         csum = res.counters.sum(dim=1, dtype=torch.int64)
         reduce_statistics(csum, status_histogram(res.status), dist if world > 1 else None, dev)
     barrier()
-    # measured FP64 roofline denominator (burst DFMA probe on this device)
-    fp64_peak = br.fp64_peak_tflops(60.0)
-    barrier()
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -348,6 +345,12 @@ def main():
         with_gather = {"value": systems_all * args.steps / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms / args.steps,
                        "gathered_bytes_per_step_into_rank0": gather_bytes,
                        "what": "solve + all_reduce of the statistics + dist.gather of y_eval, y_final, t_final, status, n_eval, counters onto rank 0 (NCCL)"}
+
+    # measured FP64 roofline denominator: burst DFMA probe on this device, run AFTER the timed regions (60 ms at full FP64 power
+    # right before them is a disturbance the measurement does not need)
+    barrier()
+    fp64_peak = br.fp64_peak_tflops(60.0)
+    barrier()
 
     # roofline of the dominant (only) kernel: algorithmic FLOPs of one launch / its duration
     out_counts = res.counters.sum(dim=1, dtype=torch.int64).cpu().numpy()
