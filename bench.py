@@ -422,9 +422,15 @@ def main():
 
         # what bounds the end-to-end rate with several ranks on one host: the plain device-to-host copy rate of a buffer of the
         # result's size into page-locked memory, all ranks copying at the same time (no kernel, no host work)
+        probe_d = probe_h = None
         try:
             probe_d = torch.empty(d2h // 8, dtype=torch.float64, device=dev)
             probe_h = torch.empty(d2h // 8, dtype=torch.float64, pin_memory=True)
+            ok = 1.0
+        except Exception as exc:
+            ok = 0.0
+            e2e["d2h_probe_error"] = repr(exc)
+        if -max_over_ranks(-ok) > 0.5:           # every rank got its buffers (a rank that did not must not leave the others in a barrier)
             probe_h.copy_(probe_d, non_blocking=True)
             barrier()
             t0 = time.perf_counter()
@@ -434,10 +440,9 @@ def main():
             dtp = max_over_ranks(time.perf_counter() - t0)
             e2e["d2h_copy_probe_gbs_all_ranks"] = 3 * d2h * world / dtp / 1e9
             e2e["d2h_bound_on_e2e"] = systems_all / (d2h * world / (e2e["d2h_copy_probe_gbs_all_ranks"] * 1e9))
-            del probe_d, probe_h
-        except Exception as exc:
+        else:
             e2e["d2h_copy_probe_gbs_all_ranks"] = None
-            e2e["d2h_probe_error"] = repr(exc)
+        del probe_d, probe_h
 
     clk.__exit__(None, None, None)
 

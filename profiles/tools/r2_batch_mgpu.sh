@@ -11,7 +11,7 @@ run() {  # tag nproc args...
 import json; d=json.loads(open('gpurun_out/r2mg_$tag.json').read().strip().splitlines()[-1]); print('$tag', 'value', round(d['value']), 'ms', round(d['ms_per_step'],2), 'e2e', d['e2e'] and round(d['e2e']['value']), 'gather', d['value_with_gather'] and round(d['value_with_gather']['value']), d['config'].get('host_placement'), d['status_histogram'])"
 }
 timeout -k 10 300 python -m pytest tests -m gpu -q -x -k "nccl" > gpurun_out/r2mg_pytest_nccl_n$N.log 2>&1; echo "pytest nccl rc=$?"; tail -2 gpurun_out/r2mg_pytest_nccl_n$N.log
-for np in 1 2 4 8; do
+for np in 2 4 8; do
   [ $np -le $N ] || continue
   run weak_n$np $np --steps 5 --warmup 3
   run strong_rob_n$np $np --workload robertson_4M --scaling strong --steps 5 --warmup 3
