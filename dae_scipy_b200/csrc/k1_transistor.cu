@@ -2,6 +2,8 @@
 // non-diagonal mass matrix built from each system's capacitances).
 #include "k1_launch.cuh"
 
+// launch geometry: one 256-thread CTA per SM (two 128-thread CTAs: 140.5 against 135.5 ms; four 64-thread CTAs: 196.6 ms --
+// GPU call 18 of round 2)
 #ifndef K1_TRA_BLOCK
 #define K1_TRA_BLOCK 256
 #endif
