@@ -50,8 +50,8 @@ WORKLOADS = {
 NCU_DRAM_BYTES_PER_SYSTEM = {
     "pendulum3_1M_tend2": ((160.46e6 + 333.03e6) / 262144, "profiles/r02_k1_ncu_summary.md (v9, 262,144 systems)"),
     "pendulum3_1M_tend10": ((160.46e6 + 333.03e6) / 262144, "profiles/r02_k1_ncu_summary.md (same kernel and output grid as t_end = 2)"),
-    "robertson_4M": ((18.2e6 + 71.0e6) / 262144, "profiles/r01_k1_ncu_summary.md (Robertson, 262,144 systems: part of that launch's output was still in L2 at kernel end)"),
-    "transistor_256k": ((10.8e6 + 12.9e6) / 65536, "profiles/r01_k1_ncu_summary.md (transistor, 65,536 systems: that launch's output was still in L2 at kernel end)"),
+    "robertson_4M": ((78.3e6 + 448.8e6) / 1048576, "profiles/r02_k1_ncu_summary.md (Robertson, 1,048,576 systems)"),
+    "transistor_256k": ((10.4e6 + 8.5e6) / 65536, "profiles/r02_k1_ncu_summary.md (transistor, 65,536 systems: part of that launch's output was still in L2 at kernel end)"),
     "npendulum_n20_16k": ((575.0e9 + 187.6e9) / 16384, "profiles/r02_k4_ncu_summary.md (K4, final capture of round 2, n = 20, 16,384 ropes)"),
 }
 
