@@ -126,3 +126,15 @@ def test_integration_md_stub_matches_the_abi():
     assert [(f[0], getattr(Batch, f[0]).offset) for f in Batch._fields_] == \
            [(f[0], getattr(_abi.BrdaeBatch, f[0]).offset) for f in _abi.BrdaeBatch._fields_]
     assert callable(ns["solve_ivp_ensemble"]) and ns["_lib"].brdae_abi_version() == _abi.ABI_VERSION
+
+
+def test_error_codes_of_the_header_match_the_python_side():
+    """include/brdae.h is the contract: the codes the host side interprets are the header's."""
+    import re
+    text = open(os.path.join(ROOT, "include", "brdae.h")).read()
+    codes = {m.group(1): int(m.group(2)) for m in re.finditer(r"(BRDAE_(?:OK|ERR_[A-Z0-9_]+))\s*=\s*(\d+)", text)}
+    assert codes["BRDAE_OK"] == 0 and codes["BRDAE_ERR_NONFINITE_Y0"] == _abi.ERR_NONFINITE_Y0 == 6
+    lib = _abi.load()
+    lib.brdae_strerror.restype = C.c_char_p
+    for name, code in codes.items():
+        assert lib.brdae_strerror(code).decode() not in ("", "unknown error"), name
